@@ -1,0 +1,281 @@
+"""ctypes binding of libnlkalman_b200.so (include/nlkalman.h + include/nlkalman_b200.h).
+
+Host-side mirror of the reference interface for Python callers (tests, bench): the six
+drop-in entry points keep the reference's names and argument meaning
+(reference src/nlkalman.h:14-53); ``Context`` wraps the additive resident-state API.
+There is no fallback of any kind: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnlkalman_b200.so")
+
+FLT1, FLT2, SMO1 = 0, 1, 2
+
+
+class NlkError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """struct nlkalman_params (include/nlkalman.h; reference src/nlkalman.h:22-37)."""
+    _fields_ = [("patch_sz", C.c_int), ("search_sz_x", C.c_int), ("search_sz_t", C.c_int),
+                ("npatches_x", C.c_int), ("npatches_t", C.c_int), ("npatches_tagg", C.c_int),
+                ("dista_lambda", C.c_float), ("beta_x", C.c_float), ("beta_t", C.c_float)]
+
+    @classmethod
+    def auto(cls, **kw):
+        """All fields -1 ("automatic", reference src/main-flt.c:39-52), then overrides."""
+        p = cls(-1, -1, -1, -1, -1, -1, -1.0, -1.0, -1.0)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+_bp = C.POINTER(C.c_ubyte)
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NlkError(f"{LIB_PATH} is missing: build it with `make -C {HERE}` "
+                       "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.nlk_last_error.restype = C.c_char_p
+    L.nlk_device_count.restype = C.c_int
+    L.nlk_ctx_create.restype = vp
+    L.nlk_ctx_create.argtypes = [C.c_int] * 4
+    L.nlk_ctx_destroy.argtypes = [vp]
+    L.nlk_ctx_destroy.restype = None
+    L.nlk_ctx_sync.argtypes = [vp]
+    L.nlk_ctx_launch_count.argtypes = [vp]
+    L.nlk_ctx_launch_count.restype = C.c_longlong
+    L.nlk_ctx_stream.argtypes = [vp]
+    L.nlk_ctx_stream.restype = vp
+    L.nlk_host_alloc.argtypes = [C.c_size_t]
+    L.nlk_host_alloc.restype = vp
+    L.nlk_host_free.argtypes = [vp]
+    L.nlk_host_free.restype = None
+    L.nlk_rgb2opp_dev.argtypes = [vp, vp, vp]
+    L.nlk_opp2rgb_dev.argtypes = [vp, vp, vp]
+    L.nlk_warp_dev.argtypes = [vp, vp, vp, vp, vp]
+    L.nlk_pass_dev.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_float, Params]
+    L.nlk_seq_reset.argtypes = [vp]
+    L.nlk_seq_filter_dev.argtypes = [vp, vp, vp, vp, C.c_float, Params, Params, vp, vp]
+    L.nlk_seq_filter_host.argtypes = [vp, vp, vp, vp, C.c_float, Params, Params, vp, vp]
+    L.nlk_seq_smooth_start_dev.argtypes = [vp, vp]
+    L.nlk_seq_smooth_dev.argtypes = [vp, vp, vp, vp, C.c_float, Params, vp]
+    L.nlk_seq_smooth_start_host.argtypes = [vp, vp]
+    L.nlk_seq_smooth_host.argtypes = [vp, vp, vp, vp, C.c_float, Params, vp]
+    L.nlk_pass_host_debug.argtypes = [vp, C.c_int, _fp, _fp, _fp, _fp, C.c_float, Params, C.c_int,
+                                      _ip, _ip, _ip, _fp, _bp, _bp, _fp]
+    L.nlk_dct_host.argtypes = [vp, _fp, C.c_int, C.c_int, C.c_int]
+    # drop-in entry points
+    L.rgb2opp.argtypes = L.opp2rgb.argtypes = [_fp, C.c_int, C.c_int, C.c_int]
+    L.warp_bicubic.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int]
+    L.nlkalman_default_params.argtypes = [C.POINTER(Params), C.c_float, C.c_int]
+    sig = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, Params, C.c_int]
+    L.nlkalman_filter_frame.argtypes = sig
+    L.nlkalman_smooth_frame.argtypes = sig
+    for f in (L.rgb2opp, L.opp2rgb, L.warp_bicubic, L.nlkalman_default_params,
+              L.nlkalman_filter_frame, L.nlkalman_smooth_frame):
+        f.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise NlkError(f"libnlkalman_b200 error {rc}: {lib().nlk_last_error().decode()}")
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.dtype == np.float32 and a.flags["C_CONTIGUOUS"], \
+        "float32 C-contiguous HWC arrays only"
+    return a.ctypes.data_as(_fp)
+
+
+def _vp(a):
+    """host ndarray, torch tensor (host or device) or raw int -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+# ---- the six reference entry points, same names and argument meaning ------------------------
+
+def default_params(sigma: float, mode: int, p: Params | None = None) -> Params:
+    p = p if p is not None else Params.auto()
+    lib().nlkalman_default_params(C.byref(p), float(sigma), int(mode))
+    return p
+
+
+def rgb2opp(im: np.ndarray) -> np.ndarray:
+    h, w, ch = im.shape
+    lib().rgb2opp(_p(im), w, h, ch)
+    return im
+
+
+def opp2rgb(im: np.ndarray) -> np.ndarray:
+    h, w, ch = im.shape
+    lib().opp2rgb(_p(im), w, h, ch)
+    return im
+
+
+def warp_bicubic(im: np.ndarray, of: np.ndarray, msk: np.ndarray | None) -> np.ndarray:
+    h, w, ch = im.shape
+    out = np.empty_like(im)
+    lib().warp_bicubic(_p(out), _p(im), _p(of), _p(msk), w, h, ch)
+    return out
+
+
+def nlkalman_filter_frame(nisy1, deno0, bsic1, sigma, prms: Params) -> np.ndarray:
+    h, w, ch = nisy1.shape
+    out = np.empty_like(nisy1)
+    lib().nlkalman_filter_frame(_p(out), _p(nisy1), _p(deno0), _p(bsic1), w, h, ch, float(sigma), prms, 0)
+    return out
+
+
+def nlkalman_smooth_frame(filt1, smoo0, bsic1, sigma, prms: Params) -> np.ndarray:
+    h, w, ch = filt1.shape
+    out = np.empty_like(filt1)
+    lib().nlkalman_smooth_frame(_p(out), _p(filt1), _p(smoo0), _p(bsic1), w, h, ch, float(sigma), prms, 0)
+    return out
+
+
+# ---- resident-state context --------------------------------------------------------------------
+
+class Context:
+    """nlk_ctx: buffers and the recursion state of one sequence resident on one GPU."""
+
+    def __init__(self, w: int, h: int, ch: int, device: int = 0):
+        L = lib()
+        self.w, self.h, self.ch, self.device = w, h, ch, device
+        self._h = L.nlk_ctx_create(w, h, ch, device)
+        if not self._h:
+            raise NlkError(f"nlk_ctx_create failed: {L.nlk_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nlk_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        _check(lib().nlk_ctx_sync(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(lib().nlk_ctx_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().nlk_ctx_stream(self._h) or 0)
+
+    # device-pointer operations (torch CUDA tensors or raw pointers)
+    def rgb2opp_dev(self, dst, src):
+        _check(lib().nlk_rgb2opp_dev(self._h, _vp(dst), _vp(src)))
+
+    def opp2rgb_dev(self, dst, src):
+        _check(lib().nlk_opp2rgb_dev(self._h, _vp(dst), _vp(src)))
+
+    def warp_dev(self, imw, im, of, msk):
+        _check(lib().nlk_warp_dev(self._h, _vp(imw), _vp(im), _vp(of), _vp(msk)))
+
+    def pass_dev(self, smooth, out, in1, prev0, bsic1, sigma, prms: Params):
+        _check(lib().nlk_pass_dev(self._h, int(smooth), _vp(out), _vp(in1), _vp(prev0), _vp(bsic1),
+                                  float(sigma), prms))
+
+    # resident sequence recursion
+    def seq_reset(self):
+        _check(lib().nlk_seq_reset(self._h))
+
+    def seq_filter_dev(self, noisy, bflo, bocc, sigma, f1: Params, f2: Params, flt1_out, flt2_out):
+        _check(lib().nlk_seq_filter_dev(self._h, _vp(noisy), _vp(bflo), _vp(bocc), float(sigma), f1, f2,
+                                        _vp(flt1_out), _vp(flt2_out)))
+
+    def seq_filter_host(self, noisy, bflo, bocc, sigma, f1: Params, f2: Params, flt1_out, flt2_out):
+        _check(lib().nlk_seq_filter_host(self._h, _vp(noisy), _vp(bflo), _vp(bocc), float(sigma), f1, f2,
+                                         _vp(flt1_out), _vp(flt2_out)))
+
+    def seq_smooth_start_dev(self, last_rgb):
+        _check(lib().nlk_seq_smooth_start_dev(self._h, _vp(last_rgb)))
+
+    def seq_smooth_dev(self, flt_rgb, fflo, focc, sigma, s1: Params, smo_out):
+        _check(lib().nlk_seq_smooth_dev(self._h, _vp(flt_rgb), _vp(fflo), _vp(focc), float(sigma), s1,
+                                        _vp(smo_out)))
+
+    def seq_smooth_start_host(self, last_rgb):
+        _check(lib().nlk_seq_smooth_start_host(self._h, _vp(last_rgb)))
+
+    def seq_smooth_host(self, flt_rgb, fflo, focc, sigma, s1: Params, smo_out):
+        _check(lib().nlk_seq_smooth_host(self._h, _vp(flt_rgb), _vp(fflo), _vp(focc), float(sigma), s1,
+                                         _vp(smo_out)))
+
+    # parity-test helpers
+    def pass_host_debug(self, smooth, in1, prev0, bsic1, sigma, prms: Params):
+        h, w, ch = in1.shape
+        assert (w, h, ch) == (self.w, self.h, self.ch)
+        psz, step = prms.patch_sz, prms.patch_sz // 2
+        gw, gh = (w - psz) // step + 1, (h - psz) // step + 1
+        G = gw * gh
+        kmax = max(prms.npatches_x, prms.npatches_t, 1)
+        out = np.empty_like(in1)
+        res = dict(kmax=kmax, gw=gw, gh=gh,
+                   nk=np.zeros(G, np.int32), np0=np.zeros(G, np.int32),
+                   knn_xy=np.full((G, kmax, 2), -1, np.int32), knn_d=np.zeros((G, kmax), np.float32),
+                   prev_p=np.zeros(G, np.uint8), active=np.zeros(G, np.uint8), vp=np.zeros(G, np.float32))
+        _check(lib().nlk_pass_host_debug(
+            self._h, int(smooth), _p(out), _p(in1), _p(prev0), _p(bsic1), float(sigma), prms, kmax,
+            res["nk"].ctypes.data_as(_ip), res["np0"].ctypes.data_as(_ip),
+            res["knn_xy"].ctypes.data_as(_ip), _p(res["knn_d"]),
+            res["prev_p"].ctypes.data_as(_bp), res["active"].ctypes.data_as(_bp), _p(res["vp"])))
+        return out, res
+
+    def dct(self, tiles: np.ndarray, inverse: bool = False) -> np.ndarray:
+        t = np.ascontiguousarray(tiles, dtype=np.float32).copy()
+        n, psz, _ = t.shape
+        _check(lib().nlk_dct_host(self._h, _p(t), psz, n, 1 if inverse else 0))
+        return t
+
+
+def device_count() -> int:
+    n = lib().nlk_device_count()
+    if n < 0:
+        raise NlkError(lib().nlk_last_error().decode())
+    return n

@@ -1,0 +1,138 @@
+// Orthonormal DCT-II / DCT-III of psz x psz tiles on CUDA cores (replaces the
+// reference's per-thread FFTW plans, src/nlkalman.c:138-360, whose net effect for a
+// depth-1 batch is the textbook orthonormal 2-D DCT, see :281-299 and :335-353).
+//
+// 1-D transforms use the even/odd split of the DCT matrix T (N even):
+//   X[2m]   = sum_j T[2m][j]   (x[j] + x[N-1-j]),   X[2m+1] = sum_j T[2m+1][j] (x[j] - x[N-1-j])
+// with T read from constant memory at compile-time offsets, so every product is one
+// FFMA with a constant-bank operand.  A tile is owned by one thread: for 8x8 the whole
+// tile lives in registers; other sizes run the row and column passes through the
+// thread's own shared-memory tile.
+#pragma once
+#include "nlk_common.cuh"
+
+namespace nlk {
+
+template <int N>
+__device__ __forceinline__ void dct1d_fwd(float (&x)[N])
+{
+    static_assert(N % 2 == 0, "even sizes only");
+    constexpr int H = N / 2;
+    float s[H], d[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) { s[j] = x[j] + x[N - 1 - j]; d[j] = x[j] - x[N - 1 - j]; }
+#pragma unroll
+    for (int m = 0; m < H; ++m) {
+        float e = 0.f, o = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            e = fmaf(c_dct[N][(2 * m) * N + j], s[j], e);
+            o = fmaf(c_dct[N][(2 * m + 1) * N + j], d[j], o);
+        }
+        x[2 * m] = e;
+        x[2 * m + 1] = o;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void dct1d_inv(float (&X)[N])
+{
+    static_assert(N % 2 == 0, "even sizes only");
+    constexpr int H = N / 2;
+    float e[H], o[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int m = 0; m < H; ++m) {
+            a = fmaf(c_dct[N][(2 * m) * N + j], X[2 * m], a);
+            b = fmaf(c_dct[N][(2 * m + 1) * N + j], X[2 * m + 1], b);
+        }
+        e[j] = a;
+        o[j] = b;
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) { X[j] = e[j] + o[j]; X[N - 1 - j] = e[j] - o[j]; }
+}
+
+// whole 8x8 tile in registers
+template <bool INVERSE>
+__device__ __forceinline__ void dct2d_8x8_smem(float *__restrict__ tile)
+{
+    float t[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) t[i] = tile[i];
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = t[y * 8 + i];
+        if (INVERSE) dct1d_inv<8>(r); else dct1d_fwd<8>(r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[y * 8 + i] = r[i];
+    }
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = t[i * 8 + x];
+        if (INVERSE) dct1d_inv<8>(r); else dct1d_fwd<8>(r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i * 8 + x] = r[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 64; ++i) tile[i] = t[i];
+}
+
+// row pass then column pass through the thread's own shared-memory tile
+template <int N, bool INVERSE>
+__device__ __forceinline__ void dct2d_passes_smem(float *__restrict__ tile)
+{
+    for (int y = 0; y < N; ++y) {
+        float r[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = tile[y * N + i];
+        if (INVERSE) dct1d_inv<N>(r); else dct1d_fwd<N>(r);
+#pragma unroll
+        for (int i = 0; i < N; ++i) tile[y * N + i] = r[i];
+    }
+    for (int x = 0; x < N; ++x) {
+        float r[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] = tile[i * N + x];
+        if (INVERSE) dct1d_inv<N>(r); else dct1d_fwd<N>(r);
+#pragma unroll
+        for (int i = 0; i < N; ++i) tile[i * N + x] = r[i];
+    }
+}
+
+// any side up to MAX_PSZ (also odd ones): plain matrix form, run-time size
+template <bool INVERSE>
+__device__ inline void dct2d_generic_smem(float *__restrict__ tile, int n)
+{
+    float r[MAX_PSZ];
+    const float *T = c_dct[n];
+    for (int pass = 0; pass < 2; ++pass) {
+        const int line_stride = pass == 0 ? n : 1, elem_stride = pass == 0 ? 1 : n;
+        for (int l = 0; l < n; ++l) {
+            float *p = tile + l * line_stride;
+            for (int i = 0; i < n; ++i) r[i] = p[i * elem_stride];
+            for (int k = 0; k < n; ++k) {
+                float acc = 0.f;
+                for (int j = 0; j < n; ++j)
+                    acc = fmaf(INVERSE ? T[j * n + k] : T[k * n + j], r[j], acc);
+                p[k * elem_stride] = acc;
+            }
+        }
+    }
+}
+
+template <int PSZ_T, bool INVERSE>
+__device__ __forceinline__ void dct2d_tile(float *__restrict__ tile, int psz_rt)
+{
+    if constexpr (PSZ_T == 8) dct2d_8x8_smem<INVERSE>(tile);
+    else if constexpr (PSZ_T != 0) dct2d_passes_smem<PSZ_T, INVERSE>(tile);
+    else dct2d_generic_smem<INVERSE>(tile, psz_rt);
+}
+
+} // namespace nlk

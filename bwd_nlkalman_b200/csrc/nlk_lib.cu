@@ -1,0 +1,701 @@
+// libnlkalman_b200.so: the C ABI (include/nlkalman.h, include/nlkalman_b200.h) over the
+// sm_100a kernels.  Single translation unit: the kernel headers are included here.
+#include "../../include/nlkalman_b200.h"
+
+#include "nlk_common.cuh"
+#include "nlk_prep.cuh"
+#include "nlk_search.cuh"
+#include "nlk_resolve.cuh"
+#include "nlk_group.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace nlk;
+
+// ---- errors -----------------------------------------------------------------------------------
+
+static thread_local std::string g_err;
+
+static int set_err(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return set_err(NLK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),  \
+                           __FILE__, __LINE__);                                                   \
+    } while (0)
+
+extern "C" const char *nlk_last_error(void) { return g_err.c_str(); }
+
+// ---- constant tables --------------------------------------------------------------------------
+
+static int upload_tables_dev()
+{
+    static float dct[MAX_PSZ + 1][MAX_PSZ * MAX_PSZ];
+    static float win[MAX_PSZ + 1][MAX_PSZ * MAX_PSZ];
+    static float inv[MAX_K + 1];
+    const double pi = 3.14159265358979323846264338327950288;
+    memset(dct, 0, sizeof dct);
+    memset(win, 0, sizeof win);
+    for (int n = 1; n <= MAX_PSZ; ++n) {
+        for (int k = 0; k < n; ++k)
+            for (int j = 0; j < n; ++j)
+                dct[n][k * n + j] = (float)(sqrt((k ? 2.0 : 1.0) / n) * cos(pi * (j + 0.5) * k / n));
+        // Gaussian window, reference src/nlkalman.c:367-368, :401-407, :413-416
+        float w1[MAX_PSZ];
+        const float N = (float)n;
+        const float N2 = (float)((N - 1.) / 2.);
+        for (int i = 0; i < n; ++i) {
+            const float s = .4f;
+            const float x = ((float)i - N2) / N2 / s;
+            w1[i] = (float)exp(-.5 * x * x);
+        }
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) win[n][i * n + j] = w1[i] * w1[j];
+    }
+    inv[0] = 0.f;
+    for (int n = 1; n <= MAX_K; ++n) inv[n] = (float)(1. / (float)n);
+    CU_TRY(cudaMemcpyToSymbol(c_dct, dct, sizeof dct));
+    CU_TRY(cudaMemcpyToSymbol(c_win, win, sizeof win));
+    CU_TRY(cudaMemcpyToSymbol(c_inv, inv, sizeof inv));
+    return NLK_OK;
+}
+
+// ---- context ----------------------------------------------------------------------------------
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return NLK_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        CU_TRY(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return NLK_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct nlk_ctx {
+    int w = 0, h = 0, ch = 0, device = 0, num_sms = 148;
+    cudaStream_t st = nullptr;
+    long long launches = 0;
+    // per-pass scratch
+    DevBuf accw, valid, valid_tmp, cand, hdr, nbr, active, counters, gmask, dbg_dist, dbg_vp;
+    // host-call staging
+    DevBuf s_in1, s_prev0, s_bsic, s_out, s_of, s_msk;
+    // sequence state (opponent colour space)
+    DevBuf q_noisy, q_warp, q_flt1[2], q_flt2[2], q_smo[2], q_tmp;
+    int q_cur = 0, q_have_prev = 0, q_have_flt2 = 0;
+    int q_smo_cur = 0, q_have_smo = 0;
+    size_t img_bytes() const { return (size_t)w * h * ch * sizeof(float); }
+};
+
+static int ctx_use(nlk_ctx *c)
+{
+    if (!c) return set_err(NLK_ERR_PARAM, "null context");
+    CU_TRY(cudaSetDevice(c->device));
+    return NLK_OK;
+}
+
+extern "C" int nlk_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return set_err(NLK_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+extern "C" nlk_ctx *nlk_ctx_create(int w, int h, int ch, int device)
+{
+    if (w <= 0 || h <= 0 || ch <= 0 || ch > MAX_CH || w > 32767 || h > 32767) {
+        set_err(NLK_ERR_PARAM, "unsupported frame %dx%dx%d (1..%d channels, sides < 32768)", w, h, ch, MAX_CH);
+        return nullptr;
+    }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        set_err(NLK_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+        return nullptr;
+    }
+    nlk_ctx *c = new nlk_ctx();
+    c->w = w; c->h = h; c->ch = ch; c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
+        upload_tables_dev() != NLK_OK || c->counters.ensure(64) != NLK_OK) {
+        if (g_err.empty()) set_err(NLK_ERR_CUDA, "context creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+extern "C" void nlk_ctx_destroy(nlk_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    DevBuf *all[] = {&c->accw, &c->valid, &c->valid_tmp, &c->cand, &c->hdr, &c->nbr, &c->active,
+                     &c->counters, &c->gmask, &c->dbg_dist, &c->dbg_vp, &c->s_in1, &c->s_prev0,
+                     &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk, &c->q_noisy, &c->q_warp,
+                     &c->q_flt1[0], &c->q_flt1[1], &c->q_flt2[0], &c->q_flt2[1], &c->q_smo[0],
+                     &c->q_smo[1], &c->q_tmp};
+    for (DevBuf *b : all) b->release();
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+
+extern "C" int nlk_ctx_sync(nlk_ctx *c)
+{
+    if (int r = ctx_use(c)) return r;
+    CU_TRY(cudaStreamSynchronize(c->st));
+    return NLK_OK;
+}
+
+extern "C" long long nlk_ctx_launch_count(const nlk_ctx *c) { return c ? c->launches : 0; }
+extern "C" void *nlk_ctx_stream(nlk_ctx *c) { return c ? (void *)c->st : nullptr; }
+
+extern "C" void *nlk_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        set_err(NLK_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void nlk_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- one pass ---------------------------------------------------------------------------------
+
+static int check_launch(nlk_ctx *c, int n, const char *what)
+{
+    if (n < 0) return set_err(NLK_ERR_PARAM, "%s: configuration not supported by the kernels", what);
+    c->launches += n;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(NLK_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+    return NLK_OK;
+}
+
+static int run_pass(nlk_ctx *c, int smooth, float *d_out, const float *d_in1, const float *d_prev0,
+                    const float *d_bsic1, float sigma, const nlkalman_params &pr, bool debug)
+{
+    const int w = c->w, h = c->h, ch = c->ch;
+    const int psz = pr.patch_sz;
+    if (psz < 2 || psz > MAX_PSZ)
+        return set_err(NLK_ERR_PARAM, "patch size %d not supported (2..%d)", psz, MAX_PSZ);
+    if (pr.search_sz_x < 0 || pr.search_sz_t < 0 || pr.npatches_x < 0 || pr.npatches_t < 0 ||
+        pr.npatches_tagg < 0)
+        return set_err(NLK_ERR_PARAM, "negative parameter: call nlkalman_default_params first");
+
+    PassParams P;
+    memset(&P, 0, sizeof P);
+    P.w = w; P.h = h; P.ch = ch; P.psz = psz; P.step = psz / 2;
+    const bool fits = (w >= psz && h >= psz);
+    P.gw = fits ? (w - psz) / P.step + 1 : 0;
+    P.gh = fits ? (h - psz) / P.step + 1 : 0;
+    P.G = P.gw * P.gh;
+    P.smooth = smooth;
+    P.r_x = pr.search_sz_x; P.r_t = pr.search_sz_t;
+    P.k_x = pr.npatches_x; P.k_t = pr.npatches_t; P.tagg = pr.npatches_tagg;
+    P.sigma2 = sigma * sigma; P.beta_x = pr.beta_x; P.beta_t = pr.beta_t;
+    P.has_prev = d_prev0 != nullptr; P.has_bsic = d_bsic1 != nullptr;
+    P.src = d_bsic1 ? d_bsic1 : d_in1;
+    P.in1 = d_in1; P.prev0 = d_prev0;
+    P.vw = w - psz + 1; P.vh = h - psz + 1;
+    const int rmax = smooth ? P.r_t : (P.r_t > P.r_x ? P.r_t : P.r_x);
+    const int ncand = (2 * rmax + 1) * (2 * rmax + 1);
+    if (ncand > SEARCH_MAX_NPAD)
+        return set_err(NLK_ERR_PARAM, "search radius %d not supported (window > %d candidates)", rmax, SEARCH_MAX_NPAD);
+    int kmax = P.k_x > P.k_t ? P.k_x : P.k_t;
+    if (kmax > ncand) kmax = ncand;
+    if (kmax < 1) kmax = 1;
+    if (kmax > MAX_K) return set_err(NLK_ERR_PARAM, "more than %d patches per group", MAX_K);
+    P.kstride = kmax;
+    P.R = rmax / P.step;
+    P.nbw = ((2 * P.R + 1) * (2 * P.R + 1) + 31) / 32;
+
+    const size_t npix = (size_t)w * h;
+    const size_t G = (size_t)(P.G > 0 ? P.G : 1);
+    if (int r = c->accw.ensure(npix * (ch + 1) * 4)) return r;
+    if (int r = c->cand.ensure(G * kmax * 4)) return r;
+    if (int r = c->hdr.ensure(G * sizeof(GroupHdr))) return r;
+    if (int r = c->nbr.ensure(G * P.nbw * 4)) return r;
+    if (int r = c->active.ensure(G * 4)) return r;
+    if (int r = c->gmask.ensure(G)) return r;
+    P.accw = c->accw.as<float>();
+    P.cand = c->cand.as<uint32_t>();
+    P.hdr = c->hdr.as<GroupHdr>();
+    P.nbr = c->nbr.as<uint32_t>();
+    P.active = c->active.as<int>();
+    P.gmask = c->gmask.as<uint8_t>();
+    P.nactive = c->counters.as<int>();
+    P.any_nbr = c->counters.as<int>() + 1;
+    P.out = d_out;
+    if (debug) {
+        if (int r = c->dbg_dist.ensure(G * kmax * 4)) return r;
+        if (int r = c->dbg_vp.ensure(G * 4)) return r;
+        P.dbg_dist = c->dbg_dist.as<float>();
+        P.dbg_vp = c->dbg_vp.as<float>();
+        CU_TRY(cudaMemsetAsync(P.dbg_dist, 0, G * kmax * 4, c->st));
+        CU_TRY(cudaMemsetAsync(P.dbg_vp, 0, G * 4, c->st));
+        CU_TRY(cudaMemsetAsync(P.cand, 0xff, G * kmax * 4, c->st));
+    }
+
+    CU_TRY(cudaMemsetAsync(P.accw, 0, npix * (ch + 1) * 4, c->st));
+    CU_TRY(cudaMemsetAsync(c->counters.p, 0, 64, c->st));
+    if (P.G > 0) {
+        if (d_prev0) {
+            if (int r = c->valid.ensure((size_t)P.vw * P.vh)) return r;
+            if (int r = c->valid_tmp.ensure((size_t)P.vw * h)) return r;
+            P.valid = c->valid.as<uint8_t>();
+            if (int r = check_launch(c, launch_valid_map(c->valid.as<uint8_t>(), c->valid_tmp.as<uint8_t>(),
+                                                         d_prev0, w, h, ch, psz, c->st), "valid_map")) return r;
+        }
+        if (int r = check_launch(c, launch_search(P, c->st), "search_knn")) return r;
+        if (int r = check_launch(c, launch_resolve(P, c->st), "mask_resolve")) return r;
+        if (int r = check_launch(c, launch_group_filter(P, c->num_sms, c->st), "group_filter")) return r;
+    }
+    if (int r = check_launch(c, launch_normalize(P, c->st), "normalize")) return r;
+    return NLK_OK;
+}
+
+extern "C" int nlk_pass_dev(nlk_ctx *c, int smooth, float *d_out, const float *d_in1,
+                            const float *d_prev0, const float *d_bsic1, float sigma,
+                            struct nlkalman_params prms)
+{
+    if (int r = ctx_use(c)) return r;
+    return run_pass(c, smooth, d_out, d_in1, d_prev0, d_bsic1, sigma, prms, false);
+}
+
+extern "C" int nlk_rgb2opp_dev(nlk_ctx *c, float *d_dst, const float *d_src)
+{
+    if (int r = ctx_use(c)) return r;
+    if (c->ch != 3) { // reference src/nlkalman.c:94: no-op unless 3 channels
+        if (d_dst != d_src) CU_TRY(cudaMemcpyAsync(d_dst, d_src, c->img_bytes(), cudaMemcpyDeviceToDevice, c->st));
+        return NLK_OK;
+    }
+    return check_launch(c, launch_rgb2opp_copy(d_dst, d_src, (long)c->w * c->h, 0, c->st), "rgb2opp");
+}
+
+extern "C" int nlk_opp2rgb_dev(nlk_ctx *c, float *d_dst, const float *d_src)
+{
+    if (int r = ctx_use(c)) return r;
+    if (c->ch != 3) {
+        if (d_dst != d_src) CU_TRY(cudaMemcpyAsync(d_dst, d_src, c->img_bytes(), cudaMemcpyDeviceToDevice, c->st));
+        return NLK_OK;
+    }
+    return check_launch(c, launch_rgb2opp_copy(d_dst, d_src, (long)c->w * c->h, 1, c->st), "opp2rgb");
+}
+
+extern "C" int nlk_warp_dev(nlk_ctx *c, float *d_imw, const float *d_im, const float *d_of,
+                            const float *d_msk)
+{
+    if (int r = ctx_use(c)) return r;
+    return check_launch(c, launch_warp(d_imw, d_im, d_of, d_msk, c->w, c->h, c->ch, c->st), "warp_bicubic");
+}
+
+// ---- resident sequence recursion --------------------------------------------------------------
+
+extern "C" int nlk_seq_reset(nlk_ctx *c)
+{
+    if (!c) return set_err(NLK_ERR_PARAM, "null context");
+    c->q_cur = 0; c->q_have_prev = 0; c->q_have_flt2 = 0; c->q_smo_cur = 0; c->q_have_smo = 0;
+    return NLK_OK;
+}
+
+extern "C" int nlk_seq_filter_dev(nlk_ctx *c, const float *d_noisy, const float *d_bflo,
+                                  const float *d_bocc, float sigma, struct nlkalman_params f1,
+                                  struct nlkalman_params f2, float *d_flt1_out, float *d_flt2_out)
+{
+    if (int r = ctx_use(c)) return r;
+    const size_t ib = c->img_bytes();
+    if (int r = c->q_noisy.ensure(ib)) return r;
+    if (int r = c->q_warp.ensure(ib)) return r;
+    for (int i = 0; i < 2; ++i) {
+        if (int r = c->q_flt1[i].ensure(ib)) return r;
+        if (int r = c->q_flt2[i].ensure(ib)) return r;
+    }
+    if (f1.patch_sz == 0) return set_err(NLK_ERR_PARAM, "the resident recursion needs the first filtering (f1_p != 0)");
+    const int cur = c->q_cur, prv = cur ^ 1;
+    float *noisy = c->q_noisy.as<float>(), *warp = c->q_warp.as<float>();
+    float *flt1 = c->q_flt1[cur].as<float>(), *flt2 = c->q_flt2[cur].as<float>();
+    if (int r = nlk_rgb2opp_dev(c, noisy, d_noisy)) return r;
+
+    // first filtering (reference src/main-flt.c:345-357)
+    const float *prev1 = nullptr;
+    if (c->q_have_prev) {
+        prev1 = c->q_flt1[prv].as<float>();
+        if (d_bflo) {
+            if (int r = nlk_warp_dev(c, warp, prev1, d_bflo, d_bocc)) return r;
+            prev1 = warp;
+        }
+    }
+    if (int r = run_pass(c, 0, flt1, noisy, prev1, nullptr, sigma, f1, false)) return r;
+    if (d_flt1_out) if (int r = nlk_opp2rgb_dev(c, d_flt1_out, flt1)) return r;
+
+    // second filtering (reference src/main-flt.c:361-374)
+    const int do2 = f2.patch_sz != 0;
+    if (do2) {
+        const float *prev2 = nullptr;
+        if (c->q_have_prev && c->q_have_flt2) {
+            prev2 = c->q_flt2[prv].as<float>();
+            if (d_bflo) {
+                if (int r = nlk_warp_dev(c, warp, prev2, d_bflo, d_bocc)) return r;
+                prev2 = warp;
+            }
+        }
+        if (int r = run_pass(c, 0, flt2, noisy, prev2, flt1, sigma, f2, false)) return r;
+        if (d_flt2_out) if (int r = nlk_opp2rgb_dev(c, d_flt2_out, flt2)) return r;
+    }
+    c->q_have_prev = 1;
+    c->q_have_flt2 = do2;
+    c->q_cur = prv;
+    return NLK_OK;
+}
+
+static int stage_in(nlk_ctx *c, DevBuf &b, const float *h, size_t bytes, const float **d)
+{
+    *d = nullptr;
+    if (!h) return NLK_OK;
+    if (int r = b.ensure(bytes)) return r;
+    CU_TRY(cudaMemcpyAsync(b.p, h, bytes, cudaMemcpyHostToDevice, c->st));
+    *d = b.as<float>();
+    return NLK_OK;
+}
+
+extern "C" int nlk_seq_filter_host(nlk_ctx *c, const float *h_noisy, const float *h_bflo,
+                                   const float *h_bocc, float sigma, struct nlkalman_params f1,
+                                   struct nlkalman_params f2, float *h_flt1_out, float *h_flt2_out)
+{
+    if (int r = ctx_use(c)) return r;
+    const size_t ib = c->img_bytes(), npix = (size_t)c->w * c->h;
+    const float *d_noisy, *d_of, *d_msk;
+    if (int r = stage_in(c, c->s_in1, h_noisy, ib, &d_noisy)) return r;
+    if (int r = stage_in(c, c->s_of, h_bflo, npix * 2 * 4, &d_of)) return r;
+    if (int r = stage_in(c, c->s_msk, h_bocc, npix * 4, &d_msk)) return r;
+    if (!d_noisy) return set_err(NLK_ERR_PARAM, "no noisy frame");
+    float *d_o1 = nullptr, *d_o2 = nullptr;
+    if (h_flt1_out) { if (int r = c->s_out.ensure(ib)) return r; d_o1 = c->s_out.as<float>(); }
+    if (h_flt2_out) { if (int r = c->s_bsic.ensure(ib)) return r; d_o2 = c->s_bsic.as<float>(); }
+    if (int r = nlk_seq_filter_dev(c, d_noisy, d_of, d_msk, sigma, f1, f2, d_o1, d_o2)) return r;
+    if (d_o1) CU_TRY(cudaMemcpyAsync(h_flt1_out, d_o1, ib, cudaMemcpyDeviceToHost, c->st));
+    if (d_o2 && f2.patch_sz != 0) CU_TRY(cudaMemcpyAsync(h_flt2_out, d_o2, ib, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaStreamSynchronize(c->st));
+    return NLK_OK;
+}
+
+extern "C" int nlk_seq_smooth_start_dev(nlk_ctx *c, const float *d_last_rgb)
+{
+    if (int r = ctx_use(c)) return r;
+    const size_t ib = c->img_bytes();
+    for (int i = 0; i < 2; ++i) if (int r = c->q_smo[i].ensure(ib)) return r;
+    c->q_smo_cur = 0;
+    if (int r = nlk_rgb2opp_dev(c, c->q_smo[0].as<float>(), d_last_rgb)) return r;
+    c->q_have_smo = 1;
+    return NLK_OK;
+}
+
+extern "C" int nlk_seq_smooth_dev(nlk_ctx *c, const float *d_flt_rgb, const float *d_fflo,
+                                  const float *d_focc, float sigma, struct nlkalman_params s1,
+                                  float *d_smo_out)
+{
+    if (int r = ctx_use(c)) return r;
+    if (!c->q_have_smo) return set_err(NLK_ERR_STATE, "nlk_seq_smooth_start_* must come first");
+    const size_t ib = c->img_bytes();
+    if (int r = c->q_tmp.ensure(ib)) return r;
+    if (int r = c->q_warp.ensure(ib)) return r;
+    const int nxt = c->q_smo_cur, cur = nxt ^ 1; // q_smo[nxt] holds the smoothed frame t+1
+    float *flt = c->q_tmp.as<float>(), *warp = c->q_warp.as<float>();
+    if (int r = nlk_rgb2opp_dev(c, flt, d_flt_rgb)) return r;
+    const float *smo0 = c->q_smo[nxt].as<float>();
+    if (d_fflo) { // reference src/main-smo.c:202-206
+        if (int r = nlk_warp_dev(c, warp, smo0, d_fflo, d_focc)) return r;
+        smo0 = warp;
+    }
+    float *smo1 = c->q_smo[cur].as<float>();
+    if (int r = run_pass(c, 1, smo1, flt, smo0, nullptr, sigma, s1, false)) return r;
+    if (d_smo_out) if (int r = nlk_opp2rgb_dev(c, d_smo_out, smo1)) return r;
+    c->q_smo_cur = cur;
+    return NLK_OK;
+}
+
+extern "C" int nlk_seq_smooth_start_host(nlk_ctx *c, const float *h_last_rgb)
+{
+    if (int r = ctx_use(c)) return r;
+    const float *d;
+    if (int r = stage_in(c, c->s_in1, h_last_rgb, c->img_bytes(), &d)) return r;
+    if (!d) return set_err(NLK_ERR_PARAM, "no frame");
+    return nlk_seq_smooth_start_dev(c, d);
+}
+
+extern "C" int nlk_seq_smooth_host(nlk_ctx *c, const float *h_flt_rgb, const float *h_fflo,
+                                   const float *h_focc, float sigma, struct nlkalman_params s1,
+                                   float *h_smo_out)
+{
+    if (int r = ctx_use(c)) return r;
+    const size_t ib = c->img_bytes(), npix = (size_t)c->w * c->h;
+    const float *d_flt, *d_of, *d_msk;
+    if (int r = stage_in(c, c->s_in1, h_flt_rgb, ib, &d_flt)) return r;
+    if (int r = stage_in(c, c->s_of, h_fflo, npix * 2 * 4, &d_of)) return r;
+    if (int r = stage_in(c, c->s_msk, h_focc, npix * 4, &d_msk)) return r;
+    if (!d_flt) return set_err(NLK_ERR_PARAM, "no filtered frame");
+    float *d_o = nullptr;
+    if (h_smo_out) { if (int r = c->s_out.ensure(ib)) return r; d_o = c->s_out.as<float>(); }
+    if (int r = nlk_seq_smooth_dev(c, d_flt, d_of, d_msk, sigma, s1, d_o)) return r;
+    if (d_o) CU_TRY(cudaMemcpyAsync(h_smo_out, d_o, ib, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaStreamSynchronize(c->st));
+    return NLK_OK;
+}
+
+// ---- host-image single pass (legacy entry points and the test dump) -----------------------
+
+static int pass_host(nlk_ctx *c, int smooth, float *h_out, const float *h_in1, const float *h_prev0,
+                     const float *h_bsic1, float sigma, const nlkalman_params &pr, bool debug)
+{
+    const size_t ib = c->img_bytes();
+    const float *d_in1, *d_prev0, *d_bsic;
+    if (int r = stage_in(c, c->s_in1, h_in1, ib, &d_in1)) return r;
+    if (int r = stage_in(c, c->s_prev0, h_prev0, ib, &d_prev0)) return r;
+    if (int r = stage_in(c, c->s_bsic, h_bsic1, ib, &d_bsic)) return r;
+    if (!d_in1) return set_err(NLK_ERR_PARAM, "no input frame");
+    if (int r = c->s_out.ensure(ib)) return r;
+    if (int r = run_pass(c, smooth, c->s_out.as<float>(), d_in1, d_prev0, d_bsic, sigma, pr, debug)) return r;
+    CU_TRY(cudaMemcpyAsync(h_out, c->s_out.p, ib, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaStreamSynchronize(c->st));
+    return NLK_OK;
+}
+
+extern "C" int nlk_pass_host_debug(nlk_ctx *c, int smooth, float *h_out, const float *h_in1,
+                                   const float *h_prev0, const float *h_bsic1, float sigma,
+                                   struct nlkalman_params prms, int kmax, int *nk, int *np0,
+                                   int *knn_xy, float *knn_d, unsigned char *prev_p,
+                                   unsigned char *active, float *vp)
+{
+    if (int r = ctx_use(c)) return r;
+    if (int r = pass_host(c, smooth, h_out, h_in1, h_prev0, h_bsic1, sigma, prms, true)) return r;
+    const int psz = prms.patch_sz, step = psz / 2;
+    if (c->w < psz || c->h < psz) return NLK_OK;
+    const int gw = (c->w - psz) / step + 1, gh = (c->h - psz) / step + 1, G = gw * gh;
+    const int rmax = smooth ? prms.search_sz_t : (prms.search_sz_t > prms.search_sz_x ? prms.search_sz_t : prms.search_sz_x);
+    int ks = prms.npatches_x > prms.npatches_t ? prms.npatches_x : prms.npatches_t;
+    if (ks > (2 * rmax + 1) * (2 * rmax + 1)) ks = (2 * rmax + 1) * (2 * rmax + 1);
+    if (ks < 1) ks = 1;
+    std::vector<GroupHdr> hdr(G);
+    std::vector<uint32_t> cand((size_t)G * ks);
+    std::vector<float> dist((size_t)G * ks), vps(G);
+    std::vector<int> act(G);
+    int counters[2];
+    CU_TRY(cudaMemcpy(hdr.data(), c->hdr.p, (size_t)G * sizeof(GroupHdr), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(cand.data(), c->cand.p, (size_t)G * ks * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(dist.data(), c->dbg_dist.p, (size_t)G * ks * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(vps.data(), c->dbg_vp.p, (size_t)G * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(act.data(), c->active.p, (size_t)G * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(counters, c->counters.p, 8, cudaMemcpyDeviceToHost));
+    if (active) memset(active, 0, G);
+    for (int i = 0; i < counters[0] && i < G; ++i)
+        if (active && act[i] >= 0 && act[i] < G) active[act[i]] = 1;
+    for (int g = 0; g < G; ++g) {
+        if (nk) nk[g] = hdr[g].nk;
+        if (np0) np0[g] = hdr[g].np0;
+        if (prev_p) prev_p[g] = (hdr[g].flags & HDR_PREV_P) ? 1 : 0;
+        if (vp) vp[g] = vps[g];
+        for (int i = 0; i < hdr[g].nk && i < kmax; ++i) {
+            const uint32_t cd = cand[(size_t)g * ks + i];
+            if (knn_xy) {
+                knn_xy[((size_t)g * kmax + i) * 2 + 0] = cand_x(cd);
+                knn_xy[((size_t)g * kmax + i) * 2 + 1] = cand_y(cd);
+            }
+            if (knn_d) knn_d[(size_t)g * kmax + i] = dist[(size_t)g * ks + i];
+        }
+    }
+    return NLK_OK;
+}
+
+// ---- batched DCT unit (tests) -----------------------------------------------------------------
+
+template <int PSZ_T>
+__global__ void k_dct_tiles(float *tiles, int n, int psz, int inverse)
+{
+    extern __shared__ float sm[];
+    const int pp = psz * psz, TS = pp + 1;
+    const int t0 = blockIdx.x * blockDim.x;
+    const int cnt = min((int)blockDim.x, n - t0);
+    for (int i = threadIdx.x; i < cnt * pp; i += blockDim.x) sm[(i / pp) * TS + i % pp] = tiles[(size_t)t0 * pp + i];
+    __syncthreads();
+    if ((int)threadIdx.x < cnt) {
+        if (inverse) dct2d_tile<PSZ_T, true>(sm + threadIdx.x * TS, psz);
+        else dct2d_tile<PSZ_T, false>(sm + threadIdx.x * TS, psz);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * pp; i += blockDim.x) tiles[(size_t)t0 * pp + i] = sm[(i / pp) * TS + i % pp];
+}
+
+extern "C" int nlk_dct_host(nlk_ctx *c, float *h_tiles, int psz, int n, int inverse)
+{
+    if (int r = ctx_use(c)) return r;
+    if (psz < 1 || psz > MAX_PSZ || n < 0) return set_err(NLK_ERR_PARAM, "bad dct request");
+    if (n == 0) return NLK_OK;
+    const size_t bytes = (size_t)n * psz * psz * 4;
+    if (int r = c->q_tmp.ensure(bytes)) return r;
+    CU_TRY(cudaMemcpyAsync(c->q_tmp.p, h_tiles, bytes, cudaMemcpyHostToDevice, c->st));
+    const int nt = psz > 12 ? 32 : 64, nb = (n + nt - 1) / nt;
+    const size_t smem = (size_t)nt * (psz * psz + 1) * 4;
+    if (psz == 8) k_dct_tiles<8><<<nb, nt, smem, c->st>>>(c->q_tmp.as<float>(), n, psz, inverse);
+    else if (psz == 12) k_dct_tiles<12><<<nb, nt, smem, c->st>>>(c->q_tmp.as<float>(), n, psz, inverse);
+    else k_dct_tiles<0><<<nb, nt, smem, c->st>>>(c->q_tmp.as<float>(), n, psz, inverse);
+    if (int r = check_launch(c, 1, "dct_tiles")) return r;
+    CU_TRY(cudaMemcpyAsync(h_tiles, c->q_tmp.p, bytes, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaStreamSynchronize(c->st));
+    return NLK_OK;
+}
+
+// ---- the six drop-in entry points (include/nlkalman.h) ------------------------------------
+// Host pointers in, host pointers out, synchronous, void: the only failure path is a
+// message on stderr and exit(1), as in the reference (src/nlkalman.c:165-177).
+
+static std::mutex g_legacy_mu;
+static nlk_ctx *g_legacy = nullptr;
+
+static void legacy_die(const char *what)
+{
+    fprintf(stderr, "nlkalman-b200: %s: %s\n", what, g_err.c_str());
+    exit(1);
+}
+
+static nlk_ctx *legacy_ctx(int w, int h, int ch)
+{
+    if (g_legacy && (g_legacy->w != w || g_legacy->h != h || g_legacy->ch != ch)) {
+        nlk_ctx_destroy(g_legacy);
+        g_legacy = nullptr;
+    }
+    if (!g_legacy) {
+        int dev = 0;
+        if (const char *e = getenv("NLK_DEVICE")) dev = atoi(e);
+        g_legacy = nlk_ctx_create(w, h, ch, dev);
+        if (!g_legacy) legacy_die("no usable CUDA device (there is no CPU fallback)");
+    }
+    if (ctx_use(g_legacy)) legacy_die("cudaSetDevice");
+    return g_legacy;
+}
+
+static void legacy_colour(float *im, int w, int h, int ch, int inverse)
+{
+    if (ch != 3) return; // reference src/nlkalman.c:94, :114
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    nlk_ctx *c = legacy_ctx(w, h, ch);
+    const float *d;
+    if (stage_in(c, c->s_in1, im, c->img_bytes(), &d)) legacy_die("colour transform");
+    int r = inverse ? nlk_opp2rgb_dev(c, c->s_in1.as<float>(), d) : nlk_rgb2opp_dev(c, c->s_in1.as<float>(), d);
+    if (r || cudaMemcpyAsync(im, c->s_in1.p, c->img_bytes(), cudaMemcpyDeviceToHost, c->st) != cudaSuccess ||
+        cudaStreamSynchronize(c->st) != cudaSuccess) {
+        if (!r) set_err(NLK_ERR_CUDA, "%s", cudaGetErrorString(cudaGetLastError()));
+        legacy_die("colour transform");
+    }
+}
+
+extern "C" void rgb2opp(float *im, int w, int h, int ch) { legacy_colour(im, w, h, ch, 0); }
+extern "C" void opp2rgb(float *im, int w, int h, int ch) { legacy_colour(im, w, h, ch, 1); }
+
+extern "C" void warp_bicubic(float *imw, float *im, float *of, float *msk, int w, int h, int ch)
+{
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    nlk_ctx *c = legacy_ctx(w, h, ch);
+    const size_t ib = c->img_bytes(), npix = (size_t)w * h;
+    const float *d_im, *d_of, *d_msk;
+    if (stage_in(c, c->s_in1, im, ib, &d_im) || stage_in(c, c->s_of, of, npix * 2 * 4, &d_of) ||
+        stage_in(c, c->s_msk, msk, npix * 4, &d_msk) || c->s_out.ensure(ib))
+        legacy_die("warp_bicubic");
+    if (nlk_warp_dev(c, c->s_out.as<float>(), d_im, d_of, d_msk)) legacy_die("warp_bicubic");
+    if (cudaMemcpyAsync(imw, c->s_out.p, ib, cudaMemcpyDeviceToHost, c->st) != cudaSuccess ||
+        cudaStreamSynchronize(c->st) != cudaSuccess) {
+        set_err(NLK_ERR_CUDA, "%s", cudaGetErrorString(cudaGetLastError()));
+        legacy_die("warp_bicubic");
+    }
+}
+
+extern "C" void nlkalman_default_params(struct nlkalman_params *p, float sigma, enum FILTER_MODE mode)
+{
+    // host arithmetic, the reference's expressions (src/nlkalman.c:456-486): double
+    // literals, truncation to int, float comparison in the max()
+    if (p->patch_sz < 0) p->patch_sz = 8;
+    if (p->search_sz_x < 0) p->search_sz_x = 10;
+    if (p->search_sz_t < 0) p->search_sz_t = 5;
+    if (p->dista_lambda < 0) p->dista_lambda = 1.0f;
+    switch (mode) {
+    case FLT1:
+        if (p->npatches_x < 0) p->npatches_x = (int)(0.5 * sigma + 40.);
+        if (p->beta_x < 0) p->beta_x = (float)(-0.04 * sigma + 3.91);
+        if (p->npatches_t < 0) p->npatches_t = 30;
+        if (p->npatches_tagg < 0) p->npatches_tagg = 20;
+        if (p->beta_t < 0) p->beta_t = (float)(-0.005 * sigma + 2.05);
+        break;
+    case FLT2:
+        if (p->npatches_x < 0) p->npatches_x = (int)(0.5 * sigma + 10.);
+        if (p->beta_x < 0) p->beta_x = (float)(0.004 * sigma + 0.21);
+        if (p->npatches_t < 0) p->npatches_t = (int)(5.f > sigma ? 5.f : sigma);
+        if (p->npatches_tagg < 0) p->npatches_tagg = 1;
+        if (p->beta_t < 0) p->beta_t = (float)(0.014 * sigma + 1.38);
+        break;
+    case SMO1:
+        if (p->npatches_x < 0) p->npatches_x = 0;
+        if (p->beta_x < 0) p->beta_x = 0;
+        if (p->npatches_t < 0) {
+            const float v = 3 * sigma - 15;
+            p->npatches_t = (int)(5.f > v ? 5.f : v);
+        }
+        if (p->npatches_tagg < 0) p->npatches_tagg = p->npatches_t;
+        if (p->beta_t < 0) {
+            const double v = -0.14 * sigma + 8.0;
+            p->beta_t = (float)(1.0 > v ? 1.0 : v);
+        }
+        break;
+    }
+}
+
+extern "C" void nlkalman_filter_frame(float *deno1, float *nisy1, float *deno0, float *bsic1, int w,
+                                      int h, int ch, float sigma, const struct nlkalman_params prms,
+                                      int frame)
+{
+    (void)frame;
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    nlk_ctx *c = legacy_ctx(w, h, ch);
+    if (pass_host(c, 0, deno1, nisy1, deno0, bsic1, sigma, prms, false)) legacy_die("nlkalman_filter_frame");
+}
+
+extern "C" void nlkalman_smooth_frame(float *smoo1, float *filt1, float *smoo0, float *bsic1, int w,
+                                      int h, int ch, float sigma, const struct nlkalman_params prms,
+                                      int frame)
+{
+    (void)frame;
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    nlk_ctx *c = legacy_ctx(w, h, ch);
+    if (pass_host(c, 1, smoo1, filt1, smoo0, bsic1, sigma, prms, false)) legacy_die("nlkalman_smooth_frame");
+}

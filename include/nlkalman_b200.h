@@ -1,0 +1,109 @@
+/* nlkalman_b200.h -- additive C ABI of libnlkalman_b200.so next to the six drop-in
+ * entry points of nlkalman.h.  It exposes what the per-frame process boundary of the
+ * reference hides: a context whose buffers (and the previous filtered frames, i.e. the
+ * recursion state that the reference passes between processes as TIFF files,
+ * scripts/nlkalman-seq.sh:80-102) stay resident in HBM across frames.
+ *
+ * Conventions: plain C types only; images are float32 interleaved HWC; "h_" pointers
+ * are host memory (pinned memory makes the copies asynchronous-capable and faster),
+ * "d_" pointers are device memory on the context's GPU.  Functions return 0 on
+ * success and a negative code on failure; nlk_last_error() gives the message.  There
+ * is no CPU fallback anywhere.
+ */
+#ifndef NLKALMAN_B200_H
+#define NLKALMAN_B200_H
+
+#include "nlkalman.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nlk_ctx nlk_ctx;
+
+#define NLK_OK 0
+#define NLK_ERR_CUDA (-1)    /* CUDA runtime error (message has the details) */
+#define NLK_ERR_PARAM (-2)   /* unsupported parameter (patch size, channels, radius ...) */
+#define NLK_ERR_STATE (-3)   /* call not valid in the current sequence state */
+
+/* number of visible CUDA devices, or a negative code */
+int nlk_device_count(void);
+const char *nlk_last_error(void);
+
+/* context for frames of w x h x ch on CUDA device `device` (own stream, lazily sized
+ * scratch).  Returns NULL on failure. */
+nlk_ctx *nlk_ctx_create(int w, int h, int ch, int device);
+void nlk_ctx_destroy(nlk_ctx *ctx);
+/* block until everything queued on the context's stream has finished */
+int nlk_ctx_sync(nlk_ctx *ctx);
+/* CUDA kernels launched by this context so far */
+long long nlk_ctx_launch_count(const nlk_ctx *ctx);
+/* the context's cudaStream_t, for callers that queue their own work around it */
+void *nlk_ctx_stream(nlk_ctx *ctx);
+
+/* pinned host memory (cudaMallocHost / cudaFreeHost) for the h_ arguments below */
+void *nlk_host_alloc(size_t bytes);
+void nlk_host_free(void *p);
+
+/* ---- single operations on device buffers (asynchronous on the context's stream) ---- */
+int nlk_rgb2opp_dev(nlk_ctx *ctx, float *d_dst, const float *d_src);   /* src may equal dst */
+int nlk_opp2rgb_dev(nlk_ctx *ctx, float *d_dst, const float *d_src);
+int nlk_warp_dev(nlk_ctx *ctx, float *d_imw, const float *d_im, const float *d_of,
+                 const float *d_msk /* may be NULL */);
+/* one filter (smooth = 0) or smoother (smooth = 1) pass, semantics of
+ * nlkalman_filter_frame / nlkalman_smooth_frame; d_prev0 and d_bsic1 may be NULL */
+int nlk_pass_dev(nlk_ctx *ctx, int smooth, float *d_out, const float *d_in1,
+                 const float *d_prev0, const float *d_bsic1, float sigma,
+                 struct nlkalman_params prms);
+
+/* ---- resident sequence recursion (what scripts/nlkalman-seq.sh does per frame) ------
+ * The context keeps the previous frame's first and second filtering outputs in
+ * opponent colour space.  One step = rgb2opp(noisy); if there is a previous frame:
+ * warp(prev flt1), filter 1, warp(prev flt2), filter 2 with filter 1 as basic estimate
+ * (reference src/main-flt.c:340-380); else the two spatial filterings of the first
+ * frame (scripts/nlkalman-seq.sh:39-41).  f2.patch_sz == 0 skips the second filtering
+ * (reference src/main-flt.c:130).  Outputs are RGB; any of them may be NULL. */
+int nlk_seq_reset(nlk_ctx *ctx);
+int nlk_seq_filter_dev(nlk_ctx *ctx, const float *d_noisy, const float *d_bflo,
+                       const float *d_bocc, float sigma, struct nlkalman_params f1,
+                       struct nlkalman_params f2, float *d_flt1_out, float *d_flt2_out);
+/* same, with host buffers: copies in, runs, copies out, returns when done */
+int nlk_seq_filter_host(nlk_ctx *ctx, const float *h_noisy, const float *h_bflo,
+                        const float *h_bocc, float sigma, struct nlkalman_params f1,
+                        struct nlkalman_params f2, float *h_flt1_out, float *h_flt2_out);
+
+/* backward smoothing recursion (scripts/nlkalman-seq.sh:122-149): start from the last
+ * filtered frame, then for each earlier frame t: warp(smoothed t+1 by the forward
+ * flow), smooth (reference src/main-smo.c:198-213). */
+int nlk_seq_smooth_start_dev(nlk_ctx *ctx, const float *d_last_rgb);
+int nlk_seq_smooth_dev(nlk_ctx *ctx, const float *d_flt_rgb, const float *d_fflo,
+                       const float *d_focc, float sigma, struct nlkalman_params s1,
+                       float *d_smo_out);
+int nlk_seq_smooth_start_host(nlk_ctx *ctx, const float *h_last_rgb);
+int nlk_seq_smooth_host(nlk_ctx *ctx, const float *h_flt_rgb, const float *h_fflo,
+                        const float *h_focc, float sigma, struct nlkalman_params s1,
+                        float *h_smo_out);
+
+/* ---- stage dumps for the parity tests (host arrays, any may be NULL) ------------------
+ * Runs one pass on host images like nlkalman_filter_frame / nlkalman_smooth_frame and
+ * also returns, per grid patch g = gy*gw + gx (gw = (w-psz)/step+1, step = psz/2):
+ *   nk[g], np0[g]         candidates kept / with a valid previous patch
+ *   knn_xy[g][kmax][2]    their (x, y) in sorted order;  knn_d[g][kmax] distances
+ *   prev_p[g]             validity of the previous-frame patch at p
+ *   active[g]             1 = processed (not skipped by the processed mask)
+ *   vp[g]                 posterior variance sum of processed groups */
+int nlk_pass_host_debug(nlk_ctx *ctx, int smooth, float *h_out, const float *h_in1,
+                        const float *h_prev0, const float *h_bsic1, float sigma,
+                        struct nlkalman_params prms, int kmax, int *nk, int *np0,
+                        int *knn_xy, float *knn_d, unsigned char *prev_p,
+                        unsigned char *active, float *vp);
+
+/* batched orthonormal 2-D DCT-II (inverse = 0) / DCT-III (inverse = 1) of n tiles of
+ * psz x psz on the device, host in/out, in place: the unit the reference's
+ * dct_threads_forward / dct_threads_inverse compute (src/nlkalman.c:248, :307) */
+int nlk_dct_host(nlk_ctx *ctx, float *h_tiles, int psz, int n, int inverse);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLKALMAN_B200_H */

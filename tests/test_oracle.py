@@ -1,0 +1,127 @@
+"""CPU tests of the checker itself: the C restatement (oracle/nlk_port.c) against the
+golden vectors produced by the unmodified reference (tests/golden/make_golden.py), and,
+where oracle/_ref is present, against the reference library directly."""
+import numpy as np
+import pytest
+
+from common import TOL_MAXABS, golden_cases, load_golden, maxabs, params_from_array
+
+
+def _port_params(O, arr):
+    return params_from_array(O.Params, arr)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_port_matches_reference_golden(port, name):
+    from oracle import oracle as O
+    g = load_golden(name)
+    sigma = float(g["sigma"])
+    f1, f2, s1 = (_port_params(O, g[k]) for k in ("f1", "f2", "s1"))
+    o0 = port.rgb2opp(g["noisy0"].copy())
+    o1 = port.rgb2opp(g["noisy1"].copy())
+    assert maxabs(o0, g["opp0"]) <= 5e-5
+    flt1_0 = port.filter_frame(g["opp0"], None, None, sigma, f1)
+    assert maxabs(flt1_0, g["flt1_0"]) <= TOL_MAXABS
+    flt2_0 = port.filter_frame(g["opp0"], None, g["flt1_0"], sigma, f2)
+    assert maxabs(flt2_0, g["flt2_0"]) <= TOL_MAXABS
+    warp1 = port.warp_bicubic(g["flt1_0"], g["bflo"], g["occ"])
+    assert maxabs(warp1, g["warp1"]) <= 1e-5
+    flt1_1 = port.filter_frame(o1, g["warp1"], None, sigma, f1)
+    assert maxabs(flt1_1, g["flt1_1"]) <= TOL_MAXABS
+    flt2_1 = port.filter_frame(o1, g["warp2"], g["flt1_1"], sigma, f2)
+    assert maxabs(flt2_1, g["flt2_1"]) <= TOL_MAXABS
+    smo = port.smooth_frame(g["flt2_0"], g["warps"], None, sigma, s1)
+    assert maxabs(smo, g["smo_0"]) <= TOL_MAXABS
+    rgb = port.opp2rgb(g["flt2_1"].copy())
+    assert maxabs(rgb, g["rgb_flt2_1"]) <= 5e-5
+
+
+def test_default_params_table(port):
+    """SURVEY.md App. A table (reference src/nlkalman.c:456-486)"""
+    from oracle import oracle as O
+    want = {10: ((45, 30, 20), (15, 10, 1), 15), 20: ((50, 30, 20), (20, 20, 1), 45),
+            30: ((55, 30, 20), (25, 30, 1), 75), 40: ((60, 30, 20), (30, 40, 1), 105)}
+    for s, (a, b, c) in want.items():
+        f1 = port.default_params(s, O.FLT1)
+        f2 = port.default_params(s, O.FLT2)
+        s1 = port.default_params(s, O.SMO1)
+        assert (f1.npatches_x, f1.npatches_t, f1.npatches_tagg) == a
+        assert (f2.npatches_x, f2.npatches_t, f2.npatches_tagg) == b
+        assert s1.npatches_t == c and s1.npatches_tagg == c and s1.npatches_x == 0
+        assert f1.patch_sz == 8 and f1.search_sz_x == 10 and f1.search_sz_t == 5
+    assert abs(port.default_params(20, O.FLT1).beta_x - 3.11) < 1e-6
+    assert abs(port.default_params(20, O.SMO1).beta_t - 5.2) < 1e-6
+
+
+def test_port_params_match_reference_library(port, ref):
+    from oracle import oracle as O
+    for mode in (O.FLT1, O.FLT2, O.SMO1):
+        for s in (0.0, 3.0, 5.0, 10.0, 20.0, 25.5, 30.0, 40.0, 57.0, 80.0):
+            assert ref.default_params(s, mode).as_dict() == port.default_params(s, mode).as_dict()
+    # user-set fields are kept
+    p = O.Params.auto(patch_sz=12, npatches_t=7, beta_t=0.5)
+    q = O.Params.auto(patch_sz=12, npatches_t=7, beta_t=0.5)
+    assert ref.default_params(20, O.FLT2, p).as_dict() == port.default_params(20, O.FLT2, q).as_dict()
+
+
+def test_port_dct_is_orthonormal(port):
+    from scipy.fft import dctn
+    rng = np.random.default_rng(0)
+    for psz in (4, 8, 12, 7):
+        t = rng.normal(0, 50, (9, psz, psz)).astype(np.float32)
+        y = port.dct2(t)
+        want = dctn(t.astype(np.float64), type=2, norm="ortho", axes=(1, 2))
+        assert np.abs(y - want).max() < 1e-4
+        back = port.dct2(y, inverse=True)
+        assert np.abs(back - t).max() < 1e-4
+
+
+def test_port_window_and_colour(port):
+    w = port.window(8)
+    n2 = 3.5
+    w1 = np.exp(-0.5 * (((np.arange(8) - n2) / n2 / 0.4) ** 2))
+    assert np.abs(w - np.outer(w1, w1)).max() < 1e-6
+    rng = np.random.default_rng(1)
+    im = rng.uniform(0, 255, (17, 23, 3)).astype(np.float32)
+    back = port.opp2rgb(port.rgb2opp(im.copy()))
+    assert np.abs(back - im).max() < 1e-3
+    gray = rng.uniform(0, 255, (5, 6, 1)).astype(np.float32)
+    assert np.array_equal(port.rgb2opp(gray.copy()), gray)
+
+
+def test_port_warp_against_numpy(port):
+    """bicubic (Keys a=-1/2) with NaN outside the image and under the mask"""
+    rng = np.random.default_rng(2)
+    h, w = 20, 24
+    im = rng.uniform(0, 255, (h, w, 1)).astype(np.float32)
+    of = np.zeros((h, w, 2), np.float32)
+    of[..., 0], of[..., 1] = 2.0, -1.0  # integer shift: exact copy where taps are inside
+    msk = np.zeros((h, w), np.float32)
+    msk[3, 4] = 255
+    out = port.warp_bicubic(im, of, msk)
+    assert np.isnan(out[3, 4, 0])
+    for y in range(h):
+        for x in range(w):
+            if msk[y, x]:
+                continue
+            ix, iy = x + 2 - 1, y - 1 - 1
+            inside = ix >= 0 and ix + 3 < w and iy >= 0 and iy + 3 < h
+            if inside:
+                assert out[y, x, 0] == im[y - 1, x + 2, 0]
+            else:
+                assert np.isnan(out[y, x, 0])
+
+
+def test_mask_separability_against_reference(port, ref):
+    """the restatement splits search / mask replay / filtering; the reference runs one
+    loop.  Same output within fp32 noise on a frame large enough for thousands of skips."""
+    from bwd_nlkalman_b200 import synth
+    from oracle import oracle as O
+    w, h, ch, sigma = 200, 152, 1, 20.0
+    n0 = synth.noisy_frame(w, h, ch, 0, sigma)
+    f1 = ref.default_params(sigma, O.FLT1)
+    a = ref.filter_frame(n0, None, None, sigma, f1)
+    b, dump = port.filter_frame(n0, None, None, sigma, f1, dump=True)
+    assert maxabs(a, b) <= TOL_MAXABS
+    frac = dump["active"].mean()
+    assert 0.5 < frac < 0.95, frac  # the mask really skips patches here
