@@ -66,6 +66,9 @@ def lib():
     L.nlk_ctx_launch_count.restype = C.c_longlong
     L.nlk_ctx_stream.argtypes = [vp]
     L.nlk_ctx_stream.restype = vp
+    L.nlk_ctx_profile.argtypes = [vp, C.c_int]
+    L.nlk_ctx_profile_collect.argtypes = [vp, C.POINTER(C.c_double), _ip]
+    L.nlk_fp32_peak.argtypes = [vp, C.c_float, C.POINTER(C.c_double)]
     L.nlk_host_alloc.argtypes = [C.c_size_t]
     L.nlk_host_alloc.restype = vp
     L.nlk_host_free.argtypes = [vp]
@@ -206,6 +209,32 @@ class Context:
     @property
     def stream(self) -> int:
         return int(lib().nlk_ctx_stream(self._h) or 0)
+
+    # per-kernel CUDA-event timing (include/nlkalman_b200.h)
+    KERNELS = ["colour", "warp_bicubic", "valid_map", "search_knn", "mask_resolve", "group_filter",
+               "normalize", "memset"]
+    PASS_KINDS = ["flt1_temporal", "flt1_spatial", "flt2_temporal", "flt2_spatial", "smoother", "other"]
+
+    def profile(self, enable: bool):
+        _check(lib().nlk_ctx_profile(self._h, 1 if enable else 0))
+
+    def profile_collect(self):
+        """{(kernel, pass_kind): (ms_sum, count)} since the last collection"""
+        nk, npk = len(self.KERNELS), len(self.PASS_KINDS)
+        ms = (C.c_double * (nk * npk))()
+        cnt = (C.c_int * (nk * npk))()
+        _check(lib().nlk_ctx_profile_collect(self._h, ms, cnt))
+        out = {}
+        for i, kn in enumerate(self.KERNELS):
+            for j, pk in enumerate(self.PASS_KINDS):
+                if cnt[i * npk + j]:
+                    out[(kn, pk)] = (ms[i * npk + j], cnt[i * npk + j])
+        return out
+
+    def fp32_peak(self, ms: float = 200.0) -> float:
+        v = C.c_double(0)
+        _check(lib().nlk_fp32_peak(self._h, float(ms), C.byref(v)))
+        return v.value
 
     # device-pointer operations (torch CUDA tensors or raw pointers)
     def rgb2opp_dev(self, dst, src):

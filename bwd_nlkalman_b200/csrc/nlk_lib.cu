@@ -115,6 +115,12 @@ struct nlk_ctx {
     DevBuf q_noisy, q_warp, q_flt1[2], q_flt2[2], q_smo[2], q_tmp;
     int q_cur = 0, q_have_prev = 0, q_have_flt2 = 0;
     int q_smo_cur = 0, q_have_smo = 0;
+    // optional per-kernel timing with CUDA events on the context's stream
+    bool prof = false;
+    int prof_kind = NLK_PASS_OTHER;
+    struct ProfRec { int kid, kind; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
     size_t img_bytes() const { return (size_t)w * h * ch * sizeof(float); }
 };
 
@@ -122,6 +128,61 @@ static int ctx_use(nlk_ctx *c)
 {
     if (!c) return set_err(NLK_ERR_PARAM, "null context");
     CU_TRY(cudaSetDevice(c->device));
+    return NLK_OK;
+}
+
+struct ProfScope {
+    nlk_ctx *c;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int kid;
+    static cudaEvent_t get(nlk_ctx *c)
+    {
+        if (!c->prof_pool.empty()) {
+            cudaEvent_t e = c->prof_pool.back();
+            c->prof_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        return e;
+    }
+    ProfScope(nlk_ctx *c_, int kid_) : c(c_), kid(kid_)
+    {
+        if (!c->prof) return;
+        a = get(c);
+        b = get(c);
+        cudaEventRecord(a, c->st);
+    }
+    ~ProfScope()
+    {
+        if (!a) return;
+        cudaEventRecord(b, c->st);
+        c->prof_recs.push_back({kid, c->prof_kind, a, b});
+    }
+};
+
+extern "C" int nlk_ctx_profile(nlk_ctx *c, int enable)
+{
+    if (!c) return set_err(NLK_ERR_PARAM, "null context");
+    c->prof = enable != 0;
+    return NLK_OK;
+}
+
+extern "C" int nlk_ctx_profile_collect(nlk_ctx *c, double *ms_sum, int *count)
+{
+    if (int r = ctx_use(c)) return r;
+    CU_TRY(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < NLK_KERNEL_COUNT * NLK_PASS_KINDS; ++i) { ms_sum[i] = 0; count[i] = 0; }
+    for (auto &r : c->prof_recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            ms_sum[r.kid * NLK_PASS_KINDS + r.kind] += ms;
+            count[r.kid * NLK_PASS_KINDS + r.kind] += 1;
+        }
+        c->prof_pool.push_back(r.a);
+        c->prof_pool.push_back(r.b);
+    }
+    c->prof_recs.clear();
     return NLK_OK;
 }
 
@@ -168,6 +229,8 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
                      &c->q_flt1[0], &c->q_flt1[1], &c->q_flt2[0], &c->q_flt2[1], &c->q_smo[0],
                      &c->q_smo[1], &c->q_tmp};
     for (DevBuf *b : all) b->release();
+    for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -269,21 +332,41 @@ static int run_pass(nlk_ctx *c, int smooth, float *d_out, const float *d_in1, co
         CU_TRY(cudaMemsetAsync(P.cand, 0xff, G * kmax * 4, c->st));
     }
 
-    CU_TRY(cudaMemsetAsync(P.accw, 0, npix * (ch + 1) * 4, c->st));
-    CU_TRY(cudaMemsetAsync(c->counters.p, 0, 64, c->st));
+    const int kind_saved = c->prof_kind;
+    c->prof_kind = smooth ? NLK_PASS_SMO : (d_bsic1 ? (d_prev0 ? NLK_PASS_FLT2_T : NLK_PASS_FLT2_X)
+                                                     : (d_prev0 ? NLK_PASS_FLT1_T : NLK_PASS_FLT1_X));
+    struct Restore { nlk_ctx *c; int k; ~Restore() { c->prof_kind = k; } } restore{c, kind_saved};
+    {
+        ProfScope ps(c, NLK_K_MEMSET);
+        CU_TRY(cudaMemsetAsync(P.accw, 0, npix * (ch + 1) * 4, c->st));
+        CU_TRY(cudaMemsetAsync(c->counters.p, 0, 64, c->st));
+    }
     if (P.G > 0) {
         if (d_prev0) {
             if (int r = c->valid.ensure((size_t)P.vw * P.vh)) return r;
             if (int r = c->valid_tmp.ensure((size_t)P.vw * h)) return r;
             P.valid = c->valid.as<uint8_t>();
+            ProfScope ps(c, NLK_K_VALID);
             if (int r = check_launch(c, launch_valid_map(c->valid.as<uint8_t>(), c->valid_tmp.as<uint8_t>(),
                                                          d_prev0, w, h, ch, psz, c->st), "valid_map")) return r;
         }
-        if (int r = check_launch(c, launch_search(P, c->st), "search_knn")) return r;
-        if (int r = check_launch(c, launch_resolve(P, c->st), "mask_resolve")) return r;
-        if (int r = check_launch(c, launch_group_filter(P, c->num_sms, c->st), "group_filter")) return r;
+        {
+            ProfScope ps(c, NLK_K_SEARCH);
+            if (int r = check_launch(c, launch_search(P, c->st), "search_knn")) return r;
+        }
+        {
+            ProfScope ps(c, NLK_K_RESOLVE);
+            if (int r = check_launch(c, launch_resolve(P, c->st), "mask_resolve")) return r;
+        }
+        {
+            ProfScope ps(c, NLK_K_GROUP);
+            if (int r = check_launch(c, launch_group_filter(P, c->num_sms, c->st), "group_filter")) return r;
+        }
     }
-    if (int r = check_launch(c, launch_normalize(P, c->st), "normalize")) return r;
+    {
+        ProfScope ps(c, NLK_K_NORMALIZE);
+        if (int r = check_launch(c, launch_normalize(P, c->st), "normalize")) return r;
+    }
     return NLK_OK;
 }
 
@@ -302,6 +385,7 @@ extern "C" int nlk_rgb2opp_dev(nlk_ctx *c, float *d_dst, const float *d_src)
         if (d_dst != d_src) CU_TRY(cudaMemcpyAsync(d_dst, d_src, c->img_bytes(), cudaMemcpyDeviceToDevice, c->st));
         return NLK_OK;
     }
+    ProfScope ps(c, NLK_K_COLOUR);
     return check_launch(c, launch_rgb2opp_copy(d_dst, d_src, (long)c->w * c->h, 0, c->st), "rgb2opp");
 }
 
@@ -312,6 +396,7 @@ extern "C" int nlk_opp2rgb_dev(nlk_ctx *c, float *d_dst, const float *d_src)
         if (d_dst != d_src) CU_TRY(cudaMemcpyAsync(d_dst, d_src, c->img_bytes(), cudaMemcpyDeviceToDevice, c->st));
         return NLK_OK;
     }
+    ProfScope ps(c, NLK_K_COLOUR);
     return check_launch(c, launch_rgb2opp_copy(d_dst, d_src, (long)c->w * c->h, 1, c->st), "opp2rgb");
 }
 
@@ -319,6 +404,7 @@ extern "C" int nlk_warp_dev(nlk_ctx *c, float *d_imw, const float *d_im, const f
                             const float *d_msk)
 {
     if (int r = ctx_use(c)) return r;
+    ProfScope ps(c, NLK_K_WARP);
     return check_launch(c, launch_warp(d_imw, d_im, d_of, d_msk, c->w, c->h, c->ch, c->st), "warp_bicubic");
 }
 
@@ -698,4 +784,50 @@ extern "C" void nlkalman_smooth_frame(float *smoo1, float *filt1, float *smoo0, 
     std::lock_guard<std::mutex> lk(g_legacy_mu);
     nlk_ctx *c = legacy_ctx(w, h, ch);
     if (pass_host(c, 1, smoo1, filt1, smoo0, bsic1, sigma, prms, false)) legacy_die("nlkalman_smooth_frame");
+}
+
+// ---- fp32 FMA peak (roofline denominator for the compute-bound kernels) ----------------------
+
+__global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a, float b)
+{
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    if (s == 123.456f) out[0] = s; // never true in practice: keeps the chain live
+}
+
+extern "C" int nlk_fp32_peak(nlk_ctx *c, float ms, double *tflops)
+{
+    if (int r = ctx_use(c)) return r;
+    if (int r = c->q_tmp.ensure(256)) return r;
+    const int nb = c->num_sms * 8, nt = 256, iters = 4096;
+    cudaEvent_t a, b;
+    CU_TRY(cudaEventCreate(&a));
+    CU_TRY(cudaEventCreate(&b));
+    // warm up, then repeat until about `ms` of device time has been measured
+    for (int i = 0; i < 3; ++i) k_fma_peak<<<nb, nt, 0, c->st>>>(c->q_tmp.as<float>(), iters, 0.999f, 1e-3f);
+    double best = 0, spent = 0;
+    while (spent < ms) {
+        CU_TRY(cudaEventRecord(a, c->st));
+        for (int i = 0; i < 8; ++i) k_fma_peak<<<nb, nt, 0, c->st>>>(c->q_tmp.as<float>(), iters, 0.999f, 1e-3f);
+        CU_TRY(cudaEventRecord(b, c->st));
+        CU_TRY(cudaEventSynchronize(b));
+        float t = 0.f;
+        CU_TRY(cudaEventElapsedTime(&t, a, b));
+        const double fl = 8.0 * nb * nt * (double)iters * 16 * 2;
+        const double tf = fl / (t * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+        spent += t;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *tflops = best;
+    return NLK_OK;
 }

@@ -41,6 +41,27 @@ long long nlk_ctx_launch_count(const nlk_ctx *ctx);
 /* the context's cudaStream_t, for callers that queue their own work around it */
 void *nlk_ctx_stream(nlk_ctx *ctx);
 
+/* Optional per-kernel timing: when enabled every kernel the context launches is
+ * bracketed by CUDA events on the context's stream.  nlk_ctx_profile_collect waits for
+ * the stream, then fills ms_sum / count, both [NLK_KERNEL_COUNT][NLK_PASS_KINDS], with
+ * the summed durations and the launch-group counts since the last collection. */
+enum { NLK_K_COLOUR = 0, NLK_K_WARP, NLK_K_VALID, NLK_K_SEARCH, NLK_K_RESOLVE, NLK_K_GROUP,
+       NLK_K_NORMALIZE, NLK_K_MEMSET, NLK_KERNEL_COUNT };
+enum { NLK_PASS_FLT1_T = 0, /* filter, previous frame given, no basic estimate */
+       NLK_PASS_FLT1_X,     /* filter, no previous frame, no basic estimate  */
+       NLK_PASS_FLT2_T,     /* filter with basic estimate, previous frame given */
+       NLK_PASS_FLT2_X,     /* filter with basic estimate, no previous frame */
+       NLK_PASS_SMO,        /* smoother */
+       NLK_PASS_OTHER,      /* outside a pass (colour transform, warp) */
+       NLK_PASS_KINDS };
+int nlk_ctx_profile(nlk_ctx *ctx, int enable);
+int nlk_ctx_profile_collect(nlk_ctx *ctx, double *ms_sum, int *count);
+
+/* sustained fp32 FMA throughput of the device in TFLOP/s (2 flops per FMA), measured
+ * with a register-resident FMA kernel for about `ms` milliseconds: the denominator of
+ * the FP32 roofline that bounds search_knn and group_filter */
+int nlk_fp32_peak(nlk_ctx *ctx, float ms, double *tflops);
+
 /* pinned host memory (cudaMallocHost / cudaFreeHost) for the h_ arguments below */
 void *nlk_host_alloc(size_t bytes);
 void nlk_host_free(void *p);
