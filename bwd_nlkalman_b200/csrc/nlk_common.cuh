@@ -57,7 +57,8 @@ struct PassParams {
     float *dbg_dist;        // [G][kstride] distances of the kept candidates, or nullptr
     int *any_nbr;           // set to 1 if some group marks a grid patch other than its own
     // resolve output
-    int *active;            // [G] indices of processed patches
+    uint8_t *actflag;       // [G] 1 = processed (written by mask_resolve)
+    int *active;            // [G] indices of processed patches, raster order
     int *nactive;
     uint8_t *gmask;         // [G] processed mask (global-memory fallback of mask_resolve)
     // aggregation

@@ -55,13 +55,16 @@ __device__ __forceinline__ void dct1d_inv(float (&X)[N])
     for (int j = 0; j < H; ++j) { X[j] = e[j] + o[j]; X[N - 1 - j] = e[j] - o[j]; }
 }
 
-// whole 8x8 tile in registers
+// whole 8x8 tile in registers; source element (y, x) at src[y*row_stride + x*col_stride]
 template <bool INVERSE>
-__device__ __forceinline__ void dct2d_8x8_smem(float *__restrict__ tile)
+__device__ __forceinline__ void dct2d_8x8_strided(const float *src, int row_stride,
+                                                  int col_stride, float *tile)
 {
     float t[64];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) t[i] = tile[i];
+    for (int y = 0; y < 8; ++y)
+#pragma unroll
+        for (int x = 0; x < 8; ++x) t[y * 8 + x] = src[y * row_stride + x * col_stride];
 #pragma unroll
     for (int y = 0; y < 8; ++y) {
         float r[8];
@@ -127,12 +130,34 @@ __device__ inline void dct2d_generic_smem(float *__restrict__ tile, int n)
     }
 }
 
+template <bool INVERSE>
+__device__ __forceinline__ void dct2d_8x8_smem(float *__restrict__ tile)
+{
+    dct2d_8x8_strided<INVERSE>(tile, 8, 1, tile);
+}
+
 template <int PSZ_T, bool INVERSE>
 __device__ __forceinline__ void dct2d_tile(float *__restrict__ tile, int psz_rt)
 {
     if constexpr (PSZ_T == 8) dct2d_8x8_smem<INVERSE>(tile);
     else if constexpr (PSZ_T != 0) dct2d_passes_smem<PSZ_T, INVERSE>(tile);
     else dct2d_generic_smem<INVERSE>(tile, psz_rt);
+}
+
+// forward transform of the patch whose element (y, x) is src[y*row_stride + x*col_stride]
+// (a window staged in shared memory) into the thread's own tile
+template <int PSZ_T>
+__device__ __forceinline__ void dct2d_from_window(const float *__restrict__ src, int row_stride,
+                                                  int col_stride, float *__restrict__ tile, int psz_rt)
+{
+    if constexpr (PSZ_T == 8) {
+        dct2d_8x8_strided<false>(src, row_stride, col_stride, tile);
+    } else {
+        const int psz = PSZ_T ? PSZ_T : psz_rt;
+        for (int y = 0; y < psz; ++y)
+            for (int x = 0; x < psz; ++x) tile[y * psz + x] = src[y * row_stride + x * col_stride];
+        dct2d_tile<PSZ_T, false>(tile, psz_rt);
+    }
 }
 
 } // namespace nlk

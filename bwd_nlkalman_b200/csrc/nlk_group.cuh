@@ -54,40 +54,21 @@ __device__ __forceinline__ float block_sum(float v, float *s_red)
     return t;
 }
 
-// gather the patches of `cnt` candidates (list `cl`, entries first..first+cnt) from up
-// to two images into tiles [(slot*2 + s)*ch + c][row*psz + hx]
-template <int PSZ_T, int CH_T>
-__device__ __forceinline__ void gather_tiles(float *__restrict__ tiles, int TS,
-                                             const uint32_t *__restrict__ cl, int first, int cnt,
-                                             const float *__restrict__ img0,
-                                             const float *__restrict__ img1, bool img1_needs_prev,
-                                             int w, int psz_rt, int ch_rt)
+// stage the window rows y0..y0+wh-1, columns x0..x0+wlen/ch-1 of an HWC image
+__device__ __forceinline__ void stage_window(float *__restrict__ win, int wrow, const float *__restrict__ img,
+                                             int w, int ch, int x0, int y0, int wlen, int wh)
 {
-    const int psz = PSZ_T ? PSZ_T : psz_rt;
-    const int ch = CH_T ? CH_T : ch_rt;
-    const int rowlen = psz * ch;
-    const int per_src = psz * rowlen;
-    const int nsrc = img1 ? 2 : 1;
-    const int total = cnt * nsrc * per_src;
-    for (int it = threadIdx.x; it < total; it += GF_THREADS) {
-        const int j = it % rowlen;
-        int rest = it / rowlen;
-        const int row = rest % psz;
-        rest /= psz;
-        const int s = rest % nsrc;
-        const int slot = rest / nsrc;
-        const uint32_t cd = cl[first + slot];
-        if (s == 1 && img1_needs_prev && !cand_prev(cd)) continue;
-        const float *img = s ? img1 : img0;
-        const float v = img[((long)(cand_y(cd) + row) * w + cand_x(cd)) * ch + j];
-        const int hx = j / ch, c = j - hx * ch;
-        tiles[((slot * 2 + s) * ch + c) * TS + row * psz + hx] = v;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = warp; row < wh; row += GF_THREADS / 32) {
+        const float *src = img + ((long)(y0 + row) * w + x0) * ch;
+        float *dst = win + row * wrow;
+        for (int j = lane; j < wlen; j += 32) dst[j] = src[j];
     }
 }
 
 template <int PSZ_T, int CH_T>
 __global__ void __launch_bounds__(GF_THREADS, 2)
-k_group_filter(const PassParams P, int cc, int kcap)
+k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
 {
     constexpr int JPT = (PSZ_T && CH_T) ? (PSZ_T * PSZ_T * CH_T + GF_THREADS - 1) / GF_THREADS
                                         : (MAX_PSZ * MAX_PSZ * MAX_CH + GF_THREADS - 1) / GF_THREADS;
@@ -98,11 +79,13 @@ k_group_filter(const PassParams P, int cc, int kcap)
     const int tid = threadIdx.x;
 
     extern __shared__ __align__(16) float smem[];
-    float *tiles = smem;                                  // [cc*2*ch][TS]
-    float *s_a = tiles + (size_t)cc * 2 * ch * TS;        // [cpp] gain
+    float *tiles = smem;                                  // [CT][TS]
+    float *winS = tiles + (size_t)CT * TS;                // source window (src, later in1)
+    float *winP = winS + win_floats;                      // previous-frame window
+    float *s_a = winP + (P.has_prev ? win_floats : 0);    // [cpp] gain
     float *s_m = s_a + cpp;                               // [cpp] group mean (M0 or M1)
     uint32_t *s_cand = reinterpret_cast<uint32_t *>(s_m + cpp); // [kcap] sorted candidates
-    uint32_t *s_grp = s_cand + kcap;                      // [tagg] group members (cand records)
+    int *s_grp = reinterpret_cast<int *>(s_cand + kcap);  // [tagg] sorted index of each group member
     float *s_red = reinterpret_cast<float *>(s_grp + max(P.tagg, 1)); // [8]
     float *W = s_red + 8;                                 // [pp] aggregation window
     __shared__ int s_nagg;
@@ -114,7 +97,8 @@ k_group_filter(const PassParams P, int cc, int kcap)
     for (int ai = blockIdx.x; ai < nactive; ai += gridDim.x) {
         const int g = P.active[ai];
         const GroupHdr hd = P.hdr[g];
-        const int px = (g % P.gw) * P.step, py = (g / P.gw) * P.step;
+        const int gy = g / P.gw, gx = g - gy * P.gw;
+        const int px = gx * P.step, py = gy * P.step;
         const int prev_p = hd.flags & HDR_PREV_P;
         int k = hd.nk;
         const int np0 = hd.np0;
@@ -140,6 +124,14 @@ k_group_filter(const PassParams P, int cc, int kcap)
             continue;
         }
 
+        // window geometry of this group (the search window, reference :637-639)
+        const int r = point ? 0 : (P.smooth ? P.r_t : (prev_p ? P.r_t : P.r_x));
+        const int x0 = max(px - r, 0), x1 = min(px + r, P.w - psz);
+        const int y0 = max(py - r, 0), y1 = min(py + r, P.h - psz);
+        const int wlen = (x1 - x0 + psz) * ch, wh = y1 - y0 + psz;
+        stage_window(winS, wrow, P.src, P.w, ch, x0, y0, wlen, wh);
+        if (prev_p) stage_window(winP, wrow, P.prev0, P.w, ch, x0, y0, wlen, wh);
+
         if (point) {
             if (tid == 0) s_cand[0] = cand_pack(px, py, 1);
             k = 1;
@@ -158,11 +150,17 @@ k_group_filter(const PassParams P, int cc, int kcap)
                 const int take = (i < k) && (np0 > 0 ? cand_prev(cd) : 1);
                 const unsigned int bal = __ballot_sync(0xffffffffu, take);
                 const int rank = cnt + __popc(bal & ((1u << tid) - 1u));
-                if (take && rank < P.tagg) s_grp[rank] = cd;
+                if (take && rank < P.tagg) s_grp[rank] = i;
                 cnt += __popc(bal);
             }
             if (tid == 0) s_nagg = min(cnt, P.tagg);
         }
+
+        // tiles of candidate slot i: (i*nsrc + s)*ch + c, s = 0 source, 1 previous frame
+        const int nsrc = prev_p ? 2 : 1;
+        const int tpc = nsrc * ch;            // tiles per candidate
+        const int cc = CT / tpc;              // candidates per chunk
+        const bool resident = (k <= cc) && !P.has_bsic;
 
         // ---- pass 1: statistics over the k candidates ------------------------------------
         float M1[JPT], V1[JPT], Mp[JPT], V0[JPT], V01[JPT], Mg[JPT];
@@ -171,55 +169,65 @@ k_group_filter(const PassParams P, int cc, int kcap)
         int n1 = 0, n0 = 0;
         for (int c0 = 0; c0 < k; c0 += cc) {
             const int cnt = min(cc, k - c0);
-            __syncthreads();
-            gather_tiles<PSZ_T, CH_T>(tiles, TS, s_cand, c0, cnt, P.src,
-                                      prev_p ? P.prev0 : nullptr, true, P.w, psz, ch);
-            __syncthreads();
-            // one thread per tile
-            for (int t = tid; t < cnt * 2 * ch; t += GF_THREADS) {
-                const int slot = t / (2 * ch), s = (t / ch) & 1;
-                if (s == 1 && !(prev_p && cand_prev(s_cand[c0 + slot]))) continue;
-                dct2d_tile<PSZ_T, false>(tiles + t * TS, psz);
+            if (c0) __syncthreads();
+            // one thread per tile: transform straight out of the staged windows
+            for (int t = tid; t < cnt * tpc; t += GF_THREADS) {
+                const int slot = t / tpc, rr = t - slot * tpc;
+                const int s = rr >= ch, c = rr - s * ch;
+                const uint32_t cd = s_cand[c0 + slot];
+                if (s == 1 && !cand_prev(cd)) continue;
+                const float *src = (s ? winP : winS) + (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * ch + c;
+                dct2d_from_window<PSZ_T>(src, wrow, ch, tiles + t * TS, psz);
             }
             __syncthreads();
             // one thread per coefficient, candidates in sorted order
-            for (int i = 0; i < cnt; ++i) {
-                const int prev = prev_p && cand_prev(s_cand[c0 + i]);
-                n1 += 1;
-                n0 += prev;
-                const float inp1 = c_inv[n1];
-                const float inp0 = c_inv[n0];
+            {
+                const int cstride = tpc * TS;
 #pragma unroll
                 for (int u = 0; u < JPT; ++u) {
                     const int j = tid + u * GF_THREADS;
-                    if (j < cpp) {
-                        const int c = j / pp, e = j - c * pp;
-                        const float p = tiles[((i * 2) * ch + c) * TS + e];
-                        if (point) {
-                            const float q = tiles[((i * 2 + 1) * ch + c) * TS + e];
-                            V1[u] = p * p;
-                            V0[u] = q * q;
-                            V01[u] = (q - p) * (q - p);
-                        } else {
-                            const float delta = p - M1[u];
-                            M1[u] += delta * inp1;              // :765
-                            V1[u] += delta * (p - M1[u]);       // :766
-                            if (prev) {
-                                const float q = tiles[((i * 2 + 1) * ch + c) * TS + e];
-                                const float d0 = q - Mp[u];     // :770-775 / :1654-1659
-                                Mp[u] += d0 * inp0;
-                                V0[u] += d0 * (q - Mp[u]);
-                                const float t = q - p;
-                                V01[u] += t * t;                // :777-778
-                                if (n0 <= P.tagg) Mg[u] += (q - Mg[u]) * inp0; // :783
-                            }
+                    if (j >= cpp) continue;
+                    const int c = j / pp, e = j - c * pp;
+                    const float *tp = tiles + c * TS + e;      // source tile of slot 0
+                    const float *tq = tp + ch * TS;            // previous-frame tile of slot 0
+                    int m1 = n1, m0 = n0;
+                    if (point) {
+                        const float p = tp[0], q = tq[0];
+                        V1[u] = p * p;
+                        V0[u] = q * q;
+                        V01[u] = (q - p) * (q - p);
+                        continue;
+                    }
+                    float aM1 = M1[u], aV1 = V1[u], aMp = Mp[u], aV0 = V0[u], aV01 = V01[u], aMg = Mg[u];
+                    for (int i = 0; i < cnt; ++i, tp += cstride, tq += cstride) {
+                        const float p = *tp;
+                        m1 += 1;
+                        const float delta = p - aM1;
+                        aM1 = fmaf(delta, c_inv[m1], aM1);            // :765
+                        aV1 = fmaf(delta, p - aM1, aV1);              // :766
+                        if (cand_prev(s_cand[c0 + i])) {              // (implies prev_p)
+                            m0 += 1;
+                            const float inp0 = c_inv[m0];
+                            const float q = *tq;
+                            const float d0 = q - aMp;                 // :770-775 / :1654-1659
+                            aMp = fmaf(d0, inp0, aMp);
+                            aV0 = fmaf(d0, q - aMp, aV0);
+                            const float t = q - p;
+                            aV01 = fmaf(t, t, aV01);                  // :777-778
+                            if (m0 <= P.tagg) aMg = fmaf(q - aMg, inp0, aMg); // :783
                         }
                     }
+                    M1[u] = aM1; V1[u] = aV1; Mp[u] = aMp; V0[u] = aV0; V01[u] = aV01; Mg[u] = aMg;
                 }
+                // the counters advance identically in every thread
+                for (int i = 0; i < cnt; ++i) { n1 += 1; n0 += cand_prev(s_cand[c0 + i]); }
             }
         }
         __syncthreads();
         const int nagg = s_nagg;
+        // with a basic estimate the group holds the noisy patches themselves (:785, :853):
+        // the source window is no longer needed, restage it from the noisy frame
+        if (P.has_bsic) stage_window(winS, wrow, P.in1, P.w, ch, x0, y0, wlen, wh);
 
         // ---- gains (:858-904, :1763-1777) -------------------------------------------------
         float vsum = 0.f;
@@ -257,75 +265,90 @@ k_group_filter(const PassParams P, int cc, int kcap)
                 }
             }
         }
-        const float vp = (float)nagg * block_sum(vsum, s_red);
+        const float vp = (float)nagg * block_sum(vsum, s_red); // (has the barriers the restage needs)
         const float wgt = __fdiv_rn(1.f, fmaxf(vp, 1e-6f)); // :911
         if (P.dbg_vp && tid == 0) P.dbg_vp[g] = vp;
 
         // ---- pass 2: update, inverse transform and aggregation of the group ------------
-        for (int n0g = 0; n0g < nagg; n0g += cc) {
-            const int cnt = min(cc, nagg - n0g);
-            __syncthreads();
-            gather_tiles<PSZ_T, CH_T>(tiles, TS, s_grp, n0g, cnt, P.in1,
-                                      P.smooth ? P.prev0 : nullptr, false, P.w, psz, ch);
-            __syncthreads();
-            const int nsrc = P.smooth ? 2 : 1;
-            for (int t = tid; t < cnt * nsrc * ch; t += GF_THREADS) {
-                const int slot = t / (nsrc * ch), r = t - slot * nsrc * ch;
-                dct2d_tile<PSZ_T, false>(tiles + (slot * 2 * ch + r) * TS, psz);
+        // resident: every candidate's transform is still in `tiles`, members are updated in
+        // place; otherwise members are transformed again, a chunk at a time
+        const int nsrc2 = P.smooth ? 2 : 1;
+        for (int m0 = 0; m0 < nagg; m0 += cc) {
+            const int cnt = min(cc, nagg - m0);
+            if (!resident) {
+                __syncthreads();
+                for (int t = tid; t < cnt * nsrc2 * ch; t += GF_THREADS) {
+                    const int ml = t / (nsrc2 * ch), rr = t - ml * nsrc2 * ch;
+                    const int s = rr >= ch, c = rr - s * ch;
+                    const uint32_t cd = s_cand[s_grp[m0 + ml]];
+                    const float *src = (s ? winP : winS) + (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * ch + c;
+                    dct2d_from_window<PSZ_T>(src, wrow, ch, tiles + (ml * tpc + rr) * TS, psz);
+                }
+                __syncthreads();
             }
-            __syncthreads();
-            for (int it = tid; it < cnt * cpp; it += GF_THREADS) {
-                const int slot = it / cpp, j = it - slot * cpp;
+            // one thread per coefficient over the members of the chunk
+#pragma unroll
+            for (int u = 0; u < JPT; ++u) {
+                const int j = tid + u * GF_THREADS;
+                if (j >= cpp) continue;
                 const int c = j / pp, e = j - c * pp;
-                float *y = tiles + ((slot * 2) * ch + c) * TS + e;
-                const float a = s_a[j];
-                if (P.smooth) *y = (1.f - a) * (*y) + a * y[ch * TS];   // :1775
-                else *y = a * (*y) + (1.f - a) * s_m[j];                // :878 / :901
+                const float a = s_a[j], oma = 1.f - a, mj = s_m[j];
+                float *yb = tiles + c * TS + e;
+                for (int ml = 0; ml < cnt; ++ml) {
+                    const int slot = resident ? s_grp[m0 + ml] : ml;
+                    float *y = yb + slot * tpc * TS;
+                    if (P.smooth) *y = oma * (*y) + a * y[ch * TS];     // :1775
+                    else *y = a * (*y) + oma * mj;                      // :878 / :901
+                }
             }
             __syncthreads();
             for (int t = tid; t < cnt * ch; t += GF_THREADS) {
-                const int slot = t / ch, c = t - slot * ch;
-                dct2d_tile<PSZ_T, true>(tiles + ((slot * 2) * ch + c) * TS, psz);
+                const int ml = t / ch, c = t - ml * ch;
+                const int slot = resident ? s_grp[m0 + ml] : ml;
+                dct2d_tile<PSZ_T, true>(tiles + (slot * tpc + c) * TS, psz);
             }
             __syncthreads();
             for (int it = tid; it < cnt * pp; it += GF_THREADS) {
-                const int slot = it / pp, e = it - slot * pp;
+                const int ml = it / pp, e = it - ml * pp;
                 const int hy = e / psz, hx = e - hy * psz;
-                const uint32_t cd = s_grp[n0g + slot];
+                const int gi = s_grp[m0 + ml];
+                const int slot = resident ? gi : ml;
+                const uint32_t cd = s_cand[gi];
                 const long pix = (long)(cand_y(cd) + hy) * P.w + cand_x(cd) + hx;
                 const float wW = __fmul_rn(wgt, W[e]);                  // :923
                 float v[MAX_CH];
                 for (int c = 0; c < ch; ++c)
-                    v[c] = __fmul_rn(wW, tiles[((slot * 2) * ch + c) * TS + e]); // :926
+                    v[c] = __fmul_rn(wW, tiles[(slot * tpc + c) * TS + e]); // :926
                 accumulate_pixel<CH_T>(P.accw + pix * (ch + 1), v, wW, ch);
             }
         }
     }
 }
 
-inline int group_filter_cc(const PassParams &P)
-{
-    const int TS = P.psz * P.psz + 1;
-    int cc = GF_THREADS / (2 * P.ch);               // one thread per tile in the DCT phase
-    const int by_smem = 64 * 1024 / (2 * P.ch * TS * 4);
-    if (cc > by_smem) cc = by_smem;
-    if (cc < 1) cc = 1;
-    return cc;
-}
-
 inline int launch_group_filter(const PassParams &P, int num_sms, cudaStream_t st)
 {
-    const int cc = group_filter_cc(P);
     const int TS = P.psz * P.psz + 1;
     const int cpp = P.ch * P.psz * P.psz;
     const int kcap = P.kstride > 1 ? P.kstride : 1;
-    const size_t smem = ((size_t)cc * 2 * P.ch * TS + 2 * cpp + kcap + (P.tagg > 1 ? P.tagg : 1) + 8 + P.psz * P.psz) * 4;
+    const int tpc = (P.has_prev ? 2 : 1) * P.ch;
+    // tiles: every candidate of a group at once when that fits (one thread per tile and
+    // about 64 KB), else chunks
+    int CT = kcap * tpc;
+    if (CT > GF_THREADS) CT = (GF_THREADS / tpc) * tpc;
+    const int by_smem = (64 * 1024 / (TS * 4)) / tpc * tpc;
+    if (CT > by_smem) CT = by_smem;
+    if (CT < tpc) CT = tpc;
+    const int r = P.smooth ? P.r_t : (P.r_t > P.r_x ? P.r_t : P.r_x);
+    const int wrow = (2 * r + P.psz) * P.ch + 1;
+    const int win_floats = (2 * r + P.psz) * wrow;
+    const size_t smem = ((size_t)CT * TS + (size_t)win_floats * (P.has_prev ? 2 : 1) + 2 * cpp + kcap +
+                         (P.tagg > 1 ? P.tagg : 1) + 8 + P.psz * P.psz) * 4;
     const int nb = num_sms * 2;
 #define NLK_LAUNCH_GF(PS, CHN)                                                                        \
     do {                                                                                              \
         cudaFuncSetAttribute(k_group_filter<PS, CHN>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                              (int)smem);                                                              \
-        k_group_filter<PS, CHN><<<nb, GF_THREADS, smem, st>>>(P, cc, kcap);                          \
+        k_group_filter<PS, CHN><<<nb, GF_THREADS, smem, st>>>(P, CT, kcap, wrow, win_floats);        \
     } while (0)
     if (smem > 220 * 1024) return -1;
     if (P.psz == 8 && P.ch == 3) NLK_LAUNCH_GF(8, 3);

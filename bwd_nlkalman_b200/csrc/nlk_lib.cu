@@ -108,7 +108,7 @@ struct nlk_ctx {
     cudaStream_t st = nullptr;
     long long launches = 0;
     // per-pass scratch
-    DevBuf accw, valid, valid_tmp, cand, hdr, nbr, active, counters, gmask, dbg_dist, dbg_vp;
+    DevBuf accw, valid, valid_tmp, cand, hdr, nbr, active, actflag, counters, gmask, dbg_dist, dbg_vp;
     // host-call staging
     DevBuf s_in1, s_prev0, s_bsic, s_out, s_of, s_msk;
     // sequence state (opponent colour space)
@@ -224,7 +224,7 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
     DevBuf *all[] = {&c->accw, &c->valid, &c->valid_tmp, &c->cand, &c->hdr, &c->nbr, &c->active,
-                     &c->counters, &c->gmask, &c->dbg_dist, &c->dbg_vp, &c->s_in1, &c->s_prev0,
+                     &c->counters, &c->gmask, &c->actflag, &c->dbg_dist, &c->dbg_vp, &c->s_in1, &c->s_prev0,
                      &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk, &c->q_noisy, &c->q_warp,
                      &c->q_flt1[0], &c->q_flt1[1], &c->q_flt2[0], &c->q_flt2[1], &c->q_smo[0],
                      &c->q_smo[1], &c->q_tmp};
@@ -313,12 +313,14 @@ static int run_pass(nlk_ctx *c, int smooth, float *d_out, const float *d_in1, co
     if (int r = c->nbr.ensure(G * P.nbw * 4)) return r;
     if (int r = c->active.ensure(G * 4)) return r;
     if (int r = c->gmask.ensure(G)) return r;
+    if (int r = c->actflag.ensure(G)) return r;
     P.accw = c->accw.as<float>();
     P.cand = c->cand.as<uint32_t>();
     P.hdr = c->hdr.as<GroupHdr>();
     P.nbr = c->nbr.as<uint32_t>();
     P.active = c->active.as<int>();
     P.gmask = c->gmask.as<uint8_t>();
+    P.actflag = c->actflag.as<uint8_t>();
     P.nactive = c->counters.as<int>();
     P.any_nbr = c->counters.as<int>() + 1;
     P.out = d_out;

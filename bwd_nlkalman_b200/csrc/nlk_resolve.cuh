@@ -8,19 +8,40 @@
 //
 // A group reaches at most R = floor(r/step) grid cells in each direction, so all cells
 // with equal t = j + (R+1) i are independent: a skewed wavefront, run by ONE thread
-// block (thread = grid row) with the mask as a bit set in shared memory.
+// block (thread = grid row).
 #pragma once
 #include "nlk_common.cuh"
+#include <type_traits>
 
 namespace nlk {
 
-template <bool SMEM_MASK>
-__global__ void __launch_bounds__(1024) k_resolve(const PassParams P)
+// No atomics and almost no work per step: thread i owns grid row i and carries, in a
+// 64-bit register, the processed-mask bits of its row for the columns j .. j+63 ahead of
+// its position.  An active cell publishes its neighbour bitmap (one shared-memory slot
+// per row, double-buffered by step parity).  With skew R+1, the cell that row i-dy handled
+// in the previous step is (i-dy, j + dy(R+1) - 1); its members in row i are the 2R+1
+// columns starting at j + (dy-1)(R+1), i.e. at or ahead of row i's position, so row i
+// ORs that (2R+1)-bit field into its window at offset (dy-1)(R+1) -- R reads per step.
+__device__ __forceinline__ unsigned int nbr_field(const unsigned int *wds, int nbw, int start, int width)
 {
-    extern __shared__ unsigned int sbits[];
-    __shared__ int s_count;
+    const int w0 = start >> 5, sh = start & 31;
+    unsigned long long v = wds[w0];
+    if (w0 + 1 < nbw) v |= (unsigned long long)wds[w0 + 1] << 32;
+    return (unsigned int)(v >> sh) & ((1u << width) - 1u);
+}
+
+// FAST: one bitmap word per cell and a 32-bit row window (R <= 4), the usual case
+template <int MAX_ROWS, bool FAST>
+__global__ void __launch_bounds__(1024) k_resolve(const PassParams P, int rw)
+{
+    typedef typename std::conditional<FAST, unsigned int, unsigned long long>::type win_t;
+    extern __shared__ unsigned int s_dyn[];
+    const int gw = P.gw, gh = P.gh, G = P.G, nbw = FAST ? 1 : P.nbw;
+    unsigned int *s_pub = s_dyn;                                      // [2][gh][nbw]
+    unsigned int *s_act = s_pub + (size_t)2 * gh * nbw;               // [gh][rw] active bits
+    int *s_base = reinterpret_cast<int *>(s_act + (size_t)gh * rw);   // [gh+1] row offsets
+    __shared__ int s_part[1024];
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int G = P.G, gw = P.gw, gh = P.gh;
 
     if (*P.any_nbr == 0) {
         // no group marks another grid patch: every patch is processed
@@ -28,71 +49,150 @@ __global__ void __launch_bounds__(1024) k_resolve(const PassParams P)
         if (tid == 0) *P.nactive = G;
         return;
     }
-    if (SMEM_MASK) {
-        for (int i = tid; i < (G + 31) / 32; i += nthr) sbits[i] = 0u;
-    } else {
-        for (int i = tid; i < G; i += nthr) P.gmask[i] = 0;
-    }
-    if (tid == 0) s_count = 0;
+    const int R = P.R, side = 2 * R + 1, skew = R + 1;
+    const int nsteps = gw + skew * (gh - 1);
+    for (int x = tid; x < 2 * gh * nbw; x += nthr) s_pub[x] = 0u;
     __syncthreads();
 
-    const int R = P.R, side = 2 * R + 1, skew = R + 1, nbw = P.nbw;
-    const int nsteps = gw + skew * (gh - 1);
-    // word 0 of the next cell of each of this thread's rows is fetched one step ahead
-    // (consecutive cells of a row share cache lines, so this is an L1 hit most steps)
-    constexpr int MAX_ROWS = 4;
-    unsigned int nxt[MAX_ROWS];
+    // Nothing is written to global memory inside the step loop (a block barrier after a
+    // global store waits for the store's round trip), and word 0 of each row's cells is
+    // fetched D steps ahead into a register pipeline (loop unrolled by D: static slots;
+    // only the first touch of a 128-byte line goes to L2, the rest are L1 hits).
+    constexpr int D = 4;
+    unsigned int q[MAX_ROWS][D], accw[MAX_ROWS];
+    win_t win[MAX_ROWS];
+    const unsigned int fmask = (1u << side) - 1u;
 #pragma unroll
     for (int m = 0; m < MAX_ROWS; ++m) {
         const int i = tid + m * nthr;
-        nxt[m] = (i == 0 && i < gh) ? P.nbr[0] : 0u;
-    }
-    for (int t = 0; t < nsteps; ++t) {
+        accw[m] = 0u;
+        win[m] = 0;
 #pragma unroll
-        for (int m = 0; m < MAX_ROWS; ++m) {
-            const int i = tid + m * nthr;
-            if (i >= gh) break;
-            const int j = t - skew * i;
-            if (j < -1 || j >= gw) continue;
-            unsigned int bits0 = nxt[m];
-            if (j + 1 < gw) nxt[m] = P.nbr[(long)(i * gw + j + 1) * nbw];
-            if (j < 0) continue;
-            const int g = i * gw + j;
-            bool done;
-            if (SMEM_MASK) done = (sbits[g >> 5] >> (g & 31)) & 1u;
-            else done = P.gmask[g] != 0;
-            if (done) continue;
-            P.active[atomicAdd(&s_count, 1)] = g;
-            for (int wd = 0; wd < nbw; ++wd) {
-                unsigned int bits = wd == 0 ? bits0 : P.nbr[(long)g * nbw + wd];
-                while (bits) {
-                    const int b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    const int bit = wd * 32 + b;
-                    const int dy = bit / side - R, dx = bit % side - R;
-                    const int g2 = (i + dy) * gw + (j + dx);
-                    if (SMEM_MASK) atomicOr(&sbits[g2 >> 5], 1u << (g2 & 31));
-                    else P.gmask[g2] = 1;
-                }
-            }
+        for (int u = 0; u < D; ++u) {
+            const int j = u - skew * i;
+            q[m][u] = (i < gh && j >= 0 && j < gw) ? P.nbr[(long)(i * gw + j) * nbw] : 0u;
         }
+    }
+    for (int t0 = 0; t0 < nsteps; t0 += D) {
+#pragma unroll
+        for (int u = 0; u < D; ++u) {
+            const int t = t0 + u;
+            if (t >= nsteps) break;
+            const unsigned int *pub_rd = s_pub + (size_t)((t + 1) & 1) * gh * nbw; // written at step t-1
+            unsigned int *pub_wr = s_pub + (size_t)(t & 1) * gh * nbw;
+#pragma unroll
+            for (int m = 0; m < MAX_ROWS; ++m) {
+                const int i = tid + m * nthr;
+                if (i >= gh) break;
+                const int j = t - skew * i;
+                const unsigned int bits0 = q[m][u];
+                const int jn = j + D;
+                if (jn >= 0 && jn < gw) q[m][u] = P.nbr[(long)(i * gw + jn) * nbw];
+                if (j >= gw) {
+                    // a row past its end must not leave a stale bitmap for the rows below
+                    if (j < gw + 2) for (int wd = 0; wd < nbw; ++wd) pub_wr[(size_t)i * nbw + wd] = 0u;
+                    continue;
+                }
+                if (j < 1 - R * skew) continue; // nothing above has reached this row's columns yet
+                // marks from the rows above (their previous step); also collected while this
+                // row has not started (j < 0): they concern columns it will visit
+                win_t wnd = win[m];
+                for (int dy = 1; dy <= R && dy <= i; ++dy) {
+                    const unsigned int f = FAST ? ((pub_rd[i - dy] >> ((dy + R) * side)) & fmask)
+                                                : nbr_field(pub_rd + (size_t)(i - dy) * nbw, nbw, (dy + R) * side, side);
+                    wnd |= (win_t)f << ((dy - 1) * skew);
+                }
+                if (j >= 0) {
+                    const bool done = wnd & 1;
+                    unsigned int w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+                    if (!done) {
+                        // own row: columns j+1 .. j+R (dy = 0, dx = 1..R)
+                        w0 = bits0;
+                        unsigned int f;
+                        if (FAST) {
+                            f = (w0 >> (R * side)) & fmask;
+                        } else {
+                            const long gb = (long)(i * gw + j) * nbw;
+                            if (nbw > 1) w1 = P.nbr[gb + 1];
+                            if (nbw > 2) w2 = P.nbr[gb + 2];
+                            if (nbw > 3) w3 = P.nbr[gb + 3];
+                            const int start = R * side, w_0 = start >> 5, sh = start & 31;
+                            const unsigned int lo = w_0 == 0 ? w0 : (w_0 == 1 ? w1 : (w_0 == 2 ? w2 : w3));
+                            const unsigned int hi = w_0 == 0 ? w1 : (w_0 == 1 ? w2 : (w_0 == 2 ? w3 : 0u));
+                            f = (unsigned int)((((unsigned long long)hi << 32) | lo) >> sh) & fmask;
+                        }
+                        wnd |= (win_t)(f >> R); // bit 0 = own column
+                    }
+                    unsigned int *pw = pub_wr + (size_t)i * nbw;
+                    pw[0] = w0;
+                    if (nbw > 1) pw[1] = w1;
+                    if (nbw > 2) pw[2] = w2;
+                    if (nbw > 3) pw[3] = w3;
+                    accw[m] |= (done ? 0u : 1u) << (j & 31);
+                    if ((j & 31) == 31 || j == gw - 1) {
+                        s_act[(size_t)i * rw + (j >> 5)] = accw[m];
+                        accw[m] = 0u;
+                    }
+                }
+                win[m] = wnd >> 1;
+            }
+            __syncthreads();
+        }
+    }
+
+    // active list in raster order: per-row counts, block scan, then one warp per row
+    for (int i = tid; i < gh; i += nthr) {
+        int c = 0;
+        for (int wd = 0; wd < rw; ++wd) c += __popc(s_act[(size_t)i * rw + wd]);
+        s_base[i + 1] = c;
+    }
+    if (tid == 0) s_base[0] = 0;
+    __syncthreads();
+    int carry = 0;
+    for (int c0 = 0; c0 < gh; c0 += nthr) {
+        const int i = c0 + tid;
+        s_part[tid] = i < gh ? s_base[i + 1] : 0;
+        __syncthreads();
+        for (int off = 1; off < nthr; off <<= 1) {
+            const int a = tid >= off ? s_part[tid - off] : 0;
+            __syncthreads();
+            s_part[tid] += a;
+            __syncthreads();
+        }
+        if (i < gh) s_base[i + 1] = carry + s_part[tid];
+        carry += s_part[nthr - 1];
         __syncthreads();
     }
-    if (tid == 0) *P.nactive = s_count;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    for (int i = warp; i < gh; i += nwarps) {
+        int pos = s_base[i];
+        for (int wd = 0; wd < rw; ++wd) {
+            const unsigned int word = s_act[(size_t)i * rw + wd];
+            if ((word >> lane) & 1u) P.active[pos + __popc(word & ((1u << lane) - 1u))] = i * gw + wd * 32 + lane;
+            pos += __popc(word);
+        }
+    }
+    if (tid == 0) *P.nactive = s_base[gh];
 }
 
 inline int launch_resolve(const PassParams &P, cudaStream_t st)
 {
-    const size_t bytes = (size_t)((P.G + 31) / 32) * 4;
-    if (P.gh > 4 * 1024) return -1; // MAX_ROWS rows per thread
+    if (P.gh > 4 * 1024) return -1;                       // MAX_ROWS rows per thread
+    if ((P.R - 1) * (P.R + 1) + 2 * P.R + 1 > 64 || P.nbw > 4) return -1; // 64-bit row window
+    const int rw = (P.gw + 31) / 32;
+    const size_t bytes = ((size_t)2 * P.gh * P.nbw + (size_t)P.gh * rw + P.gh + 1) * 4;
+    if (bytes > 200 * 1024) return -1;
     int nt = P.gh < 1024 ? ((P.gh + 31) / 32) * 32 : 1024;
     if (nt < 256) nt = 256; // the all-active fast path is a plain strided fill
-    if (bytes <= 200 * 1024) {
-        cudaFuncSetAttribute(k_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        k_resolve<true><<<1, nt, bytes, st>>>(P);
-    } else {
-        k_resolve<false><<<1, nt, 0, st>>>(P);
-    }
+    const bool fast = P.nbw == 1 && P.R <= 4;
+#define NLK_LAUNCH_RESOLVE(MR, F)                                                                  \
+    do {                                                                                           \
+        cudaFuncSetAttribute(k_resolve<MR, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
+        k_resolve<MR, F><<<1, nt, bytes, st>>>(P, rw);                                             \
+    } while (0)
+    if (P.gh <= nt) { if (fast) NLK_LAUNCH_RESOLVE(1, true); else NLK_LAUNCH_RESOLVE(1, false); }
+    else { if (fast) NLK_LAUNCH_RESOLVE(4, true); else NLK_LAUNCH_RESOLVE(4, false); }
+#undef NLK_LAUNCH_RESOLVE
     return 1;
 }
 

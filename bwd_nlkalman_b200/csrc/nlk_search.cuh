@@ -41,74 +41,15 @@ __device__ __forceinline__ float patch_dist(const float *__restrict__ cq, const 
     return ww;
 }
 
-template <int PSZ_T, int CH_T>
-__global__ void __launch_bounds__(256)
-k_search(const PassParams P, int warps_per_cta, int wrow, int win_floats, int npad_max,
-         int warp_smem_bytes)
+// warp-level: sort npad keys (ascending), keep the first k, write the candidate
+// records, the header and the grid-neighbour bitmap of patch g.  bm: 2*nbw words of
+// shared scratch private to the warp.
+__device__ __forceinline__ void sort_and_emit(const PassParams &P, int g, int px, int py, int prev_p, int k,
+                                              unsigned long long *keys, int n, int npad, int nx, int x0,
+                                              int y0, int lane, unsigned int *bm)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x * warps_per_cta + warp;
-    if (g >= P.G) return;
-
-    const int psz = PSZ_T ? PSZ_T : P.psz;
-    const int ch = CH_T ? CH_T : P.ch;
-    unsigned char *base = smem_raw + (size_t)warp * warp_smem_bytes;
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(base);
-    float *win = reinterpret_cast<float *>(base + (size_t)npad_max * 8);
-    unsigned int *bm = reinterpret_cast<unsigned int *>(win + win_floats); // [2][nbw]
-
-    const int px = (g % P.gw) * P.step, py = (g / P.gw) * P.step;
-    const int prev_p = (P.valid != nullptr) ? (int)P.valid[(long)py * P.vw + px] : 0;
-    int k = prev_p ? P.k_t : P.k_x;
     const int nbw = P.nbw;
     uint32_t *nbr_out = P.nbr + (long)g * nbw;
-
-    if (k <= 1) {
-        // no search (reference :631 / :1522).  Filter: nothing is aggregated for this
-        // patch.  Smoother: the patch at p alone (prev_p) or a plain copy (!prev_p).
-        if (lane == 0) {
-            GroupHdr hd;
-            hd.nk = 0;
-            hd.np0 = (P.smooth && prev_p) ? 1 : 0;
-            hd.flags = (prev_p ? HDR_PREV_P : 0) | ((P.smooth && prev_p) ? HDR_MARKS : 0);
-            hd.pad = 0;
-            P.hdr[g] = hd;
-        }
-        for (int i = lane; i < nbw; i += 32) nbr_out[i] = 0u;
-        return;
-    }
-
-    const int r = P.smooth ? P.r_t : (prev_p ? P.r_t : P.r_x);
-    const int x0 = max(px - r, 0), x1 = min(px + r, P.w - psz);
-    const int y0 = max(py - r, 0), y1 = min(py + r, P.h - psz);
-    const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, n = nx * ny;
-
-    // stage the window: rows y0 .. y1+psz-1, columns x0 .. x1+psz-1 (all channels)
-    const int wlen = (nx + psz - 1) * ch, wh = ny + psz - 1;
-    for (int row = 0; row < wh; ++row) {
-        const float *srow = P.src + ((long)(y0 + row) * P.w + x0) * ch;
-        for (int j = lane; j < wlen; j += 32) win[row * wrow + j] = srow[j];
-    }
-    int npad = 32;
-    while (npad < n) npad <<= 1;
-    __syncwarp();
-
-    const float *cp = win + (py - y0) * wrow + (px - x0) * ch;
-    const float npix = (float)psz * (float)psz * (float)ch;
-    for (int ci = lane; ci < npad; ci += 32) {
-        unsigned long long key = ~0ull;
-        if (ci < n) {
-            const int cy = ci / nx, cx = ci - cy * nx;
-            const float *cq = win + cy * wrow + cx * ch;
-            const float ww = patch_dist<PSZ_T, CH_T>(cq, cp, wrow, psz, ch);
-            const float d = fmaxf(__fdiv_rn(ww, npix), 0.f);
-            key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)ci;
-        }
-        keys[ci] = key;
-    }
-    __syncwarp();
-
     // bitonic sort, ascending
     for (int size = 2; size <= npad; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -183,11 +124,226 @@ k_search(const PassParams P, int warps_per_cta, int wrow, int win_floats, int np
     }
 }
 
-inline int search_max_radius(const PassParams &P) { return P.smooth ? P.r_t : max(P.r_t, P.r_x); }
-
-inline int launch_search(const PassParams &P, cudaStream_t st)
+template <int PSZ_T, int CH_T>
+__global__ void __launch_bounds__(256)
+k_search(const PassParams P, int warps_per_cta, int wrow, int win_floats, int npad_max,
+         int warp_smem_bytes, int only_r)
 {
-    const int r = search_max_radius(P);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * warps_per_cta + warp;
+    if (g >= P.G) return;
+
+    const int psz = PSZ_T ? PSZ_T : P.psz;
+    const int ch = CH_T ? CH_T : P.ch;
+    unsigned char *base = smem_raw + (size_t)warp * warp_smem_bytes;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(base);
+    float *win = reinterpret_cast<float *>(base + (size_t)npad_max * 8);
+    unsigned int *bm = reinterpret_cast<unsigned int *>(win + win_floats); // [2][nbw]
+
+    const int px = (g % P.gw) * P.step, py = (g / P.gw) * P.step;
+    const int prev_p = (P.valid != nullptr) ? (int)P.valid[(long)py * P.vw + px] : 0;
+    int k = prev_p ? P.k_t : P.k_x;
+    const int nbw = P.nbw;
+    uint32_t *nbr_out = P.nbr + (long)g * nbw;
+    const int r = P.smooth ? P.r_t : (prev_p ? P.r_t : P.r_x);
+    if (only_r >= 0 && r != only_r) return; // another launch handles this radius
+
+    if (k <= 1) {
+        // no search (reference :631 / :1522).  Filter: nothing is aggregated for this
+        // patch.  Smoother: the patch at p alone (prev_p) or a plain copy (!prev_p).
+        if (lane == 0) {
+            GroupHdr hd;
+            hd.nk = 0;
+            hd.np0 = (P.smooth && prev_p) ? 1 : 0;
+            hd.flags = (prev_p ? HDR_PREV_P : 0) | ((P.smooth && prev_p) ? HDR_MARKS : 0);
+            hd.pad = 0;
+            P.hdr[g] = hd;
+        }
+        for (int i = lane; i < nbw; i += 32) nbr_out[i] = 0u;
+        return;
+    }
+
+    const int x0 = max(px - r, 0), x1 = min(px + r, P.w - psz);
+    const int y0 = max(py - r, 0), y1 = min(py + r, P.h - psz);
+    const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, n = nx * ny;
+
+    // stage the window: rows y0 .. y1+psz-1, columns x0 .. x1+psz-1 (all channels)
+    const int wlen = (nx + psz - 1) * ch, wh = ny + psz - 1;
+    for (int row = 0; row < wh; ++row) {
+        const float *srow = P.src + ((long)(y0 + row) * P.w + x0) * ch;
+        for (int j = lane; j < wlen; j += 32) win[row * wrow + j] = srow[j];
+    }
+    int npad = 32;
+    while (npad < n) npad <<= 1;
+    __syncwarp();
+
+    const float *cp = win + (py - y0) * wrow + (px - x0) * ch;
+    const float npix = (float)psz * (float)psz * (float)ch;
+    for (int ci = lane; ci < npad; ci += 32) {
+        unsigned long long key = ~0ull;
+        if (ci < n) {
+            const int cy = ci / nx, cx = ci - cy * nx;
+            const float *cq = win + cy * wrow + cx * ch;
+            const float ww = patch_dist<PSZ_T, CH_T>(cq, cp, wrow, psz, ch);
+            const float d = fmaxf(__fdiv_rn(ww, npix), 0.f);
+            key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)ci;
+        }
+        keys[ci] = key;
+    }
+    __syncwarp();
+
+    sort_and_emit(P, g, px, py, prev_p, k, keys, n, npad, nx, x0, y0, lane, bm);
+}
+
+// ---- fast path: one thread per candidate ROW ------------------------------------------------
+// A block takes a run of consecutive grid patches of one grid row and stages their common
+// super-window once.  Thread (patch, candidate row) walks the window row by row and keeps
+// the 2*RAD+1 distances of its candidate row in registers: every staged value is loaded
+// once and used by up to PSZ candidates, and each distance still receives its terms in
+// the reference's (hy, hx, c) order with separately rounded multiply and add.
+template <int PSZ, int CH, int RAD>
+__global__ void __launch_bounds__(256)
+k_search_rows(const PassParams P, int np_cta, int runs_per_row, int wrow, int wh_max, int npad)
+{
+    constexpr int NX = 2 * RAD + 1, NR = 2 * RAD + 1, RL = PSZ * CH;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);    // [np_cta][npad]
+    float *win = reinterpret_cast<float *>(keys + (size_t)np_cta * npad);           // [wh_max][wrow]
+    unsigned int *bm = reinterpret_cast<unsigned int *>(win + (size_t)wh_max * wrow); // [8][2*nbw]
+    int *s_prev = reinterpret_cast<int *>(bm + 8 * 2 * P.nbw);                       // [np_cta]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gy = blockIdx.x / runs_per_row, run = blockIdx.x - gy * runs_per_row;
+    const int gx0 = run * np_cta;
+    const int np = min(np_cta, P.gw - gx0);
+    const int py = gy * P.step;
+
+    // which patches of the run this launch handles: those whose search radius is RAD
+    for (int s = tid; s < np; s += blockDim.x) {
+        const int px = (gx0 + s) * P.step;
+        const int prev_p = (P.valid != nullptr) ? (int)P.valid[(long)py * P.vw + px] : 0;
+        const int r = P.smooth ? P.r_t : (prev_p ? P.r_t : P.r_x);
+        s_prev[s] = (r == RAD) ? prev_p : -1;
+    }
+    __syncthreads();
+    int any = 0;
+    for (int s = 0; s < np; ++s) any |= (s_prev[s] >= 0) && ((s_prev[s] ? P.k_t : P.k_x) > 1);
+    // patches without search (k <= 1) only need their header
+    for (int s = tid; s < np; s += blockDim.x) {
+        const int prev_p = s_prev[s];
+        if (prev_p < 0 || (prev_p ? P.k_t : P.k_x) > 1) continue;
+        const int g = gy * P.gw + gx0 + s;
+        GroupHdr hd;
+        hd.nk = 0;
+        hd.np0 = (P.smooth && prev_p) ? 1 : 0;
+        hd.flags = (prev_p ? HDR_PREV_P : 0) | ((P.smooth && prev_p) ? HDR_MARKS : 0);
+        hd.pad = 0;
+        P.hdr[g] = hd;
+        for (int i = 0; i < P.nbw; ++i) P.nbr[(long)g * P.nbw + i] = 0u;
+    }
+    if (!any) return;
+
+    // super-window: rows y0 .. y1+PSZ-1, columns x0w .. x1w+PSZ-1
+    const int y0 = max(py - RAD, 0), y1 = min(py + RAD, P.h - PSZ);
+    const int ny = y1 - y0 + 1, wh = ny + PSZ - 1;
+    const int x0w = max(gx0 * P.step - RAD, 0);
+    const int x1w = min((gx0 + np - 1) * P.step + RAD, P.w - PSZ);
+    const int wlen = (x1w - x0w + PSZ) * CH;
+    for (int row = warp; row < wh; row += 8) {
+        const float *srow = P.src + ((long)(y0 + row) * P.w + x0w) * CH;
+        float *drow = win + row * wrow;
+        for (int j = lane; j < wlen; j += 32) drow[j] = srow[j];
+    }
+    __syncthreads();
+
+    // distances: thread = (patch slot, candidate row)
+    {
+        const int slot = tid / NR, ry = tid - slot * NR;
+        const int prev_p = slot < np ? s_prev[slot] : -1;
+        if (prev_p >= 0 && (prev_p ? P.k_t : P.k_x) > 1 && ry < ny) {
+            const int px = (gx0 + slot) * P.step;
+            const int x0 = max(px - RAD, 0), x1 = min(px + RAD, P.w - PSZ);
+            const int nx = x1 - x0 + 1;
+            const float *refp = win + (py - y0) * wrow + (px - x0w) * CH;
+            const float *canp = win + ry * wrow + (x0 - x0w) * CH;
+            float acc[NX];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) acc[j] = 0.f;
+#pragma unroll 1
+            for (int hy = 0; hy < PSZ; ++hy) {
+                float ref[RL];
+#pragma unroll
+                for (int i = 0; i < RL; ++i) ref[i] = refp[hy * wrow + i];
+                const float *cr = canp + hy * wrow;
+#pragma unroll
+                for (int x = 0; x < NX + PSZ - 1; ++x) {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const float v = cr[x * CH + c];
+#pragma unroll
+                        for (int j = 0; j < NX; ++j) {
+                            if (x - j >= 0 && x - j < PSZ) {
+                                const float e = __fsub_rn(v, ref[(x - j) * CH + c]);
+                                acc[j] = __fadd_rn(acc[j], __fmul_rn(e, e));
+                            }
+                        }
+                    }
+                }
+            }
+            const float npix = (float)PSZ * (float)PSZ * (float)CH;
+            unsigned long long *kp = keys + (size_t)slot * npad + ry * nx;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                if (j < nx) {
+                    const float d = fmaxf(__fdiv_rn(acc[j], npix), 0.f);
+                    kp[j] = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)(ry * nx + j);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // selection: one warp per patch
+    for (int slot = warp; slot < np; slot += 8) {
+        const int prev_p = s_prev[slot];
+        if (prev_p < 0) continue;
+        const int k = prev_p ? P.k_t : P.k_x;
+        if (k <= 1) continue;
+        const int px = (gx0 + slot) * P.step;
+        const int x0 = max(px - RAD, 0), x1 = min(px + RAD, P.w - PSZ);
+        const int nx = x1 - x0 + 1, n = nx * ny;
+        unsigned long long *kp = keys + (size_t)slot * npad;
+        int np2 = 32;
+        while (np2 < n) np2 <<= 1;
+        for (int i = n + lane; i < np2; i += 32) kp[i] = ~0ull;
+        __syncwarp();
+        sort_and_emit(P, gy * P.gw + gx0 + slot, px, py, prev_p, k, kp, n, np2, nx, x0, y0, lane,
+                      bm + warp * 2 * P.nbw);
+    }
+}
+
+template <int PSZ, int CH, int RAD>
+inline int launch_search_rows(const PassParams &P, cudaStream_t st)
+{
+    constexpr int NR = 2 * RAD + 1;
+    const int np_cta = 256 / NR;
+    int npad = 32;
+    while (npad < NR * NR) npad <<= 1;
+    int wrow = ((np_cta - 1) * P.step + 2 * RAD + PSZ) * CH;
+    wrow |= 1; // odd stride: the candidate rows of a patch fall in different banks
+    const int wh_max = 2 * RAD + PSZ;
+    const size_t smem = (size_t)np_cta * npad * 8 + (size_t)wh_max * wrow * 4 + 8 * 2 * P.nbw * 4 + np_cta * 4;
+    if (smem > 220 * 1024) return -1;
+    const int runs = (P.gw + np_cta - 1) / np_cta;
+    cudaFuncSetAttribute(k_search_rows<PSZ, CH, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_search_rows<PSZ, CH, RAD><<<runs * P.gh, 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad);
+    return 1;
+}
+
+// the generic kernel, restricted to the patches whose search radius is r (-1: all)
+inline int launch_search_generic(const PassParams &P, int r, int only_r, cudaStream_t st)
+{
     const int side = 2 * r + 1;
     int npad = 32;
     while (npad < side * side) npad <<= 1;
@@ -206,7 +362,7 @@ inline int launch_search(const PassParams &P, cudaStream_t st)
 #define NLK_LAUNCH_SEARCH(PS, CHN)                                                                \
     do {                                                                                          \
         cudaFuncSetAttribute(k_search<PS, CHN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-        k_search<PS, CHN><<<nb, nt, smem, st>>>(P, warps, wrow, win_floats, npad, warp_bytes);    \
+        k_search<PS, CHN><<<nb, nt, smem, st>>>(P, warps, wrow, win_floats, npad, warp_bytes, only_r); \
     } while (0)
     if (P.psz == 8 && P.ch == 3) NLK_LAUNCH_SEARCH(8, 3);
     else if (P.psz == 8 && P.ch == 1) NLK_LAUNCH_SEARCH(8, 1);
@@ -215,6 +371,34 @@ inline int launch_search(const PassParams &P, cudaStream_t st)
     else NLK_LAUNCH_SEARCH(0, 0);
 #undef NLK_LAUNCH_SEARCH
     return 1;
+}
+
+inline int launch_search_radius(const PassParams &P, int r, cudaStream_t st)
+{
+#define NLK_ROWS(PS, CHN, RD) if (P.psz == PS && P.ch == CHN && r == RD) return launch_search_rows<PS, CHN, RD>(P, st)
+    NLK_ROWS(8, 3, 5);
+    NLK_ROWS(8, 3, 10);
+    NLK_ROWS(8, 1, 5);
+    NLK_ROWS(8, 1, 10);
+    NLK_ROWS(12, 3, 10);
+    NLK_ROWS(12, 3, 15);
+#undef NLK_ROWS
+    return launch_search_generic(P, r, r, st);
+}
+
+inline int launch_search(const PassParams &P, cudaStream_t st)
+{
+    // a patch searches with radius r_t or r_x (reference :637, :1527): one launch per
+    // distinct radius, each skipping the patches of the other
+    int n = launch_search_radius(P, P.r_t, st);
+    if (n < 0) return n;
+    // the spatial radius is only used by the filter, for patches without a valid previous patch
+    if (!P.smooth && P.r_x != P.r_t) {
+        const int m = launch_search_radius(P, P.r_x, st);
+        if (m < 0) return m;
+        n += m;
+    }
+    return n;
 }
 
 } // namespace nlk
