@@ -60,6 +60,7 @@ struct PassParams {
     uint8_t *actflag;       // [G] 1 = processed (written by mask_resolve)
     int *active;            // [G] indices of processed patches, raster order
     int *nactive;
+    int *work;              // ticket counter of group_filter (zeroed at the start of a pass)
     uint8_t *gmask;         // [G] processed mask (global-memory fallback of mask_resolve)
     // aggregation
     float *accw;            // [h*w][ch+1]: weighted sums, then the weight

@@ -325,8 +325,12 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
     }
 }
 
+inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st);
+
 inline int launch_group_filter(const PassParams &P, int num_sms, cudaStream_t st)
 {
+    // 8x8 patches with 1 or 3 channels: the team kernel of nlk_group_warp.cuh
+    if (const int n = launch_group_team8(P, num_sms, st)) return n;
     const int TS = P.psz * P.psz + 1;
     const int cpp = P.ch * P.psz * P.psz;
     const int kcap = P.kstride > 1 ? P.kstride : 1;

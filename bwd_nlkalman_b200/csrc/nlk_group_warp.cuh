@@ -1,0 +1,375 @@
+// group_filter, 8x8 patches: one TEAM of two warps per group, several teams per block.
+//
+// Same arithmetic as the block-per-group kernel of nlk_group.cuh (reference
+// src/nlkalman.c:713-932 and :1600-1845), laid out for throughput:
+//   * a team synchronises with its own named barrier (bar.sync id, 64), so the eight
+//     teams of a block drift apart and the FMA-heavy transform phases of some overlap the
+//     shared-memory / L2 phases of the others -- no block-wide barrier in the group loop;
+//   * groups are handed out dynamically (one atomic ticket per group);
+//   * forward transforms: lane = one 8x8 tile (candidate x source x channel), whole tile
+//     in registers, straight out of the staged search windows; the tile buffer is the
+//     only exchange between the tile-owner and the coefficient-owner views;
+//   * statistics: lane = one coefficient position e (all channels), Welford recurrences
+//     over the candidates in sorted order, accumulators in registers;
+//   * update: lane = one (member, channel) tile: forward transform, shrinkage, inverse
+//     transform and window weighting without leaving registers, then the team adds the
+//     weighted patches to the accumulator image, one red.global.add.v4.f32 per pixel.
+// The smoother uses the linearity of the transform:
+//   T^-1((1-a) Y1 + a Y0) = x1 + T^-1(a * T(x0 - x1)),  one tile per lane instead of two.
+#pragma once
+#include "nlk_common.cuh"
+#include "nlk_dct.cuh"
+#include "nlk_group.cuh"
+
+namespace nlk {
+
+constexpr int GW_TEAM = 64;          // threads per team
+constexpr int GW_MAX_TEAMS = 8;      // teams per block (named barriers 1..8)
+constexpr int GW_TS = 65;            // tile stride in the exchange buffer (odd: conflict-free)
+
+struct GroupWarpGeom {
+    int teams;        // teams per block
+    int team_floats;  // shared-memory floats per team
+    int win_floats;   // floats of the window area (one spatial window or two temporal ones)
+    int wrow_t, wrow_x;   // row strides of the staged windows (temporal / spatial radius)
+    int kcap;         // capacity of the candidate list
+};
+
+__device__ __forceinline__ void team_sync(int bar_id)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(GW_TEAM) : "memory");
+}
+
+__device__ __forceinline__ void load_tile8(const float *__restrict__ src, int rs, int cs, float (&t)[64])
+{
+#pragma unroll
+    for (int y = 0; y < 8; ++y)
+#pragma unroll
+        for (int x = 0; x < 8; ++x) t[y * 8 + x] = src[y * rs + x * cs];
+}
+
+template <bool INVERSE>
+__device__ __forceinline__ void dct8x8_regs(float (&t)[64])
+{
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = t[y * 8 + i];
+        if (INVERSE) dct1d_inv<8>(r); else dct1d_fwd<8>(r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[y * 8 + i] = r[i];
+    }
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+        float r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = t[i * 8 + x];
+        if (INVERSE) dct1d_inv<8>(r); else dct1d_fwd<8>(r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i * 8 + x] = r[i];
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(GW_TEAM * GW_MAX_TEAMS, 1)
+k_group_team8(const PassParams P, const GroupWarpGeom Gm)
+{
+    constexpr int PSZ = 8, PP = 64, CPP = CH * PP, TS = GW_TS;
+    constexpr int AS = PP + 1; // channel stride of the gain / mean tables (odd)
+    extern __shared__ __align__(16) float smem[];
+    const int team = threadIdx.x / GW_TEAM;
+    const int l64 = threadIdx.x % GW_TEAM;       // lane within the team
+    const int lane = threadIdx.x & 31, wg = l64 >> 5;
+    const int bar = 1 + team;
+
+    float *base = smem + (size_t)team * Gm.team_floats;
+    float *tiles = base;                              // [64][TS]
+    float *win = tiles + 64 * TS;                     // window area
+    float *s_a = win + Gm.win_floats;                 // [CH][AS] gain
+    float *s_m = s_a + CH * AS;                       // [CH][AS] group mean (M0 or M1)
+    uint32_t *s_cand = reinterpret_cast<uint32_t *>(s_m + CH * AS);   // [kcap]
+    int *s_grp = reinterpret_cast<int *>(s_cand + Gm.kcap);           // [kcap]
+    float *s_red = reinterpret_cast<float *>(s_grp + Gm.kcap);        // [2]
+    int *s_tick = reinterpret_cast<int *>(s_red + 2);                 // [2] ticket, by parity
+
+    const int nactive = *P.nactive;
+    const float sigma2 = P.sigma2;
+    const int e_hy = l64 >> 3, e_hx = l64 & 7;       // this lane's pixel / coefficient position
+    const float We = c_win[PSZ][l64];
+
+    for (int it = 0;; ++it) {
+        // the ticket slot alternates: a lane may still be reading the previous ticket when
+        // lane 0 takes the next one, but never the one before (a barrier lies in between)
+        if (l64 == 0) s_tick[it & 1] = atomicAdd(P.work, 1);
+        team_sync(bar);
+        const int ai = s_tick[it & 1];
+        if (ai >= nactive) break;
+        const int g = P.active[ai];
+        const GroupHdr hd = P.hdr[g];
+        const int gy = g / P.gw, gx = g - gy * P.gw;
+        const int px = gx * P.step, py = gy * P.step;
+        const int prev_p = hd.flags & HDR_PREV_P;
+        int k = hd.nk;
+        const int np0 = hd.np0;
+        const bool point = P.smooth && k == 0 && prev_p;   // (reference :1699-1730)
+
+        if (!P.smooth && k == 0) continue;                 // filter, k <= 1 (:815-849, :857)
+
+        if (P.smooth && np0 == 0) {
+            // reference :1795-1804: the filtered patch at p, weight 1/1e-6, mask untouched
+            const float wgt = __fdiv_rn(1.f, 1e-6f);
+            const long pix = (long)(py + e_hy) * P.w + px + e_hx;
+            const float wW = __fmul_rn(wgt, We);
+            float v[CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) v[c] = __fmul_rn(wW, P.in1[pix * CH + c]);
+            accumulate_pixel<CH>(P.accw + pix * (CH + 1), v, wW, CH);
+            if (P.dbg_vp && l64 == 0) P.dbg_vp[g] = 0.f;
+            continue;
+        }
+
+        // ---- stage the search window(s) of this group (reference :637-639) -----------------
+        const int r = point ? 0 : (P.smooth ? P.r_t : (prev_p ? P.r_t : P.r_x));
+        const int wrow = (r == P.r_t || point) ? Gm.wrow_t : Gm.wrow_x;
+        const int x0 = max(px - r, 0), x1 = min(px + r, P.w - PSZ);
+        const int y0 = max(py - r, 0), y1 = min(py + r, P.h - PSZ);
+        const int wlen = (x1 - x0 + PSZ) * CH, wh = y1 - y0 + PSZ;
+        float *winS = win;
+        float *winP = win + wh * wrow;
+        for (int row = wg; row < wh; row += 2) {
+            const float *src = P.src + ((long)(y0 + row) * P.w + x0) * CH;
+            float *dst = winS + row * wrow;
+            for (int j = lane; j < wlen; j += 32) dst[j] = src[j];
+        }
+        if (prev_p) {
+            for (int row = wg; row < wh; row += 2) {
+                const float *src = P.prev0 + ((long)(y0 + row) * P.w + x0) * CH;
+                float *dst = winP + row * wrow;
+                for (int j = lane; j < wlen; j += 32) dst[j] = src[j];
+            }
+        }
+        if (point) {
+            if (l64 == 0) s_cand[0] = cand_pack(px, py, 1);
+            k = 1;
+        } else {
+            for (int i = l64; i < k; i += GW_TEAM) s_cand[i] = P.cand[(long)g * P.kstride + i];
+        }
+        team_sync(bar);
+
+        // group members: the first tagg candidates with a valid previous patch, or, when
+        // there is none (filter only), the first tagg candidates (:779-793, :857, :1669, :1737).
+        // Both warps compute the same list.
+        int nagg;
+        {
+            int cnt = 0;
+            for (int b0 = 0; b0 < k && cnt < P.tagg; b0 += 32) {
+                const int i = b0 + lane;
+                const uint32_t cd = i < k ? s_cand[i] : 0u;
+                const int take = (i < k) && (np0 > 0 ? cand_prev(cd) : 1);
+                const unsigned int bal = __ballot_sync(0xffffffffu, take);
+                const int rank = cnt + __popc(bal & ((1u << lane) - 1u));
+                if (take && rank < P.tagg) s_grp[rank] = i;
+                cnt += __popc(bal);
+            }
+            nagg = min(cnt, P.tagg);
+        }
+
+        // ---- pass 1: statistics over the k candidates -----------------------------------------
+        const int nsrc = prev_p ? 2 : 1;
+        const int tpc = nsrc * CH;          // tiles per candidate
+        const int cc = GW_TEAM / tpc;       // candidates per chunk
+        float M1[CH], V1[CH], Mp[CH], V0[CH], V01[CH], Mg[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u) M1[u] = V1[u] = Mp[u] = V0[u] = V01[u] = Mg[u] = 0.f;
+        int n1 = 0, n0 = 0;
+        for (int c0 = 0; c0 < k; c0 += cc) {
+            const int cnt = min(cc, k - c0);
+            if (c0) team_sync(bar);   // the previous chunk's statistics are done with `tiles`
+            if (l64 < cnt * tpc) {
+                const int slot = l64 / tpc, rr = l64 - slot * tpc;
+                const int s = rr >= CH, c = rr - s * CH;
+                const uint32_t cd = s_cand[c0 + slot];
+                if (!(s == 1 && !cand_prev(cd))) {
+                    const float *src = (s ? winP : winS) + (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * CH + c;
+                    float t[64];
+                    load_tile8(src, wrow, CH, t);
+                    dct8x8_regs<false>(t);
+                    float *dst = tiles + l64 * TS;
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) dst[i] = t[i];
+                }
+            }
+            team_sync(bar);
+            // lane = coefficient position, candidates in sorted order
+            {
+                const int cstride = tpc * TS;
+                if (point) {
+#pragma unroll
+                    for (int u = 0; u < CH; ++u) {
+                        const float p = tiles[u * TS + l64], q = tiles[(CH + u) * TS + l64];
+                        V1[u] = p * p;
+                        V0[u] = q * q;
+                        V01[u] = (q - p) * (q - p);
+                    }
+                } else {
+                    const float *tp = tiles + l64;             // source tile of slot 0, channel 0
+                    for (int i = 0; i < cnt; ++i, tp += cstride) {
+                        const int hasq = cand_prev(s_cand[c0 + i]);   // (implies prev_p)
+                        n1 += 1;
+                        const float in1v = c_inv[n1];
+                        n0 += hasq;
+                        const float in0v = c_inv[n0];
+#pragma unroll
+                        for (int u = 0; u < CH; ++u) {
+                            const float p = tp[u * TS];
+                            const float delta = p - M1[u];
+                            M1[u] = fmaf(delta, in1v, M1[u]);             // :765
+                            V1[u] = fmaf(delta, p - M1[u], V1[u]);        // :766
+                            if (hasq) {
+                                const float q = tp[(CH + u) * TS];
+                                const float d0 = q - Mp[u];               // :770-775 / :1654-1659
+                                Mp[u] = fmaf(d0, in0v, Mp[u]);
+                                V0[u] = fmaf(d0, q - Mp[u], V0[u]);
+                                const float t = q - p;
+                                V01[u] = fmaf(t, t, V01[u]);              // :777-778
+                                if (n0 <= P.tagg) Mg[u] = fmaf(q - Mg[u], in0v, Mg[u]); // :783
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- gains (:858-904, :1763-1777) -----------------------------------------------------
+        float vsum = 0.f;
+        {
+            const float inp1 = c_inv[max(n1, 1)];
+            const float inp0 = c_inv[n0];
+            const float s2 = P.has_bsic ? 0.f : sigma2;
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                float v1 = V1[u], v0 = V0[u], v01 = V01[u];
+                if (!point) {
+                    v1 *= inp1;                             // :805
+                    if (n0) { v0 *= inp0; v01 *= inp0; }    // :806-810
+                }
+                float a, m;
+                if (P.smooth) {
+                    a = __fdiv_rn(v1, v1 + P.beta_t * v01);              // :1768
+                    vsum += (1.f - a * a) * v1 + a * a * fmaxf(v0 - P.beta_t * v01, 0.f);
+                    m = 0.f;
+                } else if (n0 > 0) {
+                    const float v = v0 + fmaxf(0.f, v01 - s2);           // :867
+                    a = __fdiv_rn(v, v + P.beta_t * sigma2);             // :870
+                    vsum += (1.f - a * a) * v + a * a * sigma2;          // :875
+                    m = Mg[u];
+                } else {
+                    const float v = fmaxf(0.f, v1 - s2);                 // :890
+                    a = __fdiv_rn(v, v + P.beta_x * sigma2);             // :893
+                    vsum += a * v;                                       // :898
+                    m = M1[u];
+                }
+                s_a[u * AS + l64] = a;
+                s_m[u * AS + l64] = m;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+        if (lane == 0) s_red[wg] = vsum;
+        team_sync(bar);   // gains visible; statistics done with `tiles`
+        const float vp = (float)nagg * (s_red[0] + s_red[1]);
+        const float wgt = __fdiv_rn(1.f, fmaxf(vp, 1e-6f)); // :911
+        if (P.dbg_vp && l64 == 0) P.dbg_vp[g] = vp;
+
+        // ---- pass 2: update, inverse transform, aggregation of the group members -------------
+        constexpr int MC = GW_TEAM / CH;   // members per chunk
+        for (int m0 = 0; m0 < nagg; m0 += MC) {
+            const int cnt = min(MC, nagg - m0);
+            if (m0) team_sync(bar);   // the previous chunk's aggregation is done with `tiles`
+            if (l64 < cnt * CH) {
+                const int ml = l64 / CH, c = l64 - ml * CH;
+                const uint32_t cd = s_cand[s_grp[m0 + ml]];
+                const int qx = cand_x(cd), qy = cand_y(cd);
+                float t[64];
+                const float *wS = winS + (qy - y0) * wrow + (qx - x0) * CH + c;
+                if (P.smooth) {
+                    // x1 + T^-1(a * T(x0 - x1))                        (:1775)
+                    const float *wP = winP + (qy - y0) * wrow + (qx - x0) * CH + c;
+#pragma unroll
+                    for (int y = 0; y < 8; ++y)
+#pragma unroll
+                        for (int x = 0; x < 8; ++x)
+                            t[y * 8 + x] = wP[y * wrow + x * CH] - wS[y * wrow + x * CH];
+                    dct8x8_regs<false>(t);
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) t[i] *= s_a[c * AS + i];
+                    dct8x8_regs<true>(t);
+#pragma unroll
+                    for (int y = 0; y < 8; ++y)
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) t[y * 8 + x] += wS[y * wrow + x * CH];
+                } else {
+                    // the group holds the noisy patches (:784-785, :853): the source window when
+                    // there is no basic estimate, else the noisy frame itself
+                    if (P.has_bsic) load_tile8(P.in1 + ((long)qy * P.w + qx) * CH + c, P.w * CH, CH, t);
+                    else load_tile8(wS, wrow, CH, t);
+                    dct8x8_regs<false>(t);
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        const float a = s_a[c * AS + i];
+                        t[i] = a * t[i] + (1.f - a) * s_m[c * AS + i];   // :878 / :901
+                    }
+                    dct8x8_regs<true>(t);
+                }
+                float *dst = tiles + l64 * TS;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) dst[i] = t[i];
+            }
+            team_sync(bar);
+            // lane = pixel of the patch, one member per iteration
+            const float wW = __fmul_rn(wgt, We);                        // :923
+            for (int ml = 0; ml < cnt; ++ml) {
+                const uint32_t cd = s_cand[s_grp[m0 + ml]];
+                const long pix = (long)(cand_y(cd) + e_hy) * P.w + cand_x(cd) + e_hx;
+                float v[CH];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) v[c] = __fmul_rn(wW, tiles[(ml * CH + c) * TS + l64]); // :926
+                accumulate_pixel<CH>(P.accw + pix * (CH + 1), v, wW, CH);
+            }
+        }
+    }
+}
+
+// returns the number of launches, 0 if this kernel does not cover the configuration
+inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st)
+{
+    if (P.psz != 8 || (P.ch != 3 && P.ch != 1)) return 0;
+    const int ch = P.ch;
+    GroupWarpGeom Gm;
+    Gm.wrow_t = ((2 * P.r_t + 8) * ch) | 1;
+    Gm.wrow_x = ((2 * P.r_x + 8) * ch) | 1;
+    const int win_t = (2 * P.r_t + 8) * Gm.wrow_t * (P.has_prev ? 2 : 1);
+    const int win_x = P.smooth ? 0 : (2 * P.r_x + 8) * Gm.wrow_x;
+    Gm.win_floats = win_t > win_x ? win_t : win_x;
+    Gm.kcap = P.kstride > 1 ? P.kstride : 1;
+    int fl = 64 * GW_TS + Gm.win_floats + 2 * ch * 65 + 2 * Gm.kcap + 2 + 2;
+    fl = (fl + 3) & ~3;
+    Gm.team_floats = fl;
+    const int budget = 227 * 1024;
+    int teams = budget / (fl * 4);
+    if (teams > GW_MAX_TEAMS) teams = GW_MAX_TEAMS;
+    if (teams < 2) return 0;
+    Gm.teams = teams;
+    const size_t smem = (size_t)teams * fl * 4;
+    if (ch == 3) {
+        cudaFuncSetAttribute(k_group_team8<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_group_team8<3><<<num_sms, teams * GW_TEAM, smem, st>>>(P, Gm);
+    } else {
+        cudaFuncSetAttribute(k_group_team8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_group_team8<1><<<num_sms, teams * GW_TEAM, smem, st>>>(P, Gm);
+    }
+    return 1;
+}
+
+} // namespace nlk

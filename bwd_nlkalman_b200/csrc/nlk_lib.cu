@@ -7,6 +7,7 @@
 #include "nlk_search.cuh"
 #include "nlk_resolve.cuh"
 #include "nlk_group.cuh"
+#include "nlk_group_warp.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -323,6 +324,7 @@ static int run_pass(nlk_ctx *c, int smooth, float *d_out, const float *d_in1, co
     P.actflag = c->actflag.as<uint8_t>();
     P.nactive = c->counters.as<int>();
     P.any_nbr = c->counters.as<int>() + 1;
+    P.work = c->counters.as<int>() + 2;
     P.out = d_out;
     if (debug) {
         if (int r = c->dbg_dist.ensure(G * kmax * 4)) return r;
