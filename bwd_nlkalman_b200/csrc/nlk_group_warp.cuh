@@ -6,14 +6,15 @@
 //     teams of a block drift apart and the FMA-heavy transform phases of some overlap the
 //     shared-memory / L2 phases of the others -- no block-wide barrier in the group loop;
 //   * groups are handed out dynamically (one atomic ticket per group);
-//   * forward transforms: lane = one 8x8 tile (candidate x source x channel), whole tile
-//     in registers, straight out of the staged search windows; the tile buffer is the
-//     only exchange between the tile-owner and the coefficient-owner views;
+//   * the search windows are staged with cp.async (all rows in flight at once);
+//   * transforms: lane = one 8x8 tile, whole tile in registers.  The group loop is a
+//     sequence of ROUNDS with one producer body (so one copy of the transform code in
+//     the instruction cache): statistics rounds transform (candidate x source x channel)
+//     tiles out of the staged windows into the exchange buffer; update rounds transform
+//     (member x channel) tiles, shrink them, transform back and leave weighted pixels;
 //   * statistics: lane = one coefficient position e (all channels), Welford recurrences
 //     over the candidates in sorted order, accumulators in registers;
-//   * update: lane = one (member, channel) tile: forward transform, shrinkage, inverse
-//     transform and window weighting without leaving registers, then the team adds the
-//     weighted patches to the accumulator image, one red.global.add.v4.f32 per pixel.
+//   * aggregation: lane = one pixel of the patch, one red.global.add.v4.f32 per member.
 // The smoother uses the linearity of the transform:
 //   T^-1((1-a) Y1 + a Y0) = x1 + T^-1(a * T(x0 - x1)),  one tile per lane instead of two.
 #pragma once
@@ -40,12 +41,14 @@ __device__ __forceinline__ void team_sync(int bar_id)
     asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "n"(GW_TEAM) : "memory");
 }
 
-__device__ __forceinline__ void load_tile8(const float *__restrict__ src, int rs, int cs, float (&t)[64])
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc)
 {
-#pragma unroll
-    for (int y = 0; y < 8; ++y)
-#pragma unroll
-        for (int x = 0; x < 8; ++x) t[y * 8 + x] = src[y * rs + x * cs];
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 template <bool INVERSE>
@@ -71,12 +74,13 @@ __device__ __forceinline__ void dct8x8_regs(float (&t)[64])
     }
 }
 
-template <int CH>
+template <int CH, bool SMOOTH>
 __global__ void __launch_bounds__(GW_TEAM * GW_MAX_TEAMS, 1)
 k_group_team8(const PassParams P, const GroupWarpGeom Gm)
 {
-    constexpr int PSZ = 8, PP = 64, CPP = CH * PP, TS = GW_TS;
+    constexpr int PSZ = 8, PP = 64, TS = GW_TS;
     constexpr int AS = PP + 1; // channel stride of the gain / mean tables (odd)
+    constexpr int MC = GW_TEAM / CH;   // members per update round
     extern __shared__ __align__(16) float smem[];
     const int team = threadIdx.x / GW_TEAM;
     const int l64 = threadIdx.x % GW_TEAM;       // lane within the team
@@ -112,11 +116,11 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
         const int prev_p = hd.flags & HDR_PREV_P;
         int k = hd.nk;
         const int np0 = hd.np0;
-        const bool point = P.smooth && k == 0 && prev_p;   // (reference :1699-1730)
+        const bool point = SMOOTH && k == 0 && prev_p;   // (reference :1699-1730)
 
-        if (!P.smooth && k == 0) continue;                 // filter, k <= 1 (:815-849, :857)
+        if (!SMOOTH && k == 0) continue;                 // filter, k <= 1 (:815-849, :857)
 
-        if (P.smooth && np0 == 0) {
+        if (SMOOTH && np0 == 0) {
             // reference :1795-1804: the filtered patch at p, weight 1/1e-6, mask untouched
             const float wgt = __fdiv_rn(1.f, 1e-6f);
             const long pix = (long)(py + e_hy) * P.w + px + e_hx;
@@ -130,23 +134,26 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
         }
 
         // ---- stage the search window(s) of this group (reference :637-639) -----------------
-        const int r = point ? 0 : (P.smooth ? P.r_t : (prev_p ? P.r_t : P.r_x));
+        const int r = point ? 0 : (SMOOTH ? P.r_t : (prev_p ? P.r_t : P.r_x));
         const int wrow = (r == P.r_t || point) ? Gm.wrow_t : Gm.wrow_x;
         const int x0 = max(px - r, 0), x1 = min(px + r, P.w - PSZ);
         const int y0 = max(py - r, 0), y1 = min(py + r, P.h - PSZ);
         const int wlen = (x1 - x0 + PSZ) * CH, wh = y1 - y0 + PSZ;
         float *winS = win;
         float *winP = win + wh * wrow;
-        for (int row = wg; row < wh; row += 2) {
-            const float *src = P.src + ((long)(y0 + row) * P.w + x0) * CH;
-            float *dst = winS + row * wrow;
-            for (int j = lane; j < wlen; j += 32) dst[j] = src[j];
-        }
-        if (prev_p) {
-            for (int row = wg; row < wh; row += 2) {
-                const float *src = P.prev0 + ((long)(y0 + row) * P.w + x0) * CH;
-                float *dst = winP + row * wrow;
-                for (int j = lane; j < wlen; j += 32) dst[j] = src[j];
+        {
+            // warp wg takes rows wg, wg+2, ...; every element is its own 4-byte cp.async
+            const long g0 = ((long)(y0 + wg) * P.w + x0) * CH;
+            const long gstep = 2L * P.w * CH;
+            for (int j = lane; j < wlen; j += 32) {
+                const float *gs = P.src + g0 + j;
+                float *ds = winS + wg * wrow + j;
+                for (int row = wg; row < wh; row += 2, gs += gstep, ds += 2 * wrow) cp_async4(ds, gs);
+                if (prev_p) {
+                    const float *gp = P.prev0 + g0 + j;
+                    float *dp = winP + wg * wrow + j;
+                    for (int row = wg; row < wh; row += 2, gp += gstep, dp += 2 * wrow) cp_async4(dp, gp);
+                }
             }
         }
         if (point) {
@@ -155,6 +162,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
         } else {
             for (int i = l64; i < k; i += GW_TEAM) s_cand[i] = P.cand[(long)g * P.kstride + i];
         }
+        cp_async_wait_all();
         team_sync(bar);
 
         // group members: the first tagg candidates with a valid previous patch, or, when
@@ -175,168 +183,200 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             nagg = min(cnt, P.tagg);
         }
 
-        // ---- pass 1: statistics over the k candidates -----------------------------------------
+        // The temporal filter only uses the statistics of the candidates with a valid
+        // previous patch (V0, V01, M0: reference :867-878); M1 / V1 over all candidates are
+        // needed by the spatial branch (np0 == 0, :890-901) and by the smoother (:1768).
+        const bool need1 = SMOOTH || np0 == 0;
         const int nsrc = prev_p ? 2 : 1;
         const int tpc = nsrc * CH;          // tiles per candidate
-        const int cc = GW_TEAM / tpc;       // candidates per chunk
+        const int cc = GW_TEAM / tpc;       // candidates per statistics round
+        const int nr1 = (k + cc - 1) / cc, nr2 = (nagg + MC - 1) / MC;
         float M1[CH], V1[CH], Mp[CH], V0[CH], V01[CH], Mg[CH];
 #pragma unroll
         for (int u = 0; u < CH; ++u) M1[u] = V1[u] = Mp[u] = V0[u] = V01[u] = Mg[u] = 0.f;
         int n1 = 0, n0 = 0;
-        for (int c0 = 0; c0 < k; c0 += cc) {
-            const int cnt = min(cc, k - c0);
-            if (c0) team_sync(bar);   // the previous chunk's statistics are done with `tiles`
-            if (l64 < cnt * tpc) {
-                const int slot = l64 / tpc, rr = l64 - slot * tpc;
-                const int s = rr >= CH, c = rr - s * CH;
-                const uint32_t cd = s_cand[c0 + slot];
-                if (!(s == 1 && !cand_prev(cd))) {
-                    const float *src = (s ? winP : winS) + (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * CH + c;
+        float wgt = 0.f;
+
+        for (int round = 0; round < nr1 + nr2; ++round) {
+            const bool stat = round < nr1;
+            const int first = stat ? round * cc : (round - nr1) * MC;      // first candidate / member
+            const int cnt = stat ? min(cc, k - first) : min(MC, nagg - first);
+            if (round) team_sync(bar);   // the previous round's consumers are done with `tiles`
+
+            // ---- producer: lane = tile ----------------------------------------------------------
+            {
+                bool act;
+                int s = 0, c;
+                uint32_t cd;
+                if (stat) {
+                    const int slot = l64 / tpc, rr = l64 - slot * tpc;
+                    s = rr >= CH; c = rr - s * CH;
+                    act = l64 < cnt * tpc;
+                    cd = s_cand[first + (act ? slot : 0)];
+                    // no previous patch: no previous-frame tile; and its source tile only
+                    // matters where M1 / V1 do
+                    if (!cand_prev(cd) && (s == 1 || !need1)) act = false;
+                } else {
+                    const int ml = l64 / CH;
+                    c = l64 - ml * CH;
+                    act = l64 < cnt * CH;
+                    cd = s_cand[s_grp[first + (act ? ml : 0)]];
+                }
+                if (act) {
+                    const int off = (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * CH + c;
+                    const float *wS = winS + off, *wP = winP + off;
                     float t[64];
-                    load_tile8(src, wrow, CH, t);
+                    if (SMOOTH && !stat) {
+                        // x1 + T^-1(a * T(x0 - x1))                        (:1775)
+#pragma unroll
+                        for (int y = 0; y < 8; ++y)
+#pragma unroll
+                            for (int x = 0; x < 8; ++x)
+                                t[y * 8 + x] = wP[y * wrow + x * CH] - wS[y * wrow + x * CH];
+                    } else {
+                        const float *src = s ? wP : wS;
+#pragma unroll
+                        for (int y = 0; y < 8; ++y)
+#pragma unroll
+                            for (int x = 0; x < 8; ++x) t[y * 8 + x] = src[y * wrow + x * CH];
+                    }
                     dct8x8_regs<false>(t);
+                    if (!stat) {
+                        if (SMOOTH) {
+#pragma unroll
+                            for (int i = 0; i < 64; ++i) t[i] *= s_a[c * AS + i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 64; ++i) {
+                                const float a = s_a[c * AS + i];
+                                t[i] = a * t[i] + (1.f - a) * s_m[c * AS + i];   // :878 / :901
+                            }
+                        }
+                        dct8x8_regs<true>(t);
+                        if (SMOOTH) {
+#pragma unroll
+                            for (int y = 0; y < 8; ++y)
+#pragma unroll
+                                for (int x = 0; x < 8; ++x) t[y * 8 + x] += wS[y * wrow + x * CH];
+                        }
+                    }
                     float *dst = tiles + l64 * TS;
 #pragma unroll
                     for (int i = 0; i < 64; ++i) dst[i] = t[i];
                 }
             }
             team_sync(bar);
-            // lane = coefficient position, candidates in sorted order
-            {
-                const int cstride = tpc * TS;
-                if (point) {
+
+            if (!stat) {
+                // ---- aggregation: lane = pixel of the patch, one member per iteration ----------
+                const float wW = __fmul_rn(wgt, We);                        // :923
+                for (int ml = 0; ml < cnt; ++ml) {
+                    const uint32_t cd = s_cand[s_grp[first + ml]];
+                    const long pix = (long)(cand_y(cd) + e_hy) * P.w + cand_x(cd) + e_hx;
+                    float v[CH];
 #pragma unroll
-                    for (int u = 0; u < CH; ++u) {
-                        const float p = tiles[u * TS + l64], q = tiles[(CH + u) * TS + l64];
-                        V1[u] = p * p;
-                        V0[u] = q * q;
-                        V01[u] = (q - p) * (q - p);
-                    }
-                } else {
-                    const float *tp = tiles + l64;             // source tile of slot 0, channel 0
-                    for (int i = 0; i < cnt; ++i, tp += cstride) {
-                        const int hasq = cand_prev(s_cand[c0 + i]);   // (implies prev_p)
-                        n1 += 1;
+                    for (int c = 0; c < CH; ++c) v[c] = __fmul_rn(wW, tiles[(ml * CH + c) * TS + l64]); // :926
+                    accumulate_pixel<CH>(P.accw + pix * (CH + 1), v, wW, CH);
+                }
+                continue;
+            }
+
+            // ---- statistics: lane = coefficient position, candidates in sorted order ----------
+            if (point) {
+#pragma unroll
+                for (int u = 0; u < CH; ++u) {
+                    const float p = tiles[u * TS + l64], q = tiles[(CH + u) * TS + l64];
+                    V1[u] = p * p;
+                    V0[u] = q * q;
+                    V01[u] = (q - p) * (q - p);
+                }
+            } else {
+                const int cstride = tpc * TS;
+                const float *tp = tiles + l64;             // source tile of slot 0, channel 0
+                for (int i = 0; i < cnt; ++i, tp += cstride) {
+                    const int hasq = cand_prev(s_cand[first + i]);   // (implies prev_p)
+                    n1 += 1;
+                    n0 += hasq;
+                    if (need1) {
                         const float in1v = c_inv[n1];
-                        n0 += hasq;
-                        const float in0v = c_inv[n0];
 #pragma unroll
                         for (int u = 0; u < CH; ++u) {
                             const float p = tp[u * TS];
                             const float delta = p - M1[u];
                             M1[u] = fmaf(delta, in1v, M1[u]);             // :765
                             V1[u] = fmaf(delta, p - M1[u], V1[u]);        // :766
-                            if (hasq) {
-                                const float q = tp[(CH + u) * TS];
-                                const float d0 = q - Mp[u];               // :770-775 / :1654-1659
-                                Mp[u] = fmaf(d0, in0v, Mp[u]);
-                                V0[u] = fmaf(d0, q - Mp[u], V0[u]);
-                                const float t = q - p;
-                                V01[u] = fmaf(t, t, V01[u]);              // :777-778
-                                if (n0 <= P.tagg) Mg[u] = fmaf(q - Mg[u], in0v, Mg[u]); // :783
-                            }
+                        }
+                    }
+                    if (hasq) {
+                        const float in0v = c_inv[n0];
+                        const bool ing = n0 <= P.tagg;
+#pragma unroll
+                        for (int u = 0; u < CH; ++u) {
+                            const float p = tp[u * TS];
+                            const float q = tp[(CH + u) * TS];
+                            const float d0 = q - Mp[u];               // :770-775 / :1654-1659
+                            Mp[u] = fmaf(d0, in0v, Mp[u]);
+                            V0[u] = fmaf(d0, q - Mp[u], V0[u]);
+                            const float t = q - p;
+                            V01[u] = fmaf(t, t, V01[u]);              // :777-778
+                            if (ing) Mg[u] = fmaf(q - Mg[u], in0v, Mg[u]); // :783
                         }
                     }
                 }
             }
-        }
+            if (round != nr1 - 1) continue;
 
-        // ---- gains (:858-904, :1763-1777) -----------------------------------------------------
-        float vsum = 0.f;
-        {
-            const float inp1 = c_inv[max(n1, 1)];
-            const float inp0 = c_inv[n0];
-            const float s2 = P.has_bsic ? 0.f : sigma2;
-#pragma unroll
-            for (int u = 0; u < CH; ++u) {
-                float v1 = V1[u], v0 = V0[u], v01 = V01[u];
-                if (!point) {
-                    v1 *= inp1;                             // :805
-                    if (n0) { v0 *= inp0; v01 *= inp0; }    // :806-810
+            // ---- after the last statistics round: gains (:858-904, :1763-1777) ----------------
+            if (!SMOOTH && P.has_bsic) {
+                // the group holds the NOISY patches (:784-785, :853): the source window is no
+                // longer needed, put the members' noisy patches where their source patches were
+                for (int i = l64; i < nagg * PSZ * PSZ * CH; i += GW_TEAM) {
+                    const int ml = i / (PSZ * PSZ * CH), rem = i - ml * (PSZ * PSZ * CH);
+                    const int hy = rem / (PSZ * CH), j = rem - hy * (PSZ * CH);
+                    const uint32_t cd = s_cand[s_grp[ml]];
+                    const int qx = cand_x(cd), qy = cand_y(cd);
+                    winS[(qy - y0 + hy) * wrow + (qx - x0) * CH + j] = P.in1[((long)(qy + hy) * P.w + qx) * CH + j];
                 }
-                float a, m;
-                if (P.smooth) {
-                    a = __fdiv_rn(v1, v1 + P.beta_t * v01);              // :1768
-                    vsum += (1.f - a * a) * v1 + a * a * fmaxf(v0 - P.beta_t * v01, 0.f);
-                    m = 0.f;
-                } else if (n0 > 0) {
-                    const float v = v0 + fmaxf(0.f, v01 - s2);           // :867
-                    a = __fdiv_rn(v, v + P.beta_t * sigma2);             // :870
-                    vsum += (1.f - a * a) * v + a * a * sigma2;          // :875
-                    m = Mg[u];
-                } else {
-                    const float v = fmaxf(0.f, v1 - s2);                 // :890
-                    a = __fdiv_rn(v, v + P.beta_x * sigma2);             // :893
-                    vsum += a * v;                                       // :898
-                    m = M1[u];
-                }
-                s_a[u * AS + l64] = a;
-                s_m[u * AS + l64] = m;
             }
-        }
+            float vsum = 0.f;
+            {
+                const float inp1 = c_inv[max(n1, 1)];
+                const float inp0 = c_inv[n0];
+                const float s2 = P.has_bsic ? 0.f : sigma2;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
-        if (lane == 0) s_red[wg] = vsum;
-        team_sync(bar);   // gains visible; statistics done with `tiles`
-        const float vp = (float)nagg * (s_red[0] + s_red[1]);
-        const float wgt = __fdiv_rn(1.f, fmaxf(vp, 1e-6f)); // :911
-        if (P.dbg_vp && l64 == 0) P.dbg_vp[g] = vp;
-
-        // ---- pass 2: update, inverse transform, aggregation of the group members -------------
-        constexpr int MC = GW_TEAM / CH;   // members per chunk
-        for (int m0 = 0; m0 < nagg; m0 += MC) {
-            const int cnt = min(MC, nagg - m0);
-            if (m0) team_sync(bar);   // the previous chunk's aggregation is done with `tiles`
-            if (l64 < cnt * CH) {
-                const int ml = l64 / CH, c = l64 - ml * CH;
-                const uint32_t cd = s_cand[s_grp[m0 + ml]];
-                const int qx = cand_x(cd), qy = cand_y(cd);
-                float t[64];
-                const float *wS = winS + (qy - y0) * wrow + (qx - x0) * CH + c;
-                if (P.smooth) {
-                    // x1 + T^-1(a * T(x0 - x1))                        (:1775)
-                    const float *wP = winP + (qy - y0) * wrow + (qx - x0) * CH + c;
-#pragma unroll
-                    for (int y = 0; y < 8; ++y)
-#pragma unroll
-                        for (int x = 0; x < 8; ++x)
-                            t[y * 8 + x] = wP[y * wrow + x * CH] - wS[y * wrow + x * CH];
-                    dct8x8_regs<false>(t);
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) t[i] *= s_a[c * AS + i];
-                    dct8x8_regs<true>(t);
-#pragma unroll
-                    for (int y = 0; y < 8; ++y)
-#pragma unroll
-                        for (int x = 0; x < 8; ++x) t[y * 8 + x] += wS[y * wrow + x * CH];
-                } else {
-                    // the group holds the noisy patches (:784-785, :853): the source window when
-                    // there is no basic estimate, else the noisy frame itself
-                    if (P.has_bsic) load_tile8(P.in1 + ((long)qy * P.w + qx) * CH + c, P.w * CH, CH, t);
-                    else load_tile8(wS, wrow, CH, t);
-                    dct8x8_regs<false>(t);
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) {
-                        const float a = s_a[c * AS + i];
-                        t[i] = a * t[i] + (1.f - a) * s_m[c * AS + i];   // :878 / :901
+                for (int u = 0; u < CH; ++u) {
+                    float v1 = V1[u], v0 = V0[u], v01 = V01[u];
+                    if (!point) {
+                        v1 *= inp1;                             // :805
+                        if (n0) { v0 *= inp0; v01 *= inp0; }    // :806-810
                     }
-                    dct8x8_regs<true>(t);
+                    float a, m;
+                    if (SMOOTH) {
+                        a = __fdiv_rn(v1, v1 + P.beta_t * v01);              // :1768
+                        vsum += (1.f - a * a) * v1 + a * a * fmaxf(v0 - P.beta_t * v01, 0.f);
+                        m = 0.f;
+                    } else if (n0 > 0) {
+                        const float v = v0 + fmaxf(0.f, v01 - s2);           // :867
+                        a = __fdiv_rn(v, v + P.beta_t * sigma2);             // :870
+                        vsum += (1.f - a * a) * v + a * a * sigma2;          // :875
+                        m = Mg[u];
+                    } else {
+                        const float v = fmaxf(0.f, v1 - s2);                 // :890
+                        a = __fdiv_rn(v, v + P.beta_x * sigma2);             // :893
+                        vsum += a * v;                                       // :898
+                        m = M1[u];
+                    }
+                    s_a[u * AS + l64] = a;
+                    s_m[u * AS + l64] = m;
                 }
-                float *dst = tiles + l64 * TS;
-#pragma unroll
-                for (int i = 0; i < 64; ++i) dst[i] = t[i];
             }
-            team_sync(bar);
-            // lane = pixel of the patch, one member per iteration
-            const float wW = __fmul_rn(wgt, We);                        // :923
-            for (int ml = 0; ml < cnt; ++ml) {
-                const uint32_t cd = s_cand[s_grp[m0 + ml]];
-                const long pix = (long)(cand_y(cd) + e_hy) * P.w + cand_x(cd) + e_hx;
-                float v[CH];
 #pragma unroll
-                for (int c = 0; c < CH; ++c) v[c] = __fmul_rn(wW, tiles[(ml * CH + c) * TS + l64]); // :926
-                accumulate_pixel<CH>(P.accw + pix * (CH + 1), v, wW, CH);
-            }
+            for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+            if (lane == 0) s_red[wg] = vsum;
+            team_sync(bar);   // gains (and restaged members) visible
+            const float vp = (float)nagg * (s_red[0] + s_red[1]);
+            wgt = __fdiv_rn(1.f, fmaxf(vp, 1e-6f)); // :911
+            if (P.dbg_vp && l64 == 0) P.dbg_vp[g] = vp;
         }
     }
 }
@@ -362,13 +402,15 @@ inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st)
     if (teams < 2) return 0;
     Gm.teams = teams;
     const size_t smem = (size_t)teams * fl * 4;
-    if (ch == 3) {
-        cudaFuncSetAttribute(k_group_team8<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_group_team8<3><<<num_sms, teams * GW_TEAM, smem, st>>>(P, Gm);
-    } else {
-        cudaFuncSetAttribute(k_group_team8<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_group_team8<1><<<num_sms, teams * GW_TEAM, smem, st>>>(P, Gm);
-    }
+#define NLK_LAUNCH_TEAM(CHN, SM)                                                                      \
+    do {                                                                                              \
+        cudaFuncSetAttribute(k_group_team8<CHN, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                             (int)smem);                                                              \
+        k_group_team8<CHN, SM><<<num_sms, teams * GW_TEAM, smem, st>>>(P, Gm);                        \
+    } while (0)
+    if (ch == 3) { if (P.smooth) NLK_LAUNCH_TEAM(3, true); else NLK_LAUNCH_TEAM(3, false); }
+    else { if (P.smooth) NLK_LAUNCH_TEAM(1, true); else NLK_LAUNCH_TEAM(1, false); }
+#undef NLK_LAUNCH_TEAM
     return 1;
 }
 

@@ -83,6 +83,9 @@ def ksub_match(name, ksub):
     m = re.match(r"(\w+?)IL?i?(\d+)ELi(\d+)E", ksub)
     if m:
         return f"{m.group(1)}<(int){m.group(2)}, (int){m.group(3)}>" in name
+    m = re.match(r"(\w+?)ILi(\d+)E", ksub)
+    if m:
+        return f"{m.group(1)}<(int){m.group(2)}>" in name or f"{m.group(1)}<{m.group(2)}>" in name
     return ksub in name
 
 
