@@ -55,6 +55,45 @@ __device__ __forceinline__ void dct1d_inv(float (&X)[N])
     for (int j = 0; j < H; ++j) { X[j] = e[j] + o[j]; X[N - 1 - j] = e[j] - o[j]; }
 }
 
+// 8 points: the even half splits once more (T[2m][j] is symmetric in j <-> 3-j for
+// m even, antisymmetric for m odd): 36 operations instead of 40
+template <>
+__device__ __forceinline__ void dct1d_fwd<8>(float (&x)[8])
+{
+    const float (&T)[MAX_PSZ * MAX_PSZ] = c_dct[8];
+    const float s0 = x[0] + x[7], s1 = x[1] + x[6], s2 = x[2] + x[5], s3 = x[3] + x[4];
+    const float d0 = x[0] - x[7], d1 = x[1] - x[6], d2 = x[2] - x[5], d3 = x[3] - x[4];
+    const float ss0 = s0 + s3, ss1 = s1 + s2, sd0 = s0 - s3, sd1 = s1 - s2;
+    x[0] = fmaf(T[0 * 8 + 1], ss1, T[0 * 8 + 0] * ss0);
+    x[4] = fmaf(T[4 * 8 + 1], ss1, T[4 * 8 + 0] * ss0);
+    x[2] = fmaf(T[2 * 8 + 1], sd1, T[2 * 8 + 0] * sd0);
+    x[6] = fmaf(T[6 * 8 + 1], sd1, T[6 * 8 + 0] * sd0);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int k = 2 * m + 1;
+        x[k] = fmaf(T[k * 8 + 3], d3, fmaf(T[k * 8 + 2], d2, fmaf(T[k * 8 + 1], d1, T[k * 8 + 0] * d0)));
+    }
+}
+
+template <>
+__device__ __forceinline__ void dct1d_inv<8>(float (&X)[8])
+{
+    const float (&T)[MAX_PSZ * MAX_PSZ] = c_dct[8];
+    const float p0 = fmaf(T[4 * 8 + 0], X[4], T[0 * 8 + 0] * X[0]);
+    const float p1 = fmaf(T[4 * 8 + 1], X[4], T[0 * 8 + 1] * X[0]);
+    const float q0 = fmaf(T[6 * 8 + 0], X[6], T[2 * 8 + 0] * X[2]);
+    const float q1 = fmaf(T[6 * 8 + 1], X[6], T[2 * 8 + 1] * X[2]);
+    const float e0 = p0 + q0, e3 = p0 - q0, e1 = p1 + q1, e2 = p1 - q1;
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        o[j] = fmaf(T[7 * 8 + j], X[7], fmaf(T[5 * 8 + j], X[5], fmaf(T[3 * 8 + j], X[3], T[1 * 8 + j] * X[1])));
+    X[0] = e0 + o[0]; X[7] = e0 - o[0];
+    X[1] = e1 + o[1]; X[6] = e1 - o[1];
+    X[2] = e2 + o[2]; X[5] = e2 - o[2];
+    X[3] = e3 + o[3]; X[4] = e3 - o[3];
+}
+
 // whole 8x8 tile in registers; source element (y, x) at src[y*row_stride + x*col_stride]
 template <bool INVERSE>
 __device__ __forceinline__ void dct2d_8x8_strided(const float *src, int row_stride,

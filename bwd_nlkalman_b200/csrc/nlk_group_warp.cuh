@@ -203,8 +203,55 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             const int cnt = stat ? min(cc, k - first) : min(MC, nagg - first);
             if (round) team_sync(bar);   // the previous round's consumers are done with `tiles`
 
-            // ---- producer: lane = tile ----------------------------------------------------------
-            {
+            // ---- producer ------------------------------------------------------------------------
+            if (!stat && cnt * CH <= 8) {
+                // few members (second filtering: one): a whole tile per lane would leave the team
+                // idle behind a handful of lanes, so lane = one row / column of a tile instead
+                const int tt = l64 >> 3, y = l64 & 7;
+                const bool act = tt < cnt * CH;
+                int off = 0, c = 0;
+                if (act) {
+                    const int ml = tt / CH;
+                    c = tt - ml * CH;
+                    const uint32_t cd = s_cand[s_grp[first + ml]];
+                    off = (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * CH + c;
+                }
+                float *tb = tiles + tt * TS;
+                const float *wS = winS + off + y * wrow, *wP = winP + off + y * wrow;
+                if (act) {      // rows, forward
+                    float r[8];
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) r[x] = SMOOTH ? wP[x * CH] - wS[x * CH] : wS[x * CH];
+                    dct1d_fwd<8>(r);
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) tb[y * 8 + x] = r[x];
+                }
+                team_sync(bar);
+                if (act) {      // columns (y is the column index here): forward, shrink, inverse
+                    float r[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) r[i] = tb[i * 8 + y];
+                    dct1d_fwd<8>(r);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float a = s_a[c * AS + i * 8 + y];
+                        if (SMOOTH) r[i] *= a;                                           // :1775
+                        else r[i] = a * r[i] + (1.f - a) * s_m[c * AS + i * 8 + y];      // :878 / :901
+                    }
+                    dct1d_inv<8>(r);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) tb[i * 8 + y] = r[i];
+                }
+                team_sync(bar);
+                if (act) {      // rows, inverse
+                    float r[8];
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) r[x] = tb[y * 8 + x];
+                    dct1d_inv<8>(r);
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) tb[y * 8 + x] = SMOOTH ? r[x] + wS[x * CH] : r[x];
+                }
+            } else {
                 bool act;
                 int s = 0, c;
                 uint32_t cd;
