@@ -257,6 +257,45 @@ extern "C" void *nlk_host_alloc(size_t bytes)
 }
 extern "C" void nlk_host_free(void *p) { if (p) cudaFreeHost(p); }
 
+extern "C" void *nlk_dev_alloc(nlk_ctx *c, size_t bytes)
+{
+    if (ctx_use(c)) return nullptr;
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        set_err(NLK_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void nlk_dev_free(nlk_ctx *c, void *d_ptr)
+{
+    if (!d_ptr || ctx_use(c)) return;
+    cudaStreamSynchronize(c->st);
+    cudaFree(d_ptr);
+}
+
+extern "C" int nlk_upload(nlk_ctx *c, void *d_dst, const void *h_src, size_t bytes)
+{
+    if (int r = ctx_use(c)) return r;
+    CU_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->st));
+    return NLK_OK;
+}
+
+extern "C" int nlk_download(nlk_ctx *c, void *h_dst, const void *d_src, size_t bytes)
+{
+    if (int r = ctx_use(c)) return r;
+    CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->st));
+    return NLK_OK;
+}
+
+extern "C" int nlk_copy_dev(nlk_ctx *c, void *d_dst, const void *d_src, size_t bytes)
+{
+    if (int r = ctx_use(c)) return r;
+    CU_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, c->st));
+    return NLK_OK;
+}
+
 // ---- one pass ---------------------------------------------------------------------------------
 
 static int check_launch(nlk_ctx *c, int n, const char *what)

@@ -41,6 +41,46 @@ __device__ __forceinline__ float patch_dist(const float *__restrict__ cq, const 
     return ww;
 }
 
+// Bitonic sort of 128 keys held four per lane (element r*32 + lane in register r):
+// strides below 32 exchange through shuffles, the two larger ones between registers.
+__device__ __forceinline__ void cmpswap(unsigned long long &a, unsigned long long &b, bool asc)
+{
+    const bool sw = (a > b) == asc;
+    const unsigned long long lo = sw ? b : a, hi = sw ? a : b;
+    a = lo;
+    b = hi;
+}
+
+__device__ __forceinline__ void warp_sort128(unsigned long long (&key)[4], int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int rs = stride >> 5;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if ((r & rs) == 0) {
+                        const bool asc = (((r << 5) & size) == 0);
+                        cmpswap(key[r], key[r + rs], asc);
+                    }
+                }
+            } else {
+                const bool lower = (lane & stride) == 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key[r], stride);
+                    const bool asc = ((((r << 5) | lane) & size) == 0);
+                    const bool take_min = (lower == asc);
+                    const bool less = key[r] < other;
+                    key[r] = (less == take_min) ? key[r] : other;
+                }
+            }
+        }
+    }
+}
+
 // warp-level: sort npad keys (ascending), keep the first k, write the candidate
 // records, the header and the grid-neighbour bitmap of patch g.  bm: 2*nbw words of
 // shared scratch private to the warp.
@@ -50,7 +90,17 @@ __device__ __forceinline__ void sort_and_emit(const PassParams &P, int g, int px
 {
     const int nbw = P.nbw;
     uint32_t *nbr_out = P.nbr + (long)g * nbw;
-    // bitonic sort, ascending
+    if (npad <= 128) {
+        // the usual temporal window (121 candidates): sort in registers
+        unsigned long long key[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) key[r] = (r * 32 + lane < npad) ? keys[r * 32 + lane] : ~0ull;
+        warp_sort128(key, lane);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) if (r * 32 + lane < npad) keys[r * 32 + lane] = key[r];
+        __syncwarp();
+    } else
+    // bitonic sort in shared memory, ascending
     for (int size = 2; size <= npad; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int t = lane; t < (npad >> 1); t += 32) {

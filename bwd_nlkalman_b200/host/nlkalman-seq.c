@@ -1,0 +1,315 @@
+/* nlkalman-seq -- whole-sequence NL-Kalman filtering and smoothing with the recursion
+ * state resident in HBM, host driver.
+ *
+ * Command line and recursion follow the reference's in-memory sequence driver
+ * (reference src/main-seq.c:81-597, not built by the reference's CMake): all paths are
+ * printf patterns of the frame number; per frame, first filtering guided by the warped
+ * previous first filtering, second filtering (from the second frame on) guided by the
+ * warped previous output with the first filtering as basic estimate, then either the
+ * one-frame-lag smoother inside the forward loop or the full backward smoother
+ * (--s1_full 1).  Differences in mechanism, not in results: frames are read one at a
+ * time instead of all up front, and every filtered frame stays on the GPU (opponent
+ * colour space) until the smoother has consumed it -- nothing but the inputs goes up
+ * and nothing but the requested outputs comes back.
+ *
+ * --first_f2 1 applies the second filtering to the first frame too, which is what the
+ * per-frame pipeline script does (reference scripts/nlkalman-seq.sh:39-41).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nlk_image_io.h"
+#include "nlk_opts.h"
+#include "nlkalman_b200.h"
+
+static void auto_params(struct nlkalman_params *p, int patch)
+{
+    p->patch_sz = patch;
+    p->search_sz_x = p->search_sz_t = -1;
+    p->npatches_x = p->npatches_t = p->npatches_tagg = -1;
+    p->dista_lambda = p->beta_x = p->beta_t = -1.f;
+}
+
+static void print_params(const char *title, const struct nlkalman_params *p, int smoother)
+{
+    printf("%s\n", title);
+    printf("\tpatch      %d\n", p->patch_sz);
+    if (!smoother) printf("\tsearch_x   %d\n", p->search_sz_x);
+    printf("\tsearch_t   %d\n", p->search_sz_t);
+    if (!smoother) printf("\tnp_x       %d\n", p->npatches_x);
+    printf("\tnp_t       %d\n", p->npatches_t);
+    printf("\tnp_tagg    %d\n", p->npatches_tagg);
+    printf("\tlambda     %g\n", p->dista_lambda);
+    if (!smoother) printf("\tbeta_x     %g\n", p->beta_x);
+    printf("\tbeta_t     %g\n", p->beta_t);
+    printf("\n");
+}
+
+static nlk_ctx *ctx;
+static int w, h, c;
+static size_t ib, npix;
+
+static int gpu_fail(const char *what)
+{
+    fprintf(stderr, "nlkalman-seq: %s: %s\n", what, nlk_last_error());
+    return 1;
+}
+
+/* reads pattern % f; checks the size against the sequence; NULL if the pattern is NULL */
+static float *read_frame(const char *pattern, int f, int want_c, int *err)
+{
+    if (!pattern) return NULL;
+    char name[1024];
+    snprintf(name, sizeof name, pattern, f);
+    int w1, h1, c1;
+    float *x = nlk_read_image(name, &w1, &h1, &c1);
+    if (!x) { fprintf(stderr, "Error: %s\n", nlk_io_error()); *err = 1; return NULL; }
+    if (w1 != w || h1 != h || c1 != want_c) {
+        fprintf(stderr, "Error: %s is %dx%dx%d, expected %dx%dx%d\n", name, w1, h1, c1, w, h, want_c);
+        free(x);
+        *err = 1;
+        return NULL;
+    }
+    return x;
+}
+
+/* device (opponent space) -> RGB -> file pattern % f */
+static int write_frame(const char *pattern, int f, const float *d_opp, float *d_scratch, float *h_out)
+{
+    char name[1024];
+    snprintf(name, sizeof name, pattern, f);
+    if (nlk_opp2rgb_dev(ctx, d_scratch, d_opp) || nlk_download(ctx, h_out, d_scratch, ib) || nlk_ctx_sync(ctx))
+        return gpu_fail("output");
+    if (nlk_write_image(name, h_out, w, h, c)) return fprintf(stderr, "Error: %s\n", nlk_io_error()), 1;
+    return 0;
+}
+
+/* flow / occlusion of frame f -> device; *d_flow_out = NULL when there is no flow */
+static int load_flow(const char *flo_pat, const char *occ_pat, int f, float *d_of, float *d_occ,
+                     const float **d_flow_out, const float **d_occ_out)
+{
+    int err = 0;
+    *d_flow_out = *d_occ_out = NULL;
+    float *of = read_frame(flo_pat, f, 2, &err);
+    float *oc = of ? read_frame(occ_pat, f, 1, &err) : NULL;
+    if (err) return 1;
+    if (of) {
+        if (nlk_upload(ctx, d_of, of, npix * 2 * sizeof(float))) return gpu_fail("upload");
+        *d_flow_out = d_of;
+        if (oc) {
+            if (nlk_upload(ctx, d_occ, oc, npix * sizeof(float))) return gpu_fail("upload");
+            *d_occ_out = d_occ;
+        }
+        if (nlk_ctx_sync(ctx)) return gpu_fail("upload");   /* the host copies are freed below */
+    }
+    free(of);
+    free(oc);
+    return 0;
+}
+
+int main(int argc, const char *argv[])
+{
+    const char *nisy_path = NULL, *bflo_path = NULL, *bocc_path = NULL, *fflo_path = NULL, *focc_path = NULL;
+    const char *flt1_path = NULL, *flt2_path = NULL, *smo1_path = NULL;
+    int fframe = 0, lframe = -1, verbose = 0, full = 1, first_f2 = 0;
+    float sigma = 0.f;
+    struct nlkalman_params f1, f2, s1;
+    auto_params(&f1, -1);
+    auto_params(&f2, -1);
+    auto_params(&s1, 0);   /* smoothing is off unless --s1_p is given (reference src/main-seq.c:131) */
+
+    const struct nlk_opt options[] = {
+        {NLK_OPT_GROUP, 0, "Data i/o options (all paths in printf format)", NULL, NULL},
+        {NLK_OPT_STRING, 'i', "nisy", &nisy_path, "input noisy frames path"},
+        {NLK_OPT_STRING, 'o', "bflow", &bflo_path, "input bwd flow path"},
+        {NLK_OPT_STRING, 'k', "boccl", &bocc_path, "input bwd occlusion masks path"},
+        {NLK_OPT_STRING, 0, "fflow", &fflo_path, "input fwd flow path"},
+        {NLK_OPT_STRING, 0, "foccl", &focc_path, "input fwd occlusion masks path"},
+        {NLK_OPT_STRING, 0, "filt1", &flt1_path, "output first filtering path"},
+        {NLK_OPT_STRING, 0, "filt2", &flt2_path, "output second filtering path"},
+        {NLK_OPT_STRING, 0, "smoo1", &smo1_path, "output smoothing path"},
+        {NLK_OPT_INT, 'f', "first", &fframe, "first frame"},
+        {NLK_OPT_INT, 'l', "last", &lframe, "last frame"},
+        {NLK_OPT_FLOAT, 's', "sigma", &sigma, "noise standard dev"},
+        {NLK_OPT_GROUP, 0, "First filtering options", NULL, NULL},
+        {NLK_OPT_INT, 0, "f1_p", &f1.patch_sz, "patch size"},
+        {NLK_OPT_INT, 0, "f1_sx", &f1.search_sz_x, "search radius (spatial filtering)"},
+        {NLK_OPT_INT, 0, "f1_st", &f1.search_sz_t, "search radius (temporal filtering)"},
+        {NLK_OPT_INT, 0, "f1_nx", &f1.npatches_x, "number of similar patches spatial"},
+        {NLK_OPT_INT, 0, "f1_nt", &f1.npatches_t, "number of similar patches kalman"},
+        {NLK_OPT_INT, 0, "f1_nt_agg", &f1.npatches_tagg, "number of similar patches kalman spatial average"},
+        {NLK_OPT_FLOAT, 0, "f1_bx", &f1.beta_x, "noise multiplier in spatial filtering"},
+        {NLK_OPT_FLOAT, 0, "f1_bt", &f1.beta_t, "noise multiplier in kalman filtering"},
+        {NLK_OPT_FLOAT, 0, "f1_l", &f1.dista_lambda, "noisy patch weight in patch distance"},
+        {NLK_OPT_GROUP, 0, "Second filtering options", NULL, NULL},
+        {NLK_OPT_INT, 0, "f2_p", &f2.patch_sz, "patch size"},
+        {NLK_OPT_INT, 0, "f2_sx", &f2.search_sz_x, "search radius (spatial filtering)"},
+        {NLK_OPT_INT, 0, "f2_st", &f2.search_sz_t, "search radius (temporal filtering)"},
+        {NLK_OPT_INT, 0, "f2_nx", &f2.npatches_x, "number of similar patches spatial"},
+        {NLK_OPT_INT, 0, "f2_nt", &f2.npatches_t, "number of similar patches kalman"},
+        {NLK_OPT_INT, 0, "f2_nt_agg", &f2.npatches_tagg, "number of similar patches kalman spatial average"},
+        {NLK_OPT_FLOAT, 0, "f2_bx", &f2.beta_x, "noise multiplier in spatial filtering"},
+        {NLK_OPT_FLOAT, 0, "f2_bt", &f2.beta_t, "noise multiplier in kalman filtering"},
+        {NLK_OPT_FLOAT, 0, "f2_l", &f2.dista_lambda, "noisy patch weight in patch distance"},
+        {NLK_OPT_INT, 0, "first_f2", &first_f2, "1: second filtering on the first frame too (as nlkalman-seq.sh)"},
+        {NLK_OPT_GROUP, 0, "Smoothing options", NULL, NULL},
+        {NLK_OPT_INT, 0, "s1_p", &s1.patch_sz, "patch size"},
+        {NLK_OPT_INT, 0, "s1_st", &s1.search_sz_t, "search region radius"},
+        {NLK_OPT_INT, 0, "s1_nt", &s1.npatches_t, "number of similar patches kalman"},
+        {NLK_OPT_INT, 0, "s1_nt_agg", &s1.npatches_tagg, "number of similar patches kalman spatial average"},
+        {NLK_OPT_FLOAT, 0, "s1_bt", &s1.beta_t, "noise multiplier in kalman filtering"},
+        {NLK_OPT_FLOAT, 0, "s1_l", &s1.dista_lambda, "noisy patch weight in patch distance"},
+        {NLK_OPT_INT, 0, "s1_full", &full, "0: next frame smoothing, 1: full video smoothing (default)"},
+        {NLK_OPT_GROUP, 0, "Program options", NULL, NULL},
+        {NLK_OPT_INT, 'v', "verbose", &verbose, "verbose output"},
+        {NLK_OPT_END, 0, NULL, NULL, NULL},
+    };
+    nlk_opts_parse(options, "nlkalman-seq [options] [[--] args]",
+                   "\nA video denoiser based on non-local Kalman filtering.", argc, argv);
+
+    /* modes (reference src/main-seq.c:223-246) */
+    const int second_filt = f2.patch_sz && (flt2_path || smo1_path);
+    const int lag_smoother = !full && s1.patch_sz && smo1_path;
+    const int full_smoother = full && s1.patch_sz && smo1_path;
+    if (f1.patch_sz == 0) return fprintf(stderr, "Error: f1_p == 0, exiting\n"), 1;
+    if (!flt1_path && !(flt2_path && f2.patch_sz) && !lag_smoother && !full_smoother)
+        return fprintf(stderr, "Error: no output path given for any computed output - exiting\n"), 1;
+    if (!flt1_path && !flt2_path && s1.patch_sz == 0)
+        return fprintf(stderr, "Error: s1_p == 0 and no output paths given for filt1 and filt2\n"), 1;
+    if (f2.patch_sz == 0 && flt2_path)
+        fprintf(stderr, "Warning: f2_p == 0 - no output files will be stored in %s\n", flt2_path);
+    if (s1.patch_sz == 0 && smo1_path)
+        fprintf(stderr, "Warning: s1_p == 0 - no output files will be stored in %s\n", smo1_path);
+    if (!nisy_path || lframe < fframe) return fprintf(stderr, "Error: no input frames (-i, -f, -l)\n"), 1;
+
+    nlkalman_default_params(&f1, sigma, FLT1);
+    nlkalman_default_params(&f2, sigma, FLT2);
+    nlkalman_default_params(&s1, sigma, SMO1);
+
+    if (verbose) {
+        printf("data input:\n");
+        printf("\tnoise         %05.2f\n", sigma);
+        printf("\tfirst frame   %d\n", fframe);
+        printf("\tlast frame    %d\n", lframe);
+        printf("\tnoisy frames  %s\n", nisy_path);
+        printf("\tbwd flows     %s\n", bflo_path);
+        printf("\tfwd flows     %s\n", fflo_path);
+        printf("\tbwd occlus.   %s\n", bocc_path);
+        printf("\tfwd occlus.   %s\n", focc_path);
+        printf("\n");
+        printf("data output:\n");
+        printf("\tfiltering 1   %s\n", flt1_path);
+        printf("\tfiltering 2   %s\n", flt2_path);
+        printf("\tsmoothing 1   %s\n", smo1_path);
+        printf("\n");
+        print_params("first filtering parameters:", &f1, 0);
+        if (second_filt) print_params("second filtering parameters:", &f2, 0);
+        if (lag_smoother || full_smoother)
+            print_params(full_smoother ? "full smoother params:" : "single frame smoother params:", &s1, 1);
+    }
+
+    /* the first frame fixes the geometry */
+    {
+        char name[1024];
+        snprintf(name, sizeof name, nisy_path, fframe);
+        float *x = nlk_read_image(name, &w, &h, &c);
+        if (!x) return fprintf(stderr, "Error: %s\n", nlk_io_error()), 1;
+        free(x);
+    }
+    ib = (size_t)w * h * c * sizeof(float);
+    npix = (size_t)w * h;
+    int dev = 0;
+    if (getenv("NLK_DEVICE")) dev = atoi(getenv("NLK_DEVICE"));
+    ctx = nlk_ctx_create(w, h, c, dev);
+    if (!ctx) return gpu_fail("no usable CUDA device (there is no CPU fallback)");
+
+    /* HBM-resident state: the output of every frame when a smoother needs it later,
+     * else two slots used alternately; plus the previous first filtering */
+    const int nframes = lframe - fframe + 1;
+    const int keep_all = full_smoother;
+    const int nslots = keep_all ? nframes : 2;
+    float **d_deno = (float **)calloc((size_t)nslots, sizeof(float *));
+    for (int i = 0; i < nslots; ++i) if (!(d_deno[i] = nlk_dev_alloc(ctx, ib))) return gpu_fail("device memory");
+    float *d_nisy = nlk_dev_alloc(ctx, ib), *d_warp = nlk_dev_alloc(ctx, ib), *d_tmp = nlk_dev_alloc(ctx, ib);
+    float *d_bsic[2] = {nlk_dev_alloc(ctx, ib), nlk_dev_alloc(ctx, ib)};
+    float *d_of = nlk_dev_alloc(ctx, npix * 2 * sizeof(float)), *d_occ = nlk_dev_alloc(ctx, npix * sizeof(float));
+    float *h_io = (float *)nlk_host_alloc(ib);
+    if (!d_nisy || !d_warp || !d_tmp || !d_bsic[0] || !d_bsic[1] || !d_of || !d_occ || !h_io)
+        return gpu_fail("device memory");
+#define SLOT(f) d_deno[keep_all ? (f) - fframe : ((f) - fframe) & 1]
+
+    /* ---- forward: filtering (reference src/main-seq.c:444-550) ---------------------------- */
+    for (int f = fframe; f <= lframe; ++f) {
+        if (verbose) printf("processing frame %d\n", f);
+        int err = 0;
+        float *x = read_frame(nisy_path, f, c, &err);
+        if (!x) return 1;
+        memcpy(h_io, x, ib);
+        free(x);
+        if (nlk_upload(ctx, d_nisy, h_io, ib) || nlk_rgb2opp_dev(ctx, d_nisy, d_nisy)) return gpu_fail("upload");
+        float *bsic1 = d_bsic[(f - fframe) & 1], *bsic0 = d_bsic[(f - fframe + 1) & 1];
+        const float *d_flow = NULL, *d_mask = NULL;
+        if (f > fframe && load_flow(bflo_path, bocc_path, f, d_of, d_occ, &d_flow, &d_mask)) return 1;
+
+        /* first filtering, guided by the previous first filtering */
+        const float *prev = NULL;
+        if (f > fframe) {
+            prev = bsic0;
+            if (d_flow) { if (nlk_warp_dev(ctx, d_warp, bsic0, d_flow, d_mask)) return gpu_fail("warp"); prev = d_warp; }
+        }
+        if (nlk_pass_dev(ctx, 0, bsic1, d_nisy, prev, NULL, sigma, f1)) return gpu_fail("first filtering");
+        if (flt1_path && write_frame(flt1_path, f, bsic1, d_tmp, h_io)) return 1;
+
+        /* second filtering, guided by the previous output */
+        float *deno1 = SLOT(f);
+        if (second_filt && (f > fframe || first_f2)) {
+            prev = NULL;
+            if (f > fframe) {
+                prev = SLOT(f - 1);
+                if (d_flow) { if (nlk_warp_dev(ctx, d_warp, prev, d_flow, d_mask)) return gpu_fail("warp"); prev = d_warp; }
+            }
+            if (nlk_pass_dev(ctx, 0, deno1, d_nisy, prev, bsic1, sigma, f2)) return gpu_fail("second filtering");
+        } else {
+            /* the output of this frame is its first filtering */
+            if (nlk_copy_dev(ctx, deno1, bsic1, ib)) return gpu_fail("copy");
+        }
+        if (second_filt && flt2_path && write_frame(flt2_path, f, deno1, d_tmp, h_io)) return 1;
+
+        /* one-frame-lag smoother: frame f-1 smoothed against frame f */
+        if (lag_smoother && f > fframe) {
+            const float *d_ff = NULL, *d_fm = NULL;
+            if (load_flow(fflo_path, focc_path, f - 1, d_of, d_occ, &d_ff, &d_fm)) return 1;
+            const float *smoo0 = deno1;
+            if (d_ff) { if (nlk_warp_dev(ctx, d_warp, deno1, d_ff, d_fm)) return gpu_fail("warp"); smoo0 = d_warp; }
+            float *filt1 = SLOT(f - 1);
+            if (nlk_pass_dev(ctx, 1, d_tmp, filt1, smoo0, NULL, sigma, s1)) return gpu_fail("smoothing");
+            if (nlk_copy_dev(ctx, filt1, d_tmp, ib)) return gpu_fail("copy");
+            if (write_frame(smo1_path, f - 1, filt1, d_tmp, h_io)) return 1;
+        }
+    }
+
+    /* ---- backward: full smoother (reference src/main-seq.c:553-584) ------------------------ */
+    if (full_smoother) {
+        for (int f = lframe - 1; f >= fframe; --f) {
+            if (verbose) printf("processing frame %d\n", f);
+            const float *d_ff = NULL, *d_fm = NULL;
+            if (load_flow(fflo_path, focc_path, f, d_of, d_occ, &d_ff, &d_fm)) return 1;
+            const float *smoo0 = SLOT(f + 1);
+            if (d_ff) { if (nlk_warp_dev(ctx, d_warp, smoo0, d_ff, d_fm)) return gpu_fail("warp"); smoo0 = d_warp; }
+            float *filt1 = SLOT(f);
+            if (nlk_pass_dev(ctx, 1, d_nisy, filt1, smoo0, NULL, sigma, s1)) return gpu_fail("smoothing");
+            if (nlk_copy_dev(ctx, filt1, d_nisy, ib)) return gpu_fail("copy");
+            if (write_frame(smo1_path, f, filt1, d_tmp, h_io)) return 1;
+        }
+    }
+
+    if (nlk_ctx_sync(ctx)) return gpu_fail("sync");
+    for (int i = 0; i < nslots; ++i) nlk_dev_free(ctx, d_deno[i]);
+    free(d_deno);
+    nlk_dev_free(ctx, d_nisy); nlk_dev_free(ctx, d_warp); nlk_dev_free(ctx, d_tmp);
+    nlk_dev_free(ctx, d_bsic[0]); nlk_dev_free(ctx, d_bsic[1]); nlk_dev_free(ctx, d_of); nlk_dev_free(ctx, d_occ);
+    nlk_host_free(h_io);
+    nlk_ctx_destroy(ctx);
+    return EXIT_SUCCESS;
+}

@@ -1,0 +1,135 @@
+/* nlkalman-smo -- frame-by-frame NL-Kalman (RTS) smoothing on a B200, host driver.
+ *
+ * Command line, file conventions, messages and exit codes follow the reference driver
+ * (reference src/main-smo.c:21-223), including its exit status: the reference returns
+ * 1 after a SUCCESSFUL run (src/main-smo.c:222) and the pipeline scripts ignore it.
+ * Set NLK_SMO_EXIT0=1 to get the conventional 0 instead.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nlk_image_io.h"
+#include "nlk_opts.h"
+#include "nlkalman_b200.h"
+
+static int gpu_fail(const char *what)
+{
+    fprintf(stderr, "nlkalman-smo: %s: %s\n", what, nlk_last_error());
+    return 2;
+}
+
+int main(int argc, const char *argv[])
+{
+    const char *flt1_path = NULL, *smo0_path = NULL, *fflo_path = NULL, *focc_path = NULL, *smo1_path = NULL;
+    float sigma = 0.f;
+    int verbose = 0;
+    struct nlkalman_params s1;
+    s1.patch_sz = s1.search_sz_x = s1.search_sz_t = -1;   /* -1 means automatic value */
+    s1.npatches_x = s1.npatches_t = s1.npatches_tagg = -1;
+    s1.dista_lambda = s1.beta_x = s1.beta_t = -1.f;
+
+    const struct nlk_opt options[] = {
+        {NLK_OPT_GROUP, 0, "Data i/o options", NULL, NULL},
+        {NLK_OPT_STRING, 0, "flt1", &flt1_path, "input filtered frame path"},
+        {NLK_OPT_STRING, 0, "smo0", &smo0_path, "input next smoothed frame path"},
+        {NLK_OPT_STRING, 'o', "fflo", &fflo_path, "input fwd flow path"},
+        {NLK_OPT_STRING, 'k', "focc", &focc_path, "input fwd occlusion mask path"},
+        {NLK_OPT_STRING, 0, "smo1", &smo1_path, "output smoothed frame"},
+        {NLK_OPT_FLOAT, 's', "sigma", &sigma, "noise standard dev"},
+        {NLK_OPT_GROUP, 0, "Smoothing options", NULL, NULL},
+        {NLK_OPT_INT, 0, "s1_p", &s1.patch_sz, "patch size"},
+        {NLK_OPT_INT, 0, "s1_st", &s1.search_sz_t, "search region radius"},
+        {NLK_OPT_INT, 0, "s1_nt", &s1.npatches_t, "number of similar patches kalman"},
+        {NLK_OPT_INT, 0, "s1_nt_agg", &s1.npatches_tagg, "number of similar patches kalman spatial average"},
+        {NLK_OPT_FLOAT, 0, "s1_bt", &s1.beta_t, "noise multiplier in kalman filtering"},
+        {NLK_OPT_FLOAT, 0, "s1_l", &s1.dista_lambda, "noisy patch weight in patch distance"},
+        {NLK_OPT_GROUP, 0, "Program options", NULL, NULL},
+        {NLK_OPT_INT, 'v', "verbose", &verbose, "verbose output"},
+        {NLK_OPT_END, 0, NULL, NULL, NULL},
+    };
+    nlk_opts_parse(options, "nlkalman-smo [options] [[--] args]",
+                   "\nPatch-based Kalman smoother for video denoising.", argc, argv);
+
+    if (!smo1_path) return fprintf(stderr, "Error: no output path given\n"), 1;
+    if (s1.patch_sz == 0) return fprintf(stderr, "Error: s1_p == 0\n"), 1;
+    nlkalman_default_params(&s1, sigma, SMO1);
+
+    if (verbose) {
+        printf("data input:\n");
+        printf("\tnoise         %05.2f\n", sigma);
+        printf("\tfiltering 1   %s\n", flt1_path);
+        printf("\tfiltering 0   %s\n", smo0_path);
+        printf("\tfwd flows     %s\n", fflo_path);
+        printf("\tfwd occlus.   %s\n", focc_path);
+        printf("\n");
+        printf("data output:\n");
+        printf("\tsmoothing 1   %s\n", smo1_path);
+        printf("\n");
+        printf("smoother params:\n");
+        printf("\tpatch      %d\n", s1.patch_sz);
+        printf("\tsearch_t   %d\n", s1.search_sz_t);
+        printf("\tnp_t       %d\n", s1.npatches_t);
+        printf("\tnp_tagg    %d\n", s1.npatches_tagg);
+        printf("\tlambda     %g\n", s1.dista_lambda);
+        printf("\tbeta_t     %g\n", s1.beta_t);
+        printf("\n");
+    }
+
+    /* load data (reference src/main-smo.c:130-190) */
+    int w, h, c, w1, h1, c1;
+    float *flt1 = flt1_path ? nlk_read_image(flt1_path, &w, &h, &c) : NULL;
+    if (!flt1) return fprintf(stderr, "Opening %s failed\n", flt1_path), 1;
+    float *smo0 = smo0_path ? nlk_read_image(smo0_path, &w1, &h1, &c1) : NULL;
+    if (!smo0) return fprintf(stderr, "Opening %s failed\n", smo0_path), 1;
+    if (w * h * c != w1 * h1 * c1) return fprintf(stderr, "Filtered frames size missmatch\n"), 1;
+    float *fflo = NULL, *focc = NULL;
+    if (fflo_path) {
+        fflo = nlk_read_image(fflo_path, &w1, &h1, &c1);
+        if (!fflo) return fprintf(stderr, "Opening %s failed\n", fflo_path), 1;
+        if (w * h != w1 * h1 || c1 != 2) return fprintf(stderr, "Frame and optical flow size missmatch\n"), 1;
+    }
+    if (fflo_path && focc_path) {
+        focc = nlk_read_image(focc_path, &w1, &h1, &c1);
+        if (!focc) return fprintf(stderr, "Opening %s failed\n", focc_path), 1;
+        if (w * h != w1 * h1 || c1 != 1) return fprintf(stderr, "Frame and occlusion mask size missmatch\n"), 1;
+    }
+
+    /* run on the GPU (reference src/main-smo.c:192-213) */
+    int dev = 0;
+    if (getenv("NLK_DEVICE")) dev = atoi(getenv("NLK_DEVICE"));
+    nlk_ctx *ctx = nlk_ctx_create(w, h, c, dev);
+    if (!ctx) return gpu_fail("no usable CUDA device (there is no CPU fallback)");
+    const size_t ib = (size_t)w * h * c * sizeof(float), npix = (size_t)w * h;
+    float *d_flt1 = nlk_dev_alloc(ctx, ib), *d_smo0 = nlk_dev_alloc(ctx, ib), *d_warp = nlk_dev_alloc(ctx, ib);
+    float *d_smo1 = nlk_dev_alloc(ctx, ib);
+    float *d_of = fflo ? nlk_dev_alloc(ctx, npix * 2 * sizeof(float)) : NULL;
+    float *d_occ = focc ? nlk_dev_alloc(ctx, npix * sizeof(float)) : NULL;
+    if (!d_flt1 || !d_smo0 || !d_warp || !d_smo1 || (fflo && !d_of) || (focc && !d_occ)) return gpu_fail("device memory");
+    int rc = nlk_upload(ctx, d_flt1, flt1, ib);
+    if (!rc) rc = nlk_upload(ctx, d_smo0, smo0, ib);
+    if (!rc) rc = nlk_rgb2opp_dev(ctx, d_flt1, d_flt1);
+    if (!rc) rc = nlk_rgb2opp_dev(ctx, d_smo0, d_smo0);
+    const float *d_prev = d_smo0;
+    if (!rc && fflo) {
+        rc = nlk_upload(ctx, d_of, fflo, npix * 2 * sizeof(float));
+        if (!rc && focc) rc = nlk_upload(ctx, d_occ, focc, npix * sizeof(float));
+        if (!rc) rc = nlk_warp_dev(ctx, d_warp, d_smo0, d_of, d_occ);
+        d_prev = d_warp;
+    }
+    if (rc) return gpu_fail("upload");
+    if (nlk_pass_dev(ctx, 1, d_smo1, d_flt1, d_prev, NULL, sigma, s1)) return gpu_fail("smoothing");
+    float *out = (float *)malloc(ib);
+    if (!out) return fprintf(stderr, "out of memory\n"), 2;
+    if (nlk_opp2rgb_dev(ctx, d_smo1, d_smo1) || nlk_download(ctx, out, d_smo1, ib) || nlk_ctx_sync(ctx))
+        return gpu_fail("output");
+    if (nlk_write_image(smo1_path, out, w, h, c)) return fprintf(stderr, "%s\n", nlk_io_error()), 2;
+
+    free(out);
+    nlk_dev_free(ctx, d_flt1); nlk_dev_free(ctx, d_smo0); nlk_dev_free(ctx, d_warp); nlk_dev_free(ctx, d_smo1);
+    nlk_dev_free(ctx, d_of); nlk_dev_free(ctx, d_occ);
+    nlk_ctx_destroy(ctx);
+    free(flt1); free(smo0); free(fflo); free(focc);
+    const char *e0 = getenv("NLK_SMO_EXIT0");
+    return (e0 && *e0 == '1') ? 0 : 1;
+}

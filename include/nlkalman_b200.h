@@ -66,6 +66,14 @@ int nlk_fp32_peak(nlk_ctx *ctx, float ms, double *tflops);
 void *nlk_host_alloc(size_t bytes);
 void nlk_host_free(void *p);
 
+/* device memory on the context's GPU and copies queued on the context's stream (the
+ * copies are asynchronous when the host side is pinned; nlk_ctx_sync waits for them) */
+void *nlk_dev_alloc(nlk_ctx *ctx, size_t bytes);
+void nlk_dev_free(nlk_ctx *ctx, void *d_ptr);
+int nlk_upload(nlk_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int nlk_download(nlk_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int nlk_copy_dev(nlk_ctx *ctx, void *d_dst, const void *d_src, size_t bytes);
+
 /* ---- single operations on device buffers (asynchronous on the context's stream) ---- */
 int nlk_rgb2opp_dev(nlk_ctx *ctx, float *d_dst, const float *d_src);   /* src may equal dst */
 int nlk_opp2rgb_dev(nlk_ctx *ctx, float *d_dst, const float *d_src);

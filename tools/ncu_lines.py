@@ -79,14 +79,17 @@ def main():
 
 
 def ksub_match(name, ksub):
-    # ksub is a mangled substring like k_group_filterILi8ELi3E; compare loosely on the demangled name
-    m = re.match(r"(\w+?)IL?i?(\d+)ELi(\d+)E", ksub)
-    if m:
-        return f"{m.group(1)}<(int){m.group(2)}, (int){m.group(3)}>" in name
-    m = re.match(r"(\w+?)ILi(\d+)E", ksub)
-    if m:
-        return f"{m.group(1)}<(int){m.group(2)}>" in name or f"{m.group(1)}<{m.group(2)}>" in name
-    return ksub in name
+    # ksub is a mangled substring like k_group_filterILi8ELi3E or k_resolveILi1ELb1E: compare
+    # the base name and the template arguments, in order, with the demangled name
+    m = re.match(r"(\w+?)I((?:L[ib]\d+E)+)", ksub)
+    if not m:
+        return ksub in name
+    want = re.findall(r"L[ib](\d+)E", m.group(2))
+    d = re.search(re.escape(m.group(1)) + r"<([^>]*)>", name)
+    if not d:
+        return False
+    have = re.findall(r"\)?(\d+)", d.group(1))
+    return have[:len(want)] == want
 
 
 if __name__ == "__main__":
