@@ -175,6 +175,133 @@ __global__ void __launch_bounds__(1024) k_resolve(const PassParams P, int rw)
     if (tid == 0) *P.nactive = s_base[gh];
 }
 
+
+// ---- blocked wavefront (one bitmap word per cell, R <= 2: every BASELINE configuration) -------
+// The step count of the kernel above, gw + (R+1)(gh-1), is a chain of block barriers.  Here a
+// step handles a BLOCK of C consecutive columns per row, sequentially in registers, and row i
+// runs R columns plus one block behind row i-1:
+//     row i, step s  ->  columns [j0, j0 + C),   j0 = C (s - i) - R i
+// so that row i-1 has always finished column j + R before row i reaches column j.  Steps drop
+// to gh - 1 + ceil((gw + R (gh-1)) / C).  After its block a row publishes, for each dy, the
+// (C + 2R)-bit field of columns j0-R .. j0+C-1+R that its active cells mark in row i+dy (both
+// fields in one shared-memory word, double-buffered by step parity).  The reader ORs the field
+// of row i-dy into its window at offset (C+R)(dy-1): always at or ahead of its own position.
+template <int R, int C>
+__global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw)
+{
+    extern __shared__ unsigned int s_dyn[];
+    const int gw = P.gw, gh = P.gh, G = P.G;
+    unsigned int *s_pub = s_dyn;                              // [2][gh]
+    unsigned int *s_act = s_pub + (size_t)2 * gh;             // [gh][rw] active bits
+    int *s_base = reinterpret_cast<int *>(s_act + (size_t)gh * rw); // [gh+1] row offsets
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    if (*P.any_nbr == 0) {
+        // no group marks another grid patch: every patch is processed
+        for (int g = tid; g < G; g += nthr) P.active[g] = g;
+        if (tid == 0) *P.nactive = G;
+        return;
+    }
+    constexpr int side = 2 * R + 1, FW = C + 2 * R;
+    static_assert(FW <= 16 && (C + R) * (R - 1) + FW <= 32, "window layout");
+    constexpr unsigned int fmask = (1u << side) - 1u, ownmask = (1u << R) - 1u, fwmask = (1u << FW) - 1u;
+    const int nsteps = gh - 1 + (gw + R * (gh - 1) + C - 1) / C;
+    for (int x = tid; x < 2 * gh; x += nthr) s_pub[x] = 0u;
+    __syncthreads();
+
+    const int i = tid;
+    const bool live = i < gh;
+    const unsigned int *row = P.nbr + (long)i * gw;
+    unsigned int q[2][C];   // bitmap words of the blocks of steps s and s+1 (fetched two steps ahead)
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int j = C * (u - i) - R * i + c;
+            q[u][c] = (live && j >= 0 && j < gw) ? row[j] : 0u;
+        }
+    unsigned int wnd = 0u, accw = 0u;
+    for (int s0 = 0; s0 < nsteps; s0 += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int s = s0 + u;
+            const unsigned int *pub_rd = s_pub + (size_t)((s + 1) & 1) * gh; // written at step s-1
+            unsigned int *pub_wr = s_pub + (size_t)(s & 1) * gh;
+            if (live) {
+                const int j0 = C * (s - i) - R * i;
+#pragma unroll
+                for (int dy = 1; dy <= R; ++dy)
+                    if (i >= dy) wnd |= ((pub_rd[i - dy] >> (16 * (dy - 1))) & fwmask) << ((C + R) * (dy - 1));
+                unsigned int pub[R];
+#pragma unroll
+                for (int dy = 0; dy < R; ++dy) pub[dy] = 0u;
+                if (j0 + C > 0 && j0 < gw) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int j = j0 + c;
+                        if (j >= 0 && j < gw) {
+                            const bool act = ((wnd >> c) & 1u) == 0u;
+                            const unsigned int w0 = act ? q[u][c] : 0u;
+                            // own row, columns j+1 .. j+R
+                            wnd |= ((w0 >> (R * side + R + 1)) & ownmask) << (c + 1);
+#pragma unroll
+                            for (int dy = 1; dy <= R; ++dy) pub[dy - 1] |= ((w0 >> ((dy + R) * side)) & fmask) << c;
+                            accw |= (act ? 1u : 0u) << (j & 31);
+                            if ((j & 31) == 31 || j == gw - 1) {
+                                s_act[(size_t)i * rw + (j >> 5)] = accw;
+                                accw = 0u;
+                            }
+                        }
+                    }
+                }
+                wnd >>= C;
+                unsigned int pw = pub[0];
+                if (R > 1) pw |= pub[R - 1] << 16;
+                pub_wr[i] = pw;
+                // block of step s+2
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int j = j0 + 2 * C + c;
+                    q[u][c] = (j >= 0 && j < gw) ? row[j] : 0u;
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // active list in raster order: per-row counts, block scan, then one warp per row
+    for (int r = tid; r < gh; r += nthr) {
+        int c = 0;
+        for (int wd = 0; wd < rw; ++wd) c += __popc(s_act[(size_t)r * rw + wd]);
+        s_base[r + 1] = c;
+    }
+    if (tid == 0) s_base[0] = 0;
+    __syncthreads();
+    {
+        s_part[tid] = tid < gh ? s_base[tid + 1] : 0;
+        __syncthreads();
+        for (int off = 1; off < nthr; off <<= 1) {
+            const int a = tid >= off ? s_part[tid - off] : 0;
+            __syncthreads();
+            s_part[tid] += a;
+            __syncthreads();
+        }
+        if (tid < gh) s_base[tid + 1] = s_part[tid];
+        __syncthreads();
+    }
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    for (int r = warp; r < gh; r += nwarps) {
+        int pos = s_base[r];
+        for (int wd = 0; wd < rw; ++wd) {
+            const unsigned int word = s_act[(size_t)r * rw + wd];
+            if ((word >> lane) & 1u) P.active[pos + __popc(word & ((1u << lane) - 1u))] = r * gw + wd * 32 + lane;
+            pos += __popc(word);
+        }
+    }
+    if (tid == 0) *P.nactive = s_base[gh];
+}
+
 inline int launch_resolve(const PassParams &P, cudaStream_t st)
 {
     if (P.gh > 4 * 1024) return -1;                       // MAX_ROWS rows per thread
@@ -185,6 +312,20 @@ inline int launch_resolve(const PassParams &P, cudaStream_t st)
     int nt = P.gh < 1024 ? ((P.gh + 31) / 32) * 32 : 1024;
     if (nt < 256) nt = 256; // the all-active fast path is a plain strided fill
     const bool fast = P.nbw == 1 && P.R <= 4;
+    if (P.nbw == 1 && P.R <= 2 && P.gh <= 1024) {
+        // R = 0: no group reaches another grid cell, any_nbr stays 0 and the kernel only fills the list
+        const size_t bb = ((size_t)2 * P.gh + (size_t)P.gh * rw + P.gh + 1) * 4;
+        int nb = ((P.gh + 31) / 32) * 32;
+        if (nb < 256) nb = 256;
+        if (P.R == 2) {
+            cudaFuncSetAttribute(k_resolve_blk<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb);
+            k_resolve_blk<2, 4><<<1, nb, bb, st>>>(P, rw);
+        } else {
+            cudaFuncSetAttribute(k_resolve_blk<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb);
+            k_resolve_blk<1, 4><<<1, nb, bb, st>>>(P, rw);
+        }
+        return 1;
+    }
 #define NLK_LAUNCH_RESOLVE(MR, F)                                                                  \
     do {                                                                                           \
         cudaFuncSetAttribute(k_resolve<MR, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \

@@ -109,7 +109,8 @@ def test_flt_and_smo_against_reference_programs(scene):
     w, h, c = C.c_int(), C.c_int(), C.c_int()
     p = so.nlk_read_image(str(d / "g_a1.tif").encode(), C.byref(w), C.byref(h), C.byref(c))
     tif = np.ctypeslib.as_array(p, shape=(h.value, w.value, c.value)).copy()
-    assert np.array_equal(tif, _read_pfm(d / "g_a1.pfm"))
+    # two separate runs: the aggregation's floating-point atomics commute only up to rounding
+    assert maxabs(tif, _read_pfm(d / "g_a1.pfm")) <= TOL_MAXABS
 
 
 def test_seq_driver_matches_per_frame_chain(scene):

@@ -1,0 +1,21 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, bench (both arms), ncu launch list and full captures of
+# the hot kernels.  Usage (from the repo root, under gpurun):  bash tools/gpu_round.sh <tag> [what...]
+# what: tests bench ref launches ncu   (default: all)
+TAG=${1:-rX}; shift
+WHAT=${@:-tests bench ref launches ncu}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
+for w in $WHAT; do
+case $w in
+tests)   timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; tail -3 $OUT/${TAG}_pytest_gpu.log;;
+bench)   timeout 600 python bench.py > $OUT/${TAG}_bench_ours.json 2> $OUT/${TAG}_bench_ours.err; python tools/bench_brief.py $OUT/${TAG}_bench_ours.json;;
+ref)     timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_reference.json 2>&1; cut -c1-300 $OUT/${TAG}_bench_reference.json;;
+launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+            --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches.log 2>&1;;
+ncu)     timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_group|k_search' -s 4 -c 4 \
+            -f -o $OUT/${TAG}_hot python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu.log 2>&1
+         ls -la $OUT/${TAG}_hot.ncu-rep;;
+esac
+done
