@@ -40,6 +40,15 @@ class Params(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class StripPlan(C.Structure):
+    """struct nlk_strip_plan (include/nlkalman_b200.h): rows of one rank in a strip-sharded pass."""
+    _fields_ = [("gw", C.c_int), ("gh", C.c_int), ("nbw", C.c_int), ("gy0", C.c_int), ("gy1", C.c_int),
+                ("oy0", C.c_int), ("oy1", C.c_int), ("ey0", C.c_int), ("ey1", C.c_int)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int)
 _bp = C.POINTER(C.c_ubyte)
@@ -77,6 +86,12 @@ def lib():
     L.nlk_opp2rgb_dev.argtypes = [vp, vp, vp]
     L.nlk_warp_dev.argtypes = [vp, vp, vp, vp, vp]
     L.nlk_pass_dev.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_float, Params]
+    L.nlk_strip_plan.argtypes = [C.c_int, C.c_int, C.c_int, Params, C.c_int, C.c_int, C.POINTER(StripPlan)]
+    L.nlk_colour_rows_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
+    L.nlk_warp_rows_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int]
+    L.nlk_strip_search.argtypes = [vp, C.c_int, vp, vp, vp, C.c_float, Params, C.c_int, C.c_int, vp, vp]
+    L.nlk_strip_filter.argtypes = [vp]
+    L.nlk_strip_normalize.argtypes = [vp, vp, C.c_int, C.c_int]
     L.nlk_seq_reset.argtypes = [vp]
     L.nlk_seq_filter_dev.argtypes = [vp, vp, vp, vp, C.c_float, Params, Params, vp, vp]
     L.nlk_seq_filter_host.argtypes = [vp, vp, vp, vp, C.c_float, Params, Params, vp, vp]
@@ -126,6 +141,8 @@ def _vp(a):
     if hasattr(a, "data_ptr"):
         assert a.is_contiguous()
         return C.c_void_p(a.data_ptr())
+    if hasattr(a, "ctypes"):  # other ndarray dtypes (bitmaps)
+        return C.c_void_p(a.ctypes.data)
     raise TypeError(type(a))
 
 
@@ -250,6 +267,23 @@ class Context:
         _check(lib().nlk_pass_dev(self._h, int(smooth), _vp(out), _vp(in1), _vp(prev0), _vp(bsic1),
                                   float(sigma), prms))
 
+    # row ranges and the strip-sharded pass (full-frame device buffers, rows [row0, row1))
+    def colour_rows_dev(self, dst, src, inverse, row0, row1):
+        _check(lib().nlk_colour_rows_dev(self._h, _vp(dst), _vp(src), int(inverse), int(row0), int(row1)))
+
+    def warp_rows_dev(self, imw, im, of, msk, row0, row1):
+        _check(lib().nlk_warp_rows_dev(self._h, _vp(imw), _vp(im), _vp(of), _vp(msk), int(row0), int(row1)))
+
+    def strip_search(self, smooth, in1, prev0, bsic1, sigma, prms: Params, gy0, gy1, nbr, accw):
+        _check(lib().nlk_strip_search(self._h, int(smooth), _vp(in1), _vp(prev0), _vp(bsic1), float(sigma), prms,
+                                      int(gy0), int(gy1), _vp(nbr), _vp(accw)))
+
+    def strip_filter(self):
+        _check(lib().nlk_strip_filter(self._h))
+
+    def strip_normalize(self, out, row0, row1):
+        _check(lib().nlk_strip_normalize(self._h, _vp(out), int(row0), int(row1)))
+
     # resident sequence recursion
     def seq_reset(self):
         _check(lib().nlk_seq_reset(self._h))
@@ -301,6 +335,13 @@ class Context:
         n, psz, _ = t.shape
         _check(lib().nlk_dct_host(self._h, _p(t), psz, n, 1 if inverse else 0))
         return t
+
+
+def strip_plan(w: int, h: int, smooth: int, prms: Params, nranks: int, rank: int) -> StripPlan:
+    """nlk_strip_plan: host arithmetic only (works without a GPU)."""
+    out = StripPlan()
+    _check(lib().nlk_strip_plan(int(w), int(h), int(smooth), prms, int(nranks), int(rank), C.byref(out)))
+    return out
 
 
 def device_count() -> int:

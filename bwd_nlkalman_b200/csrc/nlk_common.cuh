@@ -38,6 +38,7 @@ constexpr int HDR_MARKS = 2;
 struct PassParams {
     int w, h, ch, psz, step;
     int gw, gh, G;          // grid of reference patches
+    int gy0, gy1;           // grid rows searched and filtered by this pass (a strip; whole frame: 0, gh)
     int smooth;             // 0: filter pass, 1: smoother pass
     int r_x, r_t;           // search radii (spatial / temporal)
     int k_x, k_t, tagg;     // patches kept (spatial / temporal), group size

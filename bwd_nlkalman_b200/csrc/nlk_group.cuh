@@ -94,7 +94,8 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
     const float sigma2 = P.sigma2;
     for (int e = tid; e < pp; e += GF_THREADS) W[e] = c_win[psz][e];
 
-    for (int ai = blockIdx.x; ai < nactive; ai += gridDim.x) {
+    // *P.work = first entry of the active list to handle (0 unless the pass is strip-sharded)
+    for (int ai = *P.work + blockIdx.x; ai < nactive; ai += gridDim.x) {
         const int g = P.active[ai];
         const GroupHdr hd = P.hdr[g];
         const int gy = g / P.gw, gx = g - gy * P.gw;

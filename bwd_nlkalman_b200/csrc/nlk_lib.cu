@@ -116,6 +116,9 @@ struct nlk_ctx {
     DevBuf q_noisy, q_warp, q_flt1[2], q_flt2[2], q_smo[2], q_tmp;
     int q_cur = 0, q_have_prev = 0, q_have_flt2 = 0;
     int q_smo_cur = 0, q_have_smo = 0;
+    // strip-sharded pass in flight (nlk_strip_search .. nlk_strip_normalize)
+    PassParams strip_P;
+    bool strip_open = false;
     // optional per-kernel timing with CUDA events on the context's stream
     bool prof = false;
     int prof_kind = NLK_PASS_OTHER;
@@ -307,8 +310,12 @@ static int check_launch(nlk_ctx *c, int n, const char *what)
     return NLK_OK;
 }
 
-static int run_pass(nlk_ctx *c, int smooth, float *d_out, const float *d_in1, const float *d_prev0,
-                    const float *d_bsic1, float sigma, const nlkalman_params &pr, bool debug)
+// fills P for one pass and sizes the scratch it points to.  The neighbour bitmaps and the
+// accumulator are the context's own unless the caller supplies them (strip-sharded pass: they
+// are exchanged between GPUs).
+static int pass_setup(nlk_ctx *c, PassParams &P, int smooth, float *d_out, const float *d_in1,
+                      const float *d_prev0, const float *d_bsic1, float sigma, const nlkalman_params &pr,
+                      bool debug, uint32_t *d_nbr_ext, float *d_accw_ext)
 {
     const int w = c->w, h = c->h, ch = c->ch;
     const int psz = pr.patch_sz;
@@ -318,13 +325,13 @@ static int run_pass(nlk_ctx *c, int smooth, float *d_out, const float *d_in1, co
         pr.npatches_tagg < 0)
         return set_err(NLK_ERR_PARAM, "negative parameter: call nlkalman_default_params first");
 
-    PassParams P;
     memset(&P, 0, sizeof P);
     P.w = w; P.h = h; P.ch = ch; P.psz = psz; P.step = psz / 2;
     const bool fits = (w >= psz && h >= psz);
     P.gw = fits ? (w - psz) / P.step + 1 : 0;
     P.gh = fits ? (h - psz) / P.step + 1 : 0;
     P.G = P.gw * P.gh;
+    P.gy0 = 0; P.gy1 = P.gh;
     P.smooth = smooth;
     P.r_x = pr.search_sz_x; P.r_t = pr.search_sz_t;
     P.k_x = pr.npatches_x; P.k_t = pr.npatches_t; P.tagg = pr.npatches_tagg;
@@ -347,17 +354,22 @@ static int run_pass(nlk_ctx *c, int smooth, float *d_out, const float *d_in1, co
 
     const size_t npix = (size_t)w * h;
     const size_t G = (size_t)(P.G > 0 ? P.G : 1);
-    if (int r = c->accw.ensure(npix * (ch + 1) * 4)) return r;
+    if (!d_accw_ext) if (int r = c->accw.ensure(npix * (ch + 1) * 4)) return r;
     if (int r = c->cand.ensure(G * kmax * 4)) return r;
     if (int r = c->hdr.ensure(G * sizeof(GroupHdr))) return r;
-    if (int r = c->nbr.ensure(G * P.nbw * 4)) return r;
+    if (!d_nbr_ext) if (int r = c->nbr.ensure(G * P.nbw * 4)) return r;
     if (int r = c->active.ensure(G * 4)) return r;
     if (int r = c->gmask.ensure(G)) return r;
     if (int r = c->actflag.ensure(G)) return r;
-    P.accw = c->accw.as<float>();
+    if (d_prev0 && P.G > 0) {
+        if (int r = c->valid.ensure((size_t)P.vw * P.vh)) return r;
+        if (int r = c->valid_tmp.ensure((size_t)P.vw * h)) return r;
+        P.valid = c->valid.as<uint8_t>();
+    }
+    P.accw = d_accw_ext ? d_accw_ext : c->accw.as<float>();
     P.cand = c->cand.as<uint32_t>();
     P.hdr = c->hdr.as<GroupHdr>();
-    P.nbr = c->nbr.as<uint32_t>();
+    P.nbr = d_nbr_ext ? d_nbr_ext : c->nbr.as<uint32_t>();
     P.active = c->active.as<int>();
     P.gmask = c->gmask.as<uint8_t>();
     P.actflag = c->actflag.as<uint8_t>();
@@ -374,43 +386,91 @@ static int run_pass(nlk_ctx *c, int smooth, float *d_out, const float *d_in1, co
         CU_TRY(cudaMemsetAsync(P.dbg_vp, 0, G * 4, c->st));
         CU_TRY(cudaMemsetAsync(P.cand, 0xff, G * kmax * 4, c->st));
     }
+    return NLK_OK;
+}
 
-    const int kind_saved = c->prof_kind;
-    c->prof_kind = smooth ? NLK_PASS_SMO : (d_bsic1 ? (d_prev0 ? NLK_PASS_FLT2_T : NLK_PASS_FLT2_X)
-                                                     : (d_prev0 ? NLK_PASS_FLT1_T : NLK_PASS_FLT1_X));
-    struct Restore { nlk_ctx *c; int k; ~Restore() { c->prof_kind = k; } } restore{c, kind_saved};
+static int pass_kind(const PassParams &P)
+{
+    return P.smooth ? NLK_PASS_SMO : (P.has_bsic ? (P.has_prev ? NLK_PASS_FLT2_T : NLK_PASS_FLT2_X)
+                                                  : (P.has_prev ? NLK_PASS_FLT1_T : NLK_PASS_FLT1_X));
+}
+
+struct KindScope {
+    nlk_ctx *c; int saved;
+    KindScope(nlk_ctx *c_, int k) : c(c_), saved(c_->prof_kind) { c->prof_kind = k; }
+    ~KindScope() { c->prof_kind = saved; }
+};
+
+// pixel rows a strip of grid rows [gy0, gy1) reads (source, previous frame) and accumulates into
+static void strip_rows(const PassParams &P, int *ey0, int *ey1)
+{
+    const int rmax = P.smooth ? P.r_t : (P.r_t > P.r_x ? P.r_t : P.r_x);
+    int a = P.gy0 * P.step - rmax, b = (P.gy1 - 1) * P.step + rmax + P.psz;
+    if (a < 0) a = 0;
+    if (b > P.h) b = P.h;
+    if (P.gy1 <= P.gy0) a = b = 0;
+    *ey0 = a; *ey1 = b;
+}
+
+// zero the accumulator rows, validity map and block matching for grid rows [P.gy0, P.gy1)
+static int pass_search(nlk_ctx *c, const PassParams &P)
+{
+    int ey0, ey1;
+    strip_rows(P, &ey0, &ey1);
     {
         ProfScope ps(c, NLK_K_MEMSET);
-        CU_TRY(cudaMemsetAsync(P.accw, 0, npix * (ch + 1) * 4, c->st));
+        const size_t rowb = (size_t)P.w * (P.ch + 1) * 4;
+        if (ey1 > ey0) CU_TRY(cudaMemsetAsync(reinterpret_cast<char *>(P.accw) + ey0 * rowb, 0, (ey1 - ey0) * rowb, c->st));
         CU_TRY(cudaMemsetAsync(c->counters.p, 0, 64, c->st));
     }
-    if (P.G > 0) {
-        if (d_prev0) {
-            if (int r = c->valid.ensure((size_t)P.vw * P.vh)) return r;
-            if (int r = c->valid_tmp.ensure((size_t)P.vw * h)) return r;
-            P.valid = c->valid.as<uint8_t>();
-            ProfScope ps(c, NLK_K_VALID);
-            if (int r = check_launch(c, launch_valid_map(c->valid.as<uint8_t>(), c->valid_tmp.as<uint8_t>(),
-                                                         d_prev0, w, h, ch, psz, c->st), "valid_map")) return r;
-        }
-        {
-            ProfScope ps(c, NLK_K_SEARCH);
-            if (int r = check_launch(c, launch_search(P, c->st), "search_knn")) return r;
-        }
-        {
-            ProfScope ps(c, NLK_K_RESOLVE);
-            if (int r = check_launch(c, launch_resolve(P, c->st), "mask_resolve")) return r;
-        }
-        {
-            ProfScope ps(c, NLK_K_GROUP);
-            if (int r = check_launch(c, launch_group_filter(P, c->num_sms, c->st), "group_filter")) return r;
-        }
+    if (P.G <= 0 || P.gy1 <= P.gy0) return NLK_OK;
+    if (P.prev0) {
+        ProfScope ps(c, NLK_K_VALID);
+        if (int r = check_launch(c, launch_valid_map(c->valid.as<uint8_t>(), c->valid_tmp.as<uint8_t>(), P.prev0,
+                                                     P.w, P.h, P.ch, P.psz, ey0, ey1 - P.psz + 1, c->st), "valid_map")) return r;
     }
+    ProfScope ps(c, NLK_K_SEARCH);
+    return check_launch(c, launch_search(P, c->st), "search_knn");
+}
+
+// processed-mask replay over the WHOLE grid (needs every row's bitmaps), then the groups of
+// rows [P.gy0, P.gy1)
+static int pass_filter(nlk_ctx *c, const PassParams &P, bool strip)
+{
+    if (P.G <= 0) return NLK_OK;
     {
-        ProfScope ps(c, NLK_K_NORMALIZE);
-        if (int r = check_launch(c, launch_normalize(P, c->st), "normalize")) return r;
+        ProfScope ps(c, NLK_K_RESOLVE);
+        if (strip) {
+            // the flag search_knn raises only covers this rank's rows: decide statically
+            k_set_flag<<<1, 1, 0, c->st>>>(P.any_nbr, (P.tagg > 1 && P.R >= 1) ? 1 : 0);
+            c->launches += 1;
+        }
+        if (int r = check_launch(c, launch_resolve(P, c->st), "mask_resolve")) return r;
+        if (strip) {
+            k_active_range<<<1, 32, 0, c->st>>>(P);
+            if (int r = check_launch(c, 1, "active_range")) return r;
+        }
     }
-    return NLK_OK;
+    if (P.gy1 <= P.gy0) return NLK_OK;
+    ProfScope ps(c, NLK_K_GROUP);
+    return check_launch(c, launch_group_filter(P, c->num_sms, c->st), "group_filter");
+}
+
+static int pass_normalize(nlk_ctx *c, const PassParams &P, int row0, int row1)
+{
+    ProfScope ps(c, NLK_K_NORMALIZE);
+    return check_launch(c, launch_normalize(P, row0, row1, c->st), "normalize");
+}
+
+static int run_pass(nlk_ctx *c, int smooth, float *d_out, const float *d_in1, const float *d_prev0,
+                    const float *d_bsic1, float sigma, const nlkalman_params &pr, bool debug)
+{
+    PassParams P;
+    if (int r = pass_setup(c, P, smooth, d_out, d_in1, d_prev0, d_bsic1, sigma, pr, debug, nullptr, nullptr)) return r;
+    KindScope ks(c, pass_kind(P));
+    if (int r = pass_search(c, P)) return r;
+    if (int r = pass_filter(c, P, false)) return r;
+    return pass_normalize(c, P, 0, P.h);
 }
 
 extern "C" int nlk_pass_dev(nlk_ctx *c, int smooth, float *d_out, const float *d_in1,
@@ -448,7 +508,100 @@ extern "C" int nlk_warp_dev(nlk_ctx *c, float *d_imw, const float *d_im, const f
 {
     if (int r = ctx_use(c)) return r;
     ProfScope ps(c, NLK_K_WARP);
-    return check_launch(c, launch_warp(d_imw, d_im, d_of, d_msk, c->w, c->h, c->ch, c->st), "warp_bicubic");
+    return check_launch(c, launch_warp(d_imw, d_im, d_of, d_msk, c->w, c->h, c->ch, 0, c->h, c->st), "warp_bicubic");
+}
+
+// ---- row ranges and the strip-sharded pass --------------------------------------
+
+static int rows_ok(nlk_ctx *c, int row0, int row1)
+{
+    if (row0 < 0 || row1 > c->h || row1 < row0) return set_err(NLK_ERR_PARAM, "row range [%d,%d) outside the frame", row0, row1);
+    return NLK_OK;
+}
+
+extern "C" int nlk_colour_rows_dev(nlk_ctx *c, float *d_dst, const float *d_src, int inverse, int row0, int row1)
+{
+    if (int r = ctx_use(c)) return r;
+    if (int r = rows_ok(c, row0, row1)) return r;
+    const size_t off = (size_t)row0 * c->w * c->ch;
+    const long npix = (long)(row1 - row0) * c->w;
+    if (npix == 0) return NLK_OK;
+    if (c->ch != 3) {
+        if (d_dst != d_src) CU_TRY(cudaMemcpyAsync(d_dst + off, d_src + off, (size_t)npix * c->ch * 4, cudaMemcpyDeviceToDevice, c->st));
+        return NLK_OK;
+    }
+    ProfScope ps(c, NLK_K_COLOUR);
+    return check_launch(c, launch_rgb2opp_copy(d_dst + off, d_src + off, npix, inverse, c->st), "colour_rows");
+}
+
+extern "C" int nlk_warp_rows_dev(nlk_ctx *c, float *d_imw, const float *d_im, const float *d_of,
+                                 const float *d_msk, int row0, int row1)
+{
+    if (int r = ctx_use(c)) return r;
+    if (int r = rows_ok(c, row0, row1)) return r;
+    ProfScope ps(c, NLK_K_WARP);
+    return check_launch(c, launch_warp(d_imw, d_im, d_of, d_msk, c->w, c->h, c->ch, row0, row1, c->st), "warp_rows");
+}
+
+extern "C" int nlk_strip_plan(int w, int h, int smooth, struct nlkalman_params pr, int nranks, int rank,
+                              struct nlk_strip_plan *out)
+{
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks) return set_err(NLK_ERR_PARAM, "bad strip request");
+    const int psz = pr.patch_sz, step = psz / 2;
+    if (psz < 2 || w < psz || h < psz) return set_err(NLK_ERR_PARAM, "frame smaller than a patch");
+    const int rmax = smooth ? pr.search_sz_t : (pr.search_sz_t > pr.search_sz_x ? pr.search_sz_t : pr.search_sz_x);
+    const int gw = (w - psz) / step + 1, gh = (h - psz) / step + 1;
+    const int R = rmax / step;
+    memset(out, 0, sizeof *out);
+    out->gw = gw; out->gh = gh; out->nbw = ((2 * R + 1) * (2 * R + 1) + 31) / 32;
+    // grid rows split as evenly as possible, the first (gh mod nranks) strips one row taller
+    const int q = gh / nranks, rem = gh % nranks;
+    const int gy0 = rank * q + (rank < rem ? rank : rem), gy1 = gy0 + q + (rank < rem ? 1 : 0);
+    out->gy0 = gy0; out->gy1 = gy1;
+    // every rank must own the rows its neighbours spill into: a strip is at least r + psz rows tall
+    if (nranks > 1 && q * step < rmax + psz)
+        return set_err(NLK_ERR_PARAM, "%d strips of %d grid rows are thinner than the halo (%d rows)", nranks, q, rmax + psz);
+    out->oy0 = rank == 0 ? 0 : gy0 * step;
+    out->oy1 = rank == nranks - 1 ? h : gy1 * step;
+    int ey0 = gy0 * step - rmax, ey1 = (gy1 - 1) * step + rmax + psz;
+    out->ey0 = ey0 < 0 ? 0 : ey0;
+    out->ey1 = ey1 > h ? h : ey1;
+    return NLK_OK;
+}
+
+extern "C" int nlk_strip_search(nlk_ctx *c, int smooth, const float *d_in1, const float *d_prev0,
+                                const float *d_bsic1, float sigma, struct nlkalman_params prms,
+                                int gy0, int gy1, unsigned int *d_nbr, float *d_accw)
+{
+    if (int r = ctx_use(c)) return r;
+    if (!d_nbr || !d_accw) return set_err(NLK_ERR_PARAM, "the strip pass needs the caller's bitmap and accumulator buffers");
+    PassParams &P = c->strip_P;
+    c->strip_open = false;
+    if (int r = pass_setup(c, P, smooth, nullptr, d_in1, d_prev0, d_bsic1, sigma, prms, false, d_nbr, d_accw)) return r;
+    if (gy0 < 0 || gy1 > P.gh || gy1 < gy0) return set_err(NLK_ERR_PARAM, "grid rows [%d,%d) outside 0..%d", gy0, gy1, P.gh);
+    P.gy0 = gy0; P.gy1 = gy1;
+    KindScope ks(c, pass_kind(P));
+    if (int r = pass_search(c, P)) return r;
+    c->strip_open = true;
+    return NLK_OK;
+}
+
+extern "C" int nlk_strip_filter(nlk_ctx *c)
+{
+    if (int r = ctx_use(c)) return r;
+    if (!c->strip_open) return set_err(NLK_ERR_STATE, "nlk_strip_search must come first");
+    KindScope ks(c, pass_kind(c->strip_P));
+    return pass_filter(c, c->strip_P, true);
+}
+
+extern "C" int nlk_strip_normalize(nlk_ctx *c, float *d_out, int row0, int row1)
+{
+    if (int r = ctx_use(c)) return r;
+    if (!c->strip_open) return set_err(NLK_ERR_STATE, "nlk_strip_search must come first");
+    if (int r = rows_ok(c, row0, row1)) return r;
+    c->strip_P.out = d_out;
+    KindScope ks(c, pass_kind(c->strip_P));
+    return pass_normalize(c, c->strip_P, row0, row1);
 }
 
 // ---- resident sequence recursion --------------------------------------------------------------

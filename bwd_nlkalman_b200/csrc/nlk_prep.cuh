@@ -72,12 +72,12 @@ __device__ __forceinline__ float cubic1(float v0, float v1, float v2, float v3, 
 template <int CH>
 __global__ void k_warp(float *__restrict__ imw, const float *__restrict__ im,
                        const float *__restrict__ of, const float *__restrict__ msk,
-                       int w, int h, int ch_rt)
+                       int w, int h, int ch_rt, int row0, int row1)
 {
     const int ch = CH ? CH : ch_rt;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
+    const int y = row0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= row1) return;
     const long pix = (long)y * w + x;
     float *o = imw + pix * ch;
     const float nanv = __int_as_float(0x7fc00000);
@@ -110,13 +110,15 @@ __global__ void k_warp(float *__restrict__ imw, const float *__restrict__ im,
     }
 }
 
+// rows [row0, row1) of the warped image (the whole frame: 0, h)
 inline int launch_warp(float *imw, const float *im, const float *of, const float *msk,
-                       int w, int h, int ch, cudaStream_t st)
+                       int w, int h, int ch, int row0, int row1, cudaStream_t st)
 {
-    dim3 nt(32, 8), nb((w + 31) / 32, (h + 7) / 8);
-    if (ch == 3) k_warp<3><<<nb, nt, 0, st>>>(imw, im, of, msk, w, h, ch);
-    else if (ch == 1) k_warp<1><<<nb, nt, 0, st>>>(imw, im, of, msk, w, h, ch);
-    else k_warp<0><<<nb, nt, 0, st>>>(imw, im, of, msk, w, h, ch);
+    if (row1 <= row0) return 0;
+    dim3 nt(32, 8), nb((w + 31) / 32, (row1 - row0 + 7) / 8);
+    if (ch == 3) k_warp<3><<<nb, nt, 0, st>>>(imw, im, of, msk, w, h, ch, row0, row1);
+    else if (ch == 1) k_warp<1><<<nb, nt, 0, st>>>(imw, im, of, msk, w, h, ch, row0, row1);
+    else k_warp<0><<<nb, nt, 0, st>>>(imw, im, of, msk, w, h, ch, row0, row1);
     return 1;
 }
 
@@ -124,10 +126,10 @@ inline int launch_warp(float *imw, const float *im, const float *of, const float
 // valid(q) <=> no NaN in channel 0 of the psz x psz patch at q (reference
 // src/nlkalman.c:605-609, :725-730).  Separable: row pass then column pass.
 __global__ void k_valid_rows(uint8_t *__restrict__ tmp, const float *__restrict__ prev0,
-                             int w, int h, int ch, int psz, int vw)
+                             int w, int h, int ch, int psz, int vw, int row0)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
+    const int y = row0 + blockIdx.y;
     if (x >= vw) return;
     const float *p = prev0 + ((long)y * w + x) * ch;
     int bad = 0;
@@ -139,24 +141,27 @@ __global__ void k_valid_rows(uint8_t *__restrict__ tmp, const float *__restrict_
 }
 
 __global__ void k_valid_cols(uint8_t *__restrict__ valid, const uint8_t *__restrict__ tmp,
-                             int vw, int vh, int psz)
+                             int vw, int vh, int psz, int row0)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
+    const int y = row0 + blockIdx.y;
     if (x >= vw || y >= vh) return;
     int bad = 0;
     for (int i = 0; i < psz; ++i) bad |= tmp[(long)(y + i) * vw + x];
     valid[(long)y * vw + x] = (uint8_t)(!bad);
 }
 
+// validity of the patches whose top row is in [q0, q1) (the whole frame: 0, h - psz + 1)
 inline int launch_valid_map(uint8_t *valid, uint8_t *tmp, const float *prev0, int w, int h, int ch,
-                            int psz, cudaStream_t st)
+                            int psz, int q0, int q1, cudaStream_t st)
 {
     const int vw = w - psz + 1, vh = h - psz + 1;
-    if (vw <= 0 || vh <= 0) return 0;
+    if (q0 < 0) q0 = 0;
+    if (q1 > vh) q1 = vh;
+    if (vw <= 0 || q1 <= q0) return 0;
     const int nt = 256;
-    k_valid_rows<<<dim3((vw + nt - 1) / nt, h), nt, 0, st>>>(tmp, prev0, w, h, ch, psz, vw);
-    k_valid_cols<<<dim3((vw + nt - 1) / nt, vh), nt, 0, st>>>(valid, tmp, vw, vh, psz);
+    k_valid_rows<<<dim3((vw + nt - 1) / nt, q1 - q0 + psz - 1), nt, 0, st>>>(tmp, prev0, w, h, ch, psz, vw, q0);
+    k_valid_cols<<<dim3((vw + nt - 1) / nt, q1 - q0), nt, 0, st>>>(valid, tmp, vw, vh, psz, q0);
     return 2;
 }
 
@@ -178,14 +183,18 @@ __global__ void k_normalize(float *__restrict__ out, const float *__restrict__ a
     }
 }
 
-inline int launch_normalize(const PassParams &P, cudaStream_t st)
+// pixel rows [row0, row1) (the whole frame: 0, h)
+inline int launch_normalize(const PassParams &P, int row0, int row1, cudaStream_t st)
 {
-    const long npix = (long)P.w * P.h;
+    if (row1 <= row0) return 0;
+    const long npix = (long)P.w * (row1 - row0), off = (long)P.w * row0;
     const int nt = 256;
     const int nb = (int)((npix + nt - 1) / nt < 148 * 16 ? (npix + nt - 1) / nt : 148 * 16);
-    if (P.ch == 3) k_normalize<3><<<nb, nt, 0, st>>>(P.out, P.accw, P.in1, npix, P.ch);
-    else if (P.ch == 1) k_normalize<1><<<nb, nt, 0, st>>>(P.out, P.accw, P.in1, npix, P.ch);
-    else k_normalize<0><<<nb, nt, 0, st>>>(P.out, P.accw, P.in1, npix, P.ch);
+    float *out = P.out + off * P.ch;
+    const float *acc = P.accw + off * (P.ch + 1), *in1 = P.in1 + off * P.ch;
+    if (P.ch == 3) k_normalize<3><<<nb, nt, 0, st>>>(out, acc, in1, npix, P.ch);
+    else if (P.ch == 1) k_normalize<1><<<nb, nt, 0, st>>>(out, acc, in1, npix, P.ch);
+    else k_normalize<0><<<nb, nt, 0, st>>>(out, acc, in1, npix, P.ch);
     return 1;
 }
 

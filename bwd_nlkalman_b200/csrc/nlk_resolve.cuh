@@ -302,6 +302,29 @@ __global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw
     if (tid == 0) *P.nactive = s_base[gh];
 }
 
+// strip-sharded pass: restrict group_filter to the processed patches of grid rows [gy0, gy1).
+// `active` is in raster order, so they form one contiguous range: its bounds go into the ticket
+// counter (first entry) and the entry count (one past the last).
+__global__ void k_active_range(const PassParams P)
+{
+    if (threadIdx.x != 0) return;
+    const int n = *P.nactive;
+    const int keys[2] = {P.gy0 * P.gw, P.gy1 * P.gw};
+    int res[2];
+    for (int q = 0; q < 2; ++q) {
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (P.active[mid] < keys[q]) lo = mid + 1; else hi = mid;
+        }
+        res[q] = lo;
+    }
+    *P.work = res[0];
+    *P.nactive = res[1];
+}
+
+__global__ void k_set_flag(int *p, int v) { *p = v; }
+
 inline int launch_resolve(const PassParams &P, cudaStream_t st)
 {
     if (P.gh > 4 * 1024) return -1;                       // MAX_ROWS rows per thread

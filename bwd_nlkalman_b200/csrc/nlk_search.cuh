@@ -181,8 +181,8 @@ k_search(const PassParams P, int warps_per_cta, int wrow, int win_floats, int np
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.x * warps_per_cta + warp;
-    if (g >= P.G) return;
+    const int g = P.gy0 * P.gw + blockIdx.x * warps_per_cta + warp;
+    if (g >= P.gy1 * P.gw) return;
 
     const int psz = PSZ_T ? PSZ_T : P.psz;
     const int ch = CH_T ? CH_T : P.ch;
@@ -264,7 +264,8 @@ k_search_rows(const PassParams P, int np_cta, int runs_per_row, int wrow, int wh
     int *s_prev = reinterpret_cast<int *>(bm + 8 * 2 * P.nbw);                       // [np_cta]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int gy = blockIdx.x / runs_per_row, run = blockIdx.x - gy * runs_per_row;
+    const int gyl = blockIdx.x / runs_per_row, run = blockIdx.x - gyl * runs_per_row;
+    const int gy = P.gy0 + gyl;
     const int gx0 = run * np_cta;
     const int np = min(np_cta, P.gw - gx0);
     const int py = gy * P.step;
@@ -387,7 +388,7 @@ inline int launch_search_rows(const PassParams &P, cudaStream_t st)
     if (smem > 220 * 1024) return -1;
     const int runs = (P.gw + np_cta - 1) / np_cta;
     cudaFuncSetAttribute(k_search_rows<PSZ, CH, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_search_rows<PSZ, CH, RAD><<<runs * P.gh, 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad);
+    k_search_rows<PSZ, CH, RAD><<<runs * (P.gy1 - P.gy0), 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad);
     return 1;
 }
 
@@ -407,7 +408,7 @@ inline int launch_search_generic(const PassParams &P, int r, int only_r, cudaStr
     // several CTAs per SM hide the staging latency: keep each CTA below ~48 KB when possible
     while (warps > 2 && warps * warp_bytes > 56 * 1024) warps >>= 1;
     const int smem = warps * warp_bytes;
-    const int nb = (P.G + warps - 1) / warps;
+    const int nb = ((P.gy1 - P.gy0) * P.gw + warps - 1) / warps;
     const int nt = warps * 32;
 #define NLK_LAUNCH_SEARCH(PS, CHN)                                                                \
     do {                                                                                          \

@@ -85,6 +85,45 @@ int nlk_pass_dev(nlk_ctx *ctx, int smooth, float *d_out, const float *d_in1,
                  const float *d_prev0, const float *d_bsic1, float sigma,
                  struct nlkalman_params prms);
 
+/* ---- row ranges and the strip-sharded pass (one GPU per horizontal strip) -----------
+ * Within a frame the reference's loop over patches (src/nlkalman.c:590-595 `for py .. for
+ * px`) shards as strips of grid-patch rows.  A rank searches and filters the reference
+ * patches of its grid rows [gy0, gy1); what crosses strips is
+ *   - the neighbour bitmaps of every grid row (the processed-mask chain of :597-600 with
+ *     :930-931 is sequential over the whole frame): d_nbr, [gh*gw][nbw] words, rows
+ *     [gy0, gy1) written by nlk_strip_search, the rest to be all-gathered by the caller;
+ *   - the aggregation (:913-928) of groups near a strip border lands in the neighbour's
+ *     pixel rows: d_accw, [h][w][ch+1] floats, rows [ey0, ey1) zeroed by
+ *     nlk_strip_search and accumulated into by nlk_strip_filter; the caller adds rows
+ *     [ey0, oy0) and [oy1, ey1) into the neighbours' buffers before normalising;
+ *   - inputs must be valid on rows [ey0, ey1) (halo = search radius + patch size).
+ * Everything is asynchronous on the context's stream; the caller queues its exchange
+ * (NCCL through torch.distributed in bwd_nlkalman_b200/strips.py) on the same stream. */
+struct nlk_strip_plan {
+    int gw, gh, nbw;   /* grid of reference patches, bitmap words per patch */
+    int gy0, gy1;      /* grid rows of this rank */
+    int oy0, oy1;      /* pixel rows this rank owns: normalised and output here */
+    int ey0, ey1;      /* pixel rows this rank reads and accumulates into (own + halo) */
+};
+/* pure host arithmetic; fails if a strip would be thinner than the halo */
+int nlk_strip_plan(int w, int h, int smooth, struct nlkalman_params prms, int nranks, int rank,
+                   struct nlk_strip_plan *out);
+/* colour transform (inverse = 0: rgb2opp, 1: opp2rgb) and warp restricted to pixel rows
+ * [row0, row1); pointers are to the full frames */
+int nlk_colour_rows_dev(nlk_ctx *ctx, float *d_dst, const float *d_src, int inverse, int row0, int row1);
+int nlk_warp_rows_dev(nlk_ctx *ctx, float *d_imw, const float *d_im, const float *d_of,
+                      const float *d_msk, int row0, int row1);
+/* stage 1: zero accumulator rows, patch validity, block matching + k-NN for [gy0, gy1) */
+int nlk_strip_search(nlk_ctx *ctx, int smooth, const float *d_in1, const float *d_prev0,
+                     const float *d_bsic1, float sigma, struct nlkalman_params prms,
+                     int gy0, int gy1, unsigned int *d_nbr, float *d_accw);
+/* stage 2 (after the bitmaps of all rows are in d_nbr): processed-mask replay over the
+ * whole grid, then the groups of this rank's rows */
+int nlk_strip_filter(nlk_ctx *ctx);
+/* stage 3 (after the border rows of the neighbours were added): pixel rows [row0, row1)
+ * of the output */
+int nlk_strip_normalize(nlk_ctx *ctx, float *d_out, int row0, int row1);
+
 /* ---- resident sequence recursion (what scripts/nlkalman-seq.sh does per frame) ------
  * The context keeps the previous frame's first and second filtering outputs in
  * opponent colour space.  One step = rgb2opp(noisy); if there is a previous frame:

@@ -1,0 +1,129 @@
+"""Host-side logic of the strip-sharded pass, on CPU: the row plan (nlk_strip_plan, pure host
+arithmetic in the C library) and the exchange primitives of bwd_nlkalman_b200/strips.py over
+torch.distributed with the gloo backend, world_size 2 and 3 (the N > 1 path of SURVEY 8(e))."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _plans(nlk, w, h, smooth, prms, n):
+    return [nlk.strip_plan(w, h, smooth, prms, n, r) for r in range(n)]
+
+
+@pytest.mark.parametrize("shape,n", [((3840, 2160), 8), ((3840, 2160), 4), ((1920, 1080), 2), ((160, 121), 3)])
+@pytest.mark.parametrize("mode", ["FLT1", "FLT2", "SMO1"])
+def test_strip_plan_partitions_the_frame(nlk, shape, n, mode):
+    w, h = shape
+    prms = nlk.default_params(10.0, getattr(nlk, mode))
+    smooth = 1 if mode == "SMO1" else 0
+    ps = _plans(nlk, w, h, smooth, prms, n)
+    psz, step = prms.patch_sz, prms.patch_sz // 2
+    r = prms.search_sz_t if smooth else max(prms.search_sz_t, prms.search_sz_x)
+    gh = (h - psz) // step + 1
+    assert ps[0].gy0 == 0 and ps[-1].gy1 == gh and ps[0].oy0 == 0 and ps[-1].oy1 == h
+    for a, b in zip(ps, ps[1:]):
+        assert a.gy1 == b.gy0 and a.oy1 == b.oy0          # no gap, no overlap
+    for k, p in enumerate(ps):
+        assert p.gh == gh and p.gw == (w - psz) // step + 1
+        assert abs((p.gy1 - p.gy0) - gh / n) < 1          # balanced
+        # halo = search radius above, search radius + patch below the last reference patch
+        assert p.ey0 == max(p.gy0 * step - r, 0) and p.ey1 == min((p.gy1 - 1) * step + r + psz, h)
+        # what spills over a border lands inside the immediate neighbour's own rows
+        if k > 0:
+            assert ps[k - 1].oy0 <= p.ey0
+        if k + 1 < n:
+            assert p.ey1 <= ps[k + 1].oy1
+        assert p.ey0 <= p.oy0 and p.oy1 <= p.ey1
+
+
+def test_strip_plan_rejects_thin_strips(nlk):
+    prms = nlk.default_params(20.0, nlk.FLT1)
+    with pytest.raises(nlk.NlkError):
+        nlk.strip_plan(128, 64, 0, prms, 8, 0)     # 15 grid rows over 8 ranks: thinner than the halo
+    one = nlk.strip_plan(128, 64, 0, prms, 1, 0)   # a single strip is always fine
+    assert (one.gy0, one.gy1, one.oy0, one.oy1, one.ey0, one.ey1) == (0, 15, 0, 64, 0, 64)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, w, h, ch, plan_rows, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bwd_nlkalman_b200 import strips
+
+        class P:  # the fields the exchange uses
+            def __init__(self, t):
+                self.gy0, self.gy1, self.oy0, self.oy1, self.ey0, self.ey1 = t
+        plans = [P(t) for t in plan_rows]
+        p = plans[rank]
+        # (1) rows: every rank fills its own rows with a rank-specific pattern
+        full = torch.arange(h * w * ch, dtype=torch.float32).reshape(h, w, ch)
+        t = torch.full((h, w, ch), -1.0)
+        t[p.oy0:p.oy1] = full[p.oy0:p.oy1] * (rank + 1)
+        strips.allgather_rows(t, [(x.oy0, x.oy1) for x in plans])
+        want = torch.empty_like(full)
+        for r, x in enumerate(plans):
+            want[x.oy0:x.oy1] = full[x.oy0:x.oy1] * (r + 1)
+        ok_rows = bool(torch.equal(t, want))
+        # (2) borders: partial accumulators, non-zero on the extended rows only
+        g = torch.Generator().manual_seed(100 + rank)
+        acc = torch.zeros(h, w, ch + 1)
+        acc[p.ey0:p.ey1] = torch.rand((p.ey1 - p.ey0, w, ch + 1), generator=g)
+        mine = acc.clone()
+        strips.add_borders(acc, plans, rank)
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        total = sum(parts)
+        ok_borders = bool(torch.allclose(acc[p.oy0:p.oy1], total[p.oy0:p.oy1], rtol=0, atol=1e-6))
+        q.put((rank, ok_rows, ok_borders))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_over_gloo(nlk, world):
+    w, h, ch = 40, 150, 3
+    prms = nlk.default_params(20.0, nlk.FLT1)
+    plan_rows = [(p.gy0, p.gy1, p.oy0, p.oy1, p.ey0, p.ey1) for p in _plans(nlk, w, h, 0, prms, world)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, w, h, ch, plan_rows, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(r, True, True) for r in range(world)]
+
+
+def test_border_ranges_are_mutually_consistent(nlk):
+    from bwd_nlkalman_b200 import strips
+    prms = nlk.default_params(10.0, nlk.SMO1)
+    plans = _plans(nlk, 3840, 2160, 1, prms, 8)
+    for r in range(8):
+        br = strips.border_ranges(plans, r)
+        if r > 0:
+            assert br["up_send"] == strips.border_ranges(plans, r - 1)["dn_recv"]
+            assert br["up_recv"] == strips.border_ranges(plans, r - 1)["dn_send"]
+        else:
+            assert br["up_send"] is None and br["up_recv"] is None
+    assert strips.border_ranges(plans, 7)["dn_send"] is None
+    step, psz, rr = prms.patch_sz // 2, prms.patch_sz, prms.search_sz_t
+    a, b = strips.border_ranges(plans, 3)["dn_send"]
+    assert b - a == rr + psz - step                      # rows below the last reference patch row
+    a, b = strips.border_ranges(plans, 3)["up_send"]
+    assert b - a == rr
