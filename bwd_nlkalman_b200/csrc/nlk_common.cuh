@@ -57,6 +57,10 @@ struct PassParams {
     int nbw, R;
     float *dbg_dist;        // [G][kstride] distances of the kept candidates, or nullptr
     int *any_nbr;           // set to 1 if some group marks a grid patch other than its own
+    // runs of the spatial-radius launch that hold a patch without a valid previous patch, queued
+    // by the temporal-radius launch: xflag[run] == epoch marks a queued run (no clearing per pass)
+    int *xlist, *xflag, *xcount;
+    int epoch, x_runs, x_np_cta;
     // resolve output
     uint8_t *actflag;       // [G] 1 = processed (written by mask_resolve)
     int *active;            // [G] indices of processed patches, raster order

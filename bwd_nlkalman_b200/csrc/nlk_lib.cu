@@ -109,13 +109,21 @@ struct nlk_ctx {
     cudaStream_t st = nullptr;
     long long launches = 0;
     // per-pass scratch
-    DevBuf accw, valid, valid_tmp, cand, hdr, nbr, active, actflag, counters, gmask, dbg_dist, dbg_vp;
+    DevBuf accw, valid, valid_tmp, cand, hdr, nbr, active, actflag, counters, gmask, dbg_dist, dbg_vp, xlist;
+    int epoch = 0;
     // host-call staging
     DevBuf s_in1, s_prev0, s_bsic, s_out, s_of, s_msk;
     // sequence state (opponent colour space)
     DevBuf q_noisy, q_warp, q_flt1[2], q_flt2[2], q_smo[2], q_tmp;
     int q_cur = 0, q_have_prev = 0, q_have_flt2 = 0;
     int q_smo_cur = 0, q_have_smo = 0;
+    // pipelined host-buffer recursion (nlk_seq_submit_host): copies on their own streams,
+    // two staging sets so that frame n+1 uploads and frame n-1 downloads while frame n computes
+    cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+    DevBuf p_in[2], p_of[2], p_msk[2], p_o1[2], p_o2[2];
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_o1[2] = {nullptr, nullptr}, ev_o2[2] = {nullptr, nullptr},
+                ev_done[2] = {nullptr, nullptr};
+    long long p_frames = 0;
     // strip-sharded pass in flight (nlk_strip_search .. nlk_strip_normalize)
     PassParams strip_P;
     bool strip_open = false;
@@ -227,12 +235,21 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
+    if (c->st_d2h) cudaStreamSynchronize(c->st_d2h);
+    if (c->st_h2d) cudaStreamSynchronize(c->st_h2d);
     DevBuf *all[] = {&c->accw, &c->valid, &c->valid_tmp, &c->cand, &c->hdr, &c->nbr, &c->active,
-                     &c->counters, &c->gmask, &c->actflag, &c->dbg_dist, &c->dbg_vp, &c->s_in1, &c->s_prev0,
+                     &c->counters, &c->gmask, &c->actflag, &c->dbg_dist, &c->dbg_vp, &c->xlist, &c->s_in1, &c->s_prev0,
                      &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk, &c->q_noisy, &c->q_warp,
                      &c->q_flt1[0], &c->q_flt1[1], &c->q_flt2[0], &c->q_flt2[1], &c->q_smo[0],
                      &c->q_smo[1], &c->q_tmp};
     for (DevBuf *b : all) b->release();
+    for (int i = 0; i < 2; ++i) {
+        c->p_in[i].release(); c->p_of[i].release(); c->p_msk[i].release(); c->p_o1[i].release(); c->p_o2[i].release();
+        cudaEvent_t *ev[] = {&c->ev_up[i], &c->ev_o1[i], &c->ev_o2[i], &c->ev_done[i]};
+        for (cudaEvent_t *e : ev) if (*e) cudaEventDestroy(*e);
+    }
+    if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
+    if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->st);
@@ -376,6 +393,17 @@ static int pass_setup(nlk_ctx *c, PassParams &P, int smooth, float *d_out, const
     P.nactive = c->counters.as<int>();
     P.any_nbr = c->counters.as<int>() + 1;
     P.work = c->counters.as<int>() + 2;
+    P.xcount = c->counters.as<int>() + 3;
+    {
+        // worklist of the second search launch: at most one run per 256/(2*r_x+1) patches
+        const size_t cap = G + 16;
+        const bool fresh = c->xlist.cap < 2 * cap * 4;
+        if (int r = c->xlist.ensure(2 * cap * 4)) return r;
+        if (fresh) { CU_TRY(cudaMemsetAsync(c->xlist.p, 0, 2 * cap * 4, c->st)); c->epoch = 0; }
+        P.xlist = c->xlist.as<int>();
+        P.xflag = c->xlist.as<int>() + cap;
+        P.epoch = ++c->epoch;
+    }
     P.out = d_out;
     if (debug) {
         if (int r = c->dbg_dist.ensure(G * kmax * 4)) return r;
@@ -413,7 +441,7 @@ static void strip_rows(const PassParams &P, int *ey0, int *ey1)
 }
 
 // zero the accumulator rows, validity map and block matching for grid rows [P.gy0, P.gy1)
-static int pass_search(nlk_ctx *c, const PassParams &P)
+static int pass_search(nlk_ctx *c, PassParams &P)
 {
     int ey0, ey1;
     strip_rows(P, &ey0, &ey1);
@@ -613,11 +641,13 @@ extern "C" int nlk_seq_reset(nlk_ctx *c)
     return NLK_OK;
 }
 
-extern "C" int nlk_seq_filter_dev(nlk_ctx *c, const float *d_noisy, const float *d_bflo,
-                                  const float *d_bocc, float sigma, struct nlkalman_params f1,
-                                  struct nlkalman_params f2, float *d_flt1_out, float *d_flt2_out)
+// one frame of the forward recursion.  hook(which) is called right after output `which`
+// (1: first filtering, 2: second) has been queued on the context's stream.
+template <class Hook>
+static int seq_filter_core(nlk_ctx *c, const float *d_noisy, const float *d_bflo, const float *d_bocc,
+                           float sigma, const nlkalman_params &f1, const nlkalman_params &f2,
+                           float *d_flt1_out, float *d_flt2_out, Hook hook)
 {
-    if (int r = ctx_use(c)) return r;
     const size_t ib = c->img_bytes();
     if (int r = c->q_noisy.ensure(ib)) return r;
     if (int r = c->q_warp.ensure(ib)) return r;
@@ -641,7 +671,10 @@ extern "C" int nlk_seq_filter_dev(nlk_ctx *c, const float *d_noisy, const float 
         }
     }
     if (int r = run_pass(c, 0, flt1, noisy, prev1, nullptr, sigma, f1, false)) return r;
-    if (d_flt1_out) if (int r = nlk_opp2rgb_dev(c, d_flt1_out, flt1)) return r;
+    if (d_flt1_out) {
+        if (int r = nlk_opp2rgb_dev(c, d_flt1_out, flt1)) return r;
+        if (int r = hook(1)) return r;
+    }
 
     // second filtering (reference src/main-flt.c:361-374)
     const int do2 = f2.patch_sz != 0;
@@ -655,12 +688,24 @@ extern "C" int nlk_seq_filter_dev(nlk_ctx *c, const float *d_noisy, const float 
             }
         }
         if (int r = run_pass(c, 0, flt2, noisy, prev2, flt1, sigma, f2, false)) return r;
-        if (d_flt2_out) if (int r = nlk_opp2rgb_dev(c, d_flt2_out, flt2)) return r;
+        if (d_flt2_out) {
+            if (int r = nlk_opp2rgb_dev(c, d_flt2_out, flt2)) return r;
+            if (int r = hook(2)) return r;
+        }
     }
     c->q_have_prev = 1;
     c->q_have_flt2 = do2;
     c->q_cur = prv;
     return NLK_OK;
+}
+
+extern "C" int nlk_seq_filter_dev(nlk_ctx *c, const float *d_noisy, const float *d_bflo,
+                                  const float *d_bocc, float sigma, struct nlkalman_params f1,
+                                  struct nlkalman_params f2, float *d_flt1_out, float *d_flt2_out)
+{
+    if (int r = ctx_use(c)) return r;
+    return seq_filter_core(c, d_noisy, d_bflo, d_bocc, sigma, f1, f2, d_flt1_out, d_flt2_out,
+                           [](int) { return NLK_OK; });
 }
 
 static int stage_in(nlk_ctx *c, DevBuf &b, const float *h, size_t bytes, const float **d)
@@ -673,25 +718,82 @@ static int stage_in(nlk_ctx *c, DevBuf &b, const float *h, size_t bytes, const f
     return NLK_OK;
 }
 
-extern "C" int nlk_seq_filter_host(nlk_ctx *c, const float *h_noisy, const float *h_bflo,
+static int pipe_init(nlk_ctx *c)
+{
+    if (c->st_h2d) return NLK_OK;
+    CU_TRY(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_o1[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_o2[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+    return NLK_OK;
+}
+
+extern "C" int nlk_seq_submit_host(nlk_ctx *c, const float *h_noisy, const float *h_bflo,
                                    const float *h_bocc, float sigma, struct nlkalman_params f1,
                                    struct nlkalman_params f2, float *h_flt1_out, float *h_flt2_out)
 {
     if (int r = ctx_use(c)) return r;
+    if (!h_noisy) return set_err(NLK_ERR_PARAM, "no noisy frame");
+    if (int r = pipe_init(c)) return r;
     const size_t ib = c->img_bytes(), npix = (size_t)c->w * c->h;
-    const float *d_noisy, *d_of, *d_msk;
-    if (int r = stage_in(c, c->s_in1, h_noisy, ib, &d_noisy)) return r;
-    if (int r = stage_in(c, c->s_of, h_bflo, npix * 2 * 4, &d_of)) return r;
-    if (int r = stage_in(c, c->s_msk, h_bocc, npix * 4, &d_msk)) return r;
-    if (!d_noisy) return set_err(NLK_ERR_PARAM, "no noisy frame");
+    const int s = (int)(c->p_frames & 1);
+    // at most two frames in flight: staging set s was last used by frame n-2
+    if (c->p_frames >= 2) CU_TRY(cudaEventSynchronize(c->ev_done[s]));
+    if (int r = c->p_in[s].ensure(ib)) return r;
+    CU_TRY(cudaMemcpyAsync(c->p_in[s].p, h_noisy, ib, cudaMemcpyHostToDevice, c->st_h2d));
+    const float *d_of = nullptr, *d_msk = nullptr;
+    if (h_bflo) {
+        if (int r = c->p_of[s].ensure(npix * 2 * 4)) return r;
+        CU_TRY(cudaMemcpyAsync(c->p_of[s].p, h_bflo, npix * 2 * 4, cudaMemcpyHostToDevice, c->st_h2d));
+        d_of = c->p_of[s].as<float>();
+    }
+    if (h_bocc) {
+        if (int r = c->p_msk[s].ensure(npix * 4)) return r;
+        CU_TRY(cudaMemcpyAsync(c->p_msk[s].p, h_bocc, npix * 4, cudaMemcpyHostToDevice, c->st_h2d));
+        d_msk = c->p_msk[s].as<float>();
+    }
+    CU_TRY(cudaEventRecord(c->ev_up[s], c->st_h2d));
+    CU_TRY(cudaStreamWaitEvent(c->st, c->ev_up[s], 0));
     float *d_o1 = nullptr, *d_o2 = nullptr;
-    if (h_flt1_out) { if (int r = c->s_out.ensure(ib)) return r; d_o1 = c->s_out.as<float>(); }
-    if (h_flt2_out) { if (int r = c->s_bsic.ensure(ib)) return r; d_o2 = c->s_bsic.as<float>(); }
-    if (int r = nlk_seq_filter_dev(c, d_noisy, d_of, d_msk, sigma, f1, f2, d_o1, d_o2)) return r;
-    if (d_o1) CU_TRY(cudaMemcpyAsync(h_flt1_out, d_o1, ib, cudaMemcpyDeviceToHost, c->st));
-    if (d_o2 && f2.patch_sz != 0) CU_TRY(cudaMemcpyAsync(h_flt2_out, d_o2, ib, cudaMemcpyDeviceToHost, c->st));
-    CU_TRY(cudaStreamSynchronize(c->st));
+    if (h_flt1_out) { if (int r = c->p_o1[s].ensure(ib)) return r; d_o1 = c->p_o1[s].as<float>(); }
+    if (h_flt2_out && f2.patch_sz != 0) { if (int r = c->p_o2[s].ensure(ib)) return r; d_o2 = c->p_o2[s].as<float>(); }
+    // each output goes back on the download stream as soon as it exists: the first
+    // filtering's copy overlaps the second filtering
+    auto hook = [&](int which) -> int {
+        cudaEvent_t ev = which == 1 ? c->ev_o1[s] : c->ev_o2[s];
+        CU_TRY(cudaEventRecord(ev, c->st));
+        CU_TRY(cudaStreamWaitEvent(c->st_d2h, ev, 0));
+        CU_TRY(cudaMemcpyAsync(which == 1 ? h_flt1_out : h_flt2_out, which == 1 ? d_o1 : d_o2, ib,
+                               cudaMemcpyDeviceToHost, c->st_d2h));
+        return NLK_OK;
+    };
+    if (int r = seq_filter_core(c, c->p_in[s].as<float>(), d_of, d_msk, sigma, f1, f2, d_o1, d_o2, hook)) return r;
+    // frame complete = its compute (the staging inputs are free again) and its downloads
+    CU_TRY(cudaEventRecord(c->ev_o2[s], c->st));
+    CU_TRY(cudaStreamWaitEvent(c->st_d2h, c->ev_o2[s], 0));
+    CU_TRY(cudaEventRecord(c->ev_done[s], c->st_d2h));
+    c->p_frames += 1;
     return NLK_OK;
+}
+
+extern "C" int nlk_seq_drain(nlk_ctx *c)
+{
+    if (int r = ctx_use(c)) return r;
+    CU_TRY(cudaStreamSynchronize(c->st));
+    if (c->st_d2h) CU_TRY(cudaStreamSynchronize(c->st_d2h));
+    return NLK_OK;
+}
+
+extern "C" int nlk_seq_filter_host(nlk_ctx *c, const float *h_noisy, const float *h_bflo,
+                                   const float *h_bocc, float sigma, struct nlkalman_params f1,
+                                   struct nlkalman_params f2, float *h_flt1_out, float *h_flt2_out)
+{
+    if (int r = nlk_seq_submit_host(c, h_noisy, h_bflo, h_bocc, sigma, f1, f2, h_flt1_out, h_flt2_out)) return r;
+    return nlk_seq_drain(c);
 }
 
 extern "C" int nlk_seq_smooth_start_dev(nlk_ctx *c, const float *d_last_rgb)

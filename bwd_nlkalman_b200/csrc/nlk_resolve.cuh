@@ -210,6 +210,9 @@ __global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw
     for (int x = tid; x < 2 * gh; x += nthr) s_pub[x] = 0u;
     __syncthreads();
 
+    for (int x = tid; x < gh * rw; x += nthr) s_act[x] = 0u;
+    __syncthreads();
+
     const int i = tid;
     const bool live = i < gh;
     const unsigned int *row = P.nbr + (long)i * gw;
@@ -221,45 +224,61 @@ __global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw
             const int j = C * (u - i) - R * i + c;
             q[u][c] = (live && j >= 0 && j < gw) ? row[j] : 0u;
         }
-    unsigned int wnd = 0u, accw = 0u;
+    unsigned int wnd = 0u;
+    constexpr unsigned int cmask = (1u << C) - 1u;
     for (int s0 = 0; s0 < nsteps; s0 += 2) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int s = s0 + u;
             const unsigned int *pub_rd = s_pub + (size_t)((s + 1) & 1) * gh; // written at step s-1
             unsigned int *pub_wr = s_pub + (size_t)(s & 1) * gh;
-            if (live) {
-                const int j0 = C * (s - i) - R * i;
+            const int j0 = C * (s - i) - R * i;
+            // in the band: the block overlaps the row, or marks for its first columns arrive
+            if (live && j0 > -32 && j0 < gw) {
 #pragma unroll
                 for (int dy = 1; dy <= R; ++dy)
                     if (i >= dy) wnd |= ((pub_rd[i - dy] >> (16 * (dy - 1))) & fwmask) << ((C + R) * (dy - 1));
-                unsigned int pub[R];
+                // the only serial part: a column is active iff its window bit is clear, and then
+                // marks the next R columns of its own row (out-of-range columns hold q = 0)
 #pragma unroll
-                for (int dy = 0; dy < R; ++dy) pub[dy] = 0u;
-                if (j0 + C > 0 && j0 < gw) {
+                for (int c = 0; c < C; ++c) {
+                    const unsigned int own = ((q[u][c] >> (R * side + R + 1)) & ownmask) << (c + 1);
+                    wnd |= ((wnd >> c) & 1u) ? 0u : own;
+                }
+                // bits of the window below C are final: column j0+c was active iff bit c is clear
+                unsigned int vm = cmask;
+                if (j0 < 0) vm &= cmask << min(-j0, C);
+                if (j0 + C > gw) vm &= cmask >> (j0 + C - gw);
+                const unsigned int act = ~wnd & vm;
+                unsigned int pw = 0u;
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const int j = j0 + c;
-                        if (j >= 0 && j < gw) {
-                            const bool act = ((wnd >> c) & 1u) == 0u;
-                            const unsigned int w0 = act ? q[u][c] : 0u;
-                            // own row, columns j+1 .. j+R
-                            wnd |= ((w0 >> (R * side + R + 1)) & ownmask) << (c + 1);
+                for (int dy = 1; dy <= R; ++dy) {
+                    unsigned int f = 0u;
 #pragma unroll
-                            for (int dy = 1; dy <= R; ++dy) pub[dy - 1] |= ((w0 >> ((dy + R) * side)) & fmask) << c;
-                            accw |= (act ? 1u : 0u) << (j & 31);
-                            if ((j & 31) == 31 || j == gw - 1) {
-                                s_act[(size_t)i * rw + (j >> 5)] = accw;
-                                accw = 0u;
-                            }
-                        }
-                    }
+                    for (int c = 0; c < C; ++c)
+                        f |= ((act >> c) & 1u) ? (((q[u][c] >> ((dy + R) * side)) & fmask) << c) : 0u;
+                    pw |= f << (16 * (dy - 1));
+                }
+                pub_wr[i] = pw;
+                if (act) {
+                    // record: row i is the only writer of its words
+                    const int jb = max(j0, 0);
+                    const unsigned int bits = j0 < 0 ? act >> (-j0) : act;
+                    unsigned int *wp = s_act + (size_t)i * rw + (jb >> 5);
+                    atomicOr(wp, bits << (jb & 31));
+                    if ((jb & 31) + C > 32 && (jb >> 5) + 1 < rw) atomicOr(wp + 1, bits >> (32 - (jb & 31)));
                 }
                 wnd >>= C;
-                unsigned int pw = pub[0];
-                if (R > 1) pw |= pub[R - 1] << 16;
-                pub_wr[i] = pw;
                 // block of step s+2
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int j = j0 + 2 * C + c;
+                    q[u][c] = (j >= 0 && j < gw) ? row[j] : 0u;
+                }
+            } else if (live && j0 >= gw && j0 < gw + 2 * C) {
+                pub_wr[i] = 0u;   // a finished row leaves no stale marks (both parities)
+            } else if (live && j0 <= -32 && j0 + 2 * C > -32) {
+                // about to enter the band: first two blocks
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const int j = j0 + 2 * C + c;

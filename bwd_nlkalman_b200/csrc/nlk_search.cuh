@@ -253,8 +253,8 @@ k_search(const PassParams P, int warps_per_cta, int wrow, int win_floats, int np
 // once and used by up to PSZ candidates, and each distance still receives its terms in
 // the reference's (hy, hx, c) order with separately rounded multiply and add.
 template <int PSZ, int CH, int RAD>
-__global__ void __launch_bounds__(256)
-k_search_rows(const PassParams P, int np_cta, int runs_per_row, int wrow, int wh_max, int npad)
+__device__ __forceinline__ void search_rows_block(const PassParams &P, int gy, int run, int np_cta, int wrow,
+                                                  int wh_max, int npad, bool feed_worklist)
 {
     constexpr int NX = 2 * RAD + 1, NR = 2 * RAD + 1, RL = PSZ * CH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -264,8 +264,6 @@ k_search_rows(const PassParams P, int np_cta, int runs_per_row, int wrow, int wh
     int *s_prev = reinterpret_cast<int *>(bm + 8 * 2 * P.nbw);                       // [np_cta]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int gyl = blockIdx.x / runs_per_row, run = blockIdx.x - gyl * runs_per_row;
-    const int gy = P.gy0 + gyl;
     const int gx0 = run * np_cta;
     const int np = min(np_cta, P.gw - gx0);
     const int py = gy * P.step;
@@ -276,6 +274,11 @@ k_search_rows(const PassParams P, int np_cta, int runs_per_row, int wrow, int wh
         const int prev_p = (P.valid != nullptr) ? (int)P.valid[(long)py * P.vw + px] : 0;
         const int r = P.smooth ? P.r_t : (prev_p ? P.r_t : P.r_x);
         s_prev[s] = (r == RAD) ? prev_p : -1;
+        if (r != RAD && feed_worklist) {
+            // a patch of the other radius: queue its run of the other launch (once per pass)
+            const int run2 = gy * P.x_runs + (gx0 + s) / P.x_np_cta;
+            if (atomicExch(&P.xflag[run2], P.epoch) != P.epoch) P.xlist[atomicAdd(P.xcount, 1)] = run2;
+        }
     }
     __syncthreads();
     int any = 0;
@@ -374,22 +377,68 @@ k_search_rows(const PassParams P, int np_cta, int runs_per_row, int wrow, int wh
     }
 }
 
+// whole grid rows [gy0, gy1): block = (grid row, run)
 template <int PSZ, int CH, int RAD>
-inline int launch_search_rows(const PassParams &P, cudaStream_t st)
+__global__ void __launch_bounds__(256)
+k_search_rows(const PassParams P, int np_cta, int runs_per_row, int wrow, int wh_max, int npad, int feed)
+{
+    const int gyl = blockIdx.x / runs_per_row, run = blockIdx.x - gyl * runs_per_row;
+    search_rows_block<PSZ, CH, RAD>(P, P.gy0 + gyl, run, np_cta, wrow, wh_max, npad, feed != 0);
+}
+
+// only the runs queued by the launch of the other radius (few: occluded or border patches)
+template <int PSZ, int CH, int RAD>
+__global__ void __launch_bounds__(256)
+k_search_rows_list(const PassParams P, int np_cta, int runs_per_row, int wrow, int wh_max, int npad)
+{
+    const int n = *P.xcount;
+    for (int wi = blockIdx.x; wi < n; wi += gridDim.x) {
+        const int run2 = P.xlist[wi];
+        const int gy = run2 / runs_per_row;
+        search_rows_block<PSZ, CH, RAD>(P, gy, run2 - gy * runs_per_row, np_cta, wrow, wh_max, npad, false);
+        __syncthreads();   // shared memory is reused by the next run
+    }
+}
+
+template <int RAD>
+inline void search_rows_geom(const PassParams &P, int PSZ, int CH, int *np_cta, int *npad, int *wrow, int *wh_max,
+                             size_t *smem)
 {
     constexpr int NR = 2 * RAD + 1;
-    const int np_cta = 256 / NR;
-    int npad = 32;
-    while (npad < NR * NR) npad <<= 1;
-    int wrow = ((np_cta - 1) * P.step + 2 * RAD + PSZ) * CH;
-    wrow |= 1; // odd stride: the candidate rows of a patch fall in different banks
-    const int wh_max = 2 * RAD + PSZ;
-    const size_t smem = (size_t)np_cta * npad * 8 + (size_t)wh_max * wrow * 4 + 8 * 2 * P.nbw * 4 + np_cta * 4;
+    *np_cta = 256 / NR;
+    *npad = 32;
+    while (*npad < NR * NR) *npad <<= 1;
+    *wrow = (((*np_cta - 1) * P.step + 2 * RAD + PSZ) * CH) | 1; // odd stride: candidate rows fall in different banks
+    *wh_max = 2 * RAD + PSZ;
+    *smem = (size_t)*np_cta * *npad * 8 + (size_t)*wh_max * *wrow * 4 + 8 * 2 * P.nbw * 4 + *np_cta * 4;
+}
+
+// mode 0: all runs of the strip; 1: all runs, queueing the runs of the other radius; 2: queued runs only
+template <int PSZ, int CH, int RAD>
+inline int launch_search_rows(const PassParams &P, int mode, cudaStream_t st)
+{
+    int np_cta, npad, wrow, wh_max;
+    size_t smem;
+    search_rows_geom<RAD>(P, PSZ, CH, &np_cta, &npad, &wrow, &wh_max, &smem);
     if (smem > 220 * 1024) return -1;
     const int runs = (P.gw + np_cta - 1) / np_cta;
-    cudaFuncSetAttribute(k_search_rows<PSZ, CH, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_search_rows<PSZ, CH, RAD><<<runs * (P.gy1 - P.gy0), 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad);
+    if (mode == 2) {
+        cudaFuncSetAttribute(k_search_rows_list<PSZ, CH, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_search_rows_list<PSZ, CH, RAD><<<2 * 148, 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad);
+    } else {
+        cudaFuncSetAttribute(k_search_rows<PSZ, CH, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_search_rows<PSZ, CH, RAD><<<runs * (P.gy1 - P.gy0), 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad, mode);
+    }
     return 1;
+}
+
+// runs per grid row and patches per run of the fast kernel for radius r, 0 if it has none
+inline int search_rows_runs(const PassParams &P, int r, int *np_cta)
+{
+#define NLK_ROWS_G(PS, CHN, RD) if (P.psz == PS && P.ch == CHN && r == RD) { int a, b, c; size_t d; search_rows_geom<RD>(P, PS, CHN, np_cta, &a, &b, &c, &d); return d > 220 * 1024 ? 0 : (P.gw + *np_cta - 1) / *np_cta; }
+    NLK_ROWS_G(8, 3, 5) NLK_ROWS_G(8, 3, 10) NLK_ROWS_G(8, 1, 5) NLK_ROWS_G(8, 1, 10) NLK_ROWS_G(12, 3, 10) NLK_ROWS_G(12, 3, 15)
+#undef NLK_ROWS_G
+    return 0;
 }
 
 // the generic kernel, restricted to the patches whose search radius is r (-1: all)
@@ -424,9 +473,9 @@ inline int launch_search_generic(const PassParams &P, int r, int only_r, cudaStr
     return 1;
 }
 
-inline int launch_search_radius(const PassParams &P, int r, cudaStream_t st)
+inline int launch_search_radius(const PassParams &P, int r, int mode, cudaStream_t st)
 {
-#define NLK_ROWS(PS, CHN, RD) if (P.psz == PS && P.ch == CHN && r == RD) return launch_search_rows<PS, CHN, RD>(P, st)
+#define NLK_ROWS(PS, CHN, RD) if (P.psz == PS && P.ch == CHN && r == RD) return launch_search_rows<PS, CHN, RD>(P, mode, st)
     NLK_ROWS(8, 3, 5);
     NLK_ROWS(8, 3, 10);
     NLK_ROWS(8, 1, 5);
@@ -437,19 +486,23 @@ inline int launch_search_radius(const PassParams &P, int r, cudaStream_t st)
     return launch_search_generic(P, r, r, st);
 }
 
-inline int launch_search(const PassParams &P, cudaStream_t st)
+inline int launch_search(PassParams &P, cudaStream_t st)
 {
-    // a patch searches with radius r_t or r_x (reference :637, :1527): one launch per
-    // distinct radius, each skipping the patches of the other
-    int n = launch_search_radius(P, P.r_t, st);
+    // a patch searches with radius r_t (it has a valid previous patch, or the pass is the
+    // smoother) or r_x (reference :637, :1527)
+    if (P.smooth || P.r_x == P.r_t) return launch_search_radius(P, P.r_t, 0, st);
+    if (!P.has_prev) return launch_search_radius(P, P.r_x, 0, st);   // no previous frame: all spatial
+    // temporal pass: the r_t launch covers the frame and queues the runs that hold patches
+    // without a valid previous patch (occlusions, warp borders) for a small r_x launch
+    int np2 = 0;
+    const int runs2 = search_rows_runs(P, P.r_x, &np2);
+    int np1 = 0;
+    const bool listed = runs2 > 0 && search_rows_runs(P, P.r_t, &np1) > 0 && P.xlist != nullptr;
+    if (listed) { P.x_runs = runs2; P.x_np_cta = np2; }
+    int n = launch_search_radius(P, P.r_t, listed ? 1 : 0, st);
     if (n < 0) return n;
-    // the spatial radius is only used by the filter, for patches without a valid previous patch
-    if (!P.smooth && P.r_x != P.r_t) {
-        const int m = launch_search_radius(P, P.r_x, st);
-        if (m < 0) return m;
-        n += m;
-    }
-    return n;
+    const int m = launch_search_radius(P, P.r_x, listed ? 2 : 0, st);
+    return m < 0 ? m : n + m;
 }
 
 } // namespace nlk

@@ -140,6 +140,17 @@ int nlk_seq_filter_host(nlk_ctx *ctx, const float *h_noisy, const float *h_bflo,
                         const float *h_bocc, float sigma, struct nlkalman_params f1,
                         struct nlkalman_params f2, float *h_flt1_out, float *h_flt2_out);
 
+/* pipelined form of nlk_seq_filter_host for streaming a sequence: queues the frame and
+ * returns.  Uploads, kernels and downloads run on three streams with two staging sets, so
+ * frame n+1 uploads and frame n-1 downloads while frame n computes (at most two frames in
+ * flight: the call blocks until frame n-2 is complete).  The host buffers of a frame
+ * (pinned memory, or the copies serialise) must stay untouched until nlk_seq_drain
+ * returns or two later submits have returned.  nlk_seq_filter_host = submit + drain. */
+int nlk_seq_submit_host(nlk_ctx *ctx, const float *h_noisy, const float *h_bflo,
+                        const float *h_bocc, float sigma, struct nlkalman_params f1,
+                        struct nlkalman_params f2, float *h_flt1_out, float *h_flt2_out);
+int nlk_seq_drain(nlk_ctx *ctx);
+
 /* backward smoothing recursion (scripts/nlkalman-seq.sh:122-149): start from the last
  * filtered frame, then for each earlier frame t: warp(smoothed t+1 by the forward
  * flow), smooth (reference src/main-smo.c:198-213). */

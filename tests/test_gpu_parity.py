@@ -225,3 +225,32 @@ def test_config1_against_reference_library(nlk, ref):
     assert maxabs(g22, r22) <= TOL_MAXABS
     assert abs(psnr_between(g22, clean1) - psnr_between(r22, clean1)) <= TOL_DPSNR
     assert psnr_between(g22, clean1) > psnr_between(n1, clean1) + 8  # it does denoise
+
+
+# ---- streaming (pipelined) host recursion ------------------------------------------------------
+
+def test_pipelined_host_recursion_matches_synchronous(nlk):
+    """nlk_seq_submit_host / nlk_seq_drain (uploads, kernels, downloads on three streams, two
+    frames in flight) give the frames nlk_seq_filter_host gives, in order"""
+    import torch
+    from bwd_nlkalman_b200 import synth
+    w, h, ch, sigma, nf = 131, 94, 3, 20.0, 6
+    f1, f2 = nlk.default_params(sigma, nlk.FLT1), nlk.default_params(sigma, nlk.FLT2)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    frames = [pin(synth.noisy_frame(w, h, ch, t, sigma)) for t in range(nf)]
+    bflo, occ = pin(synth.backward_flow(w, h)), pin(synth.occlusion_mask(w, h))
+    sync1 = [torch.empty((h, w, ch)).pin_memory() for _ in range(nf)]
+    sync2 = [torch.empty((h, w, ch)).pin_memory() for _ in range(nf)]
+    pipe1 = [torch.empty((h, w, ch)).pin_memory() for _ in range(nf)]
+    pipe2 = [torch.empty((h, w, ch)).pin_memory() for _ in range(nf)]
+    with nlk.Context(w, h, ch) as ctx:
+        for t in range(nf):
+            ctx.seq_filter_host(frames[t], bflo if t else None, occ if t else None, sigma, f1, f2, sync1[t], sync2[t])
+        ctx.seq_reset()
+        for t in range(nf):
+            ctx.seq_submit_host(frames[t], bflo if t else None, occ if t else None, sigma, f1, f2, pipe1[t], pipe2[t])
+        ctx.seq_drain()
+    for t in range(nf):
+        assert maxabs(pipe1[t].numpy(), sync1[t].numpy()) <= TOL_MAXABS, t
+        assert maxabs(pipe2[t].numpy(), sync2[t].numpy()) <= TOL_MAXABS, t
+    assert float(np.abs(sync2[-1].numpy() - frames[-1].numpy()).mean()) > 1.0   # it did filter
