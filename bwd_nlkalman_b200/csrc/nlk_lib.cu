@@ -109,7 +109,7 @@ struct nlk_ctx {
     cudaStream_t st = nullptr;
     long long launches = 0;
     // per-pass scratch
-    DevBuf accw, valid, valid_tmp, cand, hdr, nbr, active, actflag, counters, gmask, dbg_dist, dbg_vp, xlist;
+    DevBuf accw, valid, valid_tmp, cand, hdr, nbr, active, actflag, counters, gmask, dbg_dist, dbg_vp, xlist, rpack;
     int epoch = 0;
     // host-call staging
     DevBuf s_in1, s_prev0, s_bsic, s_out, s_of, s_msk;
@@ -238,7 +238,7 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     if (c->st_d2h) cudaStreamSynchronize(c->st_d2h);
     if (c->st_h2d) cudaStreamSynchronize(c->st_h2d);
     DevBuf *all[] = {&c->accw, &c->valid, &c->valid_tmp, &c->cand, &c->hdr, &c->nbr, &c->active,
-                     &c->counters, &c->gmask, &c->actflag, &c->dbg_dist, &c->dbg_vp, &c->xlist, &c->s_in1, &c->s_prev0,
+                     &c->counters, &c->gmask, &c->actflag, &c->dbg_dist, &c->dbg_vp, &c->xlist, &c->rpack, &c->s_in1, &c->s_prev0,
                      &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk, &c->q_noisy, &c->q_warp,
                      &c->q_flt1[0], &c->q_flt1[1], &c->q_flt2[0], &c->q_flt2[1], &c->q_smo[0],
                      &c->q_smo[1], &c->q_tmp};
@@ -473,7 +473,8 @@ static int pass_filter(nlk_ctx *c, const PassParams &P, bool strip)
             k_set_flag<<<1, 1, 0, c->st>>>(P.any_nbr, (P.tagg > 1 && P.R >= 1) ? 1 : 0);
             c->launches += 1;
         }
-        if (int r = check_launch(c, launch_resolve(P, c->st), "mask_resolve")) return r;
+        if (int r = c->rpack.ensure((size_t)(P.gh > 0 ? P.gh : 1) * resolve_blocks_per_row(P.gw) * 16)) return r;
+        if (int r = check_launch(c, launch_resolve(P, c->rpack.as<unsigned int>(), c->st), "mask_resolve")) return r;
         if (strip) {
             k_active_range<<<1, 32, 0, c->st>>>(P);
             if (int r = check_launch(c, 1, "active_range")) return r;

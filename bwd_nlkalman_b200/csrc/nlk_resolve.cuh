@@ -178,17 +178,49 @@ __global__ void __launch_bounds__(1024) k_resolve(const PassParams P, int rw)
 
 // ---- blocked wavefront (one bitmap word per cell, R <= 2: every BASELINE configuration) -------
 // The step count of the kernel above, gw + (R+1)(gh-1), is a chain of block barriers.  Here a
-// step handles a BLOCK of C consecutive columns per row, sequentially in registers, and row i
-// runs R columns plus one block behind row i-1:
+// step handles a BLOCK of C = 4 consecutive columns per row, sequentially in registers, and
+// row i runs R columns plus one block behind row i-1:
 //     row i, step s  ->  columns [j0, j0 + C),   j0 = C (s - i) - R i
 // so that row i-1 has always finished column j + R before row i reaches column j.  Steps drop
 // to gh - 1 + ceil((gw + R (gh-1)) / C).  After its block a row publishes, for each dy, the
-// (C + 2R)-bit field of columns j0-R .. j0+C-1+R that its active cells mark in row i+dy (both
-// fields in one shared-memory word, double-buffered by step parity).  The reader ORs the field
-// of row i-dy into its window at offset (C+R)(dy-1): always at or ahead of its own position.
-template <int R, int C>
-__global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw)
+// (C + 2R)-bit field of columns j0-R .. j0+C-1+R that its active cells mark in row i+dy (one
+// shared-memory word, double-buffered by step parity).  The reader ORs the field of row i-dy
+// into its window at offset (C+R)(dy-1): always at or ahead of its own position.
+//
+// A step is one warp-serial chain, so its instruction count is what matters: k_resolve_pack
+// (whole GPU, a few microseconds) first rewrites the bitmaps into the per-row block layout
+// the chain consumes -- one aligned 16-byte load per step, fields pre-extracted:
+//     bits 0..R-1: own row, columns j+1..j+R;  bits 8..: row i+1;  bits 16..: row i+2
+constexpr int RB_C = 4;
+
+__host__ __device__ inline int resolve_blocks_per_row(int gw) { return (gw + RB_C - 1) / RB_C + 1; }
+
+template <int R>
+__global__ void k_resolve_pack(const PassParams P, unsigned int *__restrict__ pk, int nb)
 {
+    constexpr int C = RB_C, side = 2 * R + 1;
+    const long n = (long)P.gh * nb * C;
+    if (*P.any_nbr == 0) return;   // every patch is processed: nothing to replay
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(t % C);
+        const long ib = t / C;
+        const int b = (int)(ib % nb), i = (int)(ib / nb);
+        const int j = C * b + c - (R * i) % C;
+        unsigned int v = 0u;
+        if (j >= 0 && j < P.gw) {
+            const unsigned int w0 = P.nbr[(long)i * P.gw + j];
+            v = (w0 >> (R * side + R + 1)) & ((1u << R) - 1u);
+#pragma unroll
+            for (int dy = 1; dy <= R; ++dy) v |= ((w0 >> ((dy + R) * side)) & ((1u << side) - 1u)) << (8 * dy);
+        }
+        pk[t] = v;
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw, const uint4 *__restrict__ pk, int nb)
+{
+    constexpr int C = RB_C;
     extern __shared__ unsigned int s_dyn[];
     const int gw = P.gw, gh = P.gh, G = P.G;
     unsigned int *s_pub = s_dyn;                              // [2][gh]
@@ -203,48 +235,40 @@ __global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw
         if (tid == 0) *P.nactive = G;
         return;
     }
-    constexpr int side = 2 * R + 1, FW = C + 2 * R;
-    static_assert(FW <= 16 && (C + R) * (R - 1) + FW <= 32, "window layout");
-    constexpr unsigned int fmask = (1u << side) - 1u, ownmask = (1u << R) - 1u, fwmask = (1u << FW) - 1u;
+    constexpr int FW = C + 2 * R;
+    static_assert(FW <= 8 && (C + R) * (R - 1) + FW <= 32 && R + C <= 8, "window / field layout");
+    constexpr unsigned int ownmask = (1u << R) - 1u, fwmask = (1u << FW) - 1u, cmask = (1u << C) - 1u;
     const int nsteps = gh - 1 + (gw + R * (gh - 1) + C - 1) / C;
     for (int x = tid; x < 2 * gh; x += nthr) s_pub[x] = 0u;
-    __syncthreads();
-
     for (int x = tid; x < gh * rw; x += nthr) s_act[x] = 0u;
     __syncthreads();
 
     const int i = tid;
     const bool live = i < gh;
-    const unsigned int *row = P.nbr + (long)i * gw;
-    unsigned int q[2][C];   // bitmap words of the blocks of steps s and s+1 (fetched two steps ahead)
+    const int o = (R * i) % C, sb = i + (R * i) / C;    // block b of the row is handled at step sb + b
+    const uint4 *prow = pk + (size_t)(live ? i : 0) * nb;
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    uint4 q[2];             // blocks of steps s and s+1 (fetched two steps ahead)
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            const int j = C * (u - i) - R * i + c;
-            q[u][c] = (live && j >= 0 && j < gw) ? row[j] : 0u;
-        }
+    for (int u = 0; u < 2; ++u) q[u] = (live && u - sb >= 0 && u - sb < nb) ? prow[u - sb] : zero4;
     unsigned int wnd = 0u;
-    constexpr unsigned int cmask = (1u << C) - 1u;
     for (int s0 = 0; s0 < nsteps; s0 += 2) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int s = s0 + u;
             const unsigned int *pub_rd = s_pub + (size_t)((s + 1) & 1) * gh; // written at step s-1
             unsigned int *pub_wr = s_pub + (size_t)(s & 1) * gh;
-            const int j0 = C * (s - i) - R * i;
+            const int b = s - sb, j0 = C * b - o;
             // in the band: the block overlaps the row, or marks for its first columns arrive
             if (live && j0 > -32 && j0 < gw) {
 #pragma unroll
                 for (int dy = 1; dy <= R; ++dy)
-                    if (i >= dy) wnd |= ((pub_rd[i - dy] >> (16 * (dy - 1))) & fwmask) << ((C + R) * (dy - 1));
+                    if (i >= dy) wnd |= ((pub_rd[i - dy] >> (8 * dy)) & fwmask) << ((C + R) * (dy - 1));
+                const unsigned int x[C] = {q[u].x, q[u].y, q[u].z, q[u].w};
                 // the only serial part: a column is active iff its window bit is clear, and then
-                // marks the next R columns of its own row (out-of-range columns hold q = 0)
+                // marks the next R columns of its own row (cells outside the row are packed as 0)
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const unsigned int own = ((q[u][c] >> (R * side + R + 1)) & ownmask) << (c + 1);
-                    wnd |= ((wnd >> c) & 1u) ? 0u : own;
-                }
+                for (int c = 0; c < C; ++c) wnd |= ((wnd >> c) & 1u) ? 0u : (x[c] & ownmask) << (c + 1);
                 // bits of the window below C are final: column j0+c was active iff bit c is clear
                 unsigned int vm = cmask;
                 if (j0 < 0) vm &= cmask << min(-j0, C);
@@ -252,14 +276,8 @@ __global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw
                 const unsigned int act = ~wnd & vm;
                 unsigned int pw = 0u;
 #pragma unroll
-                for (int dy = 1; dy <= R; ++dy) {
-                    unsigned int f = 0u;
-#pragma unroll
-                    for (int c = 0; c < C; ++c)
-                        f |= ((act >> c) & 1u) ? (((q[u][c] >> ((dy + R) * side)) & fmask) << c) : 0u;
-                    pw |= f << (16 * (dy - 1));
-                }
-                pub_wr[i] = pw;
+                for (int c = 0; c < C; ++c) pw |= (((act >> c) & 1u) ? x[c] : 0u) << c;
+                pub_wr[i] = pw;   // bytes 1.. hold the fields for rows i+1.. (byte 0: not read)
                 if (act) {
                     // record: row i is the only writer of its words
                     const int jb = max(j0, 0);
@@ -269,21 +287,11 @@ __global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw
                     if ((jb & 31) + C > 32 && (jb >> 5) + 1 < rw) atomicOr(wp + 1, bits >> (32 - (jb & 31)));
                 }
                 wnd >>= C;
-                // block of step s+2
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const int j = j0 + 2 * C + c;
-                    q[u][c] = (j >= 0 && j < gw) ? row[j] : 0u;
-                }
+                q[u] = (b + 2 < nb) ? prow[b + 2] : zero4;   // block of step s+2 (b + 2 >= 0 here or zero anyway)
             } else if (live && j0 >= gw && j0 < gw + 2 * C) {
                 pub_wr[i] = 0u;   // a finished row leaves no stale marks (both parities)
             } else if (live && j0 <= -32 && j0 + 2 * C > -32) {
-                // about to enter the band: first two blocks
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const int j = j0 + 2 * C + c;
-                    q[u][c] = (j >= 0 && j < gw) ? row[j] : 0u;
-                }
+                q[u] = (b + 2 >= 0 && b + 2 < nb) ? prow[b + 2] : zero4;   // about to enter the band
             }
             __syncthreads();
         }
@@ -344,7 +352,8 @@ __global__ void k_active_range(const PassParams P)
 
 __global__ void k_set_flag(int *p, int v) { *p = v; }
 
-inline int launch_resolve(const PassParams &P, cudaStream_t st)
+// pk: scratch of gh * resolve_blocks_per_row(gw) * 16 bytes for the blocked kernel (or nullptr)
+inline int launch_resolve(const PassParams &P, unsigned int *pk, cudaStream_t st)
 {
     if (P.gh > 4 * 1024) return -1;                       // MAX_ROWS rows per thread
     if ((P.R - 1) * (P.R + 1) + 2 * P.R + 1 > 64 || P.nbw > 4) return -1; // 64-bit row window
@@ -354,19 +363,24 @@ inline int launch_resolve(const PassParams &P, cudaStream_t st)
     int nt = P.gh < 1024 ? ((P.gh + 31) / 32) * 32 : 1024;
     if (nt < 256) nt = 256; // the all-active fast path is a plain strided fill
     const bool fast = P.nbw == 1 && P.R <= 4;
-    if (P.nbw == 1 && P.R <= 2 && P.gh <= 1024) {
+    if (P.nbw == 1 && P.R <= 2 && P.gh <= 1024 && pk != nullptr) {
         // R = 0: no group reaches another grid cell, any_nbr stays 0 and the kernel only fills the list
         const size_t bb = ((size_t)2 * P.gh + (size_t)P.gh * rw + P.gh + 1) * 4;
-        int nb = ((P.gh + 31) / 32) * 32;
-        if (nb < 256) nb = 256;
+        int nthr = ((P.gh + 31) / 32) * 32;
+        if (nthr < 256) nthr = 256;
+        const int nb = resolve_blocks_per_row(P.gw);
+        const long n = (long)P.gh * nb * RB_C;
+        const int pb = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
         if (P.R == 2) {
-            cudaFuncSetAttribute(k_resolve_blk<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb);
-            k_resolve_blk<2, 4><<<1, nb, bb, st>>>(P, rw);
+            k_resolve_pack<2><<<pb, 256, 0, st>>>(P, pk, nb);
+            cudaFuncSetAttribute(k_resolve_blk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb);
+            k_resolve_blk<2><<<1, nthr, bb, st>>>(P, rw, reinterpret_cast<const uint4 *>(pk), nb);
         } else {
-            cudaFuncSetAttribute(k_resolve_blk<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb);
-            k_resolve_blk<1, 4><<<1, nb, bb, st>>>(P, rw);
+            k_resolve_pack<1><<<pb, 256, 0, st>>>(P, pk, nb);
+            cudaFuncSetAttribute(k_resolve_blk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb);
+            k_resolve_blk<1><<<1, nthr, bb, st>>>(P, rw, reinterpret_cast<const uint4 *>(pk), nb);
         }
-        return 1;
+        return 2;
     }
 #define NLK_LAUNCH_RESOLVE(MR, F)                                                                  \
     do {                                                                                           \

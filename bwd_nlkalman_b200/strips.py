@@ -134,10 +134,11 @@ class StripRank:
         ps = [api.strip_plan(self.w, self.h, smooth, q, self.nranks, self.rank) for q in prms_list]
         return min(q.ey0 for q in ps), max(q.ey1 for q in ps)
 
-    def filter_step(self, d_noisy, d_bflo, d_bocc, sigma, f1, f2, d_out1=None, d_out2=None):
+    def filter_step(self, d_noisy, d_bflo, d_bocc, sigma, f1, f2, d_out1=None, d_out2=None, rows2=None):
         """One frame of the forward recursion (reference src/main-flt.c:340-380).  Inputs are
         full-frame device tensors of which rows [ey0, ey1) must be valid; the RGB outputs are
-        written on the rows this rank owns."""
+        written on the rows this rank owns (second output: on ``rows2`` if given, e.g. the
+        rows a later smoothing pass of this rank reads)."""
         ctx = self.ctx
         cur, prv = self.cur, self.cur ^ 1
         do2 = f2.patch_sz != 0
@@ -165,7 +166,8 @@ class StripRank:
             plans = yield from self.strip_pass(0, self.flt2[cur], self.noisy, prev2, self.flt1[cur], sigma, f2)
             p = plans[self.rank]
             if d_out2 is not None:
-                ctx.colour_rows_dev(d_out2, self.flt2[cur], 1, p.oy0, p.oy1)
+                a, b = rows2 if rows2 is not None else (p.oy0, p.oy1)
+                ctx.colour_rows_dev(d_out2, self.flt2[cur], 1, a, b)
         self.have_prev, self.have_flt2, self.cur = True, do2, prv
 
     def smooth_start(self, d_last_rgb):
