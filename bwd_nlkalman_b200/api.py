@@ -43,7 +43,8 @@ class Params(C.Structure):
 class StripPlan(C.Structure):
     """struct nlk_strip_plan (include/nlkalman_b200.h): rows of one rank in a strip-sharded pass."""
     _fields_ = [("gw", C.c_int), ("gh", C.c_int), ("nbw", C.c_int), ("gy0", C.c_int), ("gy1", C.c_int),
-                ("oy0", C.c_int), ("oy1", C.c_int), ("ey0", C.c_int), ("ey1", C.c_int)]
+                ("oy0", C.c_int), ("oy1", C.c_int), ("ey0", C.c_int), ("ey1", C.c_int),
+                ("chunk_g", C.c_int), ("chunk_y", C.c_int)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

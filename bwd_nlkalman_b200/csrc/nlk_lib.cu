@@ -583,14 +583,20 @@ extern "C" int nlk_strip_plan(int w, int h, int smooth, struct nlkalman_params p
     const int R = rmax / step;
     memset(out, 0, sizeof *out);
     out->gw = gw; out->gh = gh; out->nbw = ((2 * R + 1) * (2 * R + 1) + 31) / 32;
-    // grid rows split as evenly as possible, the first (gh mod nranks) strips one row taller
-    const int q = gh / nranks, rem = gh % nranks;
-    const int gy0 = rank * q + (rank < rem ? rank : rem), gy1 = gy0 + q + (rank < rem ? 1 : 0);
+    // equal chunks of q = ceil(gh / nranks) grid rows (the last strip takes what is left): a rank's
+    // rows of the bitmaps and of an output frame then sit at rank * chunk, which lets the
+    // exchanges be single in-place all-gathers
+    const int q = (gh + nranks - 1) / nranks;
+    const int gy0 = rank * q, gy1 = (gy0 + q < gh) ? gy0 + q : gh;
+    if ((nranks - 1) * q >= gh)
+        return set_err(NLK_ERR_PARAM, "%d grid rows do not split into %d strips", gh, nranks);
     out->gy0 = gy0; out->gy1 = gy1;
+    out->chunk_g = q; out->chunk_y = q * step;
     // every rank must own the rows its neighbours spill into: a strip is at least r + psz rows tall
-    if (nranks > 1 && q * step < rmax + psz)
+    const int last_rows = h - (nranks - 1) * q * step;
+    if (nranks > 1 && (q * step < rmax + psz || last_rows < rmax + psz))
         return set_err(NLK_ERR_PARAM, "%d strips of %d grid rows are thinner than the halo (%d rows)", nranks, q, rmax + psz);
-    out->oy0 = rank == 0 ? 0 : gy0 * step;
+    out->oy0 = gy0 * step;
     out->oy1 = rank == nranks - 1 ? h : gy1 * step;
     int ey0 = gy0 * step - rmax, ey1 = (gy1 - 1) * step + rmax + psz;
     out->ey0 = ey0 < 0 ? 0 : ey0;

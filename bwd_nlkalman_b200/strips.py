@@ -27,16 +27,38 @@ from . import api
 
 def allgather_rows(t, ranges, group=None):
     """Row range ``ranges[r]`` of ``t`` is valid on rank r; make all of them valid everywhere
-    (in place, one broadcast per owner: strips may differ in height)."""
+    (in place, one broadcast per owner: the general form, for strips of any height)."""
     import torch.distributed as dist
     for src, (a, b) in enumerate(ranges):
         if b > a:
             dist.broadcast(t[a:b], src=src, group=group)
 
 
+def allgather_chunks(full, chunk, nranks, rank, tail=None, group=None, async_op=False):
+    """``full`` has at least nranks*chunk rows and rank k owns rows [k*chunk, (k+1)*chunk): ONE
+    in-place all-gather (nlk_strip_plan lays the strips out this way).  ``tail`` = (a, b): rows
+    beyond nranks*chunk that the last rank owns, broadcast separately.  Returns the work
+    handles when async_op (wait on them before the gathered rows are read)."""
+    import torch.distributed as dist
+    works = []
+    out = full[:nranks * chunk]
+    w = dist.all_gather_into_tensor(out.view(-1), out[rank * chunk:(rank + 1) * chunk].reshape(-1), group=group,
+                                    async_op=async_op)
+    if async_op:
+        works.append(w)
+    if tail is not None and tail[1] > tail[0]:
+        w = dist.broadcast(full[tail[0]:tail[1]], src=nranks - 1, group=group, async_op=async_op)
+        if async_op:
+            works.append(w)
+    return works
+
+
 def border_ranges(plans, rank):
-    """Accumulator rows rank ``rank`` sends to / receives from its neighbours.
-    -> dict(up_send, dn_send, up_recv, dn_recv), each a (row0, row1) pair or None."""
+    """Rows rank ``rank`` holds for / needs from its neighbours: its halo above and below
+    (rows it reads and accumulates into but does not own).
+    -> dict(up_send, dn_send, up_recv, dn_recv), each a (row0, row1) pair or None, in the
+    accumulator sense: *_send = my halo rows, owned by the neighbour; *_recv = the neighbour's
+    halo rows, owned by me."""
     p = plans[rank]
     out = dict(up_send=None, dn_send=None, up_recv=None, dn_recv=None)
     if rank > 0:
@@ -54,28 +76,42 @@ def border_ranges(plans, rank):
     return out
 
 
-def add_borders(acc, plans, rank, group=None):
-    """Overlap-add of the accumulator rows that groups of one strip wrote into the pixel rows
-    owned by a neighbouring strip (in place on the owners' rows)."""
+def _neighbour_exchange(t, br, rank, add, group=None):
+    """add = True: overlap-add (send my halo rows, add what the neighbours accumulated into my
+    rows).  add = False: halo fill (send my own border rows, receive my halo rows)."""
     import torch
     import torch.distributed as dist
-    br = border_ranges(plans, rank)
+    send = ("up_send", "dn_send") if add else ("up_recv", "dn_recv")
+    recv = ("up_recv", "dn_recv") if add else ("up_send", "dn_send")
     ops, recvs = [], []
-    for key, peer in (("up_recv", rank - 1), ("dn_recv", rank + 1)):
+    for key, peer in zip(recv, (rank - 1, rank + 1)):
         if br[key]:
             a, b = br[key]
-            buf = torch.empty_like(acc[a:b])
+            buf = torch.empty_like(t[a:b]) if add else t[a:b]
             recvs.append((a, b, buf))
             ops.append(dist.P2POp(dist.irecv, buf, peer, group))
-    for key, peer in (("up_send", rank - 1), ("dn_send", rank + 1)):
+    for key, peer in zip(send, (rank - 1, rank + 1)):
         if br[key]:
             a, b = br[key]
-            ops.append(dist.P2POp(dist.isend, acc[a:b], peer, group))
+            ops.append(dist.P2POp(dist.isend, t[a:b], peer, group))
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-    for a, b, buf in recvs:
-        acc[a:b] += buf
+    if add:
+        for a, b, buf in recvs:
+            t[a:b] += buf
+
+
+def add_borders(acc, plans, rank, group=None):
+    """Overlap-add of the accumulator rows that groups of one strip wrote into the pixel rows
+    owned by a neighbouring strip (in place on the owners' rows)."""
+    _neighbour_exchange(acc, border_ranges(plans, rank), rank, True, group)
+
+
+def fill_halo(img, plans, rank, group=None):
+    """Fetch the halo rows [ey0, oy0) and [oy1, ey1) of ``img`` from the neighbours that own
+    them (what the next pass of this rank reads beyond its own rows)."""
+    _neighbour_exchange(img, border_ranges(plans, rank), rank, False, group)
 
 
 # ---- one rank's schedule -----------------------------------------------------------------------
@@ -84,7 +120,16 @@ class StripRank:
     """State and schedule of one strip: the resident recursion of nlk_seq_filter_dev /
     nlk_seq_smooth_dev (include/nlkalman_b200.h) with every pass strip-sharded.
     Full-frame buffers are kept on every rank (4K RGB: 100 MB each); only the rows a rank
-    needs are computed or exchanged."""
+    needs are computed or exchanged.
+
+    The schedule methods are generators yielding exchange requests:
+      ("nbr", words2d, plans)            all-gather the neighbour bitmaps (blocking)
+      ("borders", accw, plans)           overlap-add of the accumulator halo rows (blocking)
+      ("halo", frame, plans)             fetch the halo rows of a frame from the neighbours
+      ("gather", frame, plans, key)      all-gather a frame's strips; asynchronous: it overlaps
+                                         what is queued next, until ("wait", key)
+      ("wait", key)
+    """
 
     def __init__(self, w, h, ch, rank, nranks, device=0):
         import torch
@@ -93,13 +138,24 @@ class StripRank:
         self.ctx = api.Context(w, h, ch, device)
         self.dev = torch.device("cuda", device)
         self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
-        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=self.dev)
-        self.noisy, self.warp, self.tmp = f(h, w, ch), f(h, w, ch), f(h, w, ch)
-        self.flt1, self.flt2 = [f(h, w, ch), f(h, w, ch)], [f(h, w, ch), f(h, w, ch)]
-        self.smo = [f(h, w, ch), f(h, w, ch)]
-        self.accw = f(h, w, ch + 1)
+        self._full = {}
+        self.noisy, self.warp, self.tmp = self.frame(), self.frame(), self.frame()
+        self.flt1, self.flt2 = [self.frame(), self.frame()], [self.frame(), self.frame()]
+        self.smo = [self.frame(), self.frame()]
+        self.accw = torch.empty((h, w, ch + 1), dtype=torch.float32, device=self.dev)
         self.nbr = None
+        self.pending = {}
         self.reset()
+
+    def frame(self):
+        """A frame buffer [h][w][ch] whose allocation is padded to whole chunks for any patch
+        size, so that its strips can be all-gathered in place."""
+        torch = self.torch
+        hp = self.h + 16 * self.nranks
+        full = torch.zeros((hp, self.w, self.ch), dtype=torch.float32, device=self.dev)
+        t = full[:self.h]
+        self._full[t.data_ptr()] = full
+        return t
 
     def reset(self):
         self.cur, self.have_prev, self.have_flt2, self.smo_cur, self.have_smo = 0, False, False, 0, False
@@ -110,35 +166,48 @@ class StripRank:
     def plans(self, smooth, prms):
         return [api.strip_plan(self.w, self.h, smooth, prms, self.nranks, r) for r in range(self.nranks)]
 
-    # generator: yields ("rows", tensor, ranges) / ("borders", tensor, plans)
-    def strip_pass(self, smooth, out, in1, prev0, bsic1, sigma, prms, gather_out=True):
+    @staticmethod
+    def _same_rows(pa, pb):
+        return all((a.oy0, a.oy1) == (b.oy0, b.oy1) for a, b in zip(pa, pb))
+
+    def strip_pass(self, smooth, out, in1, prev0, bsic1, sigma, prms, key=None, next_plans=None):
+        """One strip-sharded pass into ``out`` (a buffer from frame()).  Afterwards the rank's
+        own rows of ``out`` are final; the gather of the other strips is in flight under
+        ``key`` (or finished, if key is None).  next_plans: plans of a pass of this same frame
+        that reads ``out`` next -- its halo rows are fetched right away."""
         torch = self.torch
         plans = self.plans(smooth, prms)
         p = plans[self.rank]
-        words = p.gh * p.gw * p.nbw
+        words = self.nranks * p.chunk_g * p.gw * p.nbw
         if self.nbr is None or self.nbr.numel() < words:
             self.nbr = torch.empty(words, dtype=torch.int32, device=self.dev)
         self.ctx.strip_search(smooth, in1, prev0, bsic1, sigma, prms, p.gy0, p.gy1, self.nbr, self.accw)
         rmax = prms.search_sz_t if smooth else max(prms.search_sz_t, prms.search_sz_x)
         if self.nranks > 1 and prms.npatches_tagg > 1 and rmax // (prms.patch_sz // 2) >= 1:
-            yield ("rows", self.nbr[:words].view(p.gh, p.gw * p.nbw), [(q.gy0, q.gy1) for q in plans])
+            yield ("nbr", self.nbr[:words].view(self.nranks * p.chunk_g, p.gw * p.nbw), plans)
         self.ctx.strip_filter()
         if self.nranks > 1:
             yield ("borders", self.accw, plans)
         self.ctx.strip_normalize(out, p.oy0, p.oy1)
-        if self.nranks > 1 and gather_out:
-            yield ("rows", out, [(q.oy0, q.oy1) for q in plans])
+        if self.nranks > 1:
+            if next_plans is not None and self._same_rows(plans, next_plans) and key is not None:
+                yield ("halo", out, next_plans)
+                yield ("gather", out, plans, key)
+            else:
+                yield ("gather", out, plans, key)
+                if next_plans is not None and key is not None:
+                    yield ("wait", key)
         return plans
 
     def _rows_needed(self, smooth, *prms_list):
         ps = [api.strip_plan(self.w, self.h, smooth, q, self.nranks, self.rank) for q in prms_list]
         return min(q.ey0 for q in ps), max(q.ey1 for q in ps)
 
-    def filter_step(self, d_noisy, d_bflo, d_bocc, sigma, f1, f2, d_out1=None, d_out2=None, rows2=None):
+    def filter_step(self, d_noisy, d_bflo, d_bocc, sigma, f1, f2, d_out1=None, d_out2=None, out2_for=None):
         """One frame of the forward recursion (reference src/main-flt.c:340-380).  Inputs are
         full-frame device tensors of which rows [ey0, ey1) must be valid; the RGB outputs are
-        written on the rows this rank owns (second output: on ``rows2`` if given, e.g. the
-        rows a later smoothing pass of this rank reads)."""
+        written on the rows this rank owns.  out2_for = smoother parameters: the second output
+        is also written on the halo rows that this rank's smoothing pass of the frame reads."""
         ctx = self.ctx
         cur, prv = self.cur, self.cur ^ 1
         do2 = f2.patch_sz != 0
@@ -147,11 +216,13 @@ class StripRank:
         prev1 = None
         if self.have_prev:
             prev1 = self.flt1[prv]
+            yield ("wait", "flt1")     # the other strips of the previous frame (warp reads anywhere)
             if d_bflo is not None:
                 a, b = self._rows_needed(0, f1)
                 ctx.warp_rows_dev(self.warp, prev1, d_bflo, d_bocc, a, b)
                 prev1 = self.warp
-        plans = yield from self.strip_pass(0, self.flt1[cur], self.noisy, prev1, None, sigma, f1)
+        plans = yield from self.strip_pass(0, self.flt1[cur], self.noisy, prev1, None, sigma, f1, key="flt1",
+                                           next_plans=self.plans(0, f2) if do2 else None)
         p = plans[self.rank]
         if d_out1 is not None:
             ctx.colour_rows_dev(d_out1, self.flt1[cur], 1, p.oy0, p.oy1)
@@ -159,37 +230,49 @@ class StripRank:
             prev2 = None
             if self.have_prev and self.have_flt2:
                 prev2 = self.flt2[prv]
+                yield ("wait", "flt2")
                 if d_bflo is not None:
                     a, b = self._rows_needed(0, f2)
                     ctx.warp_rows_dev(self.warp, prev2, d_bflo, d_bocc, a, b)
                     prev2 = self.warp
-            plans = yield from self.strip_pass(0, self.flt2[cur], self.noisy, prev2, self.flt1[cur], sigma, f2)
+            nxt = self.plans(1, out2_for) if (out2_for is not None and d_out2 is not None) else None
+            plans = yield from self.strip_pass(0, self.flt2[cur], self.noisy, prev2, self.flt1[cur], sigma, f2,
+                                               key="flt2", next_plans=nxt)
             p = plans[self.rank]
             if d_out2 is not None:
-                a, b = rows2 if rows2 is not None else (p.oy0, p.oy1)
-                ctx.colour_rows_dev(d_out2, self.flt2[cur], 1, a, b)
+                a, b = (nxt[self.rank].ey0, nxt[self.rank].ey1) if nxt is not None else (p.oy0, p.oy1)
+                ctx.colour_rows_dev(d_out2, self.flt2[cur], 1, min(a, p.oy0), max(b, p.oy1))
         self.have_prev, self.have_flt2, self.cur = True, do2, prv
+
+    def last_filtered(self, d_out_rgb, second=True):
+        """RGB of the whole most recent filtered frame on this rank (waits for its gather)."""
+        yield ("wait", "flt2" if second else "flt1")
+        src = (self.flt2 if second else self.flt1)[self.cur ^ 1]
+        self.ctx.colour_rows_dev(d_out_rgb, src, 1, 0, self.h)
 
     def smooth_start(self, d_last_rgb):
         """The last frame of a sequence is its own smoothed version (scripts/nlkalman-seq.sh:122-124).
-        d_last_rgb: full frame, valid everywhere (e.g. the gathered filter output)."""
+        d_last_rgb: full frame, valid everywhere (see last_filtered)."""
         self.ctx.colour_rows_dev(self.smo[0], d_last_rgb, 0, 0, self.h)
         self.smo_cur, self.have_smo = 0, True
+        self.pending.pop("smo", None)
         return
         yield  # noqa: makes this a generator like the other steps
 
     def smooth_step(self, d_flt_rgb, d_fflo, d_focc, sigma, s1, d_out=None):
-        """One frame of the backward recursion (reference src/main-smo.c:198-213)."""
+        """One frame of the backward recursion (reference src/main-smo.c:198-213).  d_flt_rgb:
+        the filtered frame, valid on this rank's rows [ey0, ey1) of the smoothing plan."""
         ctx = self.ctx
         assert self.have_smo, "smooth_start must come first"
         nxt, cur = self.smo_cur, self.smo_cur ^ 1
         a, b = self._rows_needed(1, s1)
         ctx.colour_rows_dev(self.tmp, d_flt_rgb, 0, a, b)
         smo0 = self.smo[nxt]
+        yield ("wait", "smo")
         if d_fflo is not None:
             ctx.warp_rows_dev(self.warp, smo0, d_fflo, d_focc, a, b)
             smo0 = self.warp
-        plans = yield from self.strip_pass(1, self.smo[cur], self.tmp, smo0, None, sigma, s1)
+        plans = yield from self.strip_pass(1, self.smo[cur], self.tmp, smo0, None, sigma, s1, key="smo")
         p = plans[self.rank]
         if d_out is not None:
             ctx.colour_rows_dev(d_out, self.smo[cur], 1, p.oy0, p.oy1)
@@ -198,15 +281,35 @@ class StripRank:
 
 # ---- drivers -----------------------------------------------------------------------------------
 
+def _tail(plans, h):
+    n, c = len(plans), plans[0].chunk_y
+    return (n * c, h) if h > n * c else None
+
+
 def run_dist(rank_obj, gen, group=None):
     """Serve one rank's schedule with torch.distributed on the context's stream."""
     torch = rank_obj.torch
+    rk, n = rank_obj.rank, rank_obj.nranks
     with torch.cuda.stream(rank_obj.stream):
-        for kind, t, arg in gen:
-            if kind == "rows":
-                allgather_rows(t, arg, group)
+        for req in gen:
+            kind = req[0]
+            if kind == "nbr":
+                allgather_chunks(req[1], req[2][0].chunk_g, n, rk, None, group)
+            elif kind == "borders":
+                add_borders(req[1], req[2], rk, group)
+            elif kind == "halo":
+                fill_halo(req[1], req[2], rk, group)
+            elif kind == "gather":
+                full = rank_obj._full[req[1].data_ptr()]
+                works = allgather_chunks(full, req[2][0].chunk_y, n, rk, _tail(req[2], rank_obj.h), group,
+                                         async_op=req[3] is not None)
+                if req[3] is not None:
+                    rank_obj.pending[req[3]] = works
+            elif kind == "wait":
+                for w in rank_obj.pending.pop(req[1], []):
+                    w.wait()          # the context's stream waits; the host does not block
             else:
-                add_borders(t, arg, rank_obj.rank, group)
+                raise ValueError(kind)
 
 
 def run_virtual(rank_objs, gens):
@@ -214,6 +317,7 @@ def run_virtual(rank_objs, gens):
     adds between the ranks' buffers.  All schedules yield the same request sequence."""
     torch = rank_objs[0].torch
     gens = list(gens)
+    n = len(gens)
     while True:
         reqs = []
         for g in gens:
@@ -224,19 +328,28 @@ def run_virtual(rank_objs, gens):
         if all(r is None for r in reqs):
             return
         assert all(r is not None for r in reqs) and len({r[0] for r in reqs}) == 1, "schedules diverged"
+        kind = reqs[0][0]
+        if kind == "wait":
+            continue
         for o in rank_objs:
             o.ctx.sync()
-        kind = reqs[0][0]
-        if kind == "rows":
-            ranges = reqs[0][2]
-            for src, (a, b) in enumerate(ranges):
-                for dst in range(len(gens)):
+        plans = reqs[0][2]
+        if kind in ("nbr", "gather"):
+            for src, p in enumerate(plans):
+                a, b = (p.gy0, p.gy1) if kind == "nbr" else (p.oy0, p.oy1)
+                for dst in range(n):
                     if dst != src and b > a:
                         reqs[dst][1][a:b].copy_(reqs[src][1][a:b])
-        else:
-            plans = reqs[0][2]
+        elif kind == "halo":
+            for r in range(n):
+                br = border_ranges(plans, r)
+                for key, peer in (("up_send", r - 1), ("dn_send", r + 1)):
+                    if br[key]:
+                        a, b = br[key]
+                        reqs[r][1][a:b].copy_(reqs[peer][1][a:b])
+        elif kind == "borders":
             stage = []
-            for r in range(len(gens)):
+            for r in range(n):
                 br = border_ranges(plans, r)
                 for key, peer in (("up_send", r - 1), ("dn_send", r + 1)):
                     if br[key]:
@@ -244,4 +357,6 @@ def run_virtual(rank_objs, gens):
                         stage.append((peer, a, b, reqs[r][1][a:b].clone()))
             for peer, a, b, buf in stage:
                 reqs[peer][1][a:b] += buf
+        else:
+            raise ValueError(kind)
         torch.cuda.synchronize()

@@ -104,8 +104,10 @@ struct nlk_strip_plan {
     int gy0, gy1;      /* grid rows of this rank */
     int oy0, oy1;      /* pixel rows this rank owns: normalised and output here */
     int ey0, ey1;      /* pixel rows this rank reads and accumulates into (own + halo) */
+    int chunk_g, chunk_y; /* grid rows / pixel rows per rank (all but the last): rank k's rows start at k * chunk */
 };
-/* pure host arithmetic; fails if a strip would be thinner than the halo */
+/* pure host arithmetic: equal chunks of ceil(gh / nranks) grid rows, the last strip takes the
+ * rest; fails if a strip would be thinner than the halo */
 int nlk_strip_plan(int w, int h, int smooth, struct nlkalman_params prms, int nranks, int rank,
                    struct nlk_strip_plan *out);
 /* colour transform (inverse = 0: rgb2opp, 1: opp2rgb) and warp restricted to pixel rows

@@ -101,7 +101,7 @@ def test_virtual_strips_match_oracle(nlk, port):
     ranks = [strips.StripRank(w, h, ch, r, nranks, 0) for r in range(nranks)]
     try:
         d_n1, d_wa = torch.from_numpy(n1).to(dev), torch.from_numpy(wa).to(dev)
-        outs = [torch.zeros_like(d_n1) for _ in ranks]
+        outs = [rk.frame() for rk in ranks]
         strips.run_virtual(ranks, [rk.strip_pass(0, outs[r], d_n1, d_wa, None, sigma, f1) for r, rk in enumerate(ranks)])
         for r, rk in enumerate(ranks):
             rk.ctx.sync()

@@ -30,7 +30,9 @@ def test_strip_plan_partitions_the_frame(nlk, shape, n, mode):
         assert a.gy1 == b.gy0 and a.oy1 == b.oy0          # no gap, no overlap
     for k, p in enumerate(ps):
         assert p.gh == gh and p.gw == (w - psz) // step + 1
-        assert abs((p.gy1 - p.gy0) - gh / n) < 1          # balanced
+        assert p.gy0 == k * p.chunk_g and p.gy1 - p.gy0 <= p.chunk_g and p.chunk_g == -(-gh // n)
+        assert p.chunk_y == p.chunk_g * step and (k == n - 1 or p.oy1 - p.oy0 == p.chunk_y)
+        assert p.oy0 == k * p.chunk_y                      # a rank's rows start at rank * chunk
         # halo = search radius above, search radius + patch below the last reference patch
         assert p.ey0 == max(p.gy0 * step - r, 0) and p.ey1 == min((p.gy1 - 1) * step + r + psz, h)
         # what spills over a border lands inside the immediate neighbour's own rows
@@ -47,6 +49,8 @@ def test_strip_plan_rejects_thin_strips(nlk):
         nlk.strip_plan(128, 64, 0, prms, 8, 0)     # 15 grid rows over 8 ranks: thinner than the halo
     one = nlk.strip_plan(128, 64, 0, prms, 1, 0)   # a single strip is always fine
     assert (one.gy0, one.gy1, one.oy0, one.oy1, one.ey0, one.ey1) == (0, 15, 0, 64, 0, 64)
+    with pytest.raises(nlk.NlkError):
+        nlk.strip_plan(64, 72, 0, prms, 4, 0)      # 17 grid rows in chunks of 5: the last strip (12 pixel rows) is thinner than the halo
 
 
 def _free_port():
@@ -65,7 +69,7 @@ def _worker(rank, world, port, w, h, ch, plan_rows, q):
 
         class P:  # the fields the exchange uses
             def __init__(self, t):
-                self.gy0, self.gy1, self.oy0, self.oy1, self.ey0, self.ey1 = t
+                self.gy0, self.gy1, self.oy0, self.oy1, self.ey0, self.ey1, self.chunk_y = t
         plans = [P(t) for t in plan_rows]
         p = plans[rank]
         # (1) rows: every rank fills its own rows with a rank-specific pattern
@@ -87,6 +91,20 @@ def _worker(rank, world, port, w, h, ch, plan_rows, q):
         dist.all_gather(parts, mine)
         total = sum(parts)
         ok_borders = bool(torch.allclose(acc[p.oy0:p.oy1], total[p.oy0:p.oy1], rtol=0, atol=1e-6))
+        # (3) chunks: the in-place all-gather of an output frame laid out in equal chunks (+ tail)
+        c, n = plan_rows[0][6], world
+        hp = max(h, n * c)
+        fullp = torch.full((hp, w, ch), -1.0)
+        fullp[p.oy0:p.oy1] = full[p.oy0:p.oy1] * (rank + 1)
+        works = strips.allgather_chunks(fullp, c, n, rank, (n * c, h) if h > n * c else None, async_op=True)
+        for wk in works:
+            wk.wait()
+        ok_rows &= bool(torch.equal(fullp[:h], want))
+        # (4) halo: own rows valid -> halo rows fetched from the neighbours
+        img = torch.full((h, w, ch), -1.0)
+        img[p.oy0:p.oy1] = want[p.oy0:p.oy1]
+        strips.fill_halo(img, plans, rank)
+        ok_rows &= bool(torch.equal(img[p.ey0:p.ey1], want[p.ey0:p.ey1]))
         q.put((rank, ok_rows, ok_borders))
     finally:
         dist.destroy_process_group()
@@ -96,7 +114,7 @@ def _worker(rank, world, port, w, h, ch, plan_rows, q):
 def test_exchange_over_gloo(nlk, world):
     w, h, ch = 40, 150, 3
     prms = nlk.default_params(20.0, nlk.FLT1)
-    plan_rows = [(p.gy0, p.gy1, p.oy0, p.oy1, p.ey0, p.ey1) for p in _plans(nlk, w, h, 0, prms, world)]
+    plan_rows = [(p.gy0, p.gy1, p.oy0, p.oy1, p.ey0, p.ey1, p.chunk_y) for p in _plans(nlk, w, h, 0, prms, world)]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

@@ -46,7 +46,6 @@ def main():
     frames = [base[t & 1] for t in range(nf)]
     bflo, fflo, occ = up(synth.backward_flow(w, h)), up(synth.forward_flow(w, h)), up(synth.occlusion_mask(w, h))
     rk = strips.StripRank(w, h, ch, rank, world, lr)
-    ps = rk.plans(1, s1)[rank]
     flt_rgb = [torch.empty_like(base[0]) for _ in range(nf)]
     out = torch.empty_like(base[0])
 
@@ -61,7 +60,8 @@ def main():
         rk.reset()
         for t in range(nf):
             run(rk.filter_step(frames[t], bflo if t else None, occ if t else None, sigma, f1, f2, None, flt_rgb[t],
-                               rows2=(0, h) if t == nf - 1 else (ps.ey0, ps.ey1)))
+                               out2_for=s1))
+        run(rk.last_filtered(flt_rgb[-1]))
         run(rk.smooth_start(flt_rgb[-1]))
         for t in range(nf - 2, -1, -1):
             run(rk.smooth_step(flt_rgb[t], fflo, occ, sigma, s1, out))
