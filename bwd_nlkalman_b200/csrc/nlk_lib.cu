@@ -473,7 +473,7 @@ static int pass_filter(nlk_ctx *c, const PassParams &P, bool strip)
             k_set_flag<<<1, 1, 0, c->st>>>(P.any_nbr, (P.tagg > 1 && P.R >= 1) ? 1 : 0);
             c->launches += 1;
         }
-        if (int r = c->rpack.ensure((size_t)(P.gh > 0 ? P.gh : 1) * resolve_blocks_per_row(P.gw) * 16)) return r;
+        if (int r = c->rpack.ensure(resolve_pack_bytes(P.gw, P.gh, P.R))) return r;
         if (int r = check_launch(c, launch_resolve(P, c->rpack.as<unsigned int>(), c->st), "mask_resolve")) return r;
         if (strip) {
             k_active_range<<<1, 32, 0, c->st>>>(P);

@@ -177,125 +177,156 @@ __global__ void __launch_bounds__(1024) k_resolve(const PassParams P, int rw)
 
 
 // ---- blocked wavefront (one bitmap word per cell, R <= 2: every BASELINE configuration) -------
-// The step count of the kernel above, gw + (R+1)(gh-1), is a chain of block barriers.  Here a
-// step handles a BLOCK of C = 4 consecutive columns per row, sequentially in registers, and
-// row i runs R columns plus one block behind row i-1:
-//     row i, step s  ->  columns [j0, j0 + C),   j0 = C (s - i) - R i
-// so that row i-1 has always finished column j + R before row i reaches column j.  Steps drop
-// to gh - 1 + ceil((gw + R (gh-1)) / C).  After its block a row publishes, for each dy, the
-// (C + 2R)-bit field of columns j0-R .. j0+C-1+R that its active cells mark in row i+dy (one
-// shared-memory word, double-buffered by step parity).  The reader ORs the field of row i-dy
-// into its window at offset (C+R)(dy-1): always at or ahead of its own position.
-//
-// A step is one warp-serial chain, so its instruction count is what matters: k_resolve_pack
-// (whole GPU, a few microseconds) first rewrites the bitmaps into the per-row block layout
-// the chain consumes -- one aligned 16-byte load per step, fields pre-extracted:
-//     bits 0..R-1: own row, columns j+1..j+R;  bits 8..: row i+1;  bits 16..: row i+2
-constexpr int RB_C = 4;
+// The step count of the kernel above, gw + (R+1)(gh-1), is a chain of block barriers, and a
+// step is one warp-serial instruction sequence.  This version
+//   * handles a BLOCK of C = 4 consecutive columns per row and step, in registers; row i runs
+//     R columns plus one block behind row i-1:
+//         row i, step s  ->  block b = s - sb(i),  columns [C b - o_i, C b - o_i + C),
+//         o_i = (R i) mod C,  sb(i) = i + floor(R i / C)          (C (s - i) - R i = C b - o_i)
+//     so row i-1 has always finished column j + R before row i reaches column j; steps drop to
+//     about gh + (gw + R gh) / C;
+//   * publishes, after a block, the (C + 2R)-bit fields that the row's active cells mark in
+//     rows i+1, i+2 (columns C b - o_i - R ..); the reader ORs the field of row i-dy into its
+//     window at offset (C+R)(dy-1): always at or ahead of its own position;
+//     (one shared-memory word per row, double-buffered by step parity, one block barrier per step);
+//   * runs straight-line code: k_resolve_pack (whole GPU, a few microseconds) rewrites the
+//     bitmaps into the per-row block layout with every field pre-shifted to where the step
+//     ORs it, cells outside the row flagged "already processed", and a pad block on either
+//     side of a row so that steps before / after the row's band need no per-row test, stored
+//     step-major (pk[s][row]) so that a warp's 32 rows read 512 contiguous bytes per step;
+//   * records the active cells as one nibble per block in a register, stored every 8 steps.
+// Packed cell c of a block (32 bits):  bits 1+c.. : own row, columns j+1..j+R
+//                                      bits 8+c.. : row i+1 (columns j-R..j+R),  bits 16+c.. : row i+2
+//                                      word 0 only, bits 28..31: cells of the block outside the row
+constexpr int RB_C = 4, RB_Q = 4;
 
 __host__ __device__ inline int resolve_blocks_per_row(int gw) { return (gw + RB_C - 1) / RB_C + 1; }
 
+// number of steps of the blocked kernel (every row must also reach its last record word: a few
+// steps beyond the wavefront's end), rounded up to the unroll factor
+__host__ __device__ inline int resolve_steps(int gw, int gh, int R)
+{
+    const int n = gh - 1 + (gw + R * (gh - 1) + RB_C - 1) / RB_C + 12;
+    return (n + RB_Q - 1) / RB_Q * RB_Q;
+}
+
+// pk[s][i] (uint4): the block row i handles at step s, or a pad block (all four cells flagged
+// as outside the row) before / after the row's band and for the lanes past the last row.  Step
+// major: the 32 rows of a warp read 512 contiguous bytes per step.
 template <int R>
-__global__ void k_resolve_pack(const PassParams P, unsigned int *__restrict__ pk, int nb)
+__global__ void k_resolve_pack(const PassParams P, unsigned int *__restrict__ pk, int nb, int nthr_blk, int nsteps)
 {
     constexpr int C = RB_C, side = 2 * R + 1;
-    const long n = (long)P.gh * nb * C;
-    if (*P.any_nbr == 0) return;   // every patch is processed: nothing to replay
-    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+    const long tid0 = blockIdx.x * (long)blockDim.x + threadIdx.x, nthr = (long)gridDim.x * blockDim.x;
+    if (*P.any_nbr == 0) {
+        // no group marks another grid patch: every patch is processed, nothing to replay
+        for (long g = tid0; g < P.G; g += nthr) P.active[g] = (int)g;
+        if (tid0 == 0) *P.nactive = P.G;
+        return;
+    }
+    const long n = (long)nsteps * nthr_blk * C;
+    for (long t = tid0; t < n; t += nthr) {
         const int c = (int)(t % C);
-        const long ib = t / C;
-        const int b = (int)(ib % nb), i = (int)(ib / nb);
-        const int j = C * b + c - (R * i) % C;
+        const long si = t / C;
+        const int i = (int)(si % nthr_blk), s = (int)(si / nthr_blk);
+        const int b = s - (i + (R * i) / C);            // block of row i at step s
+        const int o = (R * i) % C;
+        const int j = C * b + c - o;
         unsigned int v = 0u;
-        if (j >= 0 && j < P.gw) {
+        const bool row_ok = i < P.gh && b >= 0 && b < nb;
+        if (row_ok && j >= 0 && j < P.gw) {
             const unsigned int w0 = P.nbr[(long)i * P.gw + j];
-            v = (w0 >> (R * side + R + 1)) & ((1u << R) - 1u);
+            v = ((w0 >> (R * side + R + 1)) & ((1u << R) - 1u)) << (1 + c);
 #pragma unroll
-            for (int dy = 1; dy <= R; ++dy) v |= ((w0 >> ((dy + R) * side)) & ((1u << side) - 1u)) << (8 * dy);
+            for (int dy = 1; dy <= R; ++dy) v |= ((w0 >> ((dy + R) * side)) & ((1u << side) - 1u)) << (8 * dy + c);
+        }
+        if (c == 0) {
+            // flags of the four cells of the block that lie outside the row
+            for (int cc = 0; cc < C; ++cc) {
+                const int jj = C * b + cc - o;
+                if (!(row_ok && jj >= 0 && jj < P.gw)) v |= 1u << (28 + cc);
+            }
         }
         pk[t] = v;
     }
 }
 
 template <int R>
-__global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw, const uint4 *__restrict__ pk, int nb)
+__global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw, const uint4 *__restrict__ pk, int nb,
+                                                      unsigned int *__restrict__ rec, int *__restrict__ row_off)
 {
     constexpr int C = RB_C;
-    extern __shared__ unsigned int s_dyn[];
-    const int gw = P.gw, gh = P.gh, G = P.G;
-    unsigned int *s_pub = s_dyn;                              // [2][gh]
-    unsigned int *s_act = s_pub + (size_t)2 * gh;             // [gh][rw] active bits
-    int *s_base = reinterpret_cast<int *>(s_act + (size_t)gh * rw); // [gh+1] row offsets
+    extern __shared__ __align__(8) unsigned int s_dyn[];
+    const int gw = P.gw, gh = P.gh;
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    unsigned int *s_pub = s_dyn;                                        // [2][nthr] published words, by step parity
+    unsigned int *s_act = s_pub + (size_t)2 * nthr;                     // [nthr][rw] active bits, bit 4b+c of row i
+    int *s_base = reinterpret_cast<int *>(s_act + (size_t)nthr * rw);  // [gh+1] row offsets
     __shared__ int s_part[1024];
-    const int tid = threadIdx.x, nthr = blockDim.x;
 
-    if (*P.any_nbr == 0) {
-        // no group marks another grid patch: every patch is processed
-        for (int g = tid; g < G; g += nthr) P.active[g] = g;
-        if (tid == 0) *P.nactive = G;
-        return;
-    }
+    if (*P.any_nbr == 0) return;   // k_resolve_pack filled the list
     constexpr int FW = C + 2 * R;
-    static_assert(FW <= 8 && (C + R) * (R - 1) + FW <= 32 && R + C <= 8, "window / field layout");
-    constexpr unsigned int ownmask = (1u << R) - 1u, fwmask = (1u << FW) - 1u, cmask = (1u << C) - 1u;
-    const int nsteps = gh - 1 + (gw + R * (gh - 1) + C - 1) / C;
-    for (int x = tid; x < 2 * gh; x += nthr) s_pub[x] = 0u;
-    for (int x = tid; x < gh * rw; x += nthr) s_act[x] = 0u;
+    static_assert(FW <= 8 && (C + R) * (R - 1) + FW <= 32 && 1 + C - 1 + R <= 8, "window / field layout");
+    constexpr unsigned int fwmask = (1u << FW) - 1u, ownmask = ((1u << (R + C)) - 1u) << 1;
+    const int nsteps = resolve_steps(gw, gh, R);
+    for (int x = tid; x < 2 * nthr; x += nthr) s_pub[x] = 0u;
     __syncthreads();
 
-    const int i = tid;
-    const bool live = i < gh;
-    const int o = (R * i) % C, sb = i + (R * i) / C;    // block b of the row is handled at step sb + b
-    const uint4 *prow = pk + (size_t)(live ? i : 0) * nb;
-    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-    uint4 q[2];             // blocks of steps s and s+1 (fetched two steps ahead)
+    const int i = tid;                                  // lanes past the last row only see pad blocks
+    const unsigned int m1 = i >= 1 ? fwmask : 0u, m2 = i >= 2 ? fwmask : 0u;
+    const int sb = i + (R * i) / C;                     // block b of the row is handled at step sb + b
+    // steps in which some row of this warp has work: marks for its first columns arrive at most
+    // three blocks before the row starts, and the last record word closes 8 blocks after its end
+    const int i0 = warp * 32, i1 = i0 + 31;
+    const int w_first = i0 + (R * i0) / C - 3, w_last = i1 + (R * i1) / C + nb + 9;
+    const uint4 *pcol = pk + i;                         // pk[s][i]
+    const uint4 zero4 = make_uint4(0xf0000000u, 0u, 0u, 0u);   // a pad block
+    uint4 q[RB_Q];          // blocks of steps s .. s+RB_Q-1 (fetched RB_Q steps ahead)
 #pragma unroll
-    for (int u = 0; u < 2; ++u) q[u] = (live && u - sb >= 0 && u - sb < nb) ? prow[u - sb] : zero4;
-    unsigned int wnd = 0u;
-    for (int s0 = 0; s0 < nsteps; s0 += 2) {
+    for (int u = 0; u < RB_Q; ++u) q[u] = (u >= w_first && u <= w_last) ? pcol[(size_t)u * nthr] : zero4;
+    unsigned int wnd = 0u, acc = 0u;
+    unsigned int *act_row = s_act + (size_t)i * rw;
+#ifdef NLK_RESOLVE_TIMING
+    const long long t_0 = clock64();
+#endif
+    for (int s0 = 0; s0 < nsteps; s0 += RB_Q) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < RB_Q; ++u) {
             const int s = s0 + u;
-            const unsigned int *pub_rd = s_pub + (size_t)((s + 1) & 1) * gh; // written at step s-1
-            unsigned int *pub_wr = s_pub + (size_t)(s & 1) * gh;
-            const int b = s - sb, j0 = C * b - o;
-            // in the band: the block overlaps the row, or marks for its first columns arrive
-            if (live && j0 > -32 && j0 < gw) {
-#pragma unroll
-                for (int dy = 1; dy <= R; ++dy)
-                    if (i >= dy) wnd |= ((pub_rd[i - dy] >> (8 * dy)) & fwmask) << ((C + R) * (dy - 1));
-                const unsigned int x[C] = {q[u].x, q[u].y, q[u].z, q[u].w};
+            if (s >= w_first && s <= w_last) {           // warp-uniform
+                const unsigned int *pub_rd = s_pub + (size_t)((s + 1) & 1) * nthr;   // written at step s-1
+                const int b = s - sb;
+                const uint4 x = q[u];
+                wnd |= (pub_rd[max(i - 1, 0)] >> 8) & m1;
+                if (R > 1) wnd |= ((pub_rd[max(i - 2, 0)] >> 16) & m2) << (C + R);
+                wnd |= x.x >> 28;                        // cells outside the row count as processed
                 // the only serial part: a column is active iff its window bit is clear, and then
-                // marks the next R columns of its own row (cells outside the row are packed as 0)
-#pragma unroll
-                for (int c = 0; c < C; ++c) wnd |= ((wnd >> c) & 1u) ? 0u : (x[c] & ownmask) << (c + 1);
-                // bits of the window below C are final: column j0+c was active iff bit c is clear
-                unsigned int vm = cmask;
-                if (j0 < 0) vm &= cmask << min(-j0, C);
-                if (j0 + C > gw) vm &= cmask >> (j0 + C - gw);
-                const unsigned int act = ~wnd & vm;
-                unsigned int pw = 0u;
-#pragma unroll
-                for (int c = 0; c < C; ++c) pw |= (((act >> c) & 1u) ? x[c] : 0u) << c;
-                pub_wr[i] = pw;   // bytes 1.. hold the fields for rows i+1.. (byte 0: not read)
-                if (act) {
-                    // record: row i is the only writer of its words
-                    const int jb = max(j0, 0);
-                    const unsigned int bits = j0 < 0 ? act >> (-j0) : act;
-                    unsigned int *wp = s_act + (size_t)i * rw + (jb >> 5);
-                    atomicOr(wp, bits << (jb & 31));
-                    if ((jb & 31) + C > 32 && (jb >> 5) + 1 < rw) atomicOr(wp + 1, bits >> (32 - (jb & 31)));
+                // marks the next R columns of its own row
+                wnd |= x.x & ownmask & ~(unsigned int)((int)(wnd << 31) >> 31);
+                wnd |= x.y & ownmask & ~(unsigned int)((int)(wnd << 30) >> 31);
+                wnd |= x.z & ownmask & ~(unsigned int)((int)(wnd << 29) >> 31);
+                wnd |= x.w & ownmask & ~(unsigned int)((int)(wnd << 28) >> 31);
+                // bits of the window below C are final: column c of the block was active iff bit c is clear
+                s_pub[(size_t)(s & 1) * nthr + i] =
+                    (x.x & ~(unsigned int)((int)(wnd << 31) >> 31)) | (x.y & ~(unsigned int)((int)(wnd << 30) >> 31)) |
+                    (x.z & ~(unsigned int)((int)(wnd << 29) >> 31)) | (x.w & ~(unsigned int)((int)(wnd << 28) >> 31));
+                // record: nibble b of the row (pads and cells outside the row are never active)
+                acc |= (~wnd & 0xfu) << (4 * (b & 7));
+                if ((b & 7) == 7) {
+                    if (b >= 0 && (b >> 3) < rw) act_row[b >> 3] = acc;
+                    acc = 0u;
                 }
                 wnd >>= C;
-                q[u] = (b + 2 < nb) ? prow[b + 2] : zero4;   // block of step s+2 (b + 2 >= 0 here or zero anyway)
-            } else if (live && j0 >= gw && j0 < gw + 2 * C) {
-                pub_wr[i] = 0u;   // a finished row leaves no stale marks (both parities)
-            } else if (live && j0 <= -32 && j0 + 2 * C > -32) {
-                q[u] = (b + 2 >= 0 && b + 2 < nb) ? prow[b + 2] : zero4;   // about to enter the band
+                q[u] = (s + RB_Q <= w_last && s + RB_Q < nsteps) ? pcol[(size_t)(s + RB_Q) * nthr] : zero4;
+            } else if (s + RB_Q >= w_first && s + RB_Q <= w_last && s + RB_Q < nsteps) {
+                q[u] = pcol[(size_t)(s + RB_Q) * nthr];  // about to enter the band
             }
             __syncthreads();
         }
     }
+#ifdef NLK_RESOLVE_TIMING
+    const long long t_1 = clock64();
+#endif
 
     // active list in raster order: per-row counts, block scan, then one warp per row
     for (int r = tid; r < gh; r += nthr) {
@@ -317,16 +348,33 @@ __global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw
         if (tid < gh) s_base[tid + 1] = s_part[tid];
         __syncthreads();
     }
-    const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
-    for (int r = warp; r < gh; r += nwarps) {
-        int pos = s_base[r];
-        for (int wd = 0; wd < rw; ++wd) {
-            const unsigned int word = s_act[(size_t)r * rw + wd];
-            if ((word >> lane) & 1u) P.active[pos + __popc(word & ((1u << lane) - 1u))] = r * gw + wd * 32 + lane;
-            pos += __popc(word);
-        }
-    }
+    // hand the record and the row offsets to k_resolve_list (whole GPU): a single block would
+    // spend tens of microseconds writing the list
+    for (int x = tid; x < gh * rw; x += nthr) rec[x] = s_act[x];
+    for (int r = tid; r <= gh; r += nthr) row_off[r] = s_base[r];
     if (tid == 0) *P.nactive = s_base[gh];
+#ifdef NLK_RESOLVE_TIMING
+    __syncthreads();
+    if (tid == 0 && P.dbg_dist) { long long *d = reinterpret_cast<long long *>(P.dbg_dist); d[0] = t_1 - t_0; d[1] = clock64() - t_1; }
+#endif
+}
+
+// the active list in raster order from the record of k_resolve_blk: one warp per grid row
+template <int R>
+__global__ void k_resolve_list(const PassParams P, int rw, const unsigned int *__restrict__ rec,
+                               const int *__restrict__ row_off)
+{
+    if (*P.any_nbr == 0) return;   // k_resolve_pack filled the list
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= P.gh) return;
+    int pos = row_off[r];
+    const int o = (R * r) % RB_C;        // record bit 4b+c is column 4b+c-o
+    for (int wd = 0; wd < rw; ++wd) {
+        const unsigned int word = rec[(size_t)r * rw + wd];
+        if ((word >> lane) & 1u) P.active[pos + __popc(word & ((1u << lane) - 1u))] = r * P.gw + wd * 32 + lane - o;
+        pos += __popc(word);
+    }
 }
 
 // strip-sharded pass: restrict group_filter to the processed patches of grid rows [gy0, gy1).
@@ -352,7 +400,15 @@ __global__ void k_active_range(const PassParams P)
 
 __global__ void k_set_flag(int *p, int v) { *p = v; }
 
-// pk: scratch of gh * resolve_blocks_per_row(gw) * 16 bytes for the blocked kernel (or nullptr)
+// pk: scratch of resolve_pack_bytes(gw, gh, R) bytes for the blocked kernel (or nullptr)
+inline size_t resolve_pack_bytes(int gw, int gh, int R)
+{
+    if (gh < 1 || gh > 1024 || R > 2) return 16;
+    const int nthr = ((gh + 31) / 32) * 32 < 64 ? 64 : ((gh + 31) / 32) * 32;
+    const int rw8 = (resolve_blocks_per_row(gw) + 7) / 8;
+    return (size_t)resolve_steps(gw, gh, R > 0 ? R : 1) * nthr * 16 + ((size_t)gh * rw8 + gh + 1) * 4;
+}
+
 inline int launch_resolve(const PassParams &P, unsigned int *pk, cudaStream_t st)
 {
     if (P.gh > 4 * 1024) return -1;                       // MAX_ROWS rows per thread
@@ -364,23 +420,33 @@ inline int launch_resolve(const PassParams &P, unsigned int *pk, cudaStream_t st
     if (nt < 256) nt = 256; // the all-active fast path is a plain strided fill
     const bool fast = P.nbw == 1 && P.R <= 4;
     if (P.nbw == 1 && P.R <= 2 && P.gh <= 1024 && pk != nullptr) {
-        // R = 0: no group reaches another grid cell, any_nbr stays 0 and the kernel only fills the list
-        const size_t bb = ((size_t)2 * P.gh + (size_t)P.gh * rw + P.gh + 1) * 4;
+        // R = 0: no group reaches another grid cell, any_nbr stays 0 and the pack kernel fills the list
         int nthr = ((P.gh + 31) / 32) * 32;
-        if (nthr < 256) nthr = 256;
+        if (nthr < 64) nthr = 64;
         const int nb = resolve_blocks_per_row(P.gw);
-        const long n = (long)P.gh * nb * RB_C;
-        const int pb = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-        if (P.R == 2) {
-            k_resolve_pack<2><<<pb, 256, 0, st>>>(P, pk, nb);
-            cudaFuncSetAttribute(k_resolve_blk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb);
-            k_resolve_blk<2><<<1, nthr, bb, st>>>(P, rw, reinterpret_cast<const uint4 *>(pk), nb);
-        } else {
-            k_resolve_pack<1><<<pb, 256, 0, st>>>(P, pk, nb);
-            cudaFuncSetAttribute(k_resolve_blk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb);
-            k_resolve_blk<1><<<1, nthr, bb, st>>>(P, rw, reinterpret_cast<const uint4 *>(pk), nb);
+        const int rw8 = (nb + 7) / 8;          // record words per row (8 blocks each)
+        const size_t bb = ((size_t)2 * nthr + (size_t)nthr * rw8 + P.gh + 1) * 4;
+        if (bb <= 200 * 1024) {
+            const int nsteps = resolve_steps(P.gw, P.gh, P.R);
+            const long n = (long)nsteps * nthr * RB_C;
+            const int pb = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+            unsigned int *rec = pk + (size_t)nsteps * nthr * 4;
+            int *row_off = reinterpret_cast<int *>(rec + (size_t)P.gh * rw8);
+            const uint4 *pk4 = reinterpret_cast<const uint4 *>(pk);
+            const int lb = (P.gh + 7) / 8;
+            if (P.R == 2) {
+                k_resolve_pack<2><<<pb, 256, 0, st>>>(P, pk, nb, nthr, nsteps);
+                cudaFuncSetAttribute(k_resolve_blk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb);
+                k_resolve_blk<2><<<1, nthr, bb, st>>>(P, rw8, pk4, nb, rec, row_off);
+                k_resolve_list<2><<<lb, 256, 0, st>>>(P, rw8, rec, row_off);
+            } else {
+                k_resolve_pack<1><<<pb, 256, 0, st>>>(P, pk, nb, nthr, nsteps);
+                cudaFuncSetAttribute(k_resolve_blk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bb);
+                k_resolve_blk<1><<<1, nthr, bb, st>>>(P, rw8, pk4, nb, rec, row_off);
+                k_resolve_list<1><<<lb, 256, 0, st>>>(P, rw8, rec, row_off);
+            }
+            return 3;
         }
-        return 2;
     }
 #define NLK_LAUNCH_RESOLVE(MR, F)                                                                  \
     do {                                                                                           \
