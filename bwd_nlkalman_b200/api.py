@@ -87,6 +87,8 @@ def lib():
     L.nlk_opp2rgb_dev.argtypes = [vp, vp, vp]
     L.nlk_warp_dev.argtypes = [vp, vp, vp, vp, vp]
     L.nlk_pass_dev.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_float, Params]
+    L.nlk_occlusion_dev.argtypes = [vp, vp, vp, C.c_float]
+    L.nlk_occlusion_host.argtypes = [vp, vp, vp, C.c_float]
     L.nlk_strip_plan.argtypes = [C.c_int, C.c_int, C.c_int, Params, C.c_int, C.c_int, C.POINTER(StripPlan)]
     L.nlk_colour_rows_dev.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
     L.nlk_warp_rows_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int]
@@ -269,6 +271,17 @@ class Context:
     def pass_dev(self, smooth, out, in1, prev0, bsic1, sigma, prms: Params):
         _check(lib().nlk_pass_dev(self._h, int(smooth), _vp(out), _vp(in1), _vp(prev0), _vp(bsic1),
                                   float(sigma), prms))
+
+    def occlusion_dev(self, occ, of, th):
+        _check(lib().nlk_occlusion_dev(self._h, _vp(occ), _vp(of), float(th)))
+
+    def occlusion(self, of: np.ndarray, th: float) -> np.ndarray:
+        """0 / 255 mask from the divergence of the flow (reference scripts/nlkalman-seq.sh:70-72)"""
+        h, w, two = of.shape
+        assert (w, h, two) == (self.w, self.h, 2)
+        occ = np.empty((h, w), np.float32)
+        _check(lib().nlk_occlusion_host(self._h, _vp(occ), _vp(np.ascontiguousarray(of, np.float32)), float(th)))
+        return occ
 
     # row ranges and the strip-sharded pass (full-frame device buffers, rows [row0, row1))
     def colour_rows_dev(self, dst, src, inverse, row0, row1):

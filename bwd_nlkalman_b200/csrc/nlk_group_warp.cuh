@@ -26,7 +26,8 @@ namespace nlk {
 
 constexpr int GW_TEAM = 64;          // threads per team
 constexpr int GW_MAX_TEAMS = 8;      // teams per block (named barriers 1..8)
-constexpr int GW_TS = 65;            // tile stride in the exchange buffer (odd: conflict-free)
+constexpr int GW_TS = 66;            // tile stride in the exchange buffer: 8-byte aligned tiles whose 64-bit
+                                     // stores (lane = tile) fall in distinct banks per half-warp
 
 struct GroupWarpGeom {
     int teams;        // teams per block
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(GW_TEAM * GW_MAX_TEAMS, 1)
 k_group_team8(const PassParams P, const GroupWarpGeom Gm)
 {
     constexpr int PSZ = 8, PP = 64, TS = GW_TS;
-    constexpr int AS = PP + 1; // channel stride of the gain / mean tables (odd)
+    constexpr int AS = PP + 1; // channel stride of the gain table in float2 {a, (1-a)*m} (2*AS floats: banks 0, 2, 4)
     constexpr int MC = GW_TEAM / CH;   // members per update round
     extern __shared__ __align__(16) float smem[];
     const int team = threadIdx.x / GW_TEAM;
@@ -90,9 +91,8 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
     float *base = smem + (size_t)team * Gm.team_floats;
     float *tiles = base;                              // [64][TS]
     float *win = tiles + 64 * TS;                     // window area
-    float *s_a = win + Gm.win_floats;                 // [CH][AS] gain
-    float *s_m = s_a + CH * AS;                       // [CH][AS] group mean (M0 or M1)
-    uint32_t *s_cand = reinterpret_cast<uint32_t *>(s_m + CH * AS);   // [kcap]
+    float2 *s_am = reinterpret_cast<float2 *>(win + Gm.win_floats);   // [CH][AS] gain a and (1-a)*mean (M0 or M1)
+    uint32_t *s_cand = reinterpret_cast<uint32_t *>(s_am + CH * AS);  // [kcap]
     int *s_grp = reinterpret_cast<int *>(s_cand + Gm.kcap);           // [kcap]
     float *s_red = reinterpret_cast<float *>(s_grp + Gm.kcap);        // [2]
     int *s_tick = reinterpret_cast<int *>(s_red + 2);                 // [2] ticket, by parity
@@ -234,9 +234,9 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                     dct1d_fwd<8>(r);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float a = s_a[c * AS + i * 8 + y];
-                        if (SMOOTH) r[i] *= a;                                           // :1775
-                        else r[i] = a * r[i] + (1.f - a) * s_m[c * AS + i * 8 + y];      // :878 / :901
+                        const float2 am = s_am[c * AS + i * 8 + y];
+                        if (SMOOTH) r[i] *= am.x;                                        // :1775
+                        else r[i] = fmaf(am.x, r[i], am.y);                              // :878 / :901
                     }
                     dct1d_inv<8>(r);
 #pragma unroll
@@ -291,12 +291,12 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                     if (!stat) {
                         if (SMOOTH) {
 #pragma unroll
-                            for (int i = 0; i < 64; ++i) t[i] *= s_a[c * AS + i];
+                            for (int i = 0; i < 64; ++i) t[i] *= s_am[c * AS + i].x;
                         } else {
 #pragma unroll
                             for (int i = 0; i < 64; ++i) {
-                                const float a = s_a[c * AS + i];
-                                t[i] = a * t[i] + (1.f - a) * s_m[c * AS + i];   // :878 / :901
+                                const float2 am = s_am[c * AS + i];
+                                t[i] = fmaf(am.x, t[i], am.y);                   // :878 / :901
                             }
                         }
                         dct8x8_regs<true>(t);
@@ -307,9 +307,9 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                                 for (int x = 0; x < 8; ++x) t[y * 8 + x] += wS[y * wrow + x * CH];
                         }
                     }
-                    float *dst = tiles + l64 * TS;
+                    float2 *dst = reinterpret_cast<float2 *>(tiles + l64 * TS);
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) dst[i] = t[i];
+                    for (int i = 0; i < 32; ++i) dst[i] = make_float2(t[2 * i], t[2 * i + 1]);
                 }
             }
             team_sync(bar);
@@ -413,8 +413,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                         vsum += a * v;                                       // :898
                         m = M1[u];
                     }
-                    s_a[u * AS + l64] = a;
-                    s_m[u * AS + l64] = m;
+                    s_am[u * AS + l64] = make_float2(a, (1.f - a) * m);
                 }
             }
 #pragma unroll
@@ -438,7 +437,7 @@ inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st)
     Gm.wrow_x = ((2 * P.r_x + 8) * ch) | 1;
     const int win_t = (2 * P.r_t + 8) * Gm.wrow_t * (P.has_prev ? 2 : 1);
     const int win_x = P.smooth ? 0 : (2 * P.r_x + 8) * Gm.wrow_x;
-    Gm.win_floats = win_t > win_x ? win_t : win_x;
+    Gm.win_floats = ((win_t > win_x ? win_t : win_x) + 1) & ~1;   // even: the float2 table behind it stays aligned
     Gm.kcap = P.kstride > 1 ? P.kstride : 1;
     int fl = 64 * GW_TS + Gm.win_floats + 2 * ch * 65 + 2 * Gm.kcap + 2 + 2;
     fl = (fl + 3) & ~3;

@@ -540,6 +540,32 @@ extern "C" int nlk_warp_dev(nlk_ctx *c, float *d_imw, const float *d_im, const f
     return check_launch(c, launch_warp(d_imw, d_im, d_of, d_msk, c->w, c->h, c->ch, 0, c->h, c->st), "warp_bicubic");
 }
 
+static int stage_in(nlk_ctx *c, DevBuf &b, const float *h, size_t bytes, const float **d);
+
+// ---- occlusion mask from the flow -----------------------------------------------
+
+extern "C" int nlk_occlusion_dev(nlk_ctx *c, float *d_occ, const float *d_of, float th)
+{
+    if (int r = ctx_use(c)) return r;
+    if (!d_occ || !d_of) return set_err(NLK_ERR_PARAM, "null flow or mask");
+    ProfScope ps(c, NLK_K_WARP);
+    return check_launch(c, launch_occlusion(d_occ, d_of, c->w, c->h, th, c->st), "occlusion");
+}
+
+extern "C" int nlk_occlusion_host(nlk_ctx *c, float *h_occ, const float *h_of, float th)
+{
+    if (int r = ctx_use(c)) return r;
+    const size_t npix = (size_t)c->w * c->h;
+    const float *d_of;
+    if (int r = stage_in(c, c->s_of, h_of, npix * 2 * 4, &d_of)) return r;
+    if (!d_of) return set_err(NLK_ERR_PARAM, "no flow");
+    if (int r = c->s_msk.ensure(npix * 4)) return r;
+    if (int r = nlk_occlusion_dev(c, c->s_msk.as<float>(), d_of, th)) return r;
+    CU_TRY(cudaMemcpyAsync(h_occ, c->s_msk.p, npix * 4, cudaMemcpyDeviceToHost, c->st));
+    CU_TRY(cudaStreamSynchronize(c->st));
+    return NLK_OK;
+}
+
 // ---- row ranges and the strip-sharded pass --------------------------------------
 
 static int rows_ok(nlk_ctx *c, int row0, int row1)

@@ -122,6 +122,33 @@ inline int launch_warp(float *imw, const float *im, const float *of, const float
     return 1;
 }
 
+// ---- occlusion mask from the divergence of the flow ----------------------------------------
+// What the pipeline script computes with plambda between the flow and the filter (reference
+// scripts/nlkalman-seq.sh:70-72, :95-97):
+//     "x(0,0)[0] x(-1,0)[0] - x(0,0)[1] x(0,-1)[1] - + fabs TH > 255 *"
+// i.e. 255 where |(u(x,y) - u(x-1,y)) + (v(x,y) - v(x,y-1))| > TH, else 0, samples outside the
+// image replaced by the nearest one (plambda's default boundary, reference
+// lib/imscript-lite/src/getpixel.c:18-29), float arithmetic, left-to-right.
+__global__ void k_occlusion(float *__restrict__ occ, const float *__restrict__ of, int w, int h, float th)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    const long pix = (long)y * w + x;
+    const float u = of[pix * 2], v = of[pix * 2 + 1];
+    const float ul = of[((long)y * w + max(x - 1, 0)) * 2];
+    const float vu = of[((long)max(y - 1, 0) * w + x) * 2 + 1];
+    const float d = fabsf(__fadd_rn(__fsub_rn(u, ul), __fsub_rn(v, vu)));
+    occ[pix] = d > th ? 255.f : 0.f;
+}
+
+inline int launch_occlusion(float *occ, const float *of, int w, int h, float th, cudaStream_t st)
+{
+    dim3 nt(32, 8), nb((w + 31) / 32, (h + 7) / 8);
+    k_occlusion<<<nb, nt, 0, st>>>(occ, of, w, h, th);
+    return 1;
+}
+
 // ---- patch validity of the warped previous frame --------------------------------------------
 // valid(q) <=> no NaN in channel 0 of the psz x psz patch at q (reference
 // src/nlkalman.c:605-609, :725-730).  Separable: row pass then column pass.

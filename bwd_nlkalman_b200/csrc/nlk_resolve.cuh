@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(1024) k_resolve_blk(const PassParams P, int rw
     constexpr int C = RB_C;
     extern __shared__ __align__(8) unsigned int s_dyn[];
     const int gw = P.gw, gh = P.gh;
-    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+    const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5;
     unsigned int *s_pub = s_dyn;                                        // [2][nthr] published words, by step parity
     unsigned int *s_act = s_pub + (size_t)2 * nthr;                     // [nthr][rw] active bits, bit 4b+c of row i
     int *s_base = reinterpret_cast<int *>(s_act + (size_t)nthr * rw);  // [gh+1] row offsets

@@ -85,6 +85,14 @@ int nlk_pass_dev(nlk_ctx *ctx, int smooth, float *d_out, const float *d_in1,
                  const float *d_prev0, const float *d_bsic1, float sigma,
                  struct nlkalman_params prms);
 
+/* occlusion mask from the divergence of a flow field, the plambda expression of the pipeline
+ * script between tvl1flow and the filter (reference scripts/nlkalman-seq.sh:70-72, :95-97):
+ * occ = 255 where |(u(x,y) - u(x-1,y)) + (v(x,y) - v(x,y-1))| > th, else 0; neighbours outside
+ * the image are replaced by the nearest sample.  Lets flow stay on the device between the
+ * flow estimator and the filter. */
+int nlk_occlusion_dev(nlk_ctx *ctx, float *d_occ, const float *d_of, float th);
+int nlk_occlusion_host(nlk_ctx *ctx, float *h_occ, const float *h_of, float th);
+
 /* ---- row ranges and the strip-sharded pass (one GPU per horizontal strip) -----------
  * Within a frame the reference's loop over patches (src/nlkalman.c:590-595 `for py .. for
  * px`) shards as strips of grid-patch rows.  A rank searches and filters the reference

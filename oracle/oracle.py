@@ -214,3 +214,18 @@ class Port:
 
     def smooth_frame(self, filt1, smoo0, bsic1, sigma, prms, dump=False):
         return self.run_pass(PASS_SMOOTH, filt1, smoo0, bsic1, sigma, prms, dump)
+
+
+def occlusion_from_flow(of, th):
+    """TEST INFRASTRUCTURE: the plambda expression the pipeline script evaluates on a flow field
+    (reference scripts/nlkalman-seq.sh:70-72 and :95-97)
+        x(0,0)[0] x(-1,0)[0] - x(0,0)[1] x(0,-1)[1] - + fabs TH > 255 *
+    with plambda's default nearest-sample boundary (reference lib/imscript-lite/src/getpixel.c:18-29),
+    in float32 like plambda's stack machine.  of: (h, w, 2) float32 -> (h, w) float32 of 0 / 255."""
+    import numpy as np
+    of = np.asarray(of, np.float32)
+    u, v = of[..., 0], of[..., 1]
+    ul = np.concatenate([u[:, :1], u[:, :-1]], axis=1)
+    vu = np.concatenate([v[:1, :], v[:-1, :]], axis=0)
+    d = np.abs((u - ul).astype(np.float32) + (v - vu).astype(np.float32)).astype(np.float32)
+    return np.where(d > np.float32(th), np.float32(255), np.float32(0)).astype(np.float32)

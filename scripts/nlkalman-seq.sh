@@ -37,6 +37,7 @@ FLT=$(tool nlkalman-flt "${NLKALMAN_FLT:-}")
 SMO=$(tool nlkalman-smo "${NLKALMAN_SMO:-}")
 TVL1=$(tool tvl1flow "${TVL1FLOW:-}")
 PLAMBDA=$(tool plambda "${PLAMBDA:-}")
+OCC=$(tool nlkalman-occ "${NLKALMAN_OCC:-}")
 
 mkdir -p "$OUT"
 for i in $(seq "$FFR" "$STP" "$LFR"); do
@@ -52,9 +53,12 @@ smo1() { printf "$OUT/smo1-%03d.tif" "$1"; }
 # flow FROM TO OUTFILE NPROC DW FSCALE   (tvl1flow: nproc tau lambda theta nscales fscale)
 flow() { [ -f "$3" ] || "$TVL1" "$1" "$2" "$3" "$4" 0 "$5" 0 0 "$6"; }
 # occlusion FLOWFILE TH OUTFILE: |divergence of the flow| > TH, as 0 / 255
+# (nlkalman-occ evaluates the reference's plambda expression on the GPU; plambda itself is used
+# when it is the only one of the two that is installed)
 occlusion() {
-	[ -f "$3" ] || "$PLAMBDA" "$1" \
-		"x(0,0)[0] x(-1,0)[0] - x(0,0)[1] x(0,-1)[1] - + fabs $2 > 255 *" -o "$3"
+	[ -f "$3" ] && return
+	if [ -x "$OCC" ]; then "$OCC" "$1" "$2" "$3"
+	else "$PLAMBDA" "$1" "x(0,0)[0] x(-1,0)[0] - x(0,0)[1] x(0,-1)[1] - + fabs $2 > 255 *" -o "$3"; fi
 }
 
 # ---- filtering, forward in time -------------------------------------------------------

@@ -254,3 +254,31 @@ def test_pipelined_host_recursion_matches_synchronous(nlk):
         assert maxabs(pipe1[t].numpy(), sync1[t].numpy()) <= TOL_MAXABS, t
         assert maxabs(pipe2[t].numpy(), sync2[t].numpy()) <= TOL_MAXABS, t
     assert float(np.abs(sync2[-1].numpy() - frames[-1].numpy()).mean()) > 1.0   # it did filter
+
+
+# ---- occlusion mask from the flow ---------------------------------------------
+
+def test_occlusion_from_flow_divergence(nlk, tmp_path):
+    """the plambda expression of reference scripts/nlkalman-seq.sh:70-72, bit for bit, through the
+    C ABI and through the nlkalman-occ program"""
+    import subprocess
+    from oracle import oracle as O
+    rng = np.random.default_rng(11)
+    w, h = 157, 93
+    of = rng.normal(0, 0.6, (h, w, 2)).astype(np.float32)
+    of[20:40, 30:60] += rng.normal(0, 2.0, (20, 30, 2)).astype(np.float32)   # a disoccluded region
+    with nlk.Context(w, h, 1) as ctx:
+        for th in (0.25, 0.75, 2.0):
+            want = O.occlusion_from_flow(of, th)
+            got = ctx.occlusion(of, th)
+            assert np.array_equal(got, want)
+            assert 0 < int((want > 0).sum()) < want.size
+    # the program: .flo in, PNG out
+    import struct
+    flo, png = tmp_path / "f.flo", tmp_path / "o.png"
+    with open(flo, "wb") as f:
+        f.write(b"PIEH" + struct.pack("<ii", w, h) + of.tobytes())
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bwd_nlkalman_b200", "bin", "nlkalman-occ")
+    subprocess.run([exe, str(flo), "0.75", str(png)], check=True)
+    from PIL import Image
+    assert np.array_equal(np.asarray(Image.open(png)).astype(np.float32), O.occlusion_from_flow(of, 0.75))

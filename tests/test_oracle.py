@@ -125,3 +125,16 @@ def test_mask_separability_against_reference(port, ref):
     assert maxabs(a, b) <= TOL_MAXABS
     frac = dump["active"].mean()
     assert 0.5 < frac < 0.95, frac  # the mask really skips patches here
+
+
+def test_occlusion_oracle_hand_example():
+    """the numpy restatement of the script's plambda expression (reference
+    scripts/nlkalman-seq.sh:70-72) on a case small enough to do by hand"""
+    from oracle import oracle as O
+    of = np.zeros((2, 3, 2), np.float32)
+    of[0, :, 0] = [1.0, 1.5, 4.0]      # u, row 0: du/dx = 0 (clamped), 0.5, 2.5
+    of[1, :, 0] = [0.0, 0.0, 0.0]
+    of[1, :, 1] = [0.0, -3.0, 0.25]    # v, row 1: dv/dy = 0, -3, 0.25 (row 0: clamped, 0)
+    got = O.occlusion_from_flow(of, 0.75)
+    want = np.array([[0, 0, 255], [0, 255, 0]], np.float32)
+    assert np.array_equal(got, want)
