@@ -11,7 +11,8 @@ sequence order and the recursion restarts (spatial first frame) every 20 frames,
 steps are exactly one sequence.  Metric: denoised Mpixel/s = w*h*frames / seconds / 1e6.
 
 * value     -- inputs (noisy frame, flow, occlusion mask of every frame) resident in HBM,
-               state resident in HBM, CUDA-event timed on the context's stream.
+               state resident in HBM, CUDA-event timed on the context's stream (nlk_seq_submit_dev
+               per frame, nlk_seq_join before the closing event).
 * e2e       -- the same steps through the host-buffer C-ABI call (nlk_seq_filter_host):
                every step copies its inputs from pinned host memory and both outputs back.
 * roofline  -- the kernel with the largest share of the step, algorithmic flops per launch
@@ -234,7 +235,8 @@ def run_ours(args):
         t = i % SEQ_LEN
         if t == 0:
             ctx.seq_reset()
-        ctx.seq_filter_dev(d_noisy[t], d_flo[t] if t else None, d_occ[t] if t else None, SIGMA, f1, f2, d_o1, d_o2)
+        # pipelined recursion: the second filtering of a frame overlaps the first of the next one
+        ctx.seq_submit_dev(d_noisy[t], d_flo[t] if t else None, d_occ[t] if t else None, SIGMA, f1, f2, d_o1, d_o2)
 
     def step_host(i, pipelined=True):
         # the streaming call: frame i's inputs go up and its two outputs come back inside the
@@ -280,6 +282,7 @@ def run_ours(args):
         e0.record()
         for i in range(Wm, Wm + K):
             step_dev(i)
+        ctx.seq_join()          # the context's stream waits for the second filtering of the last frame
         e1.record()
     ctx.sync()
     barrier()

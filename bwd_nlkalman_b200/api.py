@@ -100,6 +100,8 @@ def lib():
     L.nlk_seq_filter_host.argtypes = [vp, vp, vp, vp, C.c_float, Params, Params, vp, vp]
     L.nlk_seq_submit_host.argtypes = [vp, vp, vp, vp, C.c_float, Params, Params, vp, vp]
     L.nlk_seq_drain.argtypes = [vp]
+    L.nlk_seq_submit_dev.argtypes = [vp, vp, vp, vp, C.c_float, Params, Params, vp, vp]
+    L.nlk_seq_join.argtypes = [vp]
     L.nlk_seq_smooth_start_dev.argtypes = [vp, vp]
     L.nlk_seq_smooth_dev.argtypes = [vp, vp, vp, vp, C.c_float, Params, vp]
     L.nlk_seq_smooth_start_host.argtypes = [vp, vp]
@@ -315,6 +317,13 @@ class Context:
     def seq_submit_host(self, noisy, bflo, bocc, sigma, f1: Params, f2: Params, flt1_out, flt2_out):
         _check(lib().nlk_seq_submit_host(self._h, _vp(noisy), _vp(bflo), _vp(bocc), float(sigma), f1, f2,
                                          _vp(flt1_out), _vp(flt2_out)))
+
+    def seq_submit_dev(self, noisy, bflo, bocc, sigma, f1: Params, f2: Params, flt1_out, flt2_out):
+        _check(lib().nlk_seq_submit_dev(self._h, _vp(noisy), _vp(bflo), _vp(bocc), float(sigma), f1, f2,
+                                        _vp(flt1_out), _vp(flt2_out)))
+
+    def seq_join(self):
+        _check(lib().nlk_seq_join(self._h))
 
     def seq_drain(self):
         _check(lib().nlk_seq_drain(self._h))

@@ -26,8 +26,7 @@ namespace nlk {
 
 constexpr int GW_TEAM = 64;          // threads per team
 constexpr int GW_MAX_TEAMS = 8;      // teams per block (named barriers 1..8)
-constexpr int GW_TS = 66;            // tile stride in the exchange buffer: 8-byte aligned tiles whose 64-bit
-                                     // stores (lane = tile) fall in distinct banks per half-warp
+constexpr int GW_TS = 65;            // tile stride in the exchange buffer (odd: conflict-free)
 
 struct GroupWarpGeom {
     int teams;        // teams per block
@@ -307,9 +306,9 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                                 for (int x = 0; x < 8; ++x) t[y * 8 + x] += wS[y * wrow + x * CH];
                         }
                     }
-                    float2 *dst = reinterpret_cast<float2 *>(tiles + l64 * TS);
+                    float *dst = tiles + l64 * TS;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) dst[i] = make_float2(t[2 * i], t[2 * i + 1]);
+                    for (int i = 0; i < 64; ++i) dst[i] = t[i];
                 }
             }
             team_sync(bar);

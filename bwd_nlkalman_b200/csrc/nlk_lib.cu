@@ -104,18 +104,37 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// Per-pass scratch and the stream it is used on.  Two lanes: everything runs on lane 0 (the
+// context's stream) except, in the pipelined recursion, the second filtering of a frame, which
+// runs on lane 1 while lane 0 already works on the first filtering of the next frame (the two
+// recursions only meet through flt1(t) -> flt2(t)).
+struct Lane {
+    cudaStream_t st = nullptr;
+    DevBuf accw, valid, valid_tmp, cand, hdr, nbr, active, actflag, counters, gmask, xlist, rpack, q_warp;
+    int epoch = 0;
+    void release()
+    {
+        DevBuf *all[] = {&accw, &valid, &valid_tmp, &cand, &hdr, &nbr, &active, &actflag, &counters, &gmask, &xlist,
+                         &rpack, &q_warp};
+        for (DevBuf *b : all) b->release();
+    }
+};
+
 struct nlk_ctx {
     int w = 0, h = 0, ch = 0, device = 0, num_sms = 148;
-    cudaStream_t st = nullptr;
+    Lane lane[2];
+    Lane *L = &lane[0];          // lane in use by the code being queued
+    int reserve_sm = 0;          // pipelined recursion: group_filter leaves one SM to the other lane's mask_resolve
+    bool b_pending = false;      // lane 1 has work that lane 0 has not waited for
+    cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr}, ev_join = nullptr;
     long long launches = 0;
-    // per-pass scratch
-    DevBuf accw, valid, valid_tmp, cand, hdr, nbr, active, actflag, counters, gmask, dbg_dist, dbg_vp, xlist, rpack;
-    int epoch = 0;
+    DevBuf dbg_dist, dbg_vp;
     // host-call staging
     DevBuf s_in1, s_prev0, s_bsic, s_out, s_of, s_msk;
     // sequence state (opponent colour space)
-    DevBuf q_noisy, q_warp, q_flt1[2], q_flt2[2], q_smo[2], q_tmp;
+    DevBuf q_noisy[2], q_flt1[2], q_flt2[2], q_smo[2], q_tmp;
     int q_cur = 0, q_have_prev = 0, q_have_flt2 = 0;
+    long long q_frames = 0;
     int q_smo_cur = 0, q_have_smo = 0;
     // pipelined host-buffer recursion (nlk_seq_submit_host): copies on their own streams,
     // two staging sets so that frame n+1 uploads and frame n-1 downloads while frame n computes
@@ -127,7 +146,7 @@ struct nlk_ctx {
     // strip-sharded pass in flight (nlk_strip_search .. nlk_strip_normalize)
     PassParams strip_P;
     bool strip_open = false;
-    // optional per-kernel timing with CUDA events on the context's stream
+    // optional per-kernel timing with CUDA events on the stream of the lane in use
     bool prof = false;
     int prof_kind = NLK_PASS_OTHER;
     struct ProfRec { int kid, kind; cudaEvent_t a, b; };
@@ -163,12 +182,12 @@ struct ProfScope {
         if (!c->prof) return;
         a = get(c);
         b = get(c);
-        cudaEventRecord(a, c->st);
+        cudaEventRecord(a, c->L->st);
     }
     ~ProfScope()
     {
         if (!a) return;
-        cudaEventRecord(b, c->st);
+        cudaEventRecord(b, c->L->st);
         c->prof_recs.push_back({kid, c->prof_kind, a, b});
     }
 };
@@ -182,8 +201,7 @@ extern "C" int nlk_ctx_profile(nlk_ctx *c, int enable)
 
 extern "C" int nlk_ctx_profile_collect(nlk_ctx *c, double *ms_sum, int *count)
 {
-    if (int r = ctx_use(c)) return r;
-    CU_TRY(cudaStreamSynchronize(c->st));
+    if (int r = nlk_ctx_sync(c)) return r;
     for (int i = 0; i < NLK_KERNEL_COUNT * NLK_PASS_KINDS; ++i) { ms_sum[i] = 0; count[i] = 0; }
     for (auto &r : c->prof_recs) {
         float ms = 0.f;
@@ -221,8 +239,15 @@ extern "C" nlk_ctx *nlk_ctx_create(int w, int h, int ch, int device)
     c->w = w; c->h = h; c->ch = ch; c->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
-        upload_tables_dev() != NLK_OK || c->counters.ensure(64) != NLK_OK) {
+    bool ok = upload_tables_dev() == NLK_OK;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = cudaStreamCreateWithFlags(&c->lane[i].st, cudaStreamNonBlocking) == cudaSuccess &&
+             c->lane[i].counters.ensure(64) == NLK_OK &&
+             cudaEventCreateWithFlags(&c->ev_a[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_b[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
         if (g_err.empty()) set_err(NLK_ERR_CUDA, "context creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete c;
         return nullptr;
@@ -234,15 +259,19 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->st);
+    for (int i = 0; i < 2; ++i) if (c->lane[i].st) cudaStreamSynchronize(c->lane[i].st);
     if (c->st_d2h) cudaStreamSynchronize(c->st_d2h);
     if (c->st_h2d) cudaStreamSynchronize(c->st_h2d);
-    DevBuf *all[] = {&c->accw, &c->valid, &c->valid_tmp, &c->cand, &c->hdr, &c->nbr, &c->active,
-                     &c->counters, &c->gmask, &c->actflag, &c->dbg_dist, &c->dbg_vp, &c->xlist, &c->rpack, &c->s_in1, &c->s_prev0,
-                     &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk, &c->q_noisy, &c->q_warp,
-                     &c->q_flt1[0], &c->q_flt1[1], &c->q_flt2[0], &c->q_flt2[1], &c->q_smo[0],
-                     &c->q_smo[1], &c->q_tmp};
+    DevBuf *all[] = {&c->dbg_dist, &c->dbg_vp, &c->s_in1, &c->s_prev0, &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk,
+                     &c->q_noisy[0], &c->q_noisy[1], &c->q_flt1[0], &c->q_flt1[1], &c->q_flt2[0], &c->q_flt2[1],
+                     &c->q_smo[0], &c->q_smo[1], &c->q_tmp};
     for (DevBuf *b : all) b->release();
+    for (int i = 0; i < 2; ++i) {
+        c->lane[i].release();
+        if (c->ev_a[i]) cudaEventDestroy(c->ev_a[i]);
+        if (c->ev_b[i]) cudaEventDestroy(c->ev_b[i]);
+    }
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (int i = 0; i < 2; ++i) {
         c->p_in[i].release(); c->p_of[i].release(); c->p_msk[i].release(); c->p_o1[i].release(); c->p_o2[i].release();
         cudaEvent_t *ev[] = {&c->ev_up[i], &c->ev_o1[i], &c->ev_o2[i], &c->ev_done[i]};
@@ -252,19 +281,38 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
-    cudaStreamDestroy(c->st);
+    for (int i = 0; i < 2; ++i) if (c->lane[i].st) cudaStreamDestroy(c->lane[i].st);
     delete c;
+}
+
+// lane 0 (the context's stream) waits for whatever the pipelined recursion left on lane 1
+static int lanes_join(nlk_ctx *c)
+{
+    c->L = &c->lane[0];
+    if (!c->b_pending) return NLK_OK;
+    CU_TRY(cudaEventRecord(c->ev_join, c->lane[1].st));
+    CU_TRY(cudaStreamWaitEvent(c->lane[0].st, c->ev_join, 0));
+    c->b_pending = false;
+    return NLK_OK;
+}
+
+static int enter(nlk_ctx *c)   // public entry points outside the pipelined recursion
+{
+    if (int r = ctx_use(c)) return r;
+    return lanes_join(c);
 }
 
 extern "C" int nlk_ctx_sync(nlk_ctx *c)
 {
     if (int r = ctx_use(c)) return r;
-    CU_TRY(cudaStreamSynchronize(c->st));
+    if (int r = lanes_join(c)) return r;
+    CU_TRY(cudaStreamSynchronize(c->lane[0].st));
+    if (c->st_d2h) CU_TRY(cudaStreamSynchronize(c->st_d2h));
     return NLK_OK;
 }
 
 extern "C" long long nlk_ctx_launch_count(const nlk_ctx *c) { return c ? c->launches : 0; }
-extern "C" void *nlk_ctx_stream(nlk_ctx *c) { return c ? (void *)c->st : nullptr; }
+extern "C" void *nlk_ctx_stream(nlk_ctx *c) { return c ? (void *)c->lane[0].st : nullptr; }
 
 extern "C" void *nlk_host_alloc(size_t bytes)
 {
@@ -291,28 +339,28 @@ extern "C" void *nlk_dev_alloc(nlk_ctx *c, size_t bytes)
 extern "C" void nlk_dev_free(nlk_ctx *c, void *d_ptr)
 {
     if (!d_ptr || ctx_use(c)) return;
-    cudaStreamSynchronize(c->st);
+    cudaStreamSynchronize(c->L->st);
     cudaFree(d_ptr);
 }
 
 extern "C" int nlk_upload(nlk_ctx *c, void *d_dst, const void *h_src, size_t bytes)
 {
-    if (int r = ctx_use(c)) return r;
-    CU_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->st));
+    if (int r = enter(c)) return r;
+    CU_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->L->st));
     return NLK_OK;
 }
 
 extern "C" int nlk_download(nlk_ctx *c, void *h_dst, const void *d_src, size_t bytes)
 {
-    if (int r = ctx_use(c)) return r;
-    CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->st));
+    if (int r = enter(c)) return r;
+    CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->L->st));
     return NLK_OK;
 }
 
 extern "C" int nlk_copy_dev(nlk_ctx *c, void *d_dst, const void *d_src, size_t bytes)
 {
-    if (int r = ctx_use(c)) return r;
-    CU_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, c->st));
+    if (int r = enter(c)) return r;
+    CU_TRY(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, c->L->st));
     return NLK_OK;
 }
 
@@ -371,38 +419,38 @@ static int pass_setup(nlk_ctx *c, PassParams &P, int smooth, float *d_out, const
 
     const size_t npix = (size_t)w * h;
     const size_t G = (size_t)(P.G > 0 ? P.G : 1);
-    if (!d_accw_ext) if (int r = c->accw.ensure(npix * (ch + 1) * 4)) return r;
-    if (int r = c->cand.ensure(G * kmax * 4)) return r;
-    if (int r = c->hdr.ensure(G * sizeof(GroupHdr))) return r;
-    if (!d_nbr_ext) if (int r = c->nbr.ensure(G * P.nbw * 4)) return r;
-    if (int r = c->active.ensure(G * 4)) return r;
-    if (int r = c->gmask.ensure(G)) return r;
-    if (int r = c->actflag.ensure(G)) return r;
+    if (!d_accw_ext) if (int r = c->L->accw.ensure(npix * (ch + 1) * 4)) return r;
+    if (int r = c->L->cand.ensure(G * kmax * 4)) return r;
+    if (int r = c->L->hdr.ensure(G * sizeof(GroupHdr))) return r;
+    if (!d_nbr_ext) if (int r = c->L->nbr.ensure(G * P.nbw * 4)) return r;
+    if (int r = c->L->active.ensure(G * 4)) return r;
+    if (int r = c->L->gmask.ensure(G)) return r;
+    if (int r = c->L->actflag.ensure(G)) return r;
     if (d_prev0 && P.G > 0) {
-        if (int r = c->valid.ensure((size_t)P.vw * P.vh)) return r;
-        if (int r = c->valid_tmp.ensure((size_t)P.vw * h)) return r;
-        P.valid = c->valid.as<uint8_t>();
+        if (int r = c->L->valid.ensure((size_t)P.vw * P.vh)) return r;
+        if (int r = c->L->valid_tmp.ensure((size_t)P.vw * h)) return r;
+        P.valid = c->L->valid.as<uint8_t>();
     }
-    P.accw = d_accw_ext ? d_accw_ext : c->accw.as<float>();
-    P.cand = c->cand.as<uint32_t>();
-    P.hdr = c->hdr.as<GroupHdr>();
-    P.nbr = d_nbr_ext ? d_nbr_ext : c->nbr.as<uint32_t>();
-    P.active = c->active.as<int>();
-    P.gmask = c->gmask.as<uint8_t>();
-    P.actflag = c->actflag.as<uint8_t>();
-    P.nactive = c->counters.as<int>();
-    P.any_nbr = c->counters.as<int>() + 1;
-    P.work = c->counters.as<int>() + 2;
-    P.xcount = c->counters.as<int>() + 3;
+    P.accw = d_accw_ext ? d_accw_ext : c->L->accw.as<float>();
+    P.cand = c->L->cand.as<uint32_t>();
+    P.hdr = c->L->hdr.as<GroupHdr>();
+    P.nbr = d_nbr_ext ? d_nbr_ext : c->L->nbr.as<uint32_t>();
+    P.active = c->L->active.as<int>();
+    P.gmask = c->L->gmask.as<uint8_t>();
+    P.actflag = c->L->actflag.as<uint8_t>();
+    P.nactive = c->L->counters.as<int>();
+    P.any_nbr = c->L->counters.as<int>() + 1;
+    P.work = c->L->counters.as<int>() + 2;
+    P.xcount = c->L->counters.as<int>() + 3;
     {
         // worklist of the second search launch: at most one run per 256/(2*r_x+1) patches
         const size_t cap = G + 16;
-        const bool fresh = c->xlist.cap < 2 * cap * 4;
-        if (int r = c->xlist.ensure(2 * cap * 4)) return r;
-        if (fresh) { CU_TRY(cudaMemsetAsync(c->xlist.p, 0, 2 * cap * 4, c->st)); c->epoch = 0; }
-        P.xlist = c->xlist.as<int>();
-        P.xflag = c->xlist.as<int>() + cap;
-        P.epoch = ++c->epoch;
+        const bool fresh = c->L->xlist.cap < 2 * cap * 4;
+        if (int r = c->L->xlist.ensure(2 * cap * 4)) return r;
+        if (fresh) { CU_TRY(cudaMemsetAsync(c->L->xlist.p, 0, 2 * cap * 4, c->L->st)); c->L->epoch = 0; }
+        P.xlist = c->L->xlist.as<int>();
+        P.xflag = c->L->xlist.as<int>() + cap;
+        P.epoch = ++c->L->epoch;
     }
     P.out = d_out;
     if (debug) {
@@ -410,9 +458,9 @@ static int pass_setup(nlk_ctx *c, PassParams &P, int smooth, float *d_out, const
         if (int r = c->dbg_vp.ensure(G * 4)) return r;
         P.dbg_dist = c->dbg_dist.as<float>();
         P.dbg_vp = c->dbg_vp.as<float>();
-        CU_TRY(cudaMemsetAsync(P.dbg_dist, 0, G * kmax * 4, c->st));
-        CU_TRY(cudaMemsetAsync(P.dbg_vp, 0, G * 4, c->st));
-        CU_TRY(cudaMemsetAsync(P.cand, 0xff, G * kmax * 4, c->st));
+        CU_TRY(cudaMemsetAsync(P.dbg_dist, 0, G * kmax * 4, c->L->st));
+        CU_TRY(cudaMemsetAsync(P.dbg_vp, 0, G * 4, c->L->st));
+        CU_TRY(cudaMemsetAsync(P.cand, 0xff, G * kmax * 4, c->L->st));
     }
     return NLK_OK;
 }
@@ -448,17 +496,17 @@ static int pass_search(nlk_ctx *c, PassParams &P)
     {
         ProfScope ps(c, NLK_K_MEMSET);
         const size_t rowb = (size_t)P.w * (P.ch + 1) * 4;
-        if (ey1 > ey0) CU_TRY(cudaMemsetAsync(reinterpret_cast<char *>(P.accw) + ey0 * rowb, 0, (ey1 - ey0) * rowb, c->st));
-        CU_TRY(cudaMemsetAsync(c->counters.p, 0, 64, c->st));
+        if (ey1 > ey0) CU_TRY(cudaMemsetAsync(reinterpret_cast<char *>(P.accw) + ey0 * rowb, 0, (ey1 - ey0) * rowb, c->L->st));
+        CU_TRY(cudaMemsetAsync(c->L->counters.p, 0, 64, c->L->st));
     }
     if (P.G <= 0 || P.gy1 <= P.gy0) return NLK_OK;
     if (P.prev0) {
         ProfScope ps(c, NLK_K_VALID);
-        if (int r = check_launch(c, launch_valid_map(c->valid.as<uint8_t>(), c->valid_tmp.as<uint8_t>(), P.prev0,
-                                                     P.w, P.h, P.ch, P.psz, ey0, ey1 - P.psz + 1, c->st), "valid_map")) return r;
+        if (int r = check_launch(c, launch_valid_map(c->L->valid.as<uint8_t>(), c->L->valid_tmp.as<uint8_t>(), P.prev0,
+                                                     P.w, P.h, P.ch, P.psz, ey0, ey1 - P.psz + 1, c->L->st), "valid_map")) return r;
     }
     ProfScope ps(c, NLK_K_SEARCH);
-    return check_launch(c, launch_search(P, c->st), "search_knn");
+    return check_launch(c, launch_search(P, c->L->st), "search_knn");
 }
 
 // processed-mask replay over the WHOLE grid (needs every row's bitmaps), then the groups of
@@ -470,25 +518,25 @@ static int pass_filter(nlk_ctx *c, const PassParams &P, bool strip)
         ProfScope ps(c, NLK_K_RESOLVE);
         if (strip) {
             // the flag search_knn raises only covers this rank's rows: decide statically
-            k_set_flag<<<1, 1, 0, c->st>>>(P.any_nbr, (P.tagg > 1 && P.R >= 1) ? 1 : 0);
+            k_set_flag<<<1, 1, 0, c->L->st>>>(P.any_nbr, (P.tagg > 1 && P.R >= 1) ? 1 : 0);
             c->launches += 1;
         }
-        if (int r = c->rpack.ensure(resolve_pack_bytes(P.gw, P.gh, P.R))) return r;
-        if (int r = check_launch(c, launch_resolve(P, c->rpack.as<unsigned int>(), c->st), "mask_resolve")) return r;
+        if (int r = c->L->rpack.ensure(resolve_pack_bytes(P.gw, P.gh, P.R))) return r;
+        if (int r = check_launch(c, launch_resolve(P, c->L->rpack.as<unsigned int>(), c->L->st), "mask_resolve")) return r;
         if (strip) {
-            k_active_range<<<1, 32, 0, c->st>>>(P);
+            k_active_range<<<1, 32, 0, c->L->st>>>(P);
             if (int r = check_launch(c, 1, "active_range")) return r;
         }
     }
     if (P.gy1 <= P.gy0) return NLK_OK;
     ProfScope ps(c, NLK_K_GROUP);
-    return check_launch(c, launch_group_filter(P, c->num_sms, c->st), "group_filter");
+    return check_launch(c, launch_group_filter(P, c->num_sms - c->reserve_sm, c->L->st), "group_filter");
 }
 
 static int pass_normalize(nlk_ctx *c, const PassParams &P, int row0, int row1)
 {
     ProfScope ps(c, NLK_K_NORMALIZE);
-    return check_launch(c, launch_normalize(P, row0, row1, c->st), "normalize");
+    return check_launch(c, launch_normalize(P, row0, row1, c->L->st), "normalize");
 }
 
 static int run_pass(nlk_ctx *c, int smooth, float *d_out, const float *d_in1, const float *d_prev0,
@@ -506,39 +554,50 @@ extern "C" int nlk_pass_dev(nlk_ctx *c, int smooth, float *d_out, const float *d
                             const float *d_prev0, const float *d_bsic1, float sigma,
                             struct nlkalman_params prms)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     return run_pass(c, smooth, d_out, d_in1, d_prev0, d_bsic1, sigma, prms, false);
 }
 
+// queued on the lane in use (c->L); the extern forms below first make lane 0 current
+static int colour_dev(nlk_ctx *c, float *d_dst, const float *d_src, int inverse);
+static int warp_dev(nlk_ctx *c, float *d_imw, const float *d_im, const float *d_of, const float *d_msk);
+
 extern "C" int nlk_rgb2opp_dev(nlk_ctx *c, float *d_dst, const float *d_src)
 {
-    if (int r = ctx_use(c)) return r;
-    if (c->ch != 3) { // reference src/nlkalman.c:94: no-op unless 3 channels
-        if (d_dst != d_src) CU_TRY(cudaMemcpyAsync(d_dst, d_src, c->img_bytes(), cudaMemcpyDeviceToDevice, c->st));
-        return NLK_OK;
-    }
-    ProfScope ps(c, NLK_K_COLOUR);
-    return check_launch(c, launch_rgb2opp_copy(d_dst, d_src, (long)c->w * c->h, 0, c->st), "rgb2opp");
+    if (int r = enter(c)) return r;
+    return colour_dev(c, d_dst, d_src, 0);
 }
 
 extern "C" int nlk_opp2rgb_dev(nlk_ctx *c, float *d_dst, const float *d_src)
 {
-    if (int r = ctx_use(c)) return r;
-    if (c->ch != 3) {
-        if (d_dst != d_src) CU_TRY(cudaMemcpyAsync(d_dst, d_src, c->img_bytes(), cudaMemcpyDeviceToDevice, c->st));
-        return NLK_OK;
-    }
-    ProfScope ps(c, NLK_K_COLOUR);
-    return check_launch(c, launch_rgb2opp_copy(d_dst, d_src, (long)c->w * c->h, 1, c->st), "opp2rgb");
+    if (int r = enter(c)) return r;
+    return colour_dev(c, d_dst, d_src, 1);
 }
 
 extern "C" int nlk_warp_dev(nlk_ctx *c, float *d_imw, const float *d_im, const float *d_of,
                             const float *d_msk)
 {
-    if (int r = ctx_use(c)) return r;
-    ProfScope ps(c, NLK_K_WARP);
-    return check_launch(c, launch_warp(d_imw, d_im, d_of, d_msk, c->w, c->h, c->ch, 0, c->h, c->st), "warp_bicubic");
+    if (int r = enter(c)) return r;
+    return warp_dev(c, d_imw, d_im, d_of, d_msk);
 }
+
+static int colour_dev(nlk_ctx *c, float *d_dst, const float *d_src, int inverse)
+{
+    if (c->ch != 3) { // reference src/nlkalman.c:94, :114: no-op unless 3 channels
+        if (d_dst != d_src) CU_TRY(cudaMemcpyAsync(d_dst, d_src, c->img_bytes(), cudaMemcpyDeviceToDevice, c->L->st));
+        return NLK_OK;
+    }
+    ProfScope ps(c, NLK_K_COLOUR);
+    return check_launch(c, launch_rgb2opp_copy(d_dst, d_src, (long)c->w * c->h, inverse, c->L->st),
+                        inverse ? "opp2rgb" : "rgb2opp");
+}
+
+static int warp_dev(nlk_ctx *c, float *d_imw, const float *d_im, const float *d_of, const float *d_msk)
+{
+    ProfScope ps(c, NLK_K_WARP);
+    return check_launch(c, launch_warp(d_imw, d_im, d_of, d_msk, c->w, c->h, c->ch, 0, c->h, c->L->st), "warp_bicubic");
+}
+
 
 static int stage_in(nlk_ctx *c, DevBuf &b, const float *h, size_t bytes, const float **d);
 
@@ -546,23 +605,23 @@ static int stage_in(nlk_ctx *c, DevBuf &b, const float *h, size_t bytes, const f
 
 extern "C" int nlk_occlusion_dev(nlk_ctx *c, float *d_occ, const float *d_of, float th)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     if (!d_occ || !d_of) return set_err(NLK_ERR_PARAM, "null flow or mask");
     ProfScope ps(c, NLK_K_WARP);
-    return check_launch(c, launch_occlusion(d_occ, d_of, c->w, c->h, th, c->st), "occlusion");
+    return check_launch(c, launch_occlusion(d_occ, d_of, c->w, c->h, th, c->L->st), "occlusion");
 }
 
 extern "C" int nlk_occlusion_host(nlk_ctx *c, float *h_occ, const float *h_of, float th)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     const size_t npix = (size_t)c->w * c->h;
     const float *d_of;
     if (int r = stage_in(c, c->s_of, h_of, npix * 2 * 4, &d_of)) return r;
     if (!d_of) return set_err(NLK_ERR_PARAM, "no flow");
     if (int r = c->s_msk.ensure(npix * 4)) return r;
     if (int r = nlk_occlusion_dev(c, c->s_msk.as<float>(), d_of, th)) return r;
-    CU_TRY(cudaMemcpyAsync(h_occ, c->s_msk.p, npix * 4, cudaMemcpyDeviceToHost, c->st));
-    CU_TRY(cudaStreamSynchronize(c->st));
+    CU_TRY(cudaMemcpyAsync(h_occ, c->s_msk.p, npix * 4, cudaMemcpyDeviceToHost, c->L->st));
+    CU_TRY(cudaStreamSynchronize(c->L->st));
     return NLK_OK;
 }
 
@@ -576,26 +635,26 @@ static int rows_ok(nlk_ctx *c, int row0, int row1)
 
 extern "C" int nlk_colour_rows_dev(nlk_ctx *c, float *d_dst, const float *d_src, int inverse, int row0, int row1)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     if (int r = rows_ok(c, row0, row1)) return r;
     const size_t off = (size_t)row0 * c->w * c->ch;
     const long npix = (long)(row1 - row0) * c->w;
     if (npix == 0) return NLK_OK;
     if (c->ch != 3) {
-        if (d_dst != d_src) CU_TRY(cudaMemcpyAsync(d_dst + off, d_src + off, (size_t)npix * c->ch * 4, cudaMemcpyDeviceToDevice, c->st));
+        if (d_dst != d_src) CU_TRY(cudaMemcpyAsync(d_dst + off, d_src + off, (size_t)npix * c->ch * 4, cudaMemcpyDeviceToDevice, c->L->st));
         return NLK_OK;
     }
     ProfScope ps(c, NLK_K_COLOUR);
-    return check_launch(c, launch_rgb2opp_copy(d_dst + off, d_src + off, npix, inverse, c->st), "colour_rows");
+    return check_launch(c, launch_rgb2opp_copy(d_dst + off, d_src + off, npix, inverse, c->L->st), "colour_rows");
 }
 
 extern "C" int nlk_warp_rows_dev(nlk_ctx *c, float *d_imw, const float *d_im, const float *d_of,
                                  const float *d_msk, int row0, int row1)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     if (int r = rows_ok(c, row0, row1)) return r;
     ProfScope ps(c, NLK_K_WARP);
-    return check_launch(c, launch_warp(d_imw, d_im, d_of, d_msk, c->w, c->h, c->ch, row0, row1, c->st), "warp_rows");
+    return check_launch(c, launch_warp(d_imw, d_im, d_of, d_msk, c->w, c->h, c->ch, row0, row1, c->L->st), "warp_rows");
 }
 
 extern "C" int nlk_strip_plan(int w, int h, int smooth, struct nlkalman_params pr, int nranks, int rank,
@@ -634,7 +693,7 @@ extern "C" int nlk_strip_search(nlk_ctx *c, int smooth, const float *d_in1, cons
                                 const float *d_bsic1, float sigma, struct nlkalman_params prms,
                                 int gy0, int gy1, unsigned int *d_nbr, float *d_accw)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     if (!d_nbr || !d_accw) return set_err(NLK_ERR_PARAM, "the strip pass needs the caller's bitmap and accumulator buffers");
     PassParams &P = c->strip_P;
     c->strip_open = false;
@@ -649,7 +708,7 @@ extern "C" int nlk_strip_search(nlk_ctx *c, int smooth, const float *d_in1, cons
 
 extern "C" int nlk_strip_filter(nlk_ctx *c)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     if (!c->strip_open) return set_err(NLK_ERR_STATE, "nlk_strip_search must come first");
     KindScope ks(c, pass_kind(c->strip_P));
     return pass_filter(c, c->strip_P, true);
@@ -657,7 +716,7 @@ extern "C" int nlk_strip_filter(nlk_ctx *c)
 
 extern "C" int nlk_strip_normalize(nlk_ctx *c, float *d_out, int row0, int row1)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     if (!c->strip_open) return set_err(NLK_ERR_STATE, "nlk_strip_search must come first");
     if (int r = rows_ok(c, row0, row1)) return r;
     c->strip_P.out = d_out;
@@ -670,65 +729,97 @@ extern "C" int nlk_strip_normalize(nlk_ctx *c, float *d_out, int row0, int row1)
 extern "C" int nlk_seq_reset(nlk_ctx *c)
 {
     if (!c) return set_err(NLK_ERR_PARAM, "null context");
+    if (int r = lanes_join(c)) return r;
     c->q_cur = 0; c->q_have_prev = 0; c->q_have_flt2 = 0; c->q_smo_cur = 0; c->q_have_smo = 0;
+    c->q_frames = 0;
     return NLK_OK;
 }
 
 // one frame of the forward recursion.  hook(which) is called right after output `which`
 // (1: first filtering, 2: second) has been queued on the context's stream.
+// One frame of the forward recursion.  hook(which) is called right after output `which`
+// (1: first filtering, 2: second) has been queued, with c->L the lane it was queued on.
+//
+// overlap = false: everything on lane 0, in order.
+// overlap = true (pipelined recursion): the first filtering runs on lane 0, the second on
+// lane 1, which lags: lane 0 goes on with the first filtering of the NEXT frame while lane 1
+// still filters this one (flt1(t+1) needs flt1(t) only; flt2(t) needs flt1(t) and flt2(t-1)).
+// The one-SM mask_resolve of one lane then runs beside the other lane's kernels.  Buffers that
+// both lanes touch are double-buffered by frame parity (noisy, flt1, flt2); lane 0 waits for
+// lane 1's frame t-2 before it overwrites them.  The flow and mask of a frame must stay valid
+// until lane 1 is done with the frame (nlk_seq_drain, or two later frames queued).
 template <class Hook>
 static int seq_filter_core(nlk_ctx *c, const float *d_noisy, const float *d_bflo, const float *d_bocc,
                            float sigma, const nlkalman_params &f1, const nlkalman_params &f2,
-                           float *d_flt1_out, float *d_flt2_out, Hook hook)
+                           float *d_flt1_out, float *d_flt2_out, bool overlap, Hook hook)
 {
     const size_t ib = c->img_bytes();
-    if (int r = c->q_noisy.ensure(ib)) return r;
-    if (int r = c->q_warp.ensure(ib)) return r;
     for (int i = 0; i < 2; ++i) {
+        if (int r = c->q_noisy[i].ensure(ib)) return r;
         if (int r = c->q_flt1[i].ensure(ib)) return r;
         if (int r = c->q_flt2[i].ensure(ib)) return r;
+        if (int r = c->lane[i].q_warp.ensure(ib)) return r;
     }
     if (f1.patch_sz == 0) return set_err(NLK_ERR_PARAM, "the resident recursion needs the first filtering (f1_p != 0)");
     const int cur = c->q_cur, prv = cur ^ 1;
-    float *noisy = c->q_noisy.as<float>(), *warp = c->q_warp.as<float>();
+    Lane *A = &c->lane[0], *B = overlap ? &c->lane[1] : &c->lane[0];
+    if (!overlap) { if (int r = lanes_join(c)) return r; }
+    c->L = A;
+    c->reserve_sm = overlap ? 1 : 0;
+    struct Restore { nlk_ctx *c; ~Restore() { c->L = &c->lane[0]; c->reserve_sm = 0; } } restore{c};
+    float *noisy = c->q_noisy[cur].as<float>();
     float *flt1 = c->q_flt1[cur].as<float>(), *flt2 = c->q_flt2[cur].as<float>();
-    if (int r = nlk_rgb2opp_dev(c, noisy, d_noisy)) return r;
+    // the buffers of this parity were last read by the second filtering two frames ago
+    if (overlap && c->q_frames >= 2) CU_TRY(cudaStreamWaitEvent(A->st, c->ev_b[cur], 0));
+    if (int r = colour_dev(c, noisy, d_noisy, 0)) return r;
 
     // first filtering (reference src/main-flt.c:345-357)
     const float *prev1 = nullptr;
     if (c->q_have_prev) {
         prev1 = c->q_flt1[prv].as<float>();
         if (d_bflo) {
-            if (int r = nlk_warp_dev(c, warp, prev1, d_bflo, d_bocc)) return r;
+            float *warp = A->q_warp.as<float>();
+            if (int r = warp_dev(c, warp, prev1, d_bflo, d_bocc)) return r;
             prev1 = warp;
         }
     }
     if (int r = run_pass(c, 0, flt1, noisy, prev1, nullptr, sigma, f1, false)) return r;
     if (d_flt1_out) {
-        if (int r = nlk_opp2rgb_dev(c, d_flt1_out, flt1)) return r;
+        if (int r = colour_dev(c, d_flt1_out, flt1, 1)) return r;
         if (int r = hook(1)) return r;
     }
 
     // second filtering (reference src/main-flt.c:361-374)
     const int do2 = f2.patch_sz != 0;
     if (do2) {
+        if (overlap) {
+            CU_TRY(cudaEventRecord(c->ev_a[cur], A->st));
+            CU_TRY(cudaStreamWaitEvent(B->st, c->ev_a[cur], 0));
+            c->L = B;
+            c->b_pending = true;
+        }
         const float *prev2 = nullptr;
         if (c->q_have_prev && c->q_have_flt2) {
             prev2 = c->q_flt2[prv].as<float>();
             if (d_bflo) {
-                if (int r = nlk_warp_dev(c, warp, prev2, d_bflo, d_bocc)) return r;
+                float *warp = B->q_warp.as<float>();
+                if (int r = warp_dev(c, warp, prev2, d_bflo, d_bocc)) return r;
                 prev2 = warp;
             }
         }
         if (int r = run_pass(c, 0, flt2, noisy, prev2, flt1, sigma, f2, false)) return r;
         if (d_flt2_out) {
-            if (int r = nlk_opp2rgb_dev(c, d_flt2_out, flt2)) return r;
+            if (int r = colour_dev(c, d_flt2_out, flt2, 1)) return r;
             if (int r = hook(2)) return r;
         }
+        if (overlap) CU_TRY(cudaEventRecord(c->ev_b[cur], B->st));
+    } else if (overlap) {
+        CU_TRY(cudaEventRecord(c->ev_b[cur], A->st));
     }
     c->q_have_prev = 1;
     c->q_have_flt2 = do2;
     c->q_cur = prv;
+    c->q_frames += 1;
     return NLK_OK;
 }
 
@@ -737,7 +828,16 @@ extern "C" int nlk_seq_filter_dev(nlk_ctx *c, const float *d_noisy, const float 
                                   struct nlkalman_params f2, float *d_flt1_out, float *d_flt2_out)
 {
     if (int r = ctx_use(c)) return r;
-    return seq_filter_core(c, d_noisy, d_bflo, d_bocc, sigma, f1, f2, d_flt1_out, d_flt2_out,
+    return seq_filter_core(c, d_noisy, d_bflo, d_bocc, sigma, f1, f2, d_flt1_out, d_flt2_out, false,
+                           [](int) { return NLK_OK; });
+}
+
+extern "C" int nlk_seq_submit_dev(nlk_ctx *c, const float *d_noisy, const float *d_bflo,
+                                  const float *d_bocc, float sigma, struct nlkalman_params f1,
+                                  struct nlkalman_params f2, float *d_flt1_out, float *d_flt2_out)
+{
+    if (int r = ctx_use(c)) return r;
+    return seq_filter_core(c, d_noisy, d_bflo, d_bocc, sigma, f1, f2, d_flt1_out, d_flt2_out, true,
                            [](int) { return NLK_OK; });
 }
 
@@ -746,7 +846,7 @@ static int stage_in(nlk_ctx *c, DevBuf &b, const float *h, size_t bytes, const f
     *d = nullptr;
     if (!h) return NLK_OK;
     if (int r = b.ensure(bytes)) return r;
-    CU_TRY(cudaMemcpyAsync(b.p, h, bytes, cudaMemcpyHostToDevice, c->st));
+    CU_TRY(cudaMemcpyAsync(b.p, h, bytes, cudaMemcpyHostToDevice, c->L->st));
     *d = b.as<float>();
     return NLK_OK;
 }
@@ -790,7 +890,7 @@ extern "C" int nlk_seq_submit_host(nlk_ctx *c, const float *h_noisy, const float
         d_msk = c->p_msk[s].as<float>();
     }
     CU_TRY(cudaEventRecord(c->ev_up[s], c->st_h2d));
-    CU_TRY(cudaStreamWaitEvent(c->st, c->ev_up[s], 0));
+    CU_TRY(cudaStreamWaitEvent(c->lane[0].st, c->ev_up[s], 0));
     float *d_o1 = nullptr, *d_o2 = nullptr;
     if (h_flt1_out) { if (int r = c->p_o1[s].ensure(ib)) return r; d_o1 = c->p_o1[s].as<float>(); }
     if (h_flt2_out && f2.patch_sz != 0) { if (int r = c->p_o2[s].ensure(ib)) return r; d_o2 = c->p_o2[s].as<float>(); }
@@ -798,27 +898,30 @@ extern "C" int nlk_seq_submit_host(nlk_ctx *c, const float *h_noisy, const float
     // filtering's copy overlaps the second filtering
     auto hook = [&](int which) -> int {
         cudaEvent_t ev = which == 1 ? c->ev_o1[s] : c->ev_o2[s];
-        CU_TRY(cudaEventRecord(ev, c->st));
+        CU_TRY(cudaEventRecord(ev, c->L->st));      // the lane the output was produced on
         CU_TRY(cudaStreamWaitEvent(c->st_d2h, ev, 0));
         CU_TRY(cudaMemcpyAsync(which == 1 ? h_flt1_out : h_flt2_out, which == 1 ? d_o1 : d_o2, ib,
                                cudaMemcpyDeviceToHost, c->st_d2h));
         return NLK_OK;
     };
-    if (int r = seq_filter_core(c, c->p_in[s].as<float>(), d_of, d_msk, sigma, f1, f2, d_o1, d_o2, hook)) return r;
-    // frame complete = its compute (the staging inputs are free again) and its downloads
-    CU_TRY(cudaEventRecord(c->ev_o2[s], c->st));
+    if (int r = seq_filter_core(c, c->p_in[s].as<float>(), d_of, d_msk, sigma, f1, f2, d_o1, d_o2, true, hook)) return r;
+    // frame complete = its compute on both lanes (the staging inputs are free again) and its
+    // downloads: lane 1 finishes a frame last (it waited for lane 0's part of it)
+    Lane *last = f2.patch_sz != 0 ? &c->lane[1] : &c->lane[0];
+    CU_TRY(cudaEventRecord(c->ev_o2[s], last->st));
     CU_TRY(cudaStreamWaitEvent(c->st_d2h, c->ev_o2[s], 0));
     CU_TRY(cudaEventRecord(c->ev_done[s], c->st_d2h));
     c->p_frames += 1;
     return NLK_OK;
 }
 
-extern "C" int nlk_seq_drain(nlk_ctx *c)
+extern "C" int nlk_seq_drain(nlk_ctx *c) { return nlk_ctx_sync(c); }
+
+// queue a wait for the pipelined recursion on the context's stream (device-side join)
+extern "C" int nlk_seq_join(nlk_ctx *c)
 {
     if (int r = ctx_use(c)) return r;
-    CU_TRY(cudaStreamSynchronize(c->st));
-    if (c->st_d2h) CU_TRY(cudaStreamSynchronize(c->st_d2h));
-    return NLK_OK;
+    return lanes_join(c);
 }
 
 extern "C" int nlk_seq_filter_host(nlk_ctx *c, const float *h_noisy, const float *h_bflo,
@@ -831,7 +934,7 @@ extern "C" int nlk_seq_filter_host(nlk_ctx *c, const float *h_noisy, const float
 
 extern "C" int nlk_seq_smooth_start_dev(nlk_ctx *c, const float *d_last_rgb)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     const size_t ib = c->img_bytes();
     for (int i = 0; i < 2; ++i) if (int r = c->q_smo[i].ensure(ib)) return r;
     c->q_smo_cur = 0;
@@ -844,13 +947,13 @@ extern "C" int nlk_seq_smooth_dev(nlk_ctx *c, const float *d_flt_rgb, const floa
                                   const float *d_focc, float sigma, struct nlkalman_params s1,
                                   float *d_smo_out)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     if (!c->q_have_smo) return set_err(NLK_ERR_STATE, "nlk_seq_smooth_start_* must come first");
     const size_t ib = c->img_bytes();
     if (int r = c->q_tmp.ensure(ib)) return r;
-    if (int r = c->q_warp.ensure(ib)) return r;
+    if (int r = c->L->q_warp.ensure(ib)) return r;
     const int nxt = c->q_smo_cur, cur = nxt ^ 1; // q_smo[nxt] holds the smoothed frame t+1
-    float *flt = c->q_tmp.as<float>(), *warp = c->q_warp.as<float>();
+    float *flt = c->q_tmp.as<float>(), *warp = c->L->q_warp.as<float>();
     if (int r = nlk_rgb2opp_dev(c, flt, d_flt_rgb)) return r;
     const float *smo0 = c->q_smo[nxt].as<float>();
     if (d_fflo) { // reference src/main-smo.c:202-206
@@ -866,7 +969,7 @@ extern "C" int nlk_seq_smooth_dev(nlk_ctx *c, const float *d_flt_rgb, const floa
 
 extern "C" int nlk_seq_smooth_start_host(nlk_ctx *c, const float *h_last_rgb)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     const float *d;
     if (int r = stage_in(c, c->s_in1, h_last_rgb, c->img_bytes(), &d)) return r;
     if (!d) return set_err(NLK_ERR_PARAM, "no frame");
@@ -877,7 +980,7 @@ extern "C" int nlk_seq_smooth_host(nlk_ctx *c, const float *h_flt_rgb, const flo
                                    const float *h_focc, float sigma, struct nlkalman_params s1,
                                    float *h_smo_out)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     const size_t ib = c->img_bytes(), npix = (size_t)c->w * c->h;
     const float *d_flt, *d_of, *d_msk;
     if (int r = stage_in(c, c->s_in1, h_flt_rgb, ib, &d_flt)) return r;
@@ -887,8 +990,8 @@ extern "C" int nlk_seq_smooth_host(nlk_ctx *c, const float *h_flt_rgb, const flo
     float *d_o = nullptr;
     if (h_smo_out) { if (int r = c->s_out.ensure(ib)) return r; d_o = c->s_out.as<float>(); }
     if (int r = nlk_seq_smooth_dev(c, d_flt, d_of, d_msk, sigma, s1, d_o)) return r;
-    if (d_o) CU_TRY(cudaMemcpyAsync(h_smo_out, d_o, ib, cudaMemcpyDeviceToHost, c->st));
-    CU_TRY(cudaStreamSynchronize(c->st));
+    if (d_o) CU_TRY(cudaMemcpyAsync(h_smo_out, d_o, ib, cudaMemcpyDeviceToHost, c->L->st));
+    CU_TRY(cudaStreamSynchronize(c->L->st));
     return NLK_OK;
 }
 
@@ -905,8 +1008,8 @@ static int pass_host(nlk_ctx *c, int smooth, float *h_out, const float *h_in1, c
     if (!d_in1) return set_err(NLK_ERR_PARAM, "no input frame");
     if (int r = c->s_out.ensure(ib)) return r;
     if (int r = run_pass(c, smooth, c->s_out.as<float>(), d_in1, d_prev0, d_bsic, sigma, pr, debug)) return r;
-    CU_TRY(cudaMemcpyAsync(h_out, c->s_out.p, ib, cudaMemcpyDeviceToHost, c->st));
-    CU_TRY(cudaStreamSynchronize(c->st));
+    CU_TRY(cudaMemcpyAsync(h_out, c->s_out.p, ib, cudaMemcpyDeviceToHost, c->L->st));
+    CU_TRY(cudaStreamSynchronize(c->L->st));
     return NLK_OK;
 }
 
@@ -916,7 +1019,7 @@ extern "C" int nlk_pass_host_debug(nlk_ctx *c, int smooth, float *h_out, const f
                                    int *knn_xy, float *knn_d, unsigned char *prev_p,
                                    unsigned char *active, float *vp)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     if (int r = pass_host(c, smooth, h_out, h_in1, h_prev0, h_bsic1, sigma, prms, true)) return r;
     const int psz = prms.patch_sz, step = psz / 2;
     if (c->w < psz || c->h < psz) return NLK_OK;
@@ -930,12 +1033,12 @@ extern "C" int nlk_pass_host_debug(nlk_ctx *c, int smooth, float *h_out, const f
     std::vector<float> dist((size_t)G * ks), vps(G);
     std::vector<int> act(G);
     int counters[2];
-    CU_TRY(cudaMemcpy(hdr.data(), c->hdr.p, (size_t)G * sizeof(GroupHdr), cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(cand.data(), c->cand.p, (size_t)G * ks * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(hdr.data(), c->L->hdr.p, (size_t)G * sizeof(GroupHdr), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(cand.data(), c->L->cand.p, (size_t)G * ks * 4, cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(dist.data(), c->dbg_dist.p, (size_t)G * ks * 4, cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(vps.data(), c->dbg_vp.p, (size_t)G * 4, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(act.data(), c->active.p, (size_t)G * 4, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(counters, c->counters.p, 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(act.data(), c->L->active.p, (size_t)G * 4, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(counters, c->L->counters.p, 8, cudaMemcpyDeviceToHost));
     if (active) memset(active, 0, G);
     for (int i = 0; i < counters[0] && i < G; ++i)
         if (active && act[i] >= 0 && act[i] < G) active[act[i]] = 1;
@@ -977,20 +1080,20 @@ __global__ void k_dct_tiles(float *tiles, int n, int psz, int inverse)
 
 extern "C" int nlk_dct_host(nlk_ctx *c, float *h_tiles, int psz, int n, int inverse)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     if (psz < 1 || psz > MAX_PSZ || n < 0) return set_err(NLK_ERR_PARAM, "bad dct request");
     if (n == 0) return NLK_OK;
     const size_t bytes = (size_t)n * psz * psz * 4;
     if (int r = c->q_tmp.ensure(bytes)) return r;
-    CU_TRY(cudaMemcpyAsync(c->q_tmp.p, h_tiles, bytes, cudaMemcpyHostToDevice, c->st));
+    CU_TRY(cudaMemcpyAsync(c->q_tmp.p, h_tiles, bytes, cudaMemcpyHostToDevice, c->L->st));
     const int nt = psz > 12 ? 32 : 64, nb = (n + nt - 1) / nt;
     const size_t smem = (size_t)nt * (psz * psz + 1) * 4;
-    if (psz == 8) k_dct_tiles<8><<<nb, nt, smem, c->st>>>(c->q_tmp.as<float>(), n, psz, inverse);
-    else if (psz == 12) k_dct_tiles<12><<<nb, nt, smem, c->st>>>(c->q_tmp.as<float>(), n, psz, inverse);
-    else k_dct_tiles<0><<<nb, nt, smem, c->st>>>(c->q_tmp.as<float>(), n, psz, inverse);
+    if (psz == 8) k_dct_tiles<8><<<nb, nt, smem, c->L->st>>>(c->q_tmp.as<float>(), n, psz, inverse);
+    else if (psz == 12) k_dct_tiles<12><<<nb, nt, smem, c->L->st>>>(c->q_tmp.as<float>(), n, psz, inverse);
+    else k_dct_tiles<0><<<nb, nt, smem, c->L->st>>>(c->q_tmp.as<float>(), n, psz, inverse);
     if (int r = check_launch(c, 1, "dct_tiles")) return r;
-    CU_TRY(cudaMemcpyAsync(h_tiles, c->q_tmp.p, bytes, cudaMemcpyDeviceToHost, c->st));
-    CU_TRY(cudaStreamSynchronize(c->st));
+    CU_TRY(cudaMemcpyAsync(h_tiles, c->q_tmp.p, bytes, cudaMemcpyDeviceToHost, c->L->st));
+    CU_TRY(cudaStreamSynchronize(c->L->st));
     return NLK_OK;
 }
 
@@ -1019,7 +1122,7 @@ static nlk_ctx *legacy_ctx(int w, int h, int ch)
         g_legacy = nlk_ctx_create(w, h, ch, dev);
         if (!g_legacy) legacy_die("no usable CUDA device (there is no CPU fallback)");
     }
-    if (ctx_use(g_legacy)) legacy_die("cudaSetDevice");
+    if (enter(g_legacy)) legacy_die("cudaSetDevice");
     return g_legacy;
 }
 
@@ -1031,8 +1134,8 @@ static void legacy_colour(float *im, int w, int h, int ch, int inverse)
     const float *d;
     if (stage_in(c, c->s_in1, im, c->img_bytes(), &d)) legacy_die("colour transform");
     int r = inverse ? nlk_opp2rgb_dev(c, c->s_in1.as<float>(), d) : nlk_rgb2opp_dev(c, c->s_in1.as<float>(), d);
-    if (r || cudaMemcpyAsync(im, c->s_in1.p, c->img_bytes(), cudaMemcpyDeviceToHost, c->st) != cudaSuccess ||
-        cudaStreamSynchronize(c->st) != cudaSuccess) {
+    if (r || cudaMemcpyAsync(im, c->s_in1.p, c->img_bytes(), cudaMemcpyDeviceToHost, c->L->st) != cudaSuccess ||
+        cudaStreamSynchronize(c->L->st) != cudaSuccess) {
         if (!r) set_err(NLK_ERR_CUDA, "%s", cudaGetErrorString(cudaGetLastError()));
         legacy_die("colour transform");
     }
@@ -1051,8 +1154,8 @@ extern "C" void warp_bicubic(float *imw, float *im, float *of, float *msk, int w
         stage_in(c, c->s_msk, msk, npix * 4, &d_msk) || c->s_out.ensure(ib))
         legacy_die("warp_bicubic");
     if (nlk_warp_dev(c, c->s_out.as<float>(), d_im, d_of, d_msk)) legacy_die("warp_bicubic");
-    if (cudaMemcpyAsync(imw, c->s_out.p, ib, cudaMemcpyDeviceToHost, c->st) != cudaSuccess ||
-        cudaStreamSynchronize(c->st) != cudaSuccess) {
+    if (cudaMemcpyAsync(imw, c->s_out.p, ib, cudaMemcpyDeviceToHost, c->L->st) != cudaSuccess ||
+        cudaStreamSynchronize(c->L->st) != cudaSuccess) {
         set_err(NLK_ERR_CUDA, "%s", cudaGetErrorString(cudaGetLastError()));
         legacy_die("warp_bicubic");
     }
@@ -1136,19 +1239,19 @@ __global__ void __launch_bounds__(256) k_fma_peak(float *out, int iters, float a
 
 extern "C" int nlk_fp32_peak(nlk_ctx *c, float ms, double *tflops)
 {
-    if (int r = ctx_use(c)) return r;
+    if (int r = enter(c)) return r;
     if (int r = c->q_tmp.ensure(256)) return r;
     const int nb = c->num_sms * 8, nt = 256, iters = 4096;
     cudaEvent_t a, b;
     CU_TRY(cudaEventCreate(&a));
     CU_TRY(cudaEventCreate(&b));
     // warm up, then repeat until about `ms` of device time has been measured
-    for (int i = 0; i < 3; ++i) k_fma_peak<<<nb, nt, 0, c->st>>>(c->q_tmp.as<float>(), iters, 0.999f, 1e-3f);
+    for (int i = 0; i < 3; ++i) k_fma_peak<<<nb, nt, 0, c->L->st>>>(c->q_tmp.as<float>(), iters, 0.999f, 1e-3f);
     double best = 0, spent = 0;
     while (spent < ms) {
-        CU_TRY(cudaEventRecord(a, c->st));
-        for (int i = 0; i < 8; ++i) k_fma_peak<<<nb, nt, 0, c->st>>>(c->q_tmp.as<float>(), iters, 0.999f, 1e-3f);
-        CU_TRY(cudaEventRecord(b, c->st));
+        CU_TRY(cudaEventRecord(a, c->L->st));
+        for (int i = 0; i < 8; ++i) k_fma_peak<<<nb, nt, 0, c->L->st>>>(c->q_tmp.as<float>(), iters, 0.999f, 1e-3f);
+        CU_TRY(cudaEventRecord(b, c->L->st));
         CU_TRY(cudaEventSynchronize(b));
         float t = 0.f;
         CU_TRY(cudaEventElapsedTime(&t, a, b));

@@ -160,6 +160,19 @@ int nlk_seq_submit_host(nlk_ctx *ctx, const float *h_noisy, const float *h_bflo,
                         const float *h_bocc, float sigma, struct nlkalman_params f1,
                         struct nlkalman_params f2, float *h_flt1_out, float *h_flt2_out);
 int nlk_seq_drain(nlk_ctx *ctx);
+/* The pipelined recursion runs the two filterings of a frame on two streams: the second
+ * filtering of frame t (it needs flt1(t) and flt2(t-1)) overlaps the first filtering of frame
+ * t+1 (it needs flt1(t) only), so that one pass's single-SM processed-mask replay and its
+ * other thin phases run beside the other pass's kernels.  nlk_seq_submit_dev is that form for
+ * device buffers: same arguments as nlk_seq_filter_dev, but d_flt2_out (and the context's
+ * stream as seen by the caller) is complete only after nlk_seq_join (queues the wait on the
+ * context's stream), nlk_seq_drain or nlk_ctx_sync (block the host); d_bflo / d_bocc of a frame
+ * must stay untouched until then or until two later frames have been submitted.  Every other
+ * entry point joins first, so the forms can be mixed. */
+int nlk_seq_submit_dev(nlk_ctx *ctx, const float *d_noisy, const float *d_bflo,
+                       const float *d_bocc, float sigma, struct nlkalman_params f1,
+                       struct nlkalman_params f2, float *d_flt1_out, float *d_flt2_out);
+int nlk_seq_join(nlk_ctx *ctx);
 
 /* backward smoothing recursion (scripts/nlkalman-seq.sh:122-149): start from the last
  * filtered frame, then for each earlier frame t: warp(smoothed t+1 by the forward

@@ -282,3 +282,38 @@ def test_occlusion_from_flow_divergence(nlk, tmp_path):
     subprocess.run([exe, str(flo), "0.75", str(png)], check=True)
     from PIL import Image
     assert np.array_equal(np.asarray(Image.open(png)).astype(np.float32), O.occlusion_from_flow(of, 0.75))
+
+
+def test_two_lane_device_recursion_matches_in_order(nlk):
+    """nlk_seq_submit_dev (second filtering of frame t on a second stream beside the first
+    filtering of frame t+1) against nlk_seq_filter_dev (everything in order), frame by frame,
+    distinct output buffers per frame; then the forms mixed in one sequence"""
+    import torch
+    from bwd_nlkalman_b200 import synth
+    w, h, ch, sigma, nf = 150, 110, 3, 20.0, 7
+    f1, f2 = nlk.default_params(sigma, nlk.FLT1), nlk.default_params(sigma, nlk.FLT2)
+    dev = torch.device("cuda", 0)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    frames = [up(synth.noisy_frame(w, h, ch, t, sigma)) for t in range(nf)]
+    flo = [up(synth.backward_flow(w, h)) for _ in range(nf)]
+    occ = [up(synth.occlusion_mask(w, h)) for _ in range(nf)]
+    mk = lambda: [torch.empty_like(frames[0]) for _ in range(nf)]
+    a1, a2, b1, b2, c2 = mk(), mk(), mk(), mk(), mk()
+    with nlk.Context(w, h, ch) as ctx:
+        for t in range(nf):
+            ctx.seq_filter_dev(frames[t], flo[t] if t else None, occ[t] if t else None, sigma, f1, f2, a1[t], a2[t])
+        ctx.sync()
+        ctx.seq_reset()
+        for t in range(nf):
+            ctx.seq_submit_dev(frames[t], flo[t] if t else None, occ[t] if t else None, sigma, f1, f2, b1[t], b2[t])
+        ctx.seq_drain()
+        ctx.seq_reset()
+        for t in range(nf):   # mixed: every third frame in order
+            call = ctx.seq_filter_dev if t % 3 == 2 else ctx.seq_submit_dev
+            call(frames[t], flo[t] if t else None, occ[t] if t else None, sigma, f1, f2, None, c2[t])
+        ctx.seq_join()
+        ctx.sync()
+    for t in range(nf):
+        assert maxabs(b1[t].cpu().numpy(), a1[t].cpu().numpy()) <= TOL_MAXABS, t
+        assert maxabs(b2[t].cpu().numpy(), a2[t].cpu().numpy()) <= TOL_MAXABS, t
+        assert maxabs(c2[t].cpu().numpy(), a2[t].cpu().numpy()) <= TOL_MAXABS, t
