@@ -40,7 +40,7 @@ def run_config(name, w, h, ch, sigma, over, smooth, nseq, nframes, reps):
             c.seq_reset()
         for t in range(nframes):          # round-robin over the sequences: their streams overlap
             for k, c in enumerate(ctxs):
-                c.seq_filter_dev(frames[t], bflo if t else None, occ if t else None, sigma, f1, f2, None, flt[k][t])
+                c.seq_submit_dev(frames[t], bflo if t else None, occ if t else None, sigma, f1, f2, None, flt[k][t])
         if smooth:
             for k, c in enumerate(ctxs):
                 c.seq_smooth_start_dev(flt[k][-1])
