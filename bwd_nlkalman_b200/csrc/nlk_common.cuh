@@ -78,6 +78,10 @@ struct PassParams {
 // orthonormal DCT-II matrices T[k*n+j] = c(k) sqrt(2/n) cos(pi (j+1/2) k / n), one per
 // supported side n (filled by the host at library initialisation)
 __constant__ float c_dct[MAX_PSZ + 1][MAX_PSZ * MAX_PSZ];
+// the 8-point matrix again for the packed-fp32 transform (nlk_dct.cuh): c_dct8u[k*8+j] =
+// (T[k][j], T[k][j]) and c_dct8v[j*4+y] = (T[2j][y], T[2j+1][y])
+__constant__ float2 c_dct8u[64];
+__constant__ float2 c_dct8v[16];
 // Gaussian aggregation windows (reference src/nlkalman.c:401-416), one per side
 __constant__ float c_win[MAX_PSZ + 1][MAX_PSZ * MAX_PSZ];
 // c_inv[n] = (float)(1. / (float)n), the reference's Welford factors (src/nlkalman.c:755-756)

@@ -74,32 +74,44 @@ __device__ __forceinline__ void dct8x8_regs(float (&t)[64])
     }
 }
 
+// per-team scalars of the current group, kept in shared memory and re-read where they are
+// used: the transform phases hold a whole tile in registers and everything that stays live
+// across them costs a spill
+enum { GP_WOFF0 = 0, GP_WROW, GP_WPOFF, GP_K, GP_NP0, GP_NAGG, GP_NR1, GP_FLAGS, GP_G, GP_COUNT = 12 };
+constexpr int GPF_PREV = 1, GPF_POINT = 2;
+
+__device__ __forceinline__ int lds_par(const int *p)
+{
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+
 template <int CH, bool SMOOTH>
 __global__ void __launch_bounds__(GW_TEAM * GW_MAX_TEAMS, 1)
 k_group_team8(const PassParams P, const GroupWarpGeom Gm)
 {
-    constexpr int PSZ = 8, PP = 64, TS = GW_TS;
-    constexpr int AS = PP + 1; // channel stride of the gain table in float2 {a, (1-a)*m} (2*AS floats: banks 0, 2, 4)
+    constexpr int PSZ = 8, TS = GW_TS;
+    // gain table: per channel 32 records {a[2j][k], a[2j+1][k], ((1-a)*m)[2j][k], ((1-a)*m)[2j+1][k]}
+    // at j*8+k -- the coefficient pairing of the packed transform (nlk_dct.cuh)
+    constexpr int GS = 32;
     constexpr int MC = GW_TEAM / CH;   // members per update round
+    constexpr int CC1 = GW_TEAM / CH, CC2 = GW_TEAM / (2 * CH);   // candidates per statistics round (1 / 2 sources)
     extern __shared__ __align__(16) float smem[];
     const int team = threadIdx.x / GW_TEAM;
     const int l64 = threadIdx.x % GW_TEAM;       // lane within the team
-    const int lane = threadIdx.x & 31, wg = l64 >> 5;
     const int bar = 1 + team;
 
-    float *base = smem + (size_t)team * Gm.team_floats;
-    float *tiles = base;                              // [64][TS]
-    float *win = tiles + 64 * TS;                     // window area
-    float2 *s_am = reinterpret_cast<float2 *>(win + Gm.win_floats);   // [CH][AS] gain a and (1-a)*mean (M0 or M1)
-    uint32_t *s_cand = reinterpret_cast<uint32_t *>(s_am + CH * AS);  // [kcap]
-    int *s_grp = reinterpret_cast<int *>(s_cand + Gm.kcap);           // [kcap]
-    float *s_red = reinterpret_cast<float *>(s_grp + Gm.kcap);        // [2]
-    int *s_tick = reinterpret_cast<int *>(s_red + 2);                 // [2] ticket, by parity
+    float *const tiles = smem + (size_t)team * Gm.team_floats;             // [64][TS]
+    float *const win = tiles + 64 * TS;                                    // window area
+    float4 *const s_am = reinterpret_cast<float4 *>(win + Gm.win_floats);  // [CH][GS] gain a and (1-a)*mean (M0 or M1)
+    uint32_t *const s_cand = reinterpret_cast<uint32_t *>(s_am + CH * GS); // [kcap]
+    int *const s_grp = reinterpret_cast<int *>(s_cand + Gm.kcap);          // [kcap]
+    float *const s_red = reinterpret_cast<float *>(s_grp + Gm.kcap);       // [2]
+    int *const s_tick = reinterpret_cast<int *>(s_red + 2);                // [2] ticket, by parity
+    int *const s_par = s_tick + 2;                                         // [GP_COUNT]
 
     const int nactive = *P.nactive;
-    const float sigma2 = P.sigma2;
-    const int e_hy = l64 >> 3, e_hx = l64 & 7;       // this lane's pixel / coefficient position
-    const float We = c_win[PSZ][l64];
 
     for (int it = 0;; ++it) {
         // the ticket slot alternates: a lane may still be reading the previous ticket when
@@ -108,67 +120,76 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
         team_sync(bar);
         const int ai = s_tick[it & 1];
         if (ai >= nactive) break;
-        const int g = P.active[ai];
-        const GroupHdr hd = P.hdr[g];
-        const int gy = g / P.gw, gx = g - gy * P.gw;
-        const int px = gx * P.step, py = gy * P.step;
-        const int prev_p = hd.flags & HDR_PREV_P;
-        int k = hd.nk;
-        const int np0 = hd.np0;
-        const bool point = SMOOTH && k == 0 && prev_p;   // (reference :1699-1730)
-
-        if (!SMOOTH && k == 0) continue;                 // filter, k <= 1 (:815-849, :857)
-
-        if (SMOOTH && np0 == 0) {
-            // reference :1795-1804: the filtered patch at p, weight 1/1e-6, mask untouched
-            const float wgt = __fdiv_rn(1.f, 1e-6f);
-            const long pix = (long)(py + e_hy) * P.w + px + e_hx;
-            const float wW = __fmul_rn(wgt, We);
-            float v[CH];
-#pragma unroll
-            for (int c = 0; c < CH; ++c) v[c] = __fmul_rn(wW, P.in1[pix * CH + c]);
-            accumulate_pixel<CH>(P.accw + pix * (CH + 1), v, wW, CH);
-            if (P.dbg_vp && l64 == 0) P.dbg_vp[g] = 0.f;
-            continue;
-        }
-
-        // ---- stage the search window(s) of this group (reference :637-639) -----------------
-        const int r = point ? 0 : (SMOOTH ? P.r_t : (prev_p ? P.r_t : P.r_x));
-        const int wrow = (r == P.r_t || point) ? Gm.wrow_t : Gm.wrow_x;
-        const int x0 = max(px - r, 0), x1 = min(px + r, P.w - PSZ);
-        const int y0 = max(py - r, 0), y1 = min(py + r, P.h - PSZ);
-        const int wlen = (x1 - x0 + PSZ) * CH, wh = y1 - y0 + PSZ;
-        float *winS = win;
-        float *winP = win + wh * wrow;
         {
-            // warp wg takes rows wg, wg+2, ...; every element is its own 4-byte cp.async
-            const long g0 = ((long)(y0 + wg) * P.w + x0) * CH;
-            const long gstep = 2L * P.w * CH;
-            for (int j = lane; j < wlen; j += 32) {
-                const float *gs = P.src + g0 + j;
-                float *ds = winS + wg * wrow + j;
-                for (int row = wg; row < wh; row += 2, gs += gstep, ds += 2 * wrow) cp_async4(ds, gs);
-                if (prev_p) {
-                    const float *gp = P.prev0 + g0 + j;
-                    float *dp = winP + wg * wrow + j;
-                    for (int row = wg; row < wh; row += 2, gp += gstep, dp += 2 * wrow) cp_async4(dp, gp);
+            const int lane = threadIdx.x & 31, wg = l64 >> 5;
+            const int g = P.active[ai];
+            const GroupHdr hd = P.hdr[g];
+            const int gy = g / P.gw, gx = g - gy * P.gw;
+            const int px = gx * P.step, py = gy * P.step;
+            const int prev_p = hd.flags & HDR_PREV_P;
+            int k = hd.nk;
+            const int np0 = hd.np0;
+            const bool point = SMOOTH && k == 0 && prev_p;   // (reference :1699-1730)
+
+            if (!SMOOTH && k == 0) continue;                 // filter, k <= 1 (:815-849, :857)
+
+            if (SMOOTH && np0 == 0) {
+                // reference :1795-1804: the filtered patch at p, weight 1/1e-6, mask untouched
+                const float wgt = __fdiv_rn(1.f, 1e-6f);
+                const long pix = (long)(py + (l64 >> 3)) * P.w + px + (l64 & 7);
+                const float wW = __fmul_rn(wgt, c_win[PSZ][l64]);
+                float v[CH];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) v[c] = __fmul_rn(wW, P.in1[pix * CH + c]);
+                accumulate_pixel<CH>(P.accw + pix * (CH + 1), v, wW, CH);
+                if (P.dbg_vp && l64 == 0) P.dbg_vp[g] = 0.f;
+                continue;
+            }
+
+            // ---- stage the search window(s) of this group (reference :637-639) -----------------
+            const int r = point ? 0 : (SMOOTH ? P.r_t : (prev_p ? P.r_t : P.r_x));
+            const int wrow = (r == P.r_t || point) ? Gm.wrow_t : Gm.wrow_x;
+            const int x0 = max(px - r, 0), x1 = min(px + r, P.w - PSZ);
+            const int y0 = max(py - r, 0), y1 = min(py + r, P.h - PSZ);
+            const int wlen = (x1 - x0 + PSZ) * CH, wh = y1 - y0 + PSZ;
+            {
+                // warp wg takes rows wg, wg+2, ...; every element is its own 4-byte cp.async
+                float *winS = win, *winP = win + wh * wrow;
+                const long g0 = ((long)(y0 + wg) * P.w + x0) * CH;
+                const long gstep = 2L * P.w * CH;
+                for (int j = lane; j < wlen; j += 32) {
+                    const float *gs = P.src + g0 + j;
+                    float *ds = winS + wg * wrow + j;
+                    for (int row = wg; row < wh; row += 2, gs += gstep, ds += 2 * wrow) cp_async4(ds, gs);
+                    if (prev_p) {
+                        const float *gp = P.prev0 + g0 + j;
+                        float *dp = winP + wg * wrow + j;
+                        for (int row = wg; row < wh; row += 2, gp += gstep, dp += 2 * wrow) cp_async4(dp, gp);
+                    }
                 }
             }
-        }
-        if (point) {
-            if (l64 == 0) s_cand[0] = cand_pack(px, py, 1);
-            k = 1;
-        } else {
-            for (int i = l64; i < k; i += GW_TEAM) s_cand[i] = P.cand[(long)g * P.kstride + i];
-        }
-        cp_async_wait_all();
-        team_sync(bar);
+            if (point) {
+                if (l64 == 0) s_cand[0] = cand_pack(px, py, 1);
+                k = 1;
+            } else {
+                for (int i = l64; i < k; i += GW_TEAM) s_cand[i] = P.cand[(long)g * P.kstride + i];
+            }
+            if (l64 == 0) {
+                s_par[GP_WOFF0] = y0 * wrow + x0 * CH;
+                s_par[GP_WROW] = wrow;
+                s_par[GP_WPOFF] = wh * wrow;
+                s_par[GP_K] = k;
+                s_par[GP_NP0] = np0;
+                s_par[GP_NR1] = prev_p ? (k + CC2 - 1) / CC2 : (k + CC1 - 1) / CC1;
+                s_par[GP_FLAGS] = (prev_p ? GPF_PREV : 0) | (point ? GPF_POINT : 0);
+                s_par[GP_G] = g;
+            }
+            cp_async_wait_all();
+            team_sync(bar);
 
-        // group members: the first tagg candidates with a valid previous patch, or, when
-        // there is none (filter only), the first tagg candidates (:779-793, :857, :1669, :1737).
-        // Both warps compute the same list.
-        int nagg;
-        {
+            // group members: the first tagg candidates with a valid previous patch, or, when
+            // there is none (filter only), the first tagg candidates (:779-793, :857, :1669, :1737).
+            // Both warps compute the same list.
             int cnt = 0;
             for (int b0 = 0; b0 < k && cnt < P.tagg; b0 += 32) {
                 const int i = b0 + lane;
@@ -179,146 +200,174 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                 if (take && rank < P.tagg) s_grp[rank] = i;
                 cnt += __popc(bal);
             }
-            nagg = min(cnt, P.tagg);
+            if (l64 == 0) s_par[GP_NAGG] = min(cnt, P.tagg);   // read after the next barrier
         }
 
-        // The temporal filter only uses the statistics of the candidates with a valid
-        // previous patch (V0, V01, M0: reference :867-878); M1 / V1 over all candidates are
-        // needed by the spatial branch (np0 == 0, :890-901) and by the smoother (:1768).
-        const bool need1 = SMOOTH || np0 == 0;
-        const int nsrc = prev_p ? 2 : 1;
-        const int tpc = nsrc * CH;          // tiles per candidate
-        const int cc = GW_TEAM / tpc;       // candidates per statistics round
-        const int nr1 = (k + cc - 1) / cc, nr2 = (nagg + MC - 1) / MC;
-        float M1[CH], V1[CH], Mp[CH], V0[CH], V01[CH], Mg[CH];
+        // statistics, in registers across the statistics rounds.  The temporal filter only uses
+        // the candidates with a valid previous patch (V0, V01, M0: reference :867-878); M1 / V1
+        // over all candidates are needed by the spatial branch (np0 == 0, :890-901, where no
+        // candidate has a previous patch) and by the smoother (:1768) -- so the filter keeps
+        // either pair in the same registers:
+        //   filter:   sA = M1 or M0V, sB = V1 or V0, sC = V01, sD = M0 (group mean)
+        //   smoother: sA = M1, sB = V1, sC = V01, sD = M0V, sE = V0
+        float sA[CH], sB[CH], sC[CH], sD[CH], sE[SMOOTH ? CH : 1];
 #pragma unroll
-        for (int u = 0; u < CH; ++u) M1[u] = V1[u] = Mp[u] = V0[u] = V01[u] = Mg[u] = 0.f;
-        int n1 = 0, n0 = 0;
-        float wgt = 0.f;
+        for (int u = 0; u < CH; ++u) sA[u] = sB[u] = sC[u] = sD[u] = 0.f;
+#pragma unroll
+        for (int u = 0; u < (SMOOTH ? CH : 1); ++u) sE[u] = 0.f;
+        int n0 = 0;
 
-        for (int round = 0; round < nr1 + nr2; ++round) {
-            const bool stat = round < nr1;
-            const int first = stat ? round * cc : (round - nr1) * MC;      // first candidate / member
-            const int cnt = stat ? min(cc, k - first) : min(MC, nagg - first);
+        for (int round = 0;; ++round) {
             if (round) team_sync(bar);   // the previous round's consumers are done with `tiles`
+            const int nr1 = lds_par(s_par + GP_NR1);
+            const bool stat = round < nr1;
+            const int flags = lds_par(s_par + GP_FLAGS);
+            const int np0 = lds_par(s_par + GP_NP0);
+            const bool need1 = SMOOTH || np0 == 0;
+            int first, cnt;
+            if (stat) {
+                const int k = lds_par(s_par + GP_K);
+                const int cc = (flags & GPF_PREV) ? CC2 : CC1;
+                first = round * cc;
+                cnt = min(cc, k - first);
+            } else {
+                const int nagg = lds_par(s_par + GP_NAGG);
+                first = (round - nr1) * MC;
+                if (first >= nagg) break;
+                cnt = min(MC, nagg - first);
+            }
 
             // ---- producer ------------------------------------------------------------------------
-            if (!stat && cnt * CH <= 8) {
-                // few members (second filtering: one): a whole tile per lane would leave the team
-                // idle behind a handful of lanes, so lane = one row / column of a tile instead
-                const int tt = l64 >> 3, y = l64 & 7;
-                const bool act = tt < cnt * CH;
-                int off = 0, c = 0;
-                if (act) {
-                    const int ml = tt / CH;
-                    c = tt - ml * CH;
-                    const uint32_t cd = s_cand[s_grp[first + ml]];
-                    off = (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * CH + c;
-                }
-                float *tb = tiles + tt * TS;
-                const float *wS = winS + off + y * wrow, *wP = winP + off + y * wrow;
-                if (act) {      // rows, forward
-                    float r[8];
-#pragma unroll
-                    for (int x = 0; x < 8; ++x) r[x] = SMOOTH ? wP[x * CH] - wS[x * CH] : wS[x * CH];
-                    dct1d_fwd<8>(r);
-#pragma unroll
-                    for (int x = 0; x < 8; ++x) tb[y * 8 + x] = r[x];
-                }
-                team_sync(bar);
-                if (act) {      // columns (y is the column index here): forward, shrink, inverse
-                    float r[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) r[i] = tb[i * 8 + y];
-                    dct1d_fwd<8>(r);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float2 am = s_am[c * AS + i * 8 + y];
-                        if (SMOOTH) r[i] *= am.x;                                        // :1775
-                        else r[i] = fmaf(am.x, r[i], am.y);                              // :878 / :901
+            {
+                const int woff0 = lds_par(s_par + GP_WOFF0), wrow = lds_par(s_par + GP_WROW);
+                const float *winS = win - woff0;                       // indexed by image coordinates
+                const float *winP = winS + lds_par(s_par + GP_WPOFF);
+                if (!stat && cnt * CH <= 8) {
+                    // few members (second filtering: one): a whole tile per lane would leave the team
+                    // idle behind a handful of lanes, so lane = one row / column of a tile instead
+                    const int tt = l64 >> 3, y = l64 & 7;
+                    const bool act = tt < cnt * CH;
+                    int off = 0, c = 0;
+                    if (act) {
+                        const int ml = tt / CH;
+                        c = tt - ml * CH;
+                        const uint32_t cd = s_cand[s_grp[first + ml]];
+                        off = cand_y(cd) * wrow + cand_x(cd) * CH + c;
                     }
-                    dct1d_inv<8>(r);
+                    float *tb = tiles + tt * TS;
+                    const float *wS = winS + off + y * wrow, *wP = winP + off + y * wrow;
+                    if (act) {      // rows, forward
+                        float r[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) tb[i * 8 + y] = r[i];
-                }
-                team_sync(bar);
-                if (act) {      // rows, inverse
-                    float r[8];
+                        for (int x = 0; x < 8; ++x) r[x] = SMOOTH ? wP[x * CH] - wS[x * CH] : wS[x * CH];
+                        dct1d_fwd<8>(r);
 #pragma unroll
-                    for (int x = 0; x < 8; ++x) r[x] = tb[y * 8 + x];
-                    dct1d_inv<8>(r);
+                        for (int x = 0; x < 8; ++x) tb[y * 8 + x] = r[x];
+                    }
+                    team_sync(bar);
+                    if (act) {      // columns (y is the column index here): forward, shrink, inverse
+                        float r[8];
 #pragma unroll
-                    for (int x = 0; x < 8; ++x) tb[y * 8 + x] = SMOOTH ? r[x] + wS[x * CH] : r[x];
-                }
-            } else {
-                bool act;
-                int s = 0, c;
-                uint32_t cd;
-                if (stat) {
-                    const int slot = l64 / tpc, rr = l64 - slot * tpc;
-                    s = rr >= CH; c = rr - s * CH;
-                    act = l64 < cnt * tpc;
-                    cd = s_cand[first + (act ? slot : 0)];
-                    // no previous patch: no previous-frame tile; and its source tile only
-                    // matters where M1 / V1 do
-                    if (!cand_prev(cd) && (s == 1 || !need1)) act = false;
+                        for (int i = 0; i < 8; ++i) r[i] = tb[i * 8 + y];
+                        dct1d_fwd<8>(r);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float *am = reinterpret_cast<const float *>(s_am + c * GS + (i >> 1) * 8 + y) + (i & 1);
+                            if (SMOOTH) r[i] *= am[0];                                       // :1775
+                            else r[i] = fmaf(am[0], r[i], am[2]);                            // :878 / :901
+                        }
+                        dct1d_inv<8>(r);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) tb[i * 8 + y] = r[i];
+                    }
+                    team_sync(bar);
+                    if (act) {      // rows, inverse
+                        float r[8];
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) r[x] = tb[y * 8 + x];
+                        dct1d_inv<8>(r);
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) tb[y * 8 + x] = SMOOTH ? r[x] + wS[x * CH] : r[x];
+                    }
                 } else {
-                    const int ml = l64 / CH;
-                    c = l64 - ml * CH;
-                    act = l64 < cnt * CH;
-                    cd = s_cand[s_grp[first + (act ? ml : 0)]];
-                }
-                if (act) {
-                    const int off = (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * CH + c;
-                    const float *wS = winS + off, *wP = winP + off;
-                    float t[64];
-                    if (SMOOTH && !stat) {
-                        // x1 + T^-1(a * T(x0 - x1))                        (:1775)
-#pragma unroll
-                        for (int y = 0; y < 8; ++y)
-#pragma unroll
-                            for (int x = 0; x < 8; ++x)
-                                t[y * 8 + x] = wP[y * wrow + x * CH] - wS[y * wrow + x * CH];
+                    bool act;
+                    int s = 0, c;
+                    uint32_t cd;
+                    if (stat) {
+                        int slot, rr;
+                        if (flags & GPF_PREV) { slot = l64 / (2 * CH); rr = l64 - slot * (2 * CH); }
+                        else { slot = l64 / CH; rr = l64 - slot * CH; }
+                        s = rr >= CH; c = rr - s * CH;
+                        act = slot < cnt;
+                        cd = s_cand[first + (act ? slot : 0)];
+                        // no previous patch: no previous-frame tile; and its source tile only
+                        // matters where M1 / V1 do
+                        if (!cand_prev(cd) && (s == 1 || !need1)) act = false;
                     } else {
-                        const float *src = s ? wP : wS;
-#pragma unroll
-                        for (int y = 0; y < 8; ++y)
-#pragma unroll
-                            for (int x = 0; x < 8; ++x) t[y * 8 + x] = src[y * wrow + x * CH];
+                        const int ml = l64 / CH;
+                        c = l64 - ml * CH;
+                        act = l64 < cnt * CH;
+                        cd = s_cand[s_grp[first + (act ? ml : 0)]];
                     }
-                    dct8x8_regs<false>(t);
-                    if (!stat) {
-                        if (SMOOTH) {
+                    if (act) {
+                        const int off = cand_y(cd) * wrow + cand_x(cd) * CH + c;
+                        const float *wS = winS + off, *wP = winP + off;
+                        // the tile as 32 register pairs (row y, row 7-y), packed-fp32 transform
+                        float *dst = tiles + l64 * TS;
+                        if (stat) {
+                            const float *src = s ? wP : wS;
+                            f32x2 Pq[4][8];
 #pragma unroll
-                            for (int i = 0; i < 64; ++i) t[i] *= s_am[c * AS + i].x;
+                            for (int y = 0; y < 4; ++y)
+#pragma unroll
+                                for (int x = 0; x < 8; ++x)
+                                    Pq[y][x] = pk2(src[y * wrow + x * CH], src[(7 - y) * wrow + x * CH]);
+                            dct8x8_fwd_x2(Pq);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int kk = 0; kk < 8; ++kk) {
+                                    float lo, hi;
+                                    upk2(Pq[j][kk], lo, hi);
+                                    dst[(2 * j) * 8 + kk] = lo;
+                                    dst[(2 * j + 1) * 8 + kk] = hi;
+                                }
                         } else {
+                            f32x2 Pq[4][8];
 #pragma unroll
-                            for (int i = 0; i < 64; ++i) {
-                                const float2 am = s_am[c * AS + i];
-                                t[i] = fmaf(am.x, t[i], am.y);                   // :878 / :901
-                            }
-                        }
-                        dct8x8_regs<true>(t);
-                        if (SMOOTH) {
+                            for (int y = 0; y < 4; ++y)
 #pragma unroll
-                            for (int y = 0; y < 8; ++y)
+                                for (int x = 0; x < 8; ++x) {
+                                    // smoother: x1 + T^-1(a * T(x0 - x1))                        (:1775)
+                                    if (SMOOTH) Pq[y][x] = pk2(wP[y * wrow + x * CH] - wS[y * wrow + x * CH],
+                                                               wP[(7 - y) * wrow + x * CH] - wS[(7 - y) * wrow + x * CH]);
+                                    else Pq[y][x] = pk2(wS[y * wrow + x * CH], wS[(7 - y) * wrow + x * CH]);
+                                }
+                            dct8x8_shrink_x2<SMOOTH>(Pq, s_am + c * GS);                             // :878 / :901
 #pragma unroll
-                                for (int x = 0; x < 8; ++x) t[y * 8 + x] += wS[y * wrow + x * CH];
+                            for (int y = 0; y < 4; ++y)
+#pragma unroll
+                                for (int x = 0; x < 8; ++x) {
+                                    float lo, hi;
+                                    upk2(Pq[y][x], lo, hi);
+                                    if (SMOOTH) { lo += wS[y * wrow + x * CH]; hi += wS[(7 - y) * wrow + x * CH]; }
+                                    dst[y * 8 + x] = lo;
+                                    dst[(7 - y) * 8 + x] = hi;
+                                }
                         }
                     }
-                    float *dst = tiles + l64 * TS;
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) dst[i] = t[i];
                 }
             }
             team_sync(bar);
 
             if (!stat) {
                 // ---- aggregation: lane = pixel of the patch, one member per iteration ----------
-                const float wW = __fmul_rn(wgt, We);                        // :923
+                const float vp = (float)lds_par(s_par + GP_NAGG) * (s_red[0] + s_red[1]);
+                const float wgt = __fdiv_rn(1.f, fmaxf(vp, 1e-6f));         // :911
+                const float wW = __fmul_rn(wgt, c_win[PSZ][l64]);           // :923
                 for (int ml = 0; ml < cnt; ++ml) {
                     const uint32_t cd = s_cand[s_grp[first + ml]];
-                    const long pix = (long)(cand_y(cd) + e_hy) * P.w + cand_x(cd) + e_hx;
+                    const long pix = (long)(cand_y(cd) + (l64 >> 3)) * P.w + cand_x(cd) + (l64 & 7);
                     float v[CH];
 #pragma unroll
                     for (int c = 0; c < CH; ++c) v[c] = __fmul_rn(wW, tiles[(ml * CH + c) * TS + l64]); // :926
@@ -328,44 +377,45 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             }
 
             // ---- statistics: lane = coefficient position, candidates in sorted order ----------
-            if (point) {
+            if (flags & GPF_POINT) {
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
                     const float p = tiles[u * TS + l64], q = tiles[(CH + u) * TS + l64];
-                    V1[u] = p * p;
-                    V0[u] = q * q;
-                    V01[u] = (q - p) * (q - p);
+                    sB[u] = p * p;                       // V1
+                    sE[SMOOTH ? u : 0] = q * q;          // V0 (the point estimate exists for the smoother only)
+                    sC[u] = (q - p) * (q - p);           // V01
                 }
             } else {
-                const int cstride = tpc * TS;
+                const int cstride = ((flags & GPF_PREV) ? 2 * CH : CH) * TS;
                 const float *tp = tiles + l64;             // source tile of slot 0, channel 0
                 for (int i = 0; i < cnt; ++i, tp += cstride) {
                     const int hasq = cand_prev(s_cand[first + i]);   // (implies prev_p)
-                    n1 += 1;
-                    n0 += hasq;
                     if (need1) {
-                        const float in1v = c_inv[n1];
+                        const float in1v = c_inv[first + i + 1];
 #pragma unroll
                         for (int u = 0; u < CH; ++u) {
                             const float p = tp[u * TS];
-                            const float delta = p - M1[u];
-                            M1[u] = fmaf(delta, in1v, M1[u]);             // :765
-                            V1[u] = fmaf(delta, p - M1[u], V1[u]);        // :766
+                            const float delta = p - sA[u];
+                            sA[u] = fmaf(delta, in1v, sA[u]);             // :765
+                            sB[u] = fmaf(delta, p - sA[u], sB[u]);        // :766
                         }
                     }
                     if (hasq) {
+                        n0 += 1;
                         const float in0v = c_inv[n0];
                         const bool ing = n0 <= P.tagg;
 #pragma unroll
                         for (int u = 0; u < CH; ++u) {
                             const float p = tp[u * TS];
                             const float q = tp[(CH + u) * TS];
-                            const float d0 = q - Mp[u];               // :770-775 / :1654-1659
-                            Mp[u] = fmaf(d0, in0v, Mp[u]);
-                            V0[u] = fmaf(d0, q - Mp[u], V0[u]);
+                            float &Mp = SMOOTH ? sD[u] : sA[u];
+                            float &V0 = SMOOTH ? sE[SMOOTH ? u : 0] : sB[u];
+                            const float d0 = q - Mp;                  // :770-775 / :1654-1659
+                            Mp = fmaf(d0, in0v, Mp);
+                            V0 = fmaf(d0, q - Mp, V0);
                             const float t = q - p;
-                            V01[u] = fmaf(t, t, V01[u]);              // :777-778
-                            if (ing) Mg[u] = fmaf(q - Mg[u], in0v, Mg[u]); // :783
+                            sC[u] = fmaf(t, t, sC[u]);                // :777-778
+                            if (!SMOOTH && ing) sD[u] = fmaf(q - sD[u], in0v, sD[u]); // :783
                         }
                     }
                 }
@@ -376,52 +426,63 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             if (!SMOOTH && P.has_bsic) {
                 // the group holds the NOISY patches (:784-785, :853): the source window is no
                 // longer needed, put the members' noisy patches where their source patches were
+                const int woff0 = lds_par(s_par + GP_WOFF0), wrow = lds_par(s_par + GP_WROW);
+                const int nagg = lds_par(s_par + GP_NAGG);
                 for (int i = l64; i < nagg * PSZ * PSZ * CH; i += GW_TEAM) {
                     const int ml = i / (PSZ * PSZ * CH), rem = i - ml * (PSZ * PSZ * CH);
                     const int hy = rem / (PSZ * CH), j = rem - hy * (PSZ * CH);
                     const uint32_t cd = s_cand[s_grp[ml]];
                     const int qx = cand_x(cd), qy = cand_y(cd);
-                    winS[(qy - y0 + hy) * wrow + (qx - x0) * CH + j] = P.in1[((long)(qy + hy) * P.w + qx) * CH + j];
+                    win[(qy + hy) * wrow + qx * CH + j - woff0] = P.in1[((long)(qy + hy) * P.w + qx) * CH + j];
                 }
             }
             float vsum = 0.f;
             {
+                const bool point = flags & GPF_POINT;
+                const int n1 = point ? 0 : lds_par(s_par + GP_K);
                 const float inp1 = c_inv[max(n1, 1)];
                 const float inp0 = c_inv[n0];
+                const float sigma2 = P.sigma2;
                 const float s2 = P.has_bsic ? 0.f : sigma2;
+                const int e_hy = l64 >> 3, e_hx = l64 & 7;
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
-                    float v1 = V1[u], v0 = V0[u], v01 = V01[u];
-                    if (!point) {
-                        v1 *= inp1;                             // :805
-                        if (n0) { v0 *= inp0; v01 *= inp0; }    // :806-810
-                    }
                     float a, m;
                     if (SMOOTH) {
+                        float v1 = sB[u], v0 = sE[SMOOTH ? u : 0], v01 = sC[u];
+                        if (!point) {
+                            v1 *= inp1;                             // :805
+                            if (n0) { v0 *= inp0; v01 *= inp0; }    // :806-810
+                        }
                         a = __fdiv_rn(v1, v1 + P.beta_t * v01);              // :1768
                         vsum += (1.f - a * a) * v1 + a * a * fmaxf(v0 - P.beta_t * v01, 0.f);
                         m = 0.f;
                     } else if (n0 > 0) {
+                        const float v0 = sB[u] * inp0, v01 = sC[u] * inp0;   // :806-810
                         const float v = v0 + fmaxf(0.f, v01 - s2);           // :867
                         a = __fdiv_rn(v, v + P.beta_t * sigma2);             // :870
                         vsum += (1.f - a * a) * v + a * a * sigma2;          // :875
-                        m = Mg[u];
+                        m = sD[u];
                     } else {
+                        const float v1 = sB[u] * inp1;                       // :805
                         const float v = fmaxf(0.f, v1 - s2);                 // :890
                         a = __fdiv_rn(v, v + P.beta_x * sigma2);             // :893
                         vsum += a * v;                                       // :898
-                        m = M1[u];
+                        m = sA[u];
                     }
-                    s_am[u * AS + l64] = make_float2(a, (1.f - a) * m);
+                    float *gp = reinterpret_cast<float *>(s_am + u * GS + (e_hy >> 1) * 8 + e_hx) + (e_hy & 1);
+                    gp[0] = a;
+                    gp[2] = (1.f - a) * m;
                 }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
-            if (lane == 0) s_red[wg] = vsum;
-            team_sync(bar);   // gains (and restaged members) visible
-            const float vp = (float)nagg * (s_red[0] + s_red[1]);
-            wgt = __fdiv_rn(1.f, fmaxf(vp, 1e-6f)); // :911
-            if (P.dbg_vp && l64 == 0) P.dbg_vp[g] = vp;
+            if ((l64 & 31) == 0) s_red[l64 >> 5] = vsum;
+            if (P.dbg_vp) {
+                team_sync(bar);
+                if (l64 == 0) P.dbg_vp[lds_par(s_par + GP_G)] = (float)lds_par(s_par + GP_NAGG) * (s_red[0] + s_red[1]);
+            }
+            // the barrier at the top of the next round makes the gains (and restaged members) visible
         }
     }
 }
@@ -436,9 +497,9 @@ inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st)
     Gm.wrow_x = ((2 * P.r_x + 8) * ch) | 1;
     const int win_t = (2 * P.r_t + 8) * Gm.wrow_t * (P.has_prev ? 2 : 1);
     const int win_x = P.smooth ? 0 : (2 * P.r_x + 8) * Gm.wrow_x;
-    Gm.win_floats = ((win_t > win_x ? win_t : win_x) + 1) & ~1;   // even: the float2 table behind it stays aligned
+    Gm.win_floats = ((win_t > win_x ? win_t : win_x) + 3) & ~3;   // the float4 gain table behind it stays aligned
     Gm.kcap = P.kstride > 1 ? P.kstride : 1;
-    int fl = 64 * GW_TS + Gm.win_floats + 2 * ch * 65 + 2 * Gm.kcap + 2 + 2;
+    int fl = 64 * GW_TS + Gm.win_floats + ch * 128 + 2 * Gm.kcap + 2 + 2 + GP_COUNT;
     fl = (fl + 3) & ~3;
     Gm.team_floats = fl;
     const int budget = 227 * 1024;

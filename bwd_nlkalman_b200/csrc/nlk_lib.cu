@@ -75,6 +75,12 @@ static int upload_tables_dev()
     inv[0] = 0.f;
     for (int n = 1; n <= MAX_K; ++n) inv[n] = (float)(1. / (float)n);
     CU_TRY(cudaMemcpyToSymbol(c_dct, dct, sizeof dct));
+    static float2 d8u[64], d8v[16];
+    for (int i = 0; i < 64; ++i) d8u[i] = make_float2(dct[8][i], dct[8][i]);
+    for (int j = 0; j < 4; ++j)
+        for (int y = 0; y < 4; ++y) d8v[j * 4 + y] = make_float2(dct[8][(2 * j) * 8 + y], dct[8][(2 * j + 1) * 8 + y]);
+    CU_TRY(cudaMemcpyToSymbol(c_dct8u, d8u, sizeof d8u));
+    CU_TRY(cudaMemcpyToSymbol(c_dct8v, d8v, sizeof d8v));
     CU_TRY(cudaMemcpyToSymbol(c_win, win, sizeof win));
     CU_TRY(cudaMemcpyToSymbol(c_inv, inv, sizeof inv));
     return NLK_OK;
