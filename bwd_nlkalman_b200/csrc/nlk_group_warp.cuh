@@ -34,6 +34,7 @@ struct GroupWarpGeom {
     int win_floats;   // floats of the window area (one spatial window or two temporal ones)
     int wrow_t, wrow_x;   // row strides of the staged windows (temporal / spatial radius)
     int kcap;         // capacity of the candidate list
+    int noisy_floats; // area for the members' noisy patches (second filtering), 0 = none
 };
 
 __device__ __forceinline__ void team_sync(int bar_id)
@@ -77,6 +78,7 @@ __device__ __forceinline__ void dct8x8_regs(float (&t)[64])
 // per-team scalars of the current group, kept in shared memory and re-read where they are
 // used: the transform phases hold a whole tile in registers and everything that stays live
 // across them costs a spill
+enum { GN_AI = 0, GN_G, GN_NK, GN_NP0, GN_FLAGS, GN_COUNT = 6 };
 enum { GP_WOFF0 = 0, GP_WROW, GP_WPOFF, GP_K, GP_NP0, GP_NAGG, GP_NR1, GP_FLAGS, GP_G, GP_COUNT = 12 };
 constexpr int GPF_PREV = 1, GPF_POINT = 2;
 
@@ -87,6 +89,31 @@ __device__ __forceinline__ int lds_par(const int *p)
     return v;
 }
 
+// The ticket chain of a team's NEXT group, one dependent global access per stage:
+//   stage 0: ticket = atomicAdd(work)   stage 1: g = active[ticket]   stage 2: hdr[g]
+// Lane 0 issues a stage at the start of a consumer phase (few live registers there) and stores
+// the result in the next iteration's slot at the end of the phase, so each round trip runs
+// under the team's own work instead of in front of it.
+__device__ __forceinline__ int4 chain_issue(int stage, const int *slot, const PassParams &P, int nactive)
+{
+    int4 v = make_int4(0, 0, 0, 0);
+    if (stage == 0) {
+        v.x = atomicAdd(P.work, 1);
+    } else if (stage == 1) {
+        const int t = slot[GN_AI];
+        if (t < nactive) v.x = P.active[t];
+    } else {
+        if (slot[GN_AI] < nactive) v = *reinterpret_cast<const int4 *>(P.hdr + slot[GN_G]);
+    }
+    return v;
+}
+__device__ __forceinline__ void chain_store(int stage, int *slot, const int4 v)
+{
+    if (stage == 0) slot[GN_AI] = v.x;
+    else if (stage == 1) slot[GN_G] = v.x;
+    else { slot[GN_NK] = v.x; slot[GN_NP0] = v.y; slot[GN_FLAGS] = v.z; }
+}
+
 template <int CH, bool SMOOTH>
 __global__ void __launch_bounds__(GW_TEAM * GW_MAX_TEAMS, 1)
 k_group_team8(const PassParams P, const GroupWarpGeom Gm)
@@ -94,7 +121,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
     constexpr int PSZ = 8, TS = GW_TS;
     // gain table: per channel 32 records {a[2j][k], a[2j+1][k], ((1-a)*m)[2j][k], ((1-a)*m)[2j+1][k]}
     // at j*8+k -- the coefficient pairing of the packed transform (nlk_dct.cuh)
-    constexpr int GS = 32;
+    constexpr int GS = 33;             // 33 records per channel: the channels of a warp read different banks
     constexpr int MC = GW_TEAM / CH;   // members per update round
     constexpr int CC1 = GW_TEAM / CH, CC2 = GW_TEAM / (2 * CH);   // candidates per statistics round (1 / 2 sources)
     extern __shared__ __align__(16) float smem[];
@@ -108,22 +135,30 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
     uint32_t *const s_cand = reinterpret_cast<uint32_t *>(s_am + CH * GS); // [kcap]
     int *const s_grp = reinterpret_cast<int *>(s_cand + Gm.kcap);          // [kcap]
     float *const s_red = reinterpret_cast<float *>(s_grp + Gm.kcap);       // [2]
-    int *const s_tick = reinterpret_cast<int *>(s_red + 2);                // [2] ticket, by parity
-    int *const s_par = s_tick + 2;                                         // [GP_COUNT]
+    int *const s_nxt = reinterpret_cast<int *>(s_red + 2);                 // [2][GN_COUNT] ticket and header of a group, by parity
+    int *const s_par = s_nxt + 2 * GN_COUNT;                               // [GP_COUNT]
+    float *const s_noisy = reinterpret_cast<float *>(s_par + GP_COUNT);    // [noisy_floats]
 
     const int nactive = *P.nactive;
 
+    // Groups are handed out by an atomic ticket; the chain ticket -> active[] -> hdr[] of the next
+    // group runs under the current one (chain_issue / chain_store), its result is read from the
+    // slot of the iteration's parity after the barrier that opens the iteration.
+    if (l64 == 0) {
+        for (int st = 0; st < 3; ++st) chain_store(st, s_nxt, chain_issue(st, s_nxt, P, nactive));
+    }
+
     for (int it = 0;; ++it) {
-        // the ticket slot alternates: a lane may still be reading the previous ticket when
-        // lane 0 takes the next one, but never the one before (a barrier lies in between)
-        if (l64 == 0) s_tick[it & 1] = atomicAdd(P.work, 1);
         team_sync(bar);
-        const int ai = s_tick[it & 1];
-        if (ai >= nactive) break;
+        const int *nx = s_nxt + (it & 1) * GN_COUNT;
+        if (nx[GN_AI] >= nactive) break;
+        int round = 0;
+        do {
         {
             const int lane = threadIdx.x & 31, wg = l64 >> 5;
-            const int g = P.active[ai];
-            const GroupHdr hd = P.hdr[g];
+            const int g = nx[GN_G];
+            GroupHdr hd;
+            hd.nk = nx[GN_NK]; hd.np0 = nx[GN_NP0]; hd.flags = nx[GN_FLAGS];
             const int gy = g / P.gw, gx = g - gy * P.gw;
             const int px = gx * P.step, py = gy * P.step;
             const int prev_p = hd.flags & HDR_PREV_P;
@@ -131,7 +166,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             const int np0 = hd.np0;
             const bool point = SMOOTH && k == 0 && prev_p;   // (reference :1699-1730)
 
-            if (!SMOOTH && k == 0) continue;                 // filter, k <= 1 (:815-849, :857)
+            if (!SMOOTH && k == 0) break;                    // filter, k <= 1 (:815-849, :857)
 
             if (SMOOTH && np0 == 0) {
                 // reference :1795-1804: the filtered patch at p, weight 1/1e-6, mask untouched
@@ -143,7 +178,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                 for (int c = 0; c < CH; ++c) v[c] = __fmul_rn(wW, P.in1[pix * CH + c]);
                 accumulate_pixel<CH>(P.accw + pix * (CH + 1), v, wW, CH);
                 if (P.dbg_vp && l64 == 0) P.dbg_vp[g] = 0.f;
-                continue;
+                break;
             }
 
             // ---- stage the search window(s) of this group (reference :637-639) -----------------
@@ -217,7 +252,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
         for (int u = 0; u < (SMOOTH ? CH : 1); ++u) sE[u] = 0.f;
         int n0 = 0;
 
-        for (int round = 0;; ++round) {
+        for (;; ++round) {
             if (round) team_sync(bar);   // the previous round's consumers are done with `tiles`
             const int nr1 = lds_par(s_par + GP_NR1);
             const bool stat = round < nr1;
@@ -237,6 +272,22 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                 cnt = min(MC, nagg - first);
             }
 
+            // second filtering: the group holds the NOISY patches of its members (:784-785, :853).
+            // They are fetched into their own area while the statistics run (issued in round 1,
+            // awaited after the gains); without room, or with a single statistics round, they
+            // replace the source patches in the window after the gains instead.
+            const bool noisy = !SMOOTH && P.has_bsic && nr1 >= 2 &&
+                               (round == 0 ? false : lds_par(s_par + GP_NAGG) * (PSZ * PSZ * CH) <= Gm.noisy_floats);
+            if (noisy && round == 1) {
+                const int nagg = lds_par(s_par + GP_NAGG);
+                for (int i = l64; i < nagg * PSZ * PSZ * CH; i += GW_TEAM) {
+                    const int ml = i / (PSZ * PSZ * CH), rem = i - ml * (PSZ * PSZ * CH);
+                    const int hy = rem / (PSZ * CH), j = rem - hy * (PSZ * CH);
+                    const uint32_t cd = s_cand[s_grp[ml]];
+                    cp_async4(s_noisy + i, P.in1 + ((long)(cand_y(cd) + hy) * P.w + cand_x(cd)) * CH + j);
+                }
+            }
+
             // ---- producer ------------------------------------------------------------------------
             {
                 const int woff0 = lds_par(s_par + GP_WOFF0), wrow = lds_par(s_par + GP_WROW);
@@ -247,15 +298,17 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                     // idle behind a handful of lanes, so lane = one row / column of a tile instead
                     const int tt = l64 >> 3, y = l64 & 7;
                     const bool act = tt < cnt * CH;
-                    int off = 0, c = 0;
+                    int off = 0, c = 0, ml = 0;
                     if (act) {
-                        const int ml = tt / CH;
+                        ml = tt / CH;
                         c = tt - ml * CH;
                         const uint32_t cd = s_cand[s_grp[first + ml]];
                         off = cand_y(cd) * wrow + cand_x(cd) * CH + c;
                     }
                     float *tb = tiles + tt * TS;
-                    const float *wS = winS + off + y * wrow, *wP = winP + off + y * wrow;
+                    const float *wS = noisy ? s_noisy + (first + ml) * (PSZ * PSZ * CH) + y * (PSZ * CH) + c
+                                            : winS + off + y * wrow;
+                    const float *wP = winP + off + y * wrow;
                     if (act) {      // rows, forward
                         float r[8];
 #pragma unroll
@@ -312,6 +365,8 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                     if (act) {
                         const int off = cand_y(cd) * wrow + cand_x(cd) * CH + c;
                         const float *wS = winS + off, *wP = winP + off;
+                        int mrow = wrow;     // the member's patch for the update: window or noisy area
+                        if (noisy && !stat) { wS = s_noisy + (first + l64 / CH) * (PSZ * PSZ * CH) + c; mrow = PSZ * CH; }
                         // the tile as 32 register pairs (row y, row 7-y), packed-fp32 transform
                         float *dst = tiles + l64 * TS;
                         if (stat) {
@@ -341,7 +396,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                                     // smoother: x1 + T^-1(a * T(x0 - x1))                        (:1775)
                                     if (SMOOTH) Pq[y][x] = pk2(wP[y * wrow + x * CH] - wS[y * wrow + x * CH],
                                                                wP[(7 - y) * wrow + x * CH] - wS[(7 - y) * wrow + x * CH]);
-                                    else Pq[y][x] = pk2(wS[y * wrow + x * CH], wS[(7 - y) * wrow + x * CH]);
+                                    else Pq[y][x] = pk2(wS[y * mrow + x * CH], wS[(7 - y) * mrow + x * CH]);
                                 }
                             dct8x8_shrink_x2<SMOOTH>(Pq, s_am + c * GS);                             // :878 / :901
 #pragma unroll
@@ -360,6 +415,11 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             }
             team_sync(bar);
 
+            // lane 0: one stage of the next group's ticket chain per consumer phase
+            int *const nxn = s_nxt + ((it + 1) & 1) * GN_COUNT;
+            int4 pf = make_int4(0, 0, 0, 0);
+            if (l64 == 0 && round < 3) pf = chain_issue(round, nxn, P, nactive);
+
             if (!stat) {
                 // ---- aggregation: lane = pixel of the patch, one member per iteration ----------
                 const float vp = (float)lds_par(s_par + GP_NAGG) * (s_red[0] + s_red[1]);
@@ -373,6 +433,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                     for (int c = 0; c < CH; ++c) v[c] = __fmul_rn(wW, tiles[(ml * CH + c) * TS + l64]); // :926
                     accumulate_pixel<CH>(P.accw + pix * (CH + 1), v, wW, CH);
                 }
+                if (l64 == 0 && round < 3) chain_store(round, nxn, pf);
                 continue;
             }
 
@@ -420,10 +481,13 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                     }
                 }
             }
+            if (l64 == 0 && round < 3) chain_store(round, nxn, pf);
             if (round != nr1 - 1) continue;
 
             // ---- after the last statistics round: gains (:858-904, :1763-1777) ----------------
-            if (!SMOOTH && P.has_bsic) {
+            if (noisy) {
+                cp_async_wait_all();
+            } else if (!SMOOTH && P.has_bsic) {
                 // the group holds the NOISY patches (:784-785, :853): the source window is no
                 // longer needed, put the members' noisy patches where their source patches were
                 const int woff0 = lds_par(s_par + GP_WOFF0), wrow = lds_par(s_par + GP_WROW);
@@ -484,6 +548,12 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             }
             // the barrier at the top of the next round makes the gains (and restaged members) visible
         }
+        } while (0);
+        // stages of the ticket chain the group had no round for (early exits, two-round groups)
+        if (l64 == 0) {
+            int *const nxn = s_nxt + ((it + 1) & 1) * GN_COUNT;
+            for (int st = min(round, 3); st < 3; ++st) chain_store(st, nxn, chain_issue(st, nxn, P, nactive));
+        }
     }
 }
 
@@ -499,10 +569,18 @@ inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st)
     const int win_x = P.smooth ? 0 : (2 * P.r_x + 8) * Gm.wrow_x;
     Gm.win_floats = ((win_t > win_x ? win_t : win_x) + 3) & ~3;   // the float4 gain table behind it stays aligned
     Gm.kcap = P.kstride > 1 ? P.kstride : 1;
-    int fl = 64 * GW_TS + Gm.win_floats + ch * 128 + 2 * Gm.kcap + 2 + 2 + GP_COUNT;
+    int fl = 64 * GW_TS + Gm.win_floats + ch * 4 * 33 + 2 * Gm.kcap + 2 + 2 * GN_COUNT + GP_COUNT;
     fl = (fl + 3) & ~3;
-    Gm.team_floats = fl;
     const int budget = 227 * 1024;
+    // second filtering: room for the noisy patches of up to three members per team, if that
+    // does not cost a team
+    Gm.noisy_floats = 0;
+    if (P.has_bsic && !P.smooth) {
+        const int want = (P.tagg < 3 ? P.tagg : 3) * 64 * ch;
+        const int t0 = budget / (fl * 4), t1 = budget / ((fl + want) * 4);
+        if ((t1 >= GW_MAX_TEAMS || t1 == t0) && t1 >= 2) { Gm.noisy_floats = want; fl += want; }
+    }
+    Gm.team_floats = fl;
     int teams = budget / (fl * 4);
     if (teams > GW_MAX_TEAMS) teams = GW_MAX_TEAMS;
     if (teams < 2) return 0;
