@@ -21,6 +21,8 @@
 #include "nlk_common.cuh"
 #include "nlk_dct.cuh"
 #include "nlk_group.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace nlk {
 
@@ -585,6 +587,10 @@ inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st)
     if (teams > GW_MAX_TEAMS) teams = GW_MAX_TEAMS;
     if (teams < 2) return 0;
     Gm.teams = teams;
+    static const bool dbg = getenv("NLK_DEBUG") != nullptr;
+    if (dbg)
+        fprintf(stderr, "[nlk] group_team8: ch %d smooth %d bsic %d: %d floats/team (window %d, noisy %d) -> %d teams\n",
+                ch, P.smooth, P.has_bsic, fl, Gm.win_floats, Gm.noisy_floats, teams);
     const size_t smem = (size_t)teams * fl * 4;
 #define NLK_LAUNCH_TEAM(CHN, SM)                                                                      \
     do {                                                                                              \

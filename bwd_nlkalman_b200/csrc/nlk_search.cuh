@@ -10,6 +10,7 @@
 // merge sort (src/nlkalman.c:706).
 #pragma once
 #include "nlk_common.cuh"
+#include "nlk_dct.cuh"   // the packed-fp32 helpers
 
 namespace nlk {
 
@@ -324,23 +325,37 @@ __device__ __forceinline__ void search_rows_block(const PassParams &P, int gy, i
             float acc[NX];
 #pragma unroll
             for (int j = 0; j < NX; ++j) acc[j] = 0.f;
+            // Per window row: the RL = PSZ*CH reference values as RL/2 register pairs, the candidate
+            // row walked pair by pair.  Candidate j meets reference term t at row element j*CH + t,
+            // so two consecutive terms are one packed subtract and one packed multiply
+            // (sub.rn.f32x2 / mul.rn.f32x2: each half rounded like the scalar instruction) against
+            // the even-aligned pair (v[2m], v[2m+1]) when j*CH is even and the odd-aligned pair
+            // (v[2m+1], v[2m+2]) when it is odd; the two products are then added one after the other
+            // with scalar adds -- the reference's (hy, hx, c) order and roundings, two issue slots per
+            // term instead of three.
+            static_assert(RL % 2 == 0, "an even number of terms per patch row");
+            constexpr int NV = (NX + PSZ - 1) * CH;
 #pragma unroll 1
             for (int hy = 0; hy < PSZ; ++hy) {
-                float ref[RL];
+                f32x2 ref2[RL / 2];
 #pragma unroll
-                for (int i = 0; i < RL; ++i) ref[i] = refp[hy * wrow + i];
+                for (int i = 0; i < RL / 2; ++i) ref2[i] = pk2(refp[hy * wrow + 2 * i], refp[hy * wrow + 2 * i + 1]);
                 const float *cr = canp + hy * wrow;
 #pragma unroll
-                for (int x = 0; x < NX + PSZ - 1; ++x) {
+                for (int m = 0; 2 * m < NV; ++m) {
+                    const float va = cr[2 * m];
+                    const float vb = (2 * m + 1 < NV) ? cr[2 * m + 1] : 0.f;
+                    const float vc = (2 * m + 2 < NV) ? cr[2 * m + 2] : 0.f;
+                    const f32x2 pe = pk2(va, vb), po = pk2(vb, vc);
 #pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                        const float v = cr[x * CH + c];
-#pragma unroll
-                        for (int j = 0; j < NX; ++j) {
-                            if (x - j >= 0 && x - j < PSZ) {
-                                const float e = __fsub_rn(v, ref[(x - j) * CH + c]);
-                                acc[j] = __fadd_rn(acc[j], __fmul_rn(e, e));
-                            }
+                    for (int j = 0; j < NX; ++j) {
+                        const bool odd = ((j * CH) & 1) != 0;
+                        const int t = (odd ? 2 * m + 1 : 2 * m) - j * CH;     // first term of the pair
+                        if (t >= 0 && t + 1 < RL) {
+                            const f32x2 e = sub2(odd ? po : pe, ref2[t / 2]);
+                            float lo, hi;
+                            upk2(mul2(e, e), lo, hi);
+                            acc[j] = __fadd_rn(__fadd_rn(acc[j], lo), hi);
                         }
                     }
                 }
