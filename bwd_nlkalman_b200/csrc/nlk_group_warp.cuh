@@ -116,7 +116,13 @@ __device__ __forceinline__ void chain_store(int stage, int *slot, const int4 v)
     else { slot[GN_NK] = v.x; slot[GN_NP0] = v.y; slot[GN_FLAGS] = v.z; }
 }
 
-template <int CH, bool SMOOTH>
+// UPD selects the code of the update rounds, so that a launch carries only the one it runs
+// (the kernel is instruction-cache bound: 16 warps per SM spread over its phases):
+//   1: lane = (member, channel) tile, any group size
+//   2: lane = row / column of a tile -- for launches whose groups have at most 8 / CH members
+//      (second filtering: one member)
+// BSIC: the pass has a basic estimate (second filtering).
+template <int CH, bool SMOOTH, int UPD, bool BSIC>
 __global__ void __launch_bounds__(GW_TEAM * GW_MAX_TEAMS, 1)
 k_group_team8(const PassParams P, const GroupWarpGeom Gm)
 {
@@ -278,7 +284,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             // They are fetched into their own area while the statistics run (issued in round 1,
             // awaited after the gains); without room, or with a single statistics round, they
             // replace the source patches in the window after the gains instead.
-            const bool noisy = !SMOOTH && P.has_bsic && nr1 >= 2 &&
+            const bool noisy = !SMOOTH && BSIC && nr1 >= 2 &&
                                (round == 0 ? false : lds_par(s_par + GP_NAGG) * (PSZ * PSZ * CH) <= Gm.noisy_floats);
             if (noisy && round == 1) {
                 const int nagg = lds_par(s_par + GP_NAGG);
@@ -295,7 +301,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                 const int woff0 = lds_par(s_par + GP_WOFF0), wrow = lds_par(s_par + GP_WROW);
                 const float *winS = win - woff0;                       // indexed by image coordinates
                 const float *winP = winS + lds_par(s_par + GP_WPOFF);
-                if (!stat && cnt * CH <= 8) {
+                if (UPD == 2 && !stat) {
                     // few members (second filtering: one): a whole tile per lane would leave the team
                     // idle behind a handful of lanes, so lane = one row / column of a tile instead
                     const int tt = l64 >> 3, y = l64 & 7;
@@ -389,7 +395,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                                     dst[(2 * j) * 8 + kk] = lo;
                                     dst[(2 * j + 1) * 8 + kk] = hi;
                                 }
-                        } else {
+                        } else if (UPD != 2) {
                             f32x2 Pq[4][8];
 #pragma unroll
                             for (int y = 0; y < 4; ++y)
@@ -427,6 +433,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                 const float vp = (float)lds_par(s_par + GP_NAGG) * (s_red[0] + s_red[1]);
                 const float wgt = __fdiv_rn(1.f, fmaxf(vp, 1e-6f));         // :911
                 const float wW = __fmul_rn(wgt, c_win[PSZ][l64]);           // :923
+#pragma unroll 1
                 for (int ml = 0; ml < cnt; ++ml) {
                     const uint32_t cd = s_cand[s_grp[first + ml]];
                     const long pix = (long)(cand_y(cd) + (l64 >> 3)) * P.w + cand_x(cd) + (l64 & 7);
@@ -451,6 +458,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             } else {
                 const int cstride = ((flags & GPF_PREV) ? 2 * CH : CH) * TS;
                 const float *tp = tiles + l64;             // source tile of slot 0, channel 0
+#pragma unroll 1
                 for (int i = 0; i < cnt; ++i, tp += cstride) {
                     const int hasq = cand_prev(s_cand[first + i]);   // (implies prev_p)
                     if (need1) {
@@ -489,7 +497,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             // ---- after the last statistics round: gains (:858-904, :1763-1777) ----------------
             if (noisy) {
                 cp_async_wait_all();
-            } else if (!SMOOTH && P.has_bsic) {
+            } else if (!SMOOTH && BSIC) {
                 // the group holds the NOISY patches (:784-785, :853): the source window is no
                 // longer needed, put the members' noisy patches where their source patches were
                 const int woff0 = lds_par(s_par + GP_WOFF0), wrow = lds_par(s_par + GP_WROW);
@@ -509,7 +517,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                 const float inp1 = c_inv[max(n1, 1)];
                 const float inp0 = c_inv[n0];
                 const float sigma2 = P.sigma2;
-                const float s2 = P.has_bsic ? 0.f : sigma2;
+                const float s2 = BSIC ? 0.f : sigma2;
                 const int e_hy = l64 >> 3, e_hx = l64 & 7;
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
@@ -592,14 +600,21 @@ inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st)
         fprintf(stderr, "[nlk] group_team8: ch %d smooth %d bsic %d: %d floats/team (window %d, noisy %d) -> %d teams\n",
                 ch, P.smooth, P.has_bsic, fl, Gm.win_floats, Gm.noisy_floats, teams);
     const size_t smem = (size_t)teams * fl * 4;
-#define NLK_LAUNCH_TEAM(CHN, SM)                                                                      \
+#define NLK_LAUNCH_TEAM(CHN, SM, UP, BS)                                                              \
     do {                                                                                              \
-        cudaFuncSetAttribute(k_group_team8<CHN, SM>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                             (int)smem);                                                              \
-        k_group_team8<CHN, SM><<<num_sms, teams * GW_TEAM, smem, st>>>(P, Gm);                        \
+        cudaFuncSetAttribute(k_group_team8<CHN, SM, UP, BS>,                                          \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+        k_group_team8<CHN, SM, UP, BS><<<num_sms, teams * GW_TEAM, smem, st>>>(P, Gm);                \
     } while (0)
-    if (ch == 3) { if (P.smooth) NLK_LAUNCH_TEAM(3, true); else NLK_LAUNCH_TEAM(3, false); }
-    else { if (P.smooth) NLK_LAUNCH_TEAM(1, true); else NLK_LAUNCH_TEAM(1, false); }
+#define NLK_LAUNCH_TEAM_CH(CHN)                                                                       \
+    do {                                                                                              \
+        const bool few = P.tagg * CHN <= 8;                                                           \
+        if (P.smooth) { if (few) NLK_LAUNCH_TEAM(CHN, true, 2, false); else NLK_LAUNCH_TEAM(CHN, true, 1, false); } \
+        else if (P.has_bsic) { if (few) NLK_LAUNCH_TEAM(CHN, false, 2, true); else NLK_LAUNCH_TEAM(CHN, false, 1, true); } \
+        else { if (few) NLK_LAUNCH_TEAM(CHN, false, 2, false); else NLK_LAUNCH_TEAM(CHN, false, 1, false); } \
+    } while (0)
+    if (ch == 3) NLK_LAUNCH_TEAM_CH(3); else NLK_LAUNCH_TEAM_CH(1);
+#undef NLK_LAUNCH_TEAM_CH
 #undef NLK_LAUNCH_TEAM
     return 1;
 }
