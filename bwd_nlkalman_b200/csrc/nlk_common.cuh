@@ -30,7 +30,7 @@ struct GroupHdr {
     int nk;     // candidates kept (0: no search, k <= 1)
     int np0;    // kept candidates with a valid previous patch
     int flags;  // bit 0: prev_p, bit 1: marks (sets the processed mask for its members)
-    int pad;
+    int pxy;    // the patch position, packed like a candidate record (x | y << 16)
 };
 constexpr int HDR_PREV_P = 1;
 constexpr int HDR_MARKS = 2;

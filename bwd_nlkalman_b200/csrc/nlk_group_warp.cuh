@@ -80,8 +80,8 @@ __device__ __forceinline__ void dct8x8_regs(float (&t)[64])
 // per-team scalars of the current group, kept in shared memory and re-read where they are
 // used: the transform phases hold a whole tile in registers and everything that stays live
 // across them costs a spill
-enum { GN_AI = 0, GN_G, GN_NK, GN_NP0, GN_FLAGS, GN_COUNT = 6 };
-enum { GP_WOFF0 = 0, GP_WROW, GP_WPOFF, GP_K, GP_NP0, GP_NAGG, GP_NR1, GP_FLAGS, GP_G, GP_COUNT = 12 };
+enum { GN_AI = 0, GN_G, GN_NK, GN_NP0, GN_FLAGS, GN_PXY, GN_COUNT = 6 };
+enum { GP_WOFF0 = 0, GP_WROW, GP_WPOFF, GP_K, GP_NP0, GP_NAGG, GP_NR1, GP_FLAGS, GP_G, GP_N0, GP_N0B, GP_COUNT = 12 };
 constexpr int GPF_PREV = 1, GPF_POINT = 2;
 
 __device__ __forceinline__ int lds_par(const int *p)
@@ -113,7 +113,7 @@ __device__ __forceinline__ void chain_store(int stage, int *slot, const int4 v)
 {
     if (stage == 0) slot[GN_AI] = v.x;
     else if (stage == 1) slot[GN_G] = v.x;
-    else { slot[GN_NK] = v.x; slot[GN_NP0] = v.y; slot[GN_FLAGS] = v.z; }
+    else { slot[GN_NK] = v.x; slot[GN_NP0] = v.y; slot[GN_FLAGS] = v.z; slot[GN_PXY] = v.w; }
 }
 
 // UPD selects the code of the update rounds, so that a launch carries only the one it runs
@@ -167,8 +167,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             const int g = nx[GN_G];
             GroupHdr hd;
             hd.nk = nx[GN_NK]; hd.np0 = nx[GN_NP0]; hd.flags = nx[GN_FLAGS];
-            const int gy = g / P.gw, gx = g - gy * P.gw;
-            const int px = gx * P.step, py = gy * P.step;
+            const int px = cand_x((uint32_t)nx[GN_PXY]), py = cand_y((uint32_t)nx[GN_PXY]);
             const int prev_p = hd.flags & HDR_PREV_P;
             int k = hd.nk;
             const int np0 = hd.np0;
@@ -200,13 +199,16 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                 float *winS = win, *winP = win + wh * wrow;
                 const long g0 = ((long)(y0 + wg) * P.w + x0) * CH;
                 const long gstep = 2L * P.w * CH;
+#pragma unroll 1
                 for (int j = lane; j < wlen; j += 32) {
                     const float *gs = P.src + g0 + j;
                     float *ds = winS + wg * wrow + j;
+#pragma unroll 2
                     for (int row = wg; row < wh; row += 2, gs += gstep, ds += 2 * wrow) cp_async4(ds, gs);
                     if (prev_p) {
                         const float *gp = P.prev0 + g0 + j;
                         float *dp = winP + wg * wrow + j;
+#pragma unroll 2
                         for (int row = wg; row < wh; row += 2, gp += gstep, dp += 2 * wrow) cp_async4(dp, gp);
                     }
                 }
@@ -253,12 +255,15 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
         // either pair in the same registers:
         //   filter:   sA = M1 or M0V, sB = V1 or V0, sC = V01, sD = M0 (group mean)
         //   smoother: sA = M1, sB = V1, sC = V01, sD = M0V, sE = V0
-        float sA[CH], sB[CH], sC[CH], sD[CH], sE[SMOOTH ? CH : 1];
+        // Between the statistics rounds only sA, sB (and sE) stay in registers: sC, sD wait in
+        // the two gain-table slots this lane will write after the last round, and the count
+        // of previous-frame candidates in the per-team scalars (by round parity) -- the
+        // transform phases in between need the registers.
+        float sA[CH], sB[CH], sE[SMOOTH ? CH : 1];
 #pragma unroll
-        for (int u = 0; u < CH; ++u) sA[u] = sB[u] = sC[u] = sD[u] = 0.f;
+        for (int u = 0; u < CH; ++u) sA[u] = sB[u] = 0.f;
 #pragma unroll
         for (int u = 0; u < (SMOOTH ? CH : 1); ++u) sE[u] = 0.f;
-        int n0 = 0;
 
         for (;; ++round) {
             if (round) team_sync(bar);   // the previous round's consumers are done with `tiles`
@@ -447,6 +452,17 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             }
 
             // ---- statistics: lane = coefficient position, candidates in sorted order ----------
+            float *const park = reinterpret_cast<float *>(s_am + (l64 >> 4) * 8 + (l64 & 7)) + ((l64 >> 3) & 1);
+            float sC[CH], sD[CH];
+            int n0 = 0;
+            if (round) {
+#pragma unroll
+                for (int u = 0; u < CH; ++u) { sC[u] = park[u * (4 * GS)]; sD[u] = park[u * (4 * GS) + 2]; }
+                n0 = lds_par(s_par + GP_N0 + (round & 1));
+            } else {
+#pragma unroll
+                for (int u = 0; u < CH; ++u) sC[u] = sD[u] = 0.f;
+            }
             if (flags & GPF_POINT) {
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
@@ -492,7 +508,12 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                 }
             }
             if (l64 == 0 && round < 3) chain_store(round, nxn, pf);
-            if (round != nr1 - 1) continue;
+            if (round != nr1 - 1) {
+#pragma unroll
+                for (int u = 0; u < CH; ++u) { park[u * (4 * GS)] = sC[u]; park[u * (4 * GS) + 2] = sD[u]; }
+                if (l64 == 0) s_par[GP_N0 + ((round + 1) & 1)] = n0;
+                continue;
+            }
 
             // ---- after the last statistics round: gains (:858-904, :1763-1777) ----------------
             if (noisy) {
@@ -518,7 +539,6 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                 const float inp0 = c_inv[n0];
                 const float sigma2 = P.sigma2;
                 const float s2 = BSIC ? 0.f : sigma2;
-                const int e_hy = l64 >> 3, e_hx = l64 & 7;
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
                     float a, m;
@@ -528,25 +548,24 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                             v1 *= inp1;                             // :805
                             if (n0) { v0 *= inp0; v01 *= inp0; }    // :806-810
                         }
-                        a = __fdiv_rn(v1, v1 + P.beta_t * v01);              // :1768
+                        a = __fdividef(v1, v1 + P.beta_t * v01);              // :1768
                         vsum += (1.f - a * a) * v1 + a * a * fmaxf(v0 - P.beta_t * v01, 0.f);
                         m = 0.f;
                     } else if (n0 > 0) {
                         const float v0 = sB[u] * inp0, v01 = sC[u] * inp0;   // :806-810
                         const float v = v0 + fmaxf(0.f, v01 - s2);           // :867
-                        a = __fdiv_rn(v, v + P.beta_t * sigma2);             // :870
+                        a = __fdividef(v, v + P.beta_t * sigma2);             // :870
                         vsum += (1.f - a * a) * v + a * a * sigma2;          // :875
                         m = sD[u];
                     } else {
                         const float v1 = sB[u] * inp1;                       // :805
                         const float v = fmaxf(0.f, v1 - s2);                 // :890
-                        a = __fdiv_rn(v, v + P.beta_x * sigma2);             // :893
+                        a = __fdividef(v, v + P.beta_x * sigma2);             // :893
                         vsum += a * v;                                       // :898
                         m = sA[u];
                     }
-                    float *gp = reinterpret_cast<float *>(s_am + u * GS + (e_hy >> 1) * 8 + e_hx) + (e_hy & 1);
-                    gp[0] = a;
-                    gp[2] = (1.f - a) * m;
+                    park[u * (4 * GS)] = a;
+                    park[u * (4 * GS) + 2] = (1.f - a) * m;
                 }
             }
 #pragma unroll

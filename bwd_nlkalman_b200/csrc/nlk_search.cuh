@@ -169,7 +169,7 @@ __device__ __forceinline__ void sort_and_emit(const PassParams &P, int g, int px
         hd.nk = k;
         hd.np0 = np0;
         hd.flags = (prev_p ? HDR_PREV_P : 0) | (marks ? HDR_MARKS : 0);
-        hd.pad = 0;
+        hd.pxy = (int)cand_pack(px, py, 0);
         P.hdr[g] = hd;
         if (others) *P.any_nbr = 1;
     }
@@ -208,7 +208,7 @@ k_search(const PassParams P, int warps_per_cta, int wrow, int win_floats, int np
             hd.nk = 0;
             hd.np0 = (P.smooth && prev_p) ? 1 : 0;
             hd.flags = (prev_p ? HDR_PREV_P : 0) | ((P.smooth && prev_p) ? HDR_MARKS : 0);
-            hd.pad = 0;
+            hd.pxy = (int)cand_pack(px, py, 0);
             P.hdr[g] = hd;
         }
         for (int i = lane; i < nbw; i += 32) nbr_out[i] = 0u;
@@ -293,7 +293,7 @@ __device__ __forceinline__ void search_rows_block(const PassParams &P, int gy, i
         hd.nk = 0;
         hd.np0 = (P.smooth && prev_p) ? 1 : 0;
         hd.flags = (prev_p ? HDR_PREV_P : 0) | ((P.smooth && prev_p) ? HDR_MARKS : 0);
-        hd.pad = 0;
+        hd.pxy = (int)cand_pack((gx0 + s) * P.step, py, 0);
         P.hdr[g] = hd;
         for (int i = 0; i < P.nbw; ++i) P.nbr[(long)g * P.nbw + i] = 0u;
     }
