@@ -143,11 +143,11 @@ struct nlk_ctx {
     long long q_frames = 0;
     int q_smo_cur = 0, q_have_smo = 0;
     // pipelined host-buffer recursion (nlk_seq_submit_host): copies on their own streams,
-    // two staging sets so that frame n+1 uploads and frame n-1 downloads while frame n computes
+    // three staging sets so that one frame uploads and one downloads while the lanes work on two more
     cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
-    DevBuf p_in[2], p_of[2], p_msk[2], p_o1[2], p_o2[2];
-    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_o1[2] = {nullptr, nullptr}, ev_o2[2] = {nullptr, nullptr},
-                ev_done[2] = {nullptr, nullptr};
+    static constexpr int PIPE_SETS = 3;   // frames in flight between the host buffers and the lanes
+    DevBuf p_in[PIPE_SETS], p_of[PIPE_SETS], p_msk[PIPE_SETS], p_o1[PIPE_SETS], p_o2[PIPE_SETS];
+    cudaEvent_t ev_up[PIPE_SETS] = {}, ev_o1[PIPE_SETS] = {}, ev_o2[PIPE_SETS] = {}, ev_done[PIPE_SETS] = {};
     long long p_frames = 0;
     // strip-sharded pass in flight (nlk_strip_search .. nlk_strip_normalize)
     PassParams strip_P;
@@ -278,7 +278,7 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
         if (c->ev_b[i]) cudaEventDestroy(c->ev_b[i]);
     }
     if (c->ev_join) cudaEventDestroy(c->ev_join);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < nlk_ctx::PIPE_SETS; ++i) {
         c->p_in[i].release(); c->p_of[i].release(); c->p_msk[i].release(); c->p_o1[i].release(); c->p_o2[i].release();
         cudaEvent_t *ev[] = {&c->ev_up[i], &c->ev_o1[i], &c->ev_o2[i], &c->ev_done[i]};
         for (cudaEvent_t *e : ev) if (*e) cudaEventDestroy(*e);
@@ -862,7 +862,7 @@ static int pipe_init(nlk_ctx *c)
     if (c->st_h2d) return NLK_OK;
     CU_TRY(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < nlk_ctx::PIPE_SETS; ++i) {
         CU_TRY(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&c->ev_o1[i], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&c->ev_o2[i], cudaEventDisableTiming));
@@ -879,9 +879,10 @@ extern "C" int nlk_seq_submit_host(nlk_ctx *c, const float *h_noisy, const float
     if (!h_noisy) return set_err(NLK_ERR_PARAM, "no noisy frame");
     if (int r = pipe_init(c)) return r;
     const size_t ib = c->img_bytes(), npix = (size_t)c->w * c->h;
-    const int s = (int)(c->p_frames & 1);
-    // at most two frames in flight: staging set s was last used by frame n-2
-    if (c->p_frames >= 2) CU_TRY(cudaEventSynchronize(c->ev_done[s]));
+    const int s = (int)(c->p_frames % nlk_ctx::PIPE_SETS);
+    // at most three frames in flight (one uploading or downloading beside the two the lanes
+    // work on): staging set s was last used by frame n-3
+    if (c->p_frames >= nlk_ctx::PIPE_SETS) CU_TRY(cudaEventSynchronize(c->ev_done[s]));
     if (int r = c->p_in[s].ensure(ib)) return r;
     CU_TRY(cudaMemcpyAsync(c->p_in[s].p, h_noisy, ib, cudaMemcpyHostToDevice, c->st_h2d));
     const float *d_of = nullptr, *d_msk = nullptr;

@@ -151,11 +151,12 @@ int nlk_seq_filter_host(nlk_ctx *ctx, const float *h_noisy, const float *h_bflo,
                         struct nlkalman_params f2, float *h_flt1_out, float *h_flt2_out);
 
 /* pipelined form of nlk_seq_filter_host for streaming a sequence: queues the frame and
- * returns.  Uploads, kernels and downloads run on three streams with two staging sets, so
- * frame n+1 uploads and frame n-1 downloads while frame n computes (at most two frames in
- * flight: the call blocks until frame n-2 is complete).  The host buffers of a frame
- * (pinned memory, or the copies serialise) must stay untouched until nlk_seq_drain
- * returns or two later submits have returned.  nlk_seq_filter_host = submit + drain. */
+ * returns.  Uploads, kernels and downloads run on their own streams with three staging
+ * sets, so a frame uploads and another downloads while the two filterings work on two more
+ * (at most three frames in flight: the call blocks until frame n-3 is complete).  The host
+ * buffers of a frame (pinned memory, or the copies serialise) must stay untouched -- and its
+ * outputs are complete only -- once nlk_seq_drain or three later submits have returned.
+ * nlk_seq_filter_host = submit + drain. */
 int nlk_seq_submit_host(nlk_ctx *ctx, const float *h_noisy, const float *h_bflo,
                         const float *h_bocc, float sigma, struct nlkalman_params f1,
                         struct nlkalman_params f2, float *h_flt1_out, float *h_flt2_out);
