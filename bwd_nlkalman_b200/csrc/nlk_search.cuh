@@ -82,9 +82,50 @@ __device__ __forceinline__ void warp_sort128(unsigned long long (&key)[4], int l
     }
 }
 
+// The 32 smallest of 128 keys (four per lane, element r*32 + lane in register r), ascending in
+// key[0]: sort the four 32-key rows (0 and 2 ascending, 1 and 3 descending), then twice
+// "element-wise minimum of an ascending and a descending row" (a bitonic row holding the 32
+// smallest of the 64) followed by its 5-stage merge.  75 compare-exchange stages on rows
+// instead of the 100 (+ 12 between registers) of the full sort; keys are unique, so the
+// result is the same list the full sort starts with.
+__device__ __forceinline__ void warp_row_stage(unsigned long long &k, int stride, bool asc_row, int lane)
+{
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, stride);
+    const bool lower = (lane & stride) == 0;
+    const bool take_min = (lower == asc_row);
+    const bool less = k < other;
+    k = (less == take_min) ? k : other;
+}
+__device__ __forceinline__ void warp_top32_of_128(unsigned long long (&key)[4], int lane)
+{
+    // full bitonic sort of each row; direction of the final merge: rows 0, 2 up, rows 1, 3 down
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const bool up = (size == 32) ? ((r & 1) == 0) : ((lane & size) == 0);
+                warp_row_stage(key[r], stride, up, lane);
+            }
+        }
+    }
+    key[0] = key[0] < key[1] ? key[0] : key[1];
+    key[2] = key[2] < key[3] ? key[2] : key[3];
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) {
+        warp_row_stage(key[0], stride, true, lane);
+        warp_row_stage(key[2], stride, false, lane);
+    }
+    key[0] = key[0] < key[2] ? key[0] : key[2];
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) warp_row_stage(key[0], stride, true, lane);
+}
+
 // warp-level: sort npad keys (ascending), keep the first k, write the candidate
 // records, the header and the grid-neighbour bitmap of patch g.  bm: 2*nbw words of
 // shared scratch private to the warp.
+template <bool TOP32 = false>
 __device__ __forceinline__ void sort_and_emit(const PassParams &P, int g, int px, int py, int prev_p, int k,
                                               unsigned long long *keys, int n, int npad, int nx, int x0,
                                               int y0, int lane, unsigned int *bm)
@@ -96,9 +137,14 @@ __device__ __forceinline__ void sort_and_emit(const PassParams &P, int g, int px
         unsigned long long key[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) key[r] = (r * 32 + lane < npad) ? keys[r * 32 + lane] : ~0ull;
-        warp_sort128(key, lane);
+        if (TOP32) {                          // the launch keeps at most 32 candidates per patch
+            warp_top32_of_128(key, lane);     // only the first k are read below
+            keys[lane] = key[0];
+        } else {
+            warp_sort128(key, lane);
 #pragma unroll
-        for (int r = 0; r < 4; ++r) if (r * 32 + lane < npad) keys[r * 32 + lane] = key[r];
+            for (int r = 0; r < 4; ++r) if (r * 32 + lane < npad) keys[r * 32 + lane] = key[r];
+        }
         __syncwarp();
     } else
     // bitonic sort in shared memory, ascending
@@ -253,7 +299,7 @@ k_search(const PassParams P, int warps_per_cta, int wrow, int win_floats, int np
 // the 2*RAD+1 distances of its candidate row in registers: every staged value is loaded
 // once and used by up to PSZ candidates, and each distance still receives its terms in
 // the reference's (hy, hx, c) order with separately rounded multiply and add.
-template <int PSZ, int CH, int RAD>
+template <int PSZ, int CH, int RAD, bool TOP32>
 __device__ __forceinline__ void search_rows_block(const PassParams &P, int gy, int run, int np_cta, int wrow,
                                                   int wh_max, int npad, bool feed_worklist)
 {
@@ -387,18 +433,18 @@ __device__ __forceinline__ void search_rows_block(const PassParams &P, int gy, i
         while (np2 < n) np2 <<= 1;
         for (int i = n + lane; i < np2; i += 32) kp[i] = ~0ull;
         __syncwarp();
-        sort_and_emit(P, gy * P.gw + gx0 + slot, px, py, prev_p, k, kp, n, np2, nx, x0, y0, lane,
-                      bm + warp * 2 * P.nbw);
+        sort_and_emit<TOP32>(P, gy * P.gw + gx0 + slot, px, py, prev_p, k, kp, n, np2, nx, x0, y0, lane,
+                             bm + warp * 2 * P.nbw);
     }
 }
 
 // whole grid rows [gy0, gy1): block = (grid row, run)
-template <int PSZ, int CH, int RAD>
+template <int PSZ, int CH, int RAD, bool TOP32>
 __global__ void __launch_bounds__(256)
 k_search_rows(const PassParams P, int np_cta, int runs_per_row, int wrow, int wh_max, int npad, int feed)
 {
     const int gyl = blockIdx.x / runs_per_row, run = blockIdx.x - gyl * runs_per_row;
-    search_rows_block<PSZ, CH, RAD>(P, P.gy0 + gyl, run, np_cta, wrow, wh_max, npad, feed != 0);
+    search_rows_block<PSZ, CH, RAD, TOP32>(P, P.gy0 + gyl, run, np_cta, wrow, wh_max, npad, feed != 0);
 }
 
 // only the runs queued by the launch of the other radius (few: occluded or border patches)
@@ -410,7 +456,7 @@ k_search_rows_list(const PassParams P, int np_cta, int runs_per_row, int wrow, i
     for (int wi = blockIdx.x; wi < n; wi += gridDim.x) {
         const int run2 = P.xlist[wi];
         const int gy = run2 / runs_per_row;
-        search_rows_block<PSZ, CH, RAD>(P, gy, run2 - gy * runs_per_row, np_cta, wrow, wh_max, npad, false);
+        search_rows_block<PSZ, CH, RAD, false>(P, gy, run2 - gy * runs_per_row, np_cta, wrow, wh_max, npad, false);
         __syncthreads();   // shared memory is reused by the next run
     }
 }
@@ -439,10 +485,22 @@ inline int launch_search_rows(const PassParams &P, int mode, cudaStream_t st)
     const int runs = (P.gw + np_cta - 1) / np_cta;
     if (mode == 2) {
         cudaFuncSetAttribute(k_search_rows_list<PSZ, CH, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_search_rows_list<PSZ, CH, RAD><<<2 * 148, 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad);
+        // one queued run per block when they fit one wave (a run is ~50 us of latency, the
+        // queue is a few hundred runs: occlusions and the warp's border rows / columns)
+        k_search_rows_list<PSZ, CH, RAD><<<6 * 148, 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad);
     } else {
-        cudaFuncSetAttribute(k_search_rows<PSZ, CH, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_search_rows<PSZ, CH, RAD><<<runs * (P.gy1 - P.gy0), 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad, mode);
+        // what the patches of this launch keep: those with a valid previous patch k_t, the others k_x
+        // (reference :631-707); with one radius for both, or in the smoother, a launch holds both kinds
+        int kmax = P.k_t > P.k_x ? P.k_t : P.k_x;
+        if (!P.smooth && P.r_t != P.r_x && P.has_prev) kmax = (RAD == P.r_t) ? P.k_t : P.k_x;
+        if (!P.has_prev && !P.smooth) kmax = P.k_x;
+        if (kmax <= 32 && npad <= 128) {
+            cudaFuncSetAttribute(k_search_rows<PSZ, CH, RAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_search_rows<PSZ, CH, RAD, true><<<runs * (P.gy1 - P.gy0), 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad, mode);
+        } else {
+            cudaFuncSetAttribute(k_search_rows<PSZ, CH, RAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_search_rows<PSZ, CH, RAD, false><<<runs * (P.gy1 - P.gy0), 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad, mode);
+        }
     }
     return 1;
 }
