@@ -5,16 +5,22 @@
 //   * a team synchronises with its own named barrier (bar.sync id, 64), so the eight
 //     teams of a block drift apart and the FMA-heavy transform phases of some overlap the
 //     shared-memory / L2 phases of the others -- no block-wide barrier in the group loop;
-//   * groups are handed out dynamically (one atomic ticket per group);
+//   * groups are handed out dynamically (one atomic ticket per group); the chain ticket ->
+//     active[] -> hdr[] of a team's next group runs under its current one;
 //   * the search windows are staged with cp.async (all rows in flight at once);
-//   * transforms: lane = one 8x8 tile, whole tile in registers.  The group loop is a
-//     sequence of ROUNDS with one producer body (so one copy of the transform code in
-//     the instruction cache): statistics rounds transform (candidate x source x channel)
-//     tiles out of the staged windows into the exchange buffer; update rounds transform
-//     (member x channel) tiles, shrink them, transform back and leave weighted pixels;
+//   * transforms: lane = one 8x8 tile, whole tile in registers as 32 packed-fp32 pairs
+//     (nlk_dct.cuh).  The group loop is a sequence of ROUNDS: statistics rounds transform
+//     (candidate x source x channel) tiles out of the staged windows into the exchange
+//     buffer; update rounds transform (member x channel) tiles, shrink them, transform back
+//     and leave weighted pixels -- or, in the launches whose groups are small (template UPD),
+//     lane = row / column of a tile;
 //   * statistics: lane = one coefficient position e (all channels), Welford recurrences
-//     over the candidates in sorted order, accumulators in registers;
+//     over the candidates in sorted order, accumulators in registers during a round and
+//     partly parked in shared memory between rounds;
 //   * aggregation: lane = one pixel of the patch, one red.global.add.v4.f32 per member.
+// The kernel is bound by its instruction footprint and its 128 registers before anything
+// else: what a launch does not run is compiled out (UPD, BSIC), loops
+// over candidates and members stay rolled.
 // The smoother uses the linearity of the transform:
 //   T^-1((1-a) Y1 + a Y0) = x1 + T^-1(a * T(x0 - x1)),  one tile per lane instead of two.
 #pragma once

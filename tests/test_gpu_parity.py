@@ -168,6 +168,38 @@ def test_generic_patch_sizes(nlk, port, psz, ch):
     _stage_check(nlk, port, O, 0, n0, None, None, sigma, f1)
 
 
+@pytest.mark.parametrize("ch", [1, 3])
+def test_team_kernel_variants(nlk, port, ch):
+    """The 8x8 team kernel is instantiated per update mode (tile per lane / row-column per lane), per
+    basic-estimate flag, and the search per selection network (32 smallest / full sort): group sizes
+    and candidate counts on both sides of each switch, on a temporal frame with an occlusion."""
+    from bwd_nlkalman_b200 import synth
+    from oracle import oracle as O
+    w, h, sigma = 93, 70, 20.0
+    f1 = nlk.default_params(sigma, nlk.FLT1)
+    n0 = port.rgb2opp(synth.noisy_frame(w, h, ch, 0, sigma))
+    n1 = port.rgb2opp(synth.noisy_frame(w, h, ch, 1, sigma))
+    bflo, fflo = synth.backward_flow(w, h), synth.forward_flow(w, h)
+    occ = np.zeros((h, w), np.float32)
+    occ[20:34, 40:60] = 255
+    c11 = port.filter_frame(n0, None, None, sigma, _same_params(nlk, O, f1))
+    w1 = port.warp_bicubic(c11, bflo, occ)
+    # first filtering: one statistics round (k small), 32 / 33 candidates kept (selection network switch),
+    # groups of one or two members through the tile-per-lane update
+    for ov in (dict(npatches_t=8, npatches_tagg=20), dict(npatches_t=32), dict(npatches_t=33),
+               dict(npatches_t=30, npatches_tagg=9)):
+        _stage_check(nlk, port, O, 0, n1, w1, None, sigma, nlk.default_params(sigma, nlk.FLT1, nlk.Params.auto(**ov)))
+    c12 = port.filter_frame(n1, w1, None, sigma, _same_params(nlk, O, f1))
+    # second filtering: 1, 2 members (row / column update where tagg * ch <= 8, noisy patches prefetched),
+    # 5 members (more than the prefetch area holds: restaged after the gains), a single statistics round
+    for ov in (dict(), dict(npatches_tagg=2), dict(npatches_tagg=5), dict(npatches_t=6), dict(npatches_t=6, npatches_tagg=3)):
+        _stage_check(nlk, port, O, 0, n1, w1, c12, sigma, nlk.default_params(sigma, nlk.FLT2, nlk.Params.auto(**ov)))
+    # smoother: small groups (row / column update), 32 candidates (selection network), default
+    ws = port.warp_bicubic(c12, fflo, occ)
+    for ov in (dict(npatches_t=12, npatches_tagg=2), dict(npatches_t=32, npatches_tagg=32), dict()):
+        _stage_check(nlk, port, O, 1, c11, ws, None, sigma, nlk.default_params(sigma, nlk.SMO1, nlk.Params.auto(**ov)))
+
+
 # ---- edge cases the reference handles ----------------------------------------------------------
 
 def test_edge_cases(nlk, port):
@@ -230,7 +262,7 @@ def test_config1_against_reference_library(nlk, ref):
 # ---- streaming (pipelined) host recursion ------------------------------------------------------
 
 def test_pipelined_host_recursion_matches_synchronous(nlk):
-    """nlk_seq_submit_host / nlk_seq_drain (uploads, kernels, downloads on three streams, two
+    """nlk_seq_submit_host / nlk_seq_drain (uploads, kernels, downloads on their own streams, three
     frames in flight) give the frames nlk_seq_filter_host gives, in order"""
     import torch
     from bwd_nlkalman_b200 import synth
