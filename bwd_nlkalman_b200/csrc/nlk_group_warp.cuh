@@ -27,6 +27,7 @@
 #include "nlk_common.cuh"
 #include "nlk_dct.cuh"
 #include "nlk_group.cuh"
+#include <cuda.h>      // CUtensorMap (the encoder is fetched through the runtime, no libcuda link)
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -41,6 +42,9 @@ struct GroupWarpGeom {
     int team_floats;  // shared-memory floats per team
     int win_floats;   // floats of the window area (one spatial window or two temporal ones)
     int wrow_t, wrow_x;   // row strides of the staged windows (temporal / spatial radius)
+    int wh_t, wh_x;       // TMA staging: rows of the window boxes
+    int wpoff_t;          // TMA staging: offset of the previous-frame window (128-byte aligned)
+    int mbar_off;         // TMA staging: float offset of the team's mbarrier in its area
     int kcap;         // capacity of the candidate list
     int noisy_floats; // area for the members' noisy patches (second filtering), 0 = none
 };
@@ -58,6 +62,48 @@ __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc)
 __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// ---- TMA staging of the search windows ------------------------------------------------------
+// One cp.async.bulk.tensor per window instead of ~30 four-byte cp.async per lane: the image is
+// a 2-D tensor (w*ch floats by h rows), the window a box at (px - r, py - r); what lies outside
+// the image is filled with zeros and never read (candidates are clamped to the image).  The
+// copy signals the team's mbarrier; every iteration of the group loop completes exactly one
+// phase of it (groups that stage nothing arrive without bytes), so the parity to wait for is
+// the iteration's.
+struct TeamMaps { CUtensorMap src_t, prev_t, src_x; };
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// (the barrier is named by its shared-memory address, re-read from the per-team scalars where
+// it is used: one register less across the transform phases)
+__device__ __forceinline__ void mbar_init(unsigned bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, int parity)
+{
+    asm volatile("{\n\t.reg .pred P1;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                 "@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(x), "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 template <bool INVERSE>
@@ -87,7 +133,7 @@ __device__ __forceinline__ void dct8x8_regs(float (&t)[64])
 // used: the transform phases hold a whole tile in registers and everything that stays live
 // across them costs a spill
 enum { GN_AI = 0, GN_G, GN_NK, GN_NP0, GN_FLAGS, GN_PXY, GN_COUNT = 6 };
-enum { GP_WOFF0 = 0, GP_WROW, GP_WPOFF, GP_K, GP_NP0, GP_NAGG, GP_NR1, GP_FLAGS, GP_G, GP_N0, GP_N0B, GP_COUNT = 12 };
+enum { GP_WOFF0 = 0, GP_WROW, GP_WPOFF, GP_K, GP_NP0, GP_NAGG, GP_NR1, GP_FLAGS, GP_G, GP_N0, GP_N0B, GP_MBAR, GP_COUNT = 12 };
 constexpr int GPF_PREV = 1, GPF_POINT = 2;
 
 __device__ __forceinline__ int lds_par(const int *p)
@@ -102,16 +148,17 @@ __device__ __forceinline__ int lds_par(const int *p)
 // Lane 0 issues a stage at the start of a consumer phase (few live registers there) and stores
 // the result in the next iteration's slot at the end of the phase, so each round trip runs
 // under the team's own work instead of in front of it.
-__device__ __forceinline__ int4 chain_issue(int stage, const int *slot, const PassParams &P, int nactive)
+__device__ __forceinline__ int4 chain_issue(int stage, const int *slot, const PassParams &P)
 {
     int4 v = make_int4(0, 0, 0, 0);
     if (stage == 0) {
-        v.x = atomicAdd(P.work, 1);
+        const int t = atomicAdd(P.work, 1);
+        v.x = t < *P.nactive ? t : -1;           // -1: the list is exhausted
     } else if (stage == 1) {
         const int t = slot[GN_AI];
-        if (t < nactive) v.x = P.active[t];
+        if (t >= 0) v.x = P.active[t];
     } else {
-        if (slot[GN_AI] < nactive) v = *reinterpret_cast<const int4 *>(P.hdr + slot[GN_G]);
+        if (slot[GN_AI] >= 0) v = *reinterpret_cast<const int4 *>(P.hdr + slot[GN_G]);
     }
     return v;
 }
@@ -128,9 +175,10 @@ __device__ __forceinline__ void chain_store(int stage, int *slot, const int4 v)
 //   2: lane = row / column of a tile -- for launches whose groups have at most 8 / CH members
 //      (second filtering: one member)
 // BSIC: the pass has a basic estimate (second filtering).
-template <int CH, bool SMOOTH, int UPD, bool BSIC>
+// TMA: the windows come by cp.async.bulk.tensor (needs the image row pitch to be a multiple of 16 bytes).
+template <int CH, bool SMOOTH, int UPD, bool BSIC, bool TMA>
 __global__ void __launch_bounds__(GW_TEAM * GW_MAX_TEAMS, 1)
-k_group_team8(const PassParams P, const GroupWarpGeom Gm)
+k_group_team8(const PassParams P, const GroupWarpGeom Gm, const __grid_constant__ TeamMaps M)
 {
     constexpr int PSZ = 8, TS = GW_TS;
     // gain table: per channel 32 records {a[2j][k], a[2j+1][k], ((1-a)*m)[2j][k], ((1-a)*m)[2j+1][k]}
@@ -138,7 +186,8 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
     constexpr int GS = 33;             // 33 records per channel: the channels of a warp read different banks
     constexpr int MC = GW_TEAM / CH;   // members per update round
     constexpr int CC1 = GW_TEAM / CH, CC2 = GW_TEAM / (2 * CH);   // candidates per statistics round (1 / 2 sources)
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem_team[];   // 128-byte aligned: TMA destinations
+    float *const smem = smem_team;
     const int team = threadIdx.x / GW_TEAM;
     const int l64 = threadIdx.x % GW_TEAM;       // lane within the team
     const int bar = 1 + team;
@@ -153,19 +202,27 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
     int *const s_par = s_nxt + 2 * GN_COUNT;                               // [GP_COUNT]
     float *const s_noisy = reinterpret_cast<float *>(s_par + GP_COUNT);    // [noisy_floats]
 
-    const int nactive = *P.nactive;
+    if (TMA) {
+        if (l64 == 0) {
+            const unsigned mb = smem_u32(tiles + Gm.mbar_off);
+            s_par[GP_MBAR] = (int)mb;
+            mbar_init(mb, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        // (the barrier that opens the first iteration orders the initialisation before its use)
+    }
 
     // Groups are handed out by an atomic ticket; the chain ticket -> active[] -> hdr[] of the next
     // group runs under the current one (chain_issue / chain_store), its result is read from the
     // slot of the iteration's parity after the barrier that opens the iteration.
     if (l64 == 0) {
-        for (int st = 0; st < 3; ++st) chain_store(st, s_nxt, chain_issue(st, s_nxt, P, nactive));
+        for (int st = 0; st < 3; ++st) chain_store(st, s_nxt, chain_issue(st, s_nxt, P));
     }
 
     for (int it = 0;; ++it) {
         team_sync(bar);
         const int *nx = s_nxt + (it & 1) * GN_COUNT;
-        if (nx[GN_AI] >= nactive) break;
+        if (nx[GN_AI] < 0) break;
         int round = 0;
         do {
         {
@@ -179,7 +236,10 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             const int np0 = hd.np0;
             const bool point = SMOOTH && k == 0 && prev_p;   // (reference :1699-1730)
 
-            if (!SMOOTH && k == 0) break;                    // filter, k <= 1 (:815-849, :857)
+            if (!SMOOTH && k == 0) {                         // filter, k <= 1 (:815-849, :857)
+                if (TMA && l64 == 0) mbar_arrive((unsigned)lds_par(s_par + GP_MBAR));
+                break;
+            }
 
             if (SMOOTH && np0 == 0) {
                 // reference :1795-1804: the filtered patch at p, weight 1/1e-6, mask untouched
@@ -191,16 +251,34 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                 for (int c = 0; c < CH; ++c) v[c] = __fmul_rn(wW, P.in1[pix * CH + c]);
                 accumulate_pixel<CH>(P.accw + pix * (CH + 1), v, wW, CH);
                 if (P.dbg_vp && l64 == 0) P.dbg_vp[g] = 0.f;
+                if (TMA && l64 == 0) mbar_arrive((unsigned)lds_par(s_par + GP_MBAR));
                 break;
             }
 
             // ---- stage the search window(s) of this group (reference :637-639) -----------------
             const int r = point ? 0 : (SMOOTH ? P.r_t : (prev_p ? P.r_t : P.r_x));
             const int wrow = (r == P.r_t || point) ? Gm.wrow_t : Gm.wrow_x;
-            const int x0 = max(px - r, 0), x1 = min(px + r, P.w - PSZ);
-            const int y0 = max(py - r, 0), y1 = min(py + r, P.h - PSZ);
-            const int wlen = (x1 - x0 + PSZ) * CH, wh = y1 - y0 + PSZ;
-            {
+            int woff0, wpoff;      // window origin in image coordinates, offset of the previous-frame window
+            if constexpr (TMA) {
+                const bool boxt = (r == P.r_t || point);
+                const int rb = boxt ? P.r_t : P.r_x;
+                const int ox = px - rb, oy = py - rb;          // may lie outside the image: zero fill
+                woff0 = oy * wrow + ox * CH;
+                wpoff = Gm.wpoff_t;
+                if (l64 == 0) {
+                    const unsigned mb = (unsigned)lds_par(s_par + GP_MBAR);
+                    fence_proxy_async();   // the window was read and written through the generic proxy
+                    const int bytes = (boxt ? Gm.wh_t : Gm.wh_x) * wrow * 4;
+                    mbar_expect_tx(mb, prev_p ? 2 * bytes : bytes);
+                    tma_load_2d(win, boxt ? &M.src_t : &M.src_x, ox * CH, oy, mb);
+                    if (prev_p) tma_load_2d(win + wpoff, &M.prev_t, ox * CH, oy, mb);
+                }
+            } else {
+                const int x0 = max(px - r, 0), x1 = min(px + r, P.w - PSZ);
+                const int y0 = max(py - r, 0), y1 = min(py + r, P.h - PSZ);
+                const int wlen = (x1 - x0 + PSZ) * CH, wh = y1 - y0 + PSZ;
+                woff0 = y0 * wrow + x0 * CH;
+                wpoff = wh * wrow;
                 // warp wg takes rows wg, wg+2, ...; every element is its own 4-byte cp.async
                 float *winS = win, *winP = win + wh * wrow;
                 const long g0 = ((long)(y0 + wg) * P.w + x0) * CH;
@@ -226,16 +304,17 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
                 for (int i = l64; i < k; i += GW_TEAM) s_cand[i] = P.cand[(long)g * P.kstride + i];
             }
             if (l64 == 0) {
-                s_par[GP_WOFF0] = y0 * wrow + x0 * CH;
+                s_par[GP_WOFF0] = woff0;
                 s_par[GP_WROW] = wrow;
-                s_par[GP_WPOFF] = wh * wrow;
+                s_par[GP_WPOFF] = wpoff;
                 s_par[GP_K] = k;
                 s_par[GP_NP0] = np0;
                 s_par[GP_NR1] = prev_p ? (k + CC2 - 1) / CC2 : (k + CC1 - 1) / CC1;
                 s_par[GP_FLAGS] = (prev_p ? GPF_PREV : 0) | (point ? GPF_POINT : 0);
                 s_par[GP_G] = g;
             }
-            cp_async_wait_all();
+            if (TMA) mbar_wait((unsigned)lds_par(s_par + GP_MBAR), it & 1);
+            else cp_async_wait_all();
             team_sync(bar);
 
             // group members: the first tagg candidates with a valid previous patch, or, when
@@ -437,7 +516,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
             // lane 0: one stage of the next group's ticket chain per consumer phase
             int *const nxn = s_nxt + ((it + 1) & 1) * GN_COUNT;
             int4 pf = make_int4(0, 0, 0, 0);
-            if (l64 == 0 && round < 3) pf = chain_issue(round, nxn, P, nactive);
+            if (l64 == 0 && round < 3) pf = chain_issue(round, nxn, P);
 
             if (!stat) {
                 // ---- aggregation: lane = pixel of the patch, one member per iteration ----------
@@ -587,9 +666,43 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm)
         // stages of the ticket chain the group had no round for (early exits, two-round groups)
         if (l64 == 0) {
             int *const nxn = s_nxt + ((it + 1) & 1) * GN_COUNT;
-            for (int st = min(round, 3); st < 3; ++st) chain_store(st, nxn, chain_issue(st, nxn, P, nactive));
+            for (int st = min(round, 3); st < 3; ++st) chain_store(st, nxn, chain_issue(st, nxn, P));
         }
     }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart only)
+typedef CUresult (*nlk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+inline nlk_encode_tiled_fn tensor_map_encoder()
+{
+    static nlk_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<nlk_encode_tiled_fn>(f);
+    }
+    return fn;
+}
+
+// the image as a (w*ch) x h fp32 tensor, boxes of bw x bh elements, zero fill outside
+inline bool window_map(CUtensorMap *m, const float *img, int w, int h, int ch, int bw, int bh)
+{
+    nlk_encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc || !img) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)w * ch, (cuuint64_t)h};
+    const cuuint64_t gstr[1] = {(cuuint64_t)w * ch * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh};
+    const cuuint32_t est[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(img), gdim, gstr, box, est,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // returns the number of launches, 0 if this kernel does not cover the configuration
@@ -597,11 +710,40 @@ inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st)
 {
     if (P.psz != 8 || (P.ch != 3 && P.ch != 1)) return 0;
     const int ch = P.ch;
+    // TMA staging is opt-in (NLK_TMA=1) until it is validated on the GPU; NLK_NO_TMA wins
+    static const bool no_tma = getenv("NLK_NO_TMA") != nullptr || getenv("NLK_TMA") == nullptr;
+    static const bool dbg = getenv("NLK_DEBUG") != nullptr;
     GroupWarpGeom Gm;
-    Gm.wrow_t = ((2 * P.r_t + 8) * ch) | 1;
-    Gm.wrow_x = ((2 * P.r_x + 8) * ch) | 1;
-    const int win_t = (2 * P.r_t + 8) * Gm.wrow_t * (P.has_prev ? 2 : 1);
-    const int win_x = P.smooth ? 0 : (2 * P.r_x + 8) * Gm.wrow_x;
+    TeamMaps M;
+    memset(&M, 0, sizeof M);
+    // TMA staging (3-channel launches): row pitch and base addresses multiples of 16 bytes, boxes
+    // of at most 256 elements a side, their width a multiple of 4 floats
+    const int bw_t = ((2 * P.r_t + 8) * ch + 3) & ~3, bw_x = ((2 * P.r_x + 8) * ch + 3) & ~3;
+    const int bh_t = 2 * P.r_t + 8, bh_x = 2 * P.r_x + 8;
+    bool tma = ch == 3 && !no_tma && ((size_t)P.w * ch * sizeof(float)) % 16 == 0 &&
+               ((uintptr_t)P.src % 16) == 0 && ((uintptr_t)P.prev0 % 16) == 0 &&
+               bw_t <= 256 && bw_x <= 256 && bh_t <= 256 && bh_x <= 256;
+    if (tma) {
+        tma = window_map(&M.src_t, P.src, P.w, P.h, ch, bw_t, bh_t);
+        if (tma && P.has_prev) tma = window_map(&M.prev_t, P.prev0, P.w, P.h, ch, bw_t, bh_t);
+        if (tma && !P.smooth) tma = window_map(&M.src_x, P.src, P.w, P.h, ch, bw_x, bh_x);
+    }
+    Gm.wh_t = bh_t;
+    Gm.wh_x = bh_x;
+    int win_t, win_x;
+    if (tma) {
+        Gm.wrow_t = bw_t;
+        Gm.wrow_x = bw_x;
+        Gm.wpoff_t = (bh_t * bw_t + 31) & ~31;                      // the second window starts 128-byte aligned
+        win_t = P.has_prev ? Gm.wpoff_t + bh_t * bw_t : bh_t * bw_t;
+        win_x = P.smooth ? 0 : bh_x * bw_x;
+    } else {
+        Gm.wrow_t = ((2 * P.r_t + 8) * ch) | 1;
+        Gm.wrow_x = ((2 * P.r_x + 8) * ch) | 1;
+        Gm.wpoff_t = 0;
+        win_t = (2 * P.r_t + 8) * Gm.wrow_t * (P.has_prev ? 2 : 1);
+        win_x = P.smooth ? 0 : (2 * P.r_x + 8) * Gm.wrow_x;
+    }
     Gm.win_floats = ((win_t > win_x ? win_t : win_x) + 3) & ~3;   // the float4 gain table behind it stays aligned
     Gm.kcap = P.kstride > 1 ? P.kstride : 1;
     int fl = 64 * GW_TS + Gm.win_floats + ch * 4 * 33 + 2 * Gm.kcap + 2 + 2 * GN_COUNT + GP_COUNT;
@@ -612,33 +754,37 @@ inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st)
     Gm.noisy_floats = 0;
     if (P.has_bsic && !P.smooth) {
         const int want = (P.tagg < 3 ? P.tagg : 3) * 64 * ch;
-        const int t0 = budget / (fl * 4), t1 = budget / ((fl + want) * 4);
+        const int t0 = budget / (fl * 4), t1 = budget / ((fl + want + 34) * 4);
         if ((t1 >= GW_MAX_TEAMS || t1 == t0) && t1 >= 2) { Gm.noisy_floats = want; fl += want; }
     }
+    // the team's mbarrier (8 bytes) at the end; team areas are multiples of 128 bytes (TMA destinations)
+    fl = (fl + 1) & ~1;
+    Gm.mbar_off = fl;
+    fl = (fl + 2 + 31) & ~31;
     Gm.team_floats = fl;
     int teams = budget / (fl * 4);
     if (teams > GW_MAX_TEAMS) teams = GW_MAX_TEAMS;
     if (teams < 2) return 0;
     Gm.teams = teams;
-    static const bool dbg = getenv("NLK_DEBUG") != nullptr;
     if (dbg)
-        fprintf(stderr, "[nlk] group_team8: ch %d smooth %d bsic %d: %d floats/team (window %d, noisy %d) -> %d teams\n",
-                ch, P.smooth, P.has_bsic, fl, Gm.win_floats, Gm.noisy_floats, teams);
+        fprintf(stderr, "[nlk] group_team8: ch %d smooth %d bsic %d tma %d: %d floats/team (window %d, noisy %d) -> %d teams\n",
+                ch, P.smooth, P.has_bsic, (int)tma, fl, Gm.win_floats, Gm.noisy_floats, teams);
     const size_t smem = (size_t)teams * fl * 4;
-#define NLK_LAUNCH_TEAM(CHN, SM, UP, BS)                                                              \
+#define NLK_LAUNCH_TEAM(CHN, SM, UP, BS, TM)                                                          \
     do {                                                                                              \
-        cudaFuncSetAttribute(k_group_team8<CHN, SM, UP, BS>,                                          \
+        cudaFuncSetAttribute(k_group_team8<CHN, SM, UP, BS, TM>,                                      \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
-        k_group_team8<CHN, SM, UP, BS><<<num_sms, teams * GW_TEAM, smem, st>>>(P, Gm);                \
+        k_group_team8<CHN, SM, UP, BS, TM><<<num_sms, teams * GW_TEAM, smem, st>>>(P, Gm, M);         \
     } while (0)
-#define NLK_LAUNCH_TEAM_CH(CHN)                                                                       \
+#define NLK_LAUNCH_TEAM_CH(CHN, TM)                                                                   \
     do {                                                                                              \
         const bool few = P.tagg * CHN <= 8;                                                           \
-        if (P.smooth) { if (few) NLK_LAUNCH_TEAM(CHN, true, 2, false); else NLK_LAUNCH_TEAM(CHN, true, 1, false); } \
-        else if (P.has_bsic) { if (few) NLK_LAUNCH_TEAM(CHN, false, 2, true); else NLK_LAUNCH_TEAM(CHN, false, 1, true); } \
-        else { if (few) NLK_LAUNCH_TEAM(CHN, false, 2, false); else NLK_LAUNCH_TEAM(CHN, false, 1, false); } \
+        if (P.smooth) { if (few) NLK_LAUNCH_TEAM(CHN, true, 2, false, TM); else NLK_LAUNCH_TEAM(CHN, true, 1, false, TM); } \
+        else if (P.has_bsic) { if (few) NLK_LAUNCH_TEAM(CHN, false, 2, true, TM); else NLK_LAUNCH_TEAM(CHN, false, 1, true, TM); } \
+        else { if (few) NLK_LAUNCH_TEAM(CHN, false, 2, false, TM); else NLK_LAUNCH_TEAM(CHN, false, 1, false, TM); } \
     } while (0)
-    if (ch == 3) NLK_LAUNCH_TEAM_CH(3); else NLK_LAUNCH_TEAM_CH(1);
+    if (ch == 3) { if (tma) NLK_LAUNCH_TEAM_CH(3, true); else NLK_LAUNCH_TEAM_CH(3, false); }
+    else NLK_LAUNCH_TEAM_CH(1, false);
 #undef NLK_LAUNCH_TEAM_CH
 #undef NLK_LAUNCH_TEAM
     return 1;
