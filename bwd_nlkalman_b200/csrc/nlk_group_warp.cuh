@@ -262,16 +262,20 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm, const __grid_constant_
             if constexpr (TMA) {
                 const bool boxt = (r == P.r_t || point);
                 const int rb = boxt ? P.r_t : P.r_x;
-                const int ox = px - rb, oy = py - rb;          // may lie outside the image: zero fill
-                woff0 = oy * wrow + ox * CH;
+                // the box starts at the window's first column rounded down to a multiple of four floats:
+                // TMA wants the innermost coordinate 16-byte aligned (tools/micro/tma_probe.cu: an
+                // unaligned one is an illegal instruction); rows and columns outside the image are
+                // filled with zeros
+                const int oxf = ((px - rb) * CH) & ~3, oy = py - rb;
+                woff0 = oy * wrow + oxf;
                 wpoff = Gm.wpoff_t;
                 if (l64 == 0) {
                     const unsigned mb = (unsigned)lds_par(s_par + GP_MBAR);
                     fence_proxy_async();   // the window was read and written through the generic proxy
                     const int bytes = (boxt ? Gm.wh_t : Gm.wh_x) * wrow * 4;
                     mbar_expect_tx(mb, prev_p ? 2 * bytes : bytes);
-                    tma_load_2d(win, boxt ? &M.src_t : &M.src_x, ox * CH, oy, mb);
-                    if (prev_p) tma_load_2d(win + wpoff, &M.prev_t, ox * CH, oy, mb);
+                    tma_load_2d(win, boxt ? &M.src_t : &M.src_x, oxf, oy, mb);
+                    if (prev_p) tma_load_2d(win + wpoff, &M.prev_t, oxf, oy, mb);
                 }
             } else {
                 const int x0 = max(px - r, 0), x1 = min(px + r, P.w - PSZ);
@@ -718,7 +722,8 @@ inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st)
     memset(&M, 0, sizeof M);
     // TMA staging (3-channel launches): row pitch and base addresses multiples of 16 bytes, boxes
     // of at most 256 elements a side, their width a multiple of 4 floats
-    const int bw_t = ((2 * P.r_t + 8) * ch + 3) & ~3, bw_x = ((2 * P.r_x + 8) * ch + 3) & ~3;
+    // (+3: the box origin is rounded down to a multiple of four floats)
+    const int bw_t = ((2 * P.r_t + 8) * ch + 3 + 3) & ~3, bw_x = ((2 * P.r_x + 8) * ch + 3 + 3) & ~3;
     const int bh_t = 2 * P.r_t + 8, bh_x = 2 * P.r_x + 8;
     bool tma = ch == 3 && !no_tma && ((size_t)P.w * ch * sizeof(float)) % 16 == 0 &&
                ((uintptr_t)P.src % 16) == 0 && ((uintptr_t)P.prev0 % 16) == 0 &&
