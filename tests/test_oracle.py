@@ -138,3 +138,34 @@ def test_occlusion_oracle_hand_example():
     got = O.occlusion_from_flow(of, 0.75)
     want = np.array([[0, 0, 255], [0, 255, 0]], np.float32)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("ch", [1, 3])
+def test_port_matches_reference_on_parameter_variants(port, ref, ch):
+    """The parameter combinations of tests/test_gpu_parity.py::test_team_kernel_variants (group
+    sizes, candidate counts, single statistics round, second filtering with several members,
+    small smoother groups): the restatement the GPU is checked against must itself agree with
+    the unmodified reference there."""
+    from bwd_nlkalman_b200 import synth
+    from oracle import oracle as O
+    w, h, sigma = 93, 70, 20.0
+    f1 = ref.default_params(sigma, O.FLT1)
+    n0 = port.rgb2opp(synth.noisy_frame(w, h, ch, 0, sigma))
+    n1 = port.rgb2opp(synth.noisy_frame(w, h, ch, 1, sigma))
+    bflo, fflo = synth.backward_flow(w, h), synth.forward_flow(w, h)
+    occ = np.zeros((h, w), np.float32)
+    occ[20:34, 40:60] = 255
+    c11 = ref.filter_frame(n0, None, None, sigma, f1)
+    w1 = ref.warp_bicubic(c11, bflo, occ)
+    for ov in (dict(npatches_t=8, npatches_tagg=20), dict(npatches_t=32), dict(npatches_t=33),
+               dict(npatches_t=30, npatches_tagg=9)):
+        p = ref.default_params(sigma, O.FLT1, O.Params.auto(**ov))
+        assert maxabs(ref.filter_frame(n1, w1, None, sigma, p), port.filter_frame(n1, w1, None, sigma, p)) <= TOL_MAXABS, ov
+    c12 = ref.filter_frame(n1, w1, None, sigma, f1)
+    for ov in (dict(), dict(npatches_tagg=2), dict(npatches_tagg=5), dict(npatches_t=6), dict(npatches_t=6, npatches_tagg=3)):
+        p = ref.default_params(sigma, O.FLT2, O.Params.auto(**ov))
+        assert maxabs(ref.filter_frame(n1, w1, c12, sigma, p), port.filter_frame(n1, w1, c12, sigma, p)) <= TOL_MAXABS, ov
+    ws = ref.warp_bicubic(c12, fflo, occ)
+    for ov in (dict(npatches_t=12, npatches_tagg=2), dict(npatches_t=32, npatches_tagg=32), dict()):
+        p = ref.default_params(sigma, O.SMO1, O.Params.auto(**ov))
+        assert maxabs(ref.smooth_frame(c11, ws, None, sigma, p), port.smooth_frame(c11, ws, None, sigma, p)) <= TOL_MAXABS, ov
