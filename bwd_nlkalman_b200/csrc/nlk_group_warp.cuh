@@ -106,29 +106,6 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <bool INVERSE>
-__device__ __forceinline__ void dct8x8_regs(float (&t)[64])
-{
-#pragma unroll
-    for (int y = 0; y < 8; ++y) {
-        float r[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = t[y * 8 + i];
-        if (INVERSE) dct1d_inv<8>(r); else dct1d_fwd<8>(r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t[y * 8 + i] = r[i];
-    }
-#pragma unroll
-    for (int x = 0; x < 8; ++x) {
-        float r[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) r[i] = t[i * 8 + x];
-        if (INVERSE) dct1d_inv<8>(r); else dct1d_fwd<8>(r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t[i * 8 + x] = r[i];
-    }
-}
-
 // per-team scalars of the current group, kept in shared memory and re-read where they are
 // used: the transform phases hold a whole tile in registers and everything that stays live
 // across them costs a spill

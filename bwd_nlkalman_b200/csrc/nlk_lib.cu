@@ -741,8 +741,6 @@ extern "C" int nlk_seq_reset(nlk_ctx *c)
     return NLK_OK;
 }
 
-// one frame of the forward recursion.  hook(which) is called right after output `which`
-// (1: first filtering, 2: second) has been queued on the context's stream.
 // One frame of the forward recursion.  hook(which) is called right after output `which`
 // (1: first filtering, 2: second) has been queued, with c->L the lane it was queued on.
 //
