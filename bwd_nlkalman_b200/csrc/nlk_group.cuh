@@ -101,12 +101,8 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
         const int gy = g / P.gw, gx = g - gy * P.gw;
         const int px = gx * P.step, py = gy * P.step;
         const int prev_p = hd.flags & HDR_PREV_P;
-        int k = hd.nk;
+        const int k = hd.nk;
         const int np0 = hd.np0;
-        // smoother without search but with a valid previous patch: single-patch estimate
-        // (reference :1699-1730; the group is the patch at p, see oracle/nlk_port.c)
-        const bool point = P.smooth && k == 0 && prev_p;
-
         if (!P.smooth && k == 0) continue; // filter, k <= 1: nothing aggregated (:815-849,:857)
 
         __syncthreads(); // previous group done with shared memory
@@ -126,19 +122,14 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
         }
 
         // window geometry of this group (the search window, reference :637-639)
-        const int r = point ? 0 : (P.smooth ? P.r_t : (prev_p ? P.r_t : P.r_x));
+        const int r = P.smooth ? P.r_t : (prev_p ? P.r_t : P.r_x);
         const int x0 = max(px - r, 0), x1 = min(px + r, P.w - psz);
         const int y0 = max(py - r, 0), y1 = min(py + r, P.h - psz);
         const int wlen = (x1 - x0 + psz) * ch, wh = y1 - y0 + psz;
         stage_window(winS, wrow, P.src, P.w, ch, x0, y0, wlen, wh);
         if (prev_p) stage_window(winP, wrow, P.prev0, P.w, ch, x0, y0, wlen, wh);
 
-        if (point) {
-            if (tid == 0) s_cand[0] = cand_pack(px, py, 1);
-            k = 1;
-        } else {
-            for (int i = tid; i < k; i += GF_THREADS) s_cand[i] = P.cand[(long)g * P.kstride + i];
-        }
+        for (int i = tid; i < k; i += GF_THREADS) s_cand[i] = P.cand[(long)g * P.kstride + i];
         __syncthreads();
 
         // group members: the first tagg candidates with a valid previous patch, or, when
@@ -192,13 +183,6 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
                     const float *tp = tiles + c * TS + e;      // source tile of slot 0
                     const float *tq = tp + ch * TS;            // previous-frame tile of slot 0
                     int m1 = n1, m0 = n0;
-                    if (point) {
-                        const float p = tp[0], q = tq[0];
-                        V1[u] = p * p;
-                        V0[u] = q * q;
-                        V01[u] = (q - p) * (q - p);
-                        continue;
-                    }
                     float aM1 = M1[u], aV1 = V1[u], aMp = Mp[u], aV0 = V0[u], aV01 = V01[u], aMg = Mg[u];
                     for (int i = 0; i < cnt; ++i, tp += cstride, tq += cstride) {
                         const float p = *tp;
@@ -241,10 +225,8 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
                 const int j = tid + u * GF_THREADS;
                 if (j < cpp) {
                     float v1 = V1[u], v0 = V0[u], v01 = V01[u];
-                    if (!point) {
-                        v1 *= inp1;                             // :805
-                        if (n0) { v0 *= inp0; v01 *= inp0; }    // :806-810
-                    }
+                    v1 *= inp1;                                 // :805
+                    if (n0) { v0 *= inp0; v01 *= inp0; }        // :806-810
                     float a, m;
                     if (P.smooth) {
                         a = __fdiv_rn(v1, v1 + P.beta_t * v01);              // :1768

@@ -111,7 +111,7 @@ __device__ __forceinline__ void fence_proxy_async()
 // across them costs a spill
 enum { GN_AI = 0, GN_G, GN_NK, GN_NP0, GN_FLAGS, GN_PXY, GN_COUNT = 6 };
 enum { GP_WOFF0 = 0, GP_WROW, GP_WPOFF, GP_K, GP_NP0, GP_NAGG, GP_NR1, GP_FLAGS, GP_G, GP_N0, GP_N0B, GP_MBAR, GP_COUNT = 12 };
-constexpr int GPF_PREV = 1, GPF_POINT = 2;
+constexpr int GPF_PREV = 1;
 
 __device__ __forceinline__ int lds_par(const int *p)
 {
@@ -211,7 +211,6 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm, const __grid_constant_
             const int prev_p = hd.flags & HDR_PREV_P;
             int k = hd.nk;
             const int np0 = hd.np0;
-            const bool point = SMOOTH && k == 0 && prev_p;   // (reference :1699-1730)
 
             if (!SMOOTH && k == 0) {                         // filter, k <= 1 (:815-849, :857)
                 if (TMA && l64 == 0) mbar_arrive((unsigned)lds_par(s_par + GP_MBAR));
@@ -233,11 +232,11 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm, const __grid_constant_
             }
 
             // ---- stage the search window(s) of this group (reference :637-639) -----------------
-            const int r = point ? 0 : (SMOOTH ? P.r_t : (prev_p ? P.r_t : P.r_x));
-            const int wrow = (r == P.r_t || point) ? Gm.wrow_t : Gm.wrow_x;
+            const int r = SMOOTH ? P.r_t : (prev_p ? P.r_t : P.r_x);
+            const int wrow = (r == P.r_t) ? Gm.wrow_t : Gm.wrow_x;
             int woff0, wpoff;      // window origin in image coordinates, offset of the previous-frame window
             if constexpr (TMA) {
-                const bool boxt = (r == P.r_t || point);
+                const bool boxt = (r == P.r_t);
                 const int rb = boxt ? P.r_t : P.r_x;
                 // the box starts at the window's first column rounded down to a multiple of four floats:
                 // TMA wants the innermost coordinate 16-byte aligned (tools/micro/tma_probe.cu: an
@@ -278,12 +277,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm, const __grid_constant_
                     }
                 }
             }
-            if (point) {
-                if (l64 == 0) s_cand[0] = cand_pack(px, py, 1);
-                k = 1;
-            } else {
-                for (int i = l64; i < k; i += GW_TEAM) s_cand[i] = P.cand[(long)g * P.kstride + i];
-            }
+            for (int i = l64; i < k; i += GW_TEAM) s_cand[i] = P.cand[(long)g * P.kstride + i];
             if (l64 == 0) {
                 s_par[GP_WOFF0] = woff0;
                 s_par[GP_WROW] = wrow;
@@ -291,7 +285,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm, const __grid_constant_
                 s_par[GP_K] = k;
                 s_par[GP_NP0] = np0;
                 s_par[GP_NR1] = prev_p ? (k + CC2 - 1) / CC2 : (k + CC1 - 1) / CC1;
-                s_par[GP_FLAGS] = (prev_p ? GPF_PREV : 0) | (point ? GPF_POINT : 0);
+                s_par[GP_FLAGS] = prev_p ? GPF_PREV : 0;
                 s_par[GP_G] = g;
             }
             if (TMA) mbar_wait((unsigned)lds_par(s_par + GP_MBAR), it & 1);
@@ -529,15 +523,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm, const __grid_constant_
 #pragma unroll
                 for (int u = 0; u < CH; ++u) sC[u] = sD[u] = 0.f;
             }
-            if (flags & GPF_POINT) {
-#pragma unroll
-                for (int u = 0; u < CH; ++u) {
-                    const float p = tiles[u * TS + l64], q = tiles[(CH + u) * TS + l64];
-                    sB[u] = p * p;                       // V1
-                    sE[SMOOTH ? u : 0] = q * q;          // V0 (the point estimate exists for the smoother only)
-                    sC[u] = (q - p) * (q - p);           // V01
-                }
-            } else {
+            {
                 const int cstride = ((flags & GPF_PREV) ? 2 * CH : CH) * TS;
                 const float *tp = tiles + l64;             // source tile of slot 0, channel 0
 #pragma unroll 1
@@ -599,8 +585,7 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm, const __grid_constant_
             }
             float vsum = 0.f;
             {
-                const bool point = flags & GPF_POINT;
-                const int n1 = point ? 0 : lds_par(s_par + GP_K);
+                const int n1 = lds_par(s_par + GP_K);
                 const float inp1 = c_inv[max(n1, 1)];
                 const float inp0 = c_inv[n0];
                 const float sigma2 = P.sigma2;
@@ -610,10 +595,8 @@ k_group_team8(const PassParams P, const GroupWarpGeom Gm, const __grid_constant_
                     float a, m;
                     if (SMOOTH) {
                         float v1 = sB[u], v0 = sE[SMOOTH ? u : 0], v01 = sC[u];
-                        if (!point) {
-                            v1 *= inp1;                             // :805
-                            if (n0) { v0 *= inp0; v01 *= inp0; }    // :806-810
-                        }
+                        v1 *= inp1;                                 // :805
+                        if (n0) { v0 *= inp0; v01 *= inp0; }        // :806-810
                         a = __fdividef(v1, v1 + P.beta_t * v01);              // :1768
                         vsum += (1.f - a * a) * v1 + a * a * fmaxf(v0 - P.beta_t * v01, 0.f);
                         m = 0.f;
@@ -690,6 +673,10 @@ inline bool window_map(CUtensorMap *m, const float *img, int w, int h, int ch, i
 inline int launch_group_team8(const PassParams &P, int num_sms, cudaStream_t st)
 {
     if (P.psz != 8 || (P.ch != 3 && P.ch != 1)) return 0;
+    // smoother with a basic estimate: statistics on bsic1, members from filt1 (reference
+    // src/nlkalman.c:1669) -- the team kernel takes both from one window; the block-per-group
+    // kernel restages the members.  No reference driver passes one (src/main-smo.c:209).
+    if (P.smooth && P.has_bsic) return 0;
     const int ch = P.ch;
     // TMA staging is opt-in (NLK_TMA=1) until it is validated on the GPU; NLK_NO_TMA wins
     static const bool no_tma = getenv("NLK_NO_TMA") != nullptr || getenv("NLK_TMA") == nullptr;

@@ -395,6 +395,12 @@ static int pass_setup(nlk_ctx *c, PassParams &P, int smooth, float *d_out, const
     if (pr.search_sz_x < 0 || pr.search_sz_t < 0 || pr.npatches_x < 0 || pr.npatches_t < 0 ||
         pr.npatches_tagg < 0)
         return set_err(NLK_ERR_PARAM, "negative parameter: call nlkalman_default_params first");
+    // The smoother's single-patch branch (k <= 1 with a valid previous patch, reference
+    // src/nlkalman.c:1699-1730) aggregates at uninitialised coordinates in the reference: there is
+    // no defined result to reproduce, so the configuration is refused.
+    if (smooth && d_prev0 && pr.npatches_t <= 1)
+        return set_err(NLK_ERR_PARAM, "smoother with npatches_t = %d <= 1 is undefined in the reference "
+                                      "(src/nlkalman.c:1699-1730) and not supported", pr.npatches_t);
 
     memset(&P, 0, sizeof P);
     P.w = w; P.h = h; P.ch = ch; P.psz = psz; P.step = psz / 2;

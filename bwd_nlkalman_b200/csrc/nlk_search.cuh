@@ -248,12 +248,13 @@ k_search(const PassParams P, int warps_per_cta, int wrow, int win_floats, int np
 
     if (k <= 1) {
         // no search (reference :631 / :1522).  Filter: nothing is aggregated for this
-        // patch.  Smoother: the patch at p alone (prev_p) or a plain copy (!prev_p).
+        // patch.  Smoother: a plain copy (no valid previous patch; with one, k_t <= 1 is
+        // rejected by pass_setup: the reference's branch :1699-1730 reads uninitialised memory).
         if (lane == 0) {
             GroupHdr hd;
             hd.nk = 0;
-            hd.np0 = (P.smooth && prev_p) ? 1 : 0;
-            hd.flags = (prev_p ? HDR_PREV_P : 0) | ((P.smooth && prev_p) ? HDR_MARKS : 0);
+            hd.np0 = 0;
+            hd.flags = prev_p ? HDR_PREV_P : 0;
             hd.pxy = (int)cand_pack(px, py, 0);
             P.hdr[g] = hd;
         }
@@ -337,8 +338,8 @@ __device__ __forceinline__ void search_rows_block(const PassParams &P, int gy, i
         const int g = gy * P.gw + gx0 + s;
         GroupHdr hd;
         hd.nk = 0;
-        hd.np0 = (P.smooth && prev_p) ? 1 : 0;
-        hd.flags = (prev_p ? HDR_PREV_P : 0) | ((P.smooth && prev_p) ? HDR_MARKS : 0);
+        hd.np0 = 0;
+        hd.flags = prev_p ? HDR_PREV_P : 0;
         hd.pxy = (int)cand_pack((gx0 + s) * P.step, py, 0);
         P.hdr[g] = hd;
         for (int i = 0; i < P.nbw; ++i) P.nbr[(long)g * P.nbw + i] = 0u;

@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: full-size parity against the 1-thread reference (minutes of CPU time)")
 
 
 @pytest.fixture(scope="session")

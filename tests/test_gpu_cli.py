@@ -113,6 +113,39 @@ def test_flt_and_smo_against_reference_programs(scene):
     assert maxabs(tif, _read_pfm(d / "g_a1.pfm")) <= TOL_MAXABS
 
 
+def test_reference_drivers_linked_against_the_library(scene):
+    """The drop-in claim itself: the reference's OWN drivers (src/main-flt.c, src/main-smo.c, unmodified,
+    with its iio and argparse; oracle/Makefile target `dropin`) linked against libnlkalman_b200.so
+    instead of src/nlkalman.c, against the all-reference programs on the same files and command lines
+    (scripts/nlkalman-seq.sh:39-41, :80-81, :100-102, :147-149)."""
+    d, sigma = scene
+    di_flt, di_smo = os.path.join(REF, "nlkalman-flt-dropin"), os.path.join(REF, "nlkalman-smo-dropin")
+    ref_flt, ref_smo = os.path.join(REF, "nlkalman-flt-ref"), os.path.join(REF, "nlkalman-smo-ref")
+    if not (os.path.exists(di_flt) and os.path.exists(ref_flt)):
+        pytest.skip("oracle/_ref drop-in drivers not built (needs /root/reference)")
+    one = {"OMP_NUM_THREADS": "1", "OMP_THREAD_LIMIT": "1"}
+    _run(ref_flt, "-i", d / "n0.pfm", "-s", sigma, "--flt11", d / "R_a1.pfm", "--flt21", d / "R_a2.pfm", env=one)
+    _run(di_flt, "-i", d / "n0.pfm", "-s", sigma, "--flt11", d / "D_a1.pfm", "--flt21", d / "D_a2.pfm")
+    assert maxabs(_read_pfm(d / "D_a1.pfm"), _read_pfm(d / "R_a1.pfm")) <= TOL_MAXABS
+    assert maxabs(_read_pfm(d / "D_a2.pfm"), _read_pfm(d / "R_a2.pfm")) <= TOL_MAXABS
+    for exe, tag, env in ((ref_flt, "R", one), (di_flt, "D", None)):
+        _run(exe, "-i", d / "n1.pfm", "-s", sigma, "--f2_p", 0, "-o", d / "bflo.flo", "-k", d / "occ.pgm",
+             "--flt10", d / "R_a1.pfm", "--flt11", d / f"{tag}_b1.pfm", env=env)
+    assert maxabs(_read_pfm(d / "D_b1.pfm"), _read_pfm(d / "R_b1.pfm")) <= TOL_MAXABS
+    for exe, tag, env in ((ref_flt, "R", one), (di_flt, "D", None)):
+        _run(exe, "-i", d / "n1.pfm", "-s", sigma, "--f1_p", 0, "-o", d / "bflo.flo", "-k", d / "occ.pgm",
+             "--flt11", d / "R_b1.pfm", "--flt20", d / "R_a2.pfm", "--flt21", d / f"{tag}_b2.pfm", env=env)
+    assert maxabs(_read_pfm(d / "D_b2.pfm"), _read_pfm(d / "R_b2.pfm")) <= TOL_MAXABS
+    for exe, tag, env in ((ref_smo, "R", one), (di_smo, "D", None)):
+        _run(exe, "--flt1", d / "R_a2.pfm", "--smo0", d / "R_b2.pfm", "-s", sigma, "-o", d / "fflo.flo",
+             "-k", d / "occ.pgm", "--smo1", d / f"{tag}_s0.pfm", ok=(1,), env=env)
+    assert maxabs(_read_pfm(d / "D_s0.pfm"), _read_pfm(d / "R_s0.pfm")) <= TOL_MAXABS
+    # the configuration the library refuses (reference UB, src/nlkalman.c:1699-1730): message + exit 1
+    r = _run(di_smo, "--flt1", d / "R_a2.pfm", "--smo0", d / "R_b2.pfm", "-s", sigma, "-o", d / "fflo.flo",
+             "--s1_nt", 1, "--smo1", d / "D_bad.pfm", ok=(1,))
+    assert "npatches_t" in r.stderr and not os.path.exists(d / "D_bad.pfm")
+
+
 def test_seq_driver_matches_per_frame_chain(scene):
     """nlkalman-seq keeps every frame in HBM in opponent space; the per-frame chain passes RGB
     files between processes -- same recursion (with --first_f2 1), results equal up to the

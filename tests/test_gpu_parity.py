@@ -349,3 +349,47 @@ def test_two_lane_device_recursion_matches_in_order(nlk):
         assert maxabs(b1[t].cpu().numpy(), a1[t].cpu().numpy()) <= TOL_MAXABS, t
         assert maxabs(b2[t].cpu().numpy(), a2[t].cpu().numpy()) <= TOL_MAXABS, t
         assert maxabs(c2[t].cpu().numpy(), a2[t].cpu().numpy()) <= TOL_MAXABS, t
+
+
+# ---- branches outside the drivers' call patterns ---------------------------------------------
+
+def test_smoother_with_basic_estimate(nlk, port):
+    """nlkalman_smooth_frame with bsic1 != NULL: search and statistics on bsic1, the updated
+    members from filt1 (reference src/nlkalman.c:1669).  No reference driver passes one
+    (src/main-smo.c:209), the entry point accepts it: 8x8 RGB and gray, and 12x12."""
+    from bwd_nlkalman_b200 import synth
+    from oracle import oracle as O
+    sigma = 20.0
+    for (w, h, ch, ov) in ((93, 70, 3, {}), (88, 66, 1, {}), (90, 66, 3, dict(patch_sz=12, search_sz_t=6))):
+        s1 = nlk.default_params(sigma, nlk.SMO1, nlk.Params.auto(npatches_t=24, npatches_tagg=10, **ov))
+        rng = np.random.default_rng(w)
+        clean0 = port.rgb2opp(synth.clean_frame(w, h, ch, 0))
+        flt = clean0 + rng.normal(0, 4, clean0.shape).astype(np.float32)      # "filtered" frame t
+        bsic = clean0 + rng.normal(0, 2, clean0.shape).astype(np.float32)     # a better estimate of it
+        nxt = port.rgb2opp(synth.clean_frame(w, h, ch, 1)) + rng.normal(0, 2, clean0.shape).astype(np.float32)
+        occ = np.zeros((h, w), np.float32)
+        occ[20:34, 40:60] = 255
+        ws = port.warp_bicubic(nxt, synth.forward_flow(w, h), occ)
+        out, cpu_out, cd = _stage_check(nlk, port, O, 1, flt, ws, bsic, sigma, s1)
+        assert (cd["np0"] > 0).any() and (cd["np0"] == 0).any()
+        # the basic estimate matters: without it the result differs
+        plain = port.smooth_frame(flt, ws, None, sigma, _same_params(nlk, O, s1))
+        assert maxabs(cpu_out, plain) > 0.05
+
+
+def test_smoother_single_patch_branch_is_rejected(nlk):
+    """--s1_nt <= 1 with a valid next frame: the reference's branch (src/nlkalman.c:1699-1730)
+    aggregates at uninitialised coordinates -- there is no defined result, the
+    library refuses the configuration instead of inventing one.  Without a next frame (plain copy,
+    :1795-1804) and for the filter (k <= 1: nothing aggregated, :815-849) the call stays valid."""
+    from bwd_nlkalman_b200 import synth
+    sigma, w, h, ch = 20.0, 64, 48, 1
+    n0 = synth.noisy_frame(w, h, ch, 0, sigma)
+    prev = synth.noisy_frame(w, h, ch, 1, sigma)
+    for nt in (1, 0):
+        s1 = nlk.default_params(sigma, nlk.SMO1, nlk.Params.auto(npatches_t=nt, npatches_tagg=1))
+        with nlk.Context(w, h, ch) as ctx:
+            with pytest.raises(nlk.NlkError, match="npatches_t"):
+                ctx.pass_host_debug(1, n0, prev, None, sigma, s1)
+            out, _ = ctx.pass_host_debug(1, n0, None, None, sigma, s1)     # no next frame: copy
+            assert maxabs(out, n0) <= TOL_MAXABS

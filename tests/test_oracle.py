@@ -169,3 +169,51 @@ def test_port_matches_reference_on_parameter_variants(port, ref, ch):
     for ov in (dict(npatches_t=12, npatches_tagg=2), dict(npatches_t=32, npatches_tagg=32), dict()):
         p = ref.default_params(sigma, O.SMO1, O.Params.auto(**ov))
         assert maxabs(ref.smooth_frame(c11, ws, None, sigma, p), port.smooth_frame(c11, ws, None, sigma, p)) <= TOL_MAXABS, ov
+
+
+def test_port_smoother_with_basic_estimate_matches_reference(port, ref):
+    """nlkalman_smooth_frame with bsic1 != NULL (reference src/nlkalman.c:1669, :1734): the inputs of
+    tests/test_gpu_parity.py::test_smoother_with_basic_estimate, restatement vs the reference library"""
+    from bwd_nlkalman_b200 import synth
+    from oracle import oracle as O
+    sigma = 20.0
+    for (w, h, ch, ov) in ((93, 70, 3, {}), (88, 66, 1, {}), (90, 66, 3, dict(patch_sz=12, search_sz_t=6))):
+        s1 = ref.default_params(sigma, O.SMO1, O.Params.auto(npatches_t=24, npatches_tagg=10, **ov))
+        rng = np.random.default_rng(w)
+        clean0 = port.rgb2opp(synth.clean_frame(w, h, ch, 0))
+        flt = clean0 + rng.normal(0, 4, clean0.shape).astype(np.float32)
+        bsic = clean0 + rng.normal(0, 2, clean0.shape).astype(np.float32)
+        nxt = port.rgb2opp(synth.clean_frame(w, h, ch, 1)) + rng.normal(0, 2, clean0.shape).astype(np.float32)
+        occ = np.zeros((h, w), np.float32)
+        occ[20:34, 40:60] = 255
+        ws = port.warp_bicubic(nxt, synth.forward_flow(w, h), occ)
+        assert maxabs(ref.smooth_frame(flt, ws, bsic, sigma, s1), port.smooth_frame(flt, ws, bsic, sigma, s1)) <= TOL_MAXABS
+
+
+def test_occlusion_oracle_pinned_to_reference_plambda(tmp_path):
+    """the occlusion mask is the reference's plambda tool (lib/imscript-lite/src/plambda.c,
+    compiled unmodified as oracle/_ref/plambda-ref) run with the exact expression of
+    scripts/nlkalman-seq.sh:70-72; the numpy restatement the GPU kernel is checked against must
+    reproduce it bit for bit (boundary = nearest sample, plambda.c:2176)."""
+    import os
+    import struct
+    import subprocess
+    from oracle import oracle as O
+    exe = os.path.join(os.path.dirname(O.REF_SO), "plambda-ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/plambda-ref not built (needs /root/reference)")
+    rng = np.random.default_rng(11)
+    for (w, h) in ((157, 93), (33, 2), (1, 40)):
+        of = rng.normal(0, 0.6, (h, w, 2)).astype(np.float32)
+        of[h // 4:h // 2, w // 5:w // 2] += rng.normal(0, 2.0, (h // 2 - h // 4, w // 2 - w // 5, 2)).astype(np.float32)
+        flo, out = tmp_path / "f.flo", tmp_path / "o.pfm"
+        with open(flo, "wb") as f:
+            f.write(b"PIEH" + struct.pack("<ii", w, h) + of.tobytes())
+        for th in (0.25, 0.75, 2.0):
+            expr = f"x(0,0)[0] x(-1,0)[0] - x(0,0)[1] x(0,-1)[1] - + fabs {th} > 255 *"
+            subprocess.run([exe, str(flo), expr, "-o", str(out)], check=True)
+            raw = open(out, "rb").read()
+            head = raw.split(b"\n", 3)
+            ww, hh = (int(x) for x in head[1].split())
+            got = np.frombuffer(head[3], np.float32).reshape(hh, ww)
+            assert np.array_equal(got, O.occlusion_from_flow(of, th)), (w, h, th)
