@@ -95,6 +95,18 @@ def lib():
     L.nlk_strip_search.argtypes = [vp, C.c_int, vp, vp, vp, C.c_float, Params, C.c_int, C.c_int, vp, vp]
     L.nlk_strip_filter.argtypes = [vp]
     L.nlk_strip_normalize.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.nlk_peer_header_bytes.restype = C.c_size_t
+    L.nlk_peer_slab_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.nlk_peer_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    L.nlk_peer_ipc_import.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.nlk_peer_bind.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.c_size_t]
+    L.nlk_peer_push.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_uint, C.c_int, C.c_uint, C.c_int]
+    L.nlk_peer_push_add.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_uint]
+    L.nlk_peer_signal.argtypes = [vp, C.c_int, C.c_uint, C.c_uint]
+    L.nlk_peer_wait.argtypes = [vp, C.c_int, C.c_uint, C.c_uint]
+    L.nlk_peer_error.argtypes = [vp, C.POINTER(C.c_uint)]
+    L.nlk_dev_free.argtypes = [vp, vp]
+    L.nlk_dev_free.restype = None
     L.nlk_seq_reset.argtypes = [vp]
     L.nlk_seq_filter_dev.argtypes = [vp, vp, vp, vp, C.c_float, Params, Params, vp, vp]
     L.nlk_seq_filter_host.argtypes = [vp, vp, vp, vp, C.c_float, Params, Params, vp, vp]
@@ -301,6 +313,46 @@ class Context:
 
     def strip_normalize(self, out, row0, row1):
         _check(lib().nlk_strip_normalize(self._h, _vp(out), int(row0), int(row1)))
+
+    # peer-memory exchanges between the strips' GPUs (include/nlkalman_b200.h)
+    def peer_slab_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        _check(lib().nlk_peer_slab_alloc(self._h, int(nbytes), C.byref(p)))
+        return int(p.value)
+
+    def peer_ipc_export(self, slab: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib().nlk_peer_ipc_export(self._h, C.c_void_p(slab), buf))
+        return buf.raw
+
+    def peer_ipc_import(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        _check(lib().nlk_peer_ipc_import(self._h, handle, C.byref(p)))
+        return int(p.value)
+
+    def peer_bind(self, rank: int, nranks: int, slabs, slab_bytes: int):
+        arr = (C.c_void_p * nranks)(*[C.c_void_p(int(x)) for x in slabs])
+        _check(lib().nlk_peer_bind(self._h, int(rank), int(nranks), arr, int(slab_bytes)))
+
+    def peer_push(self, off, nbytes, peer_mask, slot, value, side=0):
+        _check(lib().nlk_peer_push(self._h, int(off), int(nbytes), int(peer_mask), int(slot), int(value) & 0xffffffff, int(side)))
+
+    def peer_push_add(self, off, nbytes, peer, slot, value):
+        _check(lib().nlk_peer_push_add(self._h, int(off), int(nbytes), int(peer), int(slot), int(value) & 0xffffffff))
+
+    def peer_signal(self, slot, value, peer_mask):
+        _check(lib().nlk_peer_signal(self._h, int(slot), int(value) & 0xffffffff, int(peer_mask)))
+
+    def peer_wait(self, slot, value, src_mask):
+        _check(lib().nlk_peer_wait(self._h, int(slot), int(value) & 0xffffffff, int(src_mask)))
+
+    def peer_error(self) -> int:
+        v = C.c_uint(0)
+        _check(lib().nlk_peer_error(self._h, C.byref(v)))
+        return int(v.value)
+
+    def dev_free(self, ptr: int):
+        lib().nlk_dev_free(self._h, C.c_void_p(int(ptr)))
 
     # resident sequence recursion
     def seq_reset(self):

@@ -8,6 +8,7 @@
 #include "nlk_resolve.cuh"
 #include "nlk_group.cuh"
 #include "nlk_group_warp.cuh"
+#include "nlk_peer.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -152,6 +153,15 @@ struct nlk_ctx {
     // strip-sharded pass in flight (nlk_strip_search .. nlk_strip_normalize)
     PassParams strip_P;
     bool strip_open = false;
+    // peer-memory exchanges between the strips' GPUs (nlk_peer_*)
+    PeerTable peer;
+    bool peer_on = false;
+    size_t slab_bytes = 0;
+    std::vector<void *> ipc_opened;
+    cudaStream_t st_side = nullptr;            // whole-strip pushes (copy engines) beside the next pass
+    cudaEvent_t ev_side_fork = nullptr, ev_side_done = nullptr;
+    bool side_pending = false;
+    unsigned int cnt_rot = 0;
     // optional per-kernel timing with CUDA events on the stream of the lane in use
     bool prof = false;
     int prof_kind = NLK_PASS_OTHER;
@@ -285,6 +295,10 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     }
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
     if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
+    if (c->st_side) { cudaStreamSynchronize(c->st_side); cudaStreamDestroy(c->st_side); }
+    if (c->ev_side_fork) cudaEventDestroy(c->ev_side_fork);
+    if (c->ev_side_done) cudaEventDestroy(c->ev_side_done);
+    for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) if (c->lane[i].st) cudaStreamDestroy(c->lane[i].st);
@@ -314,6 +328,7 @@ extern "C" int nlk_ctx_sync(nlk_ctx *c)
     if (int r = lanes_join(c)) return r;
     CU_TRY(cudaStreamSynchronize(c->lane[0].st));
     if (c->st_d2h) CU_TRY(cudaStreamSynchronize(c->st_d2h));
+    if (c->st_side) CU_TRY(cudaStreamSynchronize(c->st_side));
     return NLK_OK;
 }
 
@@ -732,8 +747,172 @@ extern "C" int nlk_strip_normalize(nlk_ctx *c, float *d_out, int row0, int row1)
     if (!c->strip_open) return set_err(NLK_ERR_STATE, "nlk_strip_search must come first");
     if (int r = rows_ok(c, row0, row1)) return r;
     c->strip_P.out = d_out;
+    if (c->side_pending) {      // the previous frame buffer's whole-strip push reads what this may overwrite
+        CU_TRY(cudaStreamWaitEvent(c->L->st, c->ev_side_done, 0));
+        c->side_pending = false;
+    }
     KindScope ks(c, pass_kind(c->strip_P));
     return pass_normalize(c, c->strip_P, row0, row1);
+}
+
+// ---- peer-memory exchanges between strips (nlk_peer.cuh) ---------------------------------------
+
+extern "C" size_t nlk_peer_header_bytes(void) { return PEER_HDR_BYTES; }
+
+extern "C" int nlk_peer_slab_alloc(nlk_ctx *c, size_t bytes, void **d_slab)
+{
+    if (int r = enter(c)) return r;
+    if (!d_slab || bytes < PEER_HDR_BYTES) return set_err(NLK_ERR_PARAM, "slab smaller than its header (%zu bytes)", PEER_HDR_BYTES);
+    void *p = nullptr;
+    CU_TRY(cudaMalloc(&p, bytes));       // plain cudaMalloc: exportable with cudaIpcGetMemHandle
+    CU_TRY(cudaMemsetAsync(p, 0, bytes, c->L->st));
+    CU_TRY(cudaStreamSynchronize(c->L->st));
+    *d_slab = p;
+    return NLK_OK;
+}
+
+extern "C" int nlk_peer_ipc_export(nlk_ctx *c, void *d_slab, unsigned char *handle64)
+{
+    if (int r = enter(c)) return r;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, d_slab));
+    memcpy(handle64, &h, 64);
+    return NLK_OK;
+}
+
+extern "C" int nlk_peer_ipc_import(nlk_ctx *c, const unsigned char *handle64, void **d_ptr)
+{
+    if (int r = enter(c)) return r;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->ipc_opened.push_back(p);
+    *d_ptr = p;
+    return NLK_OK;
+}
+
+extern "C" int nlk_peer_bind(nlk_ctx *c, int rank, int nranks, void *const *slabs, size_t slab_bytes)
+{
+    if (int r = enter(c)) return r;
+    if (nranks < 1 || nranks > PEER_MAX || rank < 0 || rank >= nranks || !slabs)
+        return set_err(NLK_ERR_PARAM, "bad peer table (1..%d ranks)", PEER_MAX);
+    memset(&c->peer, 0, sizeof c->peer);
+    for (int i = 0; i < nranks; ++i) {
+        if (!slabs[i]) return set_err(NLK_ERR_PARAM, "null slab of rank %d", i);
+        c->peer.slab[i] = static_cast<char *>(slabs[i]);
+    }
+    c->peer.rank = rank; c->peer.nranks = nranks;
+    c->slab_bytes = slab_bytes;
+    if (!c->st_side) {
+        CU_TRY(cudaStreamCreateWithFlags(&c->st_side, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_side_fork, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_side_done, cudaEventDisableTiming));
+    }
+    c->peer_on = true;
+    return NLK_OK;
+}
+
+static int peer_ok(nlk_ctx *c, size_t off, size_t bytes, unsigned int mask)
+{
+    if (!c->peer_on) return set_err(NLK_ERR_STATE, "nlk_peer_bind must come first");
+    if (off + bytes > c->slab_bytes) return set_err(NLK_ERR_PARAM, "range [%zu, %zu) outside the slab", off, off + bytes);
+    if (mask >> c->peer.nranks) return set_err(NLK_ERR_PARAM, "peer mask 0x%x names ranks beyond %d", mask, c->peer.nranks);
+    return NLK_OK;
+}
+
+extern "C" int nlk_peer_signal(nlk_ctx *c, int slot, unsigned int value, unsigned int peer_mask)
+{
+    if (int r = enter(c)) return r;
+    if (int r = peer_ok(c, 0, 0, peer_mask)) return r;
+    if (slot < 0 || slot >= PEER_SLOTS) return set_err(NLK_ERR_PARAM, "flag slot %d", slot);
+    if (!peer_mask) return NLK_OK;
+    k_peer_signal<<<1, 32, 0, c->L->st>>>(c->peer, slot, value, peer_mask);
+    return check_launch(c, 1, "peer_signal");
+}
+
+extern "C" int nlk_peer_wait(nlk_ctx *c, int slot, unsigned int value, unsigned int src_mask)
+{
+    if (int r = enter(c)) return r;
+    if (int r = peer_ok(c, 0, 0, src_mask)) return r;
+    if (slot < 0 || slot >= PEER_SLOTS) return set_err(NLK_ERR_PARAM, "flag slot %d", slot);
+    if (!src_mask) return NLK_OK;
+    static const unsigned long long tmo = getenv("NLK_PEER_TIMEOUT_MS") ? strtoull(getenv("NLK_PEER_TIMEOUT_MS"), nullptr, 10) * 1000000ull
+                                                                         : 4000000000ull;
+    k_peer_wait<<<1, 32, 0, c->L->st>>>(c->peer, slot, value, src_mask, tmo);
+    return check_launch(c, 1, "peer_wait");
+}
+
+// side = 0: a copy kernel on the context's stream (small, latency-critical ranges).
+// side = 1: copy engines on a side stream that forks from the context's stream here and runs
+// beside what is queued next (whole strips of an output frame); the context's stream joins
+// it again before the next nlk_strip_normalize.
+extern "C" int nlk_peer_push(nlk_ctx *c, size_t off, size_t bytes, unsigned int peer_mask, int slot,
+                             unsigned int value, int side)
+{
+    if (int r = enter(c)) return r;
+    if (int r = peer_ok(c, off, bytes, peer_mask)) return r;
+    if (slot >= PEER_SLOTS) return set_err(NLK_ERR_PARAM, "flag slot %d", slot);
+    peer_mask &= ~(1u << c->peer.rank);
+    if (!peer_mask) return NLK_OK;
+    if (side) {
+        CU_TRY(cudaEventRecord(c->ev_side_fork, c->L->st));
+        CU_TRY(cudaStreamWaitEvent(c->st_side, c->ev_side_fork, 0));
+        const char *src = c->peer.slab[c->peer.rank] + off;
+        // nearest ranks first: they read the rows soonest
+        for (int d = 1; d < c->peer.nranks; ++d)
+            for (int sgn = -1; sgn <= 1; sgn += 2) {
+                const int p = c->peer.rank + sgn * d;
+                if (p < 0 || p >= c->peer.nranks || !((peer_mask >> p) & 1u)) continue;
+                if (bytes) CU_TRY(cudaMemcpyAsync(c->peer.slab[p] + off, src, bytes, cudaMemcpyDeviceToDevice, c->st_side));
+            }
+        if (slot >= 0) {
+            k_peer_signal<<<1, 32, 0, c->st_side>>>(c->peer, slot, value, peer_mask);
+            if (int r = check_launch(c, 1, "peer_signal")) return r;
+        }
+        CU_TRY(cudaEventRecord(c->ev_side_done, c->st_side));
+        c->side_pending = true;
+        return NLK_OK;
+    }
+    const int cnt = (int)(c->cnt_rot++ & 7);
+    const bool v16 = (off % 16 == 0) && (bytes % 16 == 0);
+    const size_t n = v16 ? bytes / 16 : bytes / 4;
+    if (bytes % 4) return set_err(NLK_ERR_PARAM, "push of %zu bytes: not a multiple of 4", bytes);
+    int nb = (int)((n + 255) / 256);
+    if (nb > 2 * c->num_sms) nb = 2 * c->num_sms;
+    if (nb < 1) nb = 1;
+    if (v16) k_peer_push<uint4><<<nb, 256, 0, c->L->st>>>(c->peer, off, n, peer_mask, slot, value, cnt);
+    else k_peer_push<unsigned int><<<nb, 256, 0, c->L->st>>>(c->peer, off, n, peer_mask, slot, value, cnt);
+    return check_launch(c, 1, "peer_push");
+}
+
+extern "C" int nlk_peer_push_add(nlk_ctx *c, size_t off, size_t bytes, int peer, int slot, unsigned int value)
+{
+    if (int r = enter(c)) return r;
+    if (peer < 0 || peer >= PEER_MAX) return set_err(NLK_ERR_PARAM, "peer %d", peer);
+    if (int r = peer_ok(c, off, bytes, 1u << peer)) return r;
+    if (slot >= PEER_SLOTS || bytes % 4) return set_err(NLK_ERR_PARAM, "bad push_add request");
+    if (peer == c->peer.rank) return set_err(NLK_ERR_PARAM, "push_add to oneself");
+    const int cnt = (int)(c->cnt_rot++ & 7);
+    const size_t n = bytes / 4;
+    const bool v4 = (off % 16 == 0) && (n % 4 == 0);
+    int nb = (int)(((v4 ? n / 4 : n) + 255) / 256);
+    if (nb > 2 * c->num_sms) nb = 2 * c->num_sms;
+    if (nb < 1) nb = 1;
+    if (v4) k_peer_push_add<4><<<nb, 256, 0, c->L->st>>>(c->peer, off, n, peer, slot, value, cnt);
+    else k_peer_push_add<1><<<nb, 256, 0, c->L->st>>>(c->peer, off, n, peer, slot, value, cnt);
+    return check_launch(c, 1, "peer_push_add");
+}
+
+// nonzero once a wait has timed out (the flag never came): (0x10000 | slot << 8 | source rank)
+extern "C" int nlk_peer_error(nlk_ctx *c, unsigned int *code)
+{
+    if (int r = nlk_ctx_sync(c)) return r;
+    if (!c->peer_on) return set_err(NLK_ERR_STATE, "nlk_peer_bind must come first");
+    if (c->st_side) CU_TRY(cudaStreamSynchronize(c->st_side));
+    CU_TRY(cudaMemcpy(code, c->peer.slab[c->peer.rank] + PEER_ERR_OFF, 4, cudaMemcpyDeviceToHost));
+    return NLK_OK;
 }
 
 // ---- resident sequence recursion --------------------------------------------------------------

@@ -13,10 +13,26 @@ strips, per pass (reference loop: src/nlkalman.c:590-595 over py, px):
   3. ``rows`` of the output -- the next pass searches r + psz rows beyond the strip and the
      next frame's warp (src/nlkalman.c:66-88) reads at flow-displaced positions.
 
-The schedule of one rank is written as a generator that yields these exchange requests;
-``run_dist`` serves them with torch.distributed (NCCL on GPUs, gloo in the CPU tests) and
-``run_virtual`` serves N ranks living in one process (all strips on one GPU, lock-step),
-which is how the strip logic is parity-tested on a single-GPU box.
+Two transports move them:
+
+  * ``transport="peer"`` (the product path on one NVSwitch box): every rank keeps its exchange
+    buffers in one slab at the same offsets, the peers' slabs are mapped with CUDA IPC, and the
+    kernels of the ``nlk_peer_*`` C ABI store / reduce straight into the peer's memory over NVLink
+    and flag completion there; consumers wait on the flags on the device.  No collective library
+    call and no host-side wait in the data path: the bitmaps are pushed to every rank, the
+    accumulator halo rows are ``red.global.add``-ed into their owner (no staging copy, no separate
+    add), an output strip goes to the neighbours' halo rows at once and to everybody with the copy
+    engines beside the next pass.
+  * ``transport="nccl"``: the same schedule on torch.distributed collectives (NCCL on GPUs, gloo
+    in the CPU tests) -- the baseline the peer transport is measured against.
+
+The schedule of one rank is a generator.  With the NCCL transport it yields the exchange
+requests, which ``run_dist`` serves with torch.distributed and ``run_virtual`` serves for N ranks
+living in one process (all strips on one GPU, lock-step) -- how the strip logic is parity-tested
+on a single-GPU box.  With the peer transport it issues the exchanges itself and yields only
+("sync",) markers: points where every rank has queued what the others are about to wait for
+(ignored by ``run_dist``; ``run_virtual`` drains all contexts there, so that no wait kernel ever
+spins on a stream that shares a hardware queue with its producer).
 """
 from __future__ import annotations
 
@@ -131,29 +147,90 @@ class StripRank:
       ("wait", key)
     """
 
-    def __init__(self, w, h, ch, rank, nranks, device=0):
+    # flag slots of the peer transport (include/nlkalman_b200.h: nlk_peer_wait)
+    SLOT_SEARCH, SLOT_ACC, SLOT_HALO, SLOT_FRAME = 0, 1, 8, 16      # HALO + b, FRAME + b for frame buffer b
+
+    def __init__(self, w, h, ch, rank, nranks, device=0, transport="nccl"):
         import torch
         self.torch = torch
         self.w, self.h, self.ch, self.rank, self.nranks = w, h, ch, rank, nranks
+        self.transport = transport
         self.ctx = api.Context(w, h, ch, device)
         self.dev = torch.device("cuda", device)
         self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
         self._full = {}
-        self.noisy, self.warp, self.tmp = self.frame(), self.frame(), self.frame()
+        self._buf = {}                   # data_ptr of an exchanged frame buffer -> (index, slab offset)
+        self.slab = 0
+        if transport == "peer":
+            self._carve_slab()
+        elif transport != "nccl":
+            raise ValueError(transport)
+        self.noisy, self.warp, self.tmp = self.frame(local=True), self.frame(local=True), self.frame(local=True)
         self.flt1, self.flt2 = [self.frame(), self.frame()], [self.frame(), self.frame()]
         self.smo = [self.frame(), self.frame()]
-        self.accw = torch.empty((h, w, ch + 1), dtype=torch.float32, device=self.dev)
-        self.nbr = None
+        if transport == "peer":
+            self.accw = self._view(self.off_accw, (h, w, ch + 1), "<f4")
+            self.nbr = self._view(self.off_nbr, (self.nbr_words,), "<i4")
+        else:
+            self.accw = torch.empty((h, w, ch + 1), dtype=torch.float32, device=self.dev)
+            self.nbr = None
         self.pending = {}
+        self.seq = {}                    # flag slot -> last sequence number used (same on every rank)
+        self.waited = {}
         self.reset()
 
-    def frame(self):
+    # ---- peer transport: the slab ---------------------------------------------------------------
+    def _carve_slab(self):
+        """header | neighbour bitmaps | accumulator | six frame buffers, the same offsets on every rank"""
+        al = lambda x: (x + 255) // 256 * 256
+        self.hp = self.h + 16 * self.nranks
+        self.frame_bytes = al(self.hp * self.w * self.ch * 4)
+        # bitmaps: one word per grid patch for any patch side >= 4 (step >= 2), whole chunks per rank
+        self.nbr_words = (self.w // 2 + 1) * (self.h // 2 + 1 + self.nranks)
+        off = al(api.lib().nlk_peer_header_bytes())
+        self.off_nbr = off
+        off = al(off + self.nbr_words * 4)
+        self.off_accw = off
+        off = al(off + self.h * self.w * (self.ch + 1) * 4)
+        self.off_frames = off
+        self.n_slab_frames = 6
+        self.slab_bytes = off + self.n_slab_frames * self.frame_bytes
+        self.slab = self.ctx.peer_slab_alloc(self.slab_bytes)
+        self._next_frame = 0
+
+    def _view(self, off, shape, typestr):
+        """torch tensor over a range of the slab (CUDA array interface, no copy)"""
+        class _Mem:
+            pass
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (self.slab + off, False),
+                                      "version": 2, "strides": None}
+        t = self.torch.as_tensor(m, device=self.dev)
+        assert t.data_ptr() == self.slab + off
+        return t
+
+    def bind_peers(self, slabs):
+        """slabs[r]: rank r's slab as mapped in this process (own included)"""
+        assert self.transport == "peer" and len(slabs) == self.nranks and slabs[self.rank] == self.slab
+        self.ctx.peer_bind(self.rank, self.nranks, slabs, self.slab_bytes)
+
+    def frame(self, local=False):
         """A frame buffer [h][w][ch] whose allocation is padded to whole chunks for any patch
-        size, so that its strips can be all-gathered in place."""
+        size, so that its strips can be all-gathered in place.  Exchanged buffers of the peer
+        transport live in the slab."""
         torch = self.torch
         hp = self.h + 16 * self.nranks
-        full = torch.zeros((hp, self.w, self.ch), dtype=torch.float32, device=self.dev)
-        t = full[:self.h]
+        if self.transport == "peer" and not local:
+            if self._next_frame >= self.n_slab_frames:
+                raise RuntimeError("the slab holds six exchanged frame buffers")
+            idx, off = self._next_frame, self.off_frames + self._next_frame * self.frame_bytes
+            self._next_frame += 1
+            full = self._view(off, (hp, self.w, self.ch), "<f4")
+            t = full[:self.h]
+            self._buf[t.data_ptr()] = (idx, off)
+        else:
+            full = torch.zeros((hp, self.w, self.ch), dtype=torch.float32, device=self.dev)
+            t = full[:self.h]
         self._full[t.data_ptr()] = full
         return t
 
@@ -161,7 +238,57 @@ class StripRank:
         self.cur, self.have_prev, self.have_flt2, self.smo_cur, self.have_smo = 0, False, False, 0, False
 
     def close(self):
+        if self.slab:
+            self.ctx.sync()
+            self.accw = self.nbr = None
+            self.flt1 = self.flt2 = self.smo = None
+            self._full.clear()
+            self.ctx.dev_free(self.slab)
+            self.slab = 0
         self.ctx.close()
+
+    # ---- peer transport: masks, sequence numbers, waits -------------------------------------------
+    def _mask_all(self):
+        return ((1 << self.nranks) - 1) & ~(1 << self.rank)
+
+    def _mask_nb(self):
+        m = 0
+        if self.rank > 0:
+            m |= 1 << (self.rank - 1)
+        if self.rank + 1 < self.nranks:
+            m |= 1 << (self.rank + 1)
+        return m
+
+    def _next_seq(self, slot):
+        self.seq[slot] = self.seq.get(slot, 0) + 1
+        return self.seq[slot]
+
+    def _await(self, slot, mask):
+        """queue a device-side wait for the latest sequence number of `slot` from `mask` (once)"""
+        v = self.seq.get(slot, 0)
+        if v == 0 or mask == 0 or self.waited.get((slot, mask), 0) >= v:
+            return
+        yield ("sync",)
+        self.ctx.peer_wait(slot, v, mask)
+        self.waited[(slot, mask)] = v
+
+    def need_frame(self, buf, key):
+        """before reading rows of `buf` that OTHER strips produced, anywhere in the frame"""
+        if self.nranks == 1:
+            return
+        if self.transport == "peer":
+            yield from self._await(self.SLOT_FRAME + self._buf[buf.data_ptr()][0], self._mask_all())
+        else:
+            yield ("wait", key)
+
+    def need_halo(self, buf, same_rows=True):
+        """before reading the halo rows of `buf` (the neighbours' border rows); when the reading
+        pass cuts the frame into other strips than the pass that wrote `buf`, the whole frame"""
+        if self.nranks > 1 and self.transport == "peer":
+            if same_rows:
+                yield from self._await(self.SLOT_HALO + self._buf[buf.data_ptr()][0], self._mask_nb())
+            else:
+                yield from self._await(self.SLOT_FRAME + self._buf[buf.data_ptr()][0], self._mask_all())
 
     def plans(self, smooth, prms):
         return [api.strip_plan(self.w, self.h, smooth, prms, self.nranks, r) for r in range(self.nranks)]
@@ -179,6 +306,9 @@ class StripRank:
         plans = self.plans(smooth, prms)
         p = plans[self.rank]
         words = self.nranks * p.chunk_g * p.gw * p.nbw
+        if self.transport == "peer":
+            yield from self._strip_pass_peer(smooth, out, in1, prev0, bsic1, sigma, prms, plans, next_plans)
+            return plans
         if self.nbr is None or self.nbr.numel() < words:
             self.nbr = torch.empty(words, dtype=torch.int32, device=self.dev)
         self.ctx.strip_search(smooth, in1, prev0, bsic1, sigma, prms, p.gy0, p.gy1, self.nbr, self.accw)
@@ -199,6 +329,63 @@ class StripRank:
                     yield ("wait", key)
         return plans
 
+    def _strip_pass_peer(self, smooth, out, in1, prev0, bsic1, sigma, prms, plans, next_plans):
+        """The pass with the exchanges done by the kernels themselves over peer memory."""
+        ctx, rk, n = self.ctx, self.rank, self.nranks
+        p = plans[rk]
+        words = n * p.chunk_g * p.gw * p.nbw
+        if words > self.nbr_words:
+            raise api.NlkError(f"peer transport: {words} bitmap words exceed the slab's {self.nbr_words}")
+        ctx.strip_search(smooth, in1, prev0, bsic1, sigma, prms, p.gy0, p.gy1, self.nbr, self.accw)
+        if n > 1:
+            # (A) every rank has searched: its bitmap rows are here (when groups can mark other grid
+            # cells), its accumulator rows are zeroed, and it is done reading the frame buffers that
+            # the peers overwrite after this pass
+            rmax = prms.search_sz_t if smooth else max(prms.search_sz_t, prms.search_sz_x)
+            v = self._next_seq(self.SLOT_SEARCH)
+            if prms.npatches_tagg > 1 and rmax // (prms.patch_sz // 2) >= 1:
+                rowb = p.gw * p.nbw * 4
+                ctx.peer_push(self.off_nbr + p.gy0 * rowb, (p.gy1 - p.gy0) * rowb, self._mask_all(), self.SLOT_SEARCH, v, 0)
+            else:
+                ctx.peer_signal(self.SLOT_SEARCH, v, self._mask_all())
+            yield from self._await(self.SLOT_SEARCH, self._mask_all())
+        ctx.strip_filter()
+        if n > 1:
+            # (B) overlap-add: the rows this strip's groups aggregated into beyond its border go
+            # straight into the owner's accumulator
+            v = self._next_seq(self.SLOT_ACC)
+            br = border_ranges(plans, rk)
+            rowb = self.w * (self.ch + 1) * 4
+            for key, peer in (("up_send", rk - 1), ("dn_send", rk + 1)):
+                if not 0 <= peer < n:
+                    continue
+                if br[key]:
+                    a, b = br[key]
+                    ctx.peer_push_add(self.off_accw + a * rowb, (b - a) * rowb, peer, self.SLOT_ACC, v)
+                else:
+                    ctx.peer_signal(self.SLOT_ACC, v, 1 << peer)
+            yield from self._await(self.SLOT_ACC, self._mask_nb())
+        ctx.strip_normalize(out, p.oy0, p.oy1)
+        if n > 1:
+            # (C) publish the strip: border rows to the neighbours at once (what the next pass of
+            # this frame searches), the whole strip to everybody beside the next pass (the next
+            # frame's warp reads at flow-displaced positions)
+            idx, off = self._buf[out.data_ptr()]
+            v = self._next_seq(self.SLOT_HALO + idx)
+            self.seq[self.SLOT_FRAME + idx] = v
+            rowb = self.w * self.ch * 4
+            br = border_ranges(next_plans if next_plans is not None else plans, rk)
+            for key, peer in (("up_recv", rk - 1), ("dn_recv", rk + 1)):
+                if not 0 <= peer < n:
+                    continue
+                a, b = br[key] if br[key] else (0, 0)
+                a, b = max(a, p.oy0), min(b, p.oy1)
+                if b > a:
+                    ctx.peer_push(off + a * rowb, (b - a) * rowb, 1 << peer, self.SLOT_HALO + idx, v, 0)
+                else:
+                    ctx.peer_signal(self.SLOT_HALO + idx, v, 1 << peer)
+            ctx.peer_push(off + p.oy0 * rowb, (p.oy1 - p.oy0) * rowb, self._mask_all(), self.SLOT_FRAME + idx, v, 1)
+
     def _rows_needed(self, smooth, *prms_list):
         ps = [api.strip_plan(self.w, self.h, smooth, q, self.nranks, self.rank) for q in prms_list]
         return min(q.ey0 for q in ps), max(q.ey1 for q in ps)
@@ -216,7 +403,7 @@ class StripRank:
         prev1 = None
         if self.have_prev:
             prev1 = self.flt1[prv]
-            yield ("wait", "flt1")     # the other strips of the previous frame (warp reads anywhere)
+            yield from self.need_frame(prev1, "flt1")   # the other strips of the previous frame (warp reads anywhere)
             if d_bflo is not None:
                 a, b = self._rows_needed(0, f1)
                 ctx.warp_rows_dev(self.warp, prev1, d_bflo, d_bocc, a, b)
@@ -230,24 +417,28 @@ class StripRank:
             prev2 = None
             if self.have_prev and self.have_flt2:
                 prev2 = self.flt2[prv]
-                yield ("wait", "flt2")
+                yield from self.need_frame(prev2, "flt2")
                 if d_bflo is not None:
                     a, b = self._rows_needed(0, f2)
                     ctx.warp_rows_dev(self.warp, prev2, d_bflo, d_bocc, a, b)
                     prev2 = self.warp
             nxt = self.plans(1, out2_for) if (out2_for is not None and d_out2 is not None) else None
+            # the basic estimate on the rows beyond the strip
+            yield from self.need_halo(self.flt1[cur], self._same_rows(plans, self.plans(0, f2)))
             plans = yield from self.strip_pass(0, self.flt2[cur], self.noisy, prev2, self.flt1[cur], sigma, f2,
                                                key="flt2", next_plans=nxt)
             p = plans[self.rank]
             if d_out2 is not None:
                 a, b = (nxt[self.rank].ey0, nxt[self.rank].ey1) if nxt is not None else (p.oy0, p.oy1)
+                if nxt is not None:
+                    yield from self.need_halo(self.flt2[cur], self._same_rows(plans, nxt))
                 ctx.colour_rows_dev(d_out2, self.flt2[cur], 1, min(a, p.oy0), max(b, p.oy1))
         self.have_prev, self.have_flt2, self.cur = True, do2, prv
 
     def last_filtered(self, d_out_rgb, second=True):
         """RGB of the whole most recent filtered frame on this rank (waits for its gather)."""
-        yield ("wait", "flt2" if second else "flt1")
         src = (self.flt2 if second else self.flt1)[self.cur ^ 1]
+        yield from self.need_frame(src, "flt2" if second else "flt1")
         self.ctx.colour_rows_dev(d_out_rgb, src, 1, 0, self.h)
 
     def smooth_start(self, d_last_rgb):
@@ -268,7 +459,7 @@ class StripRank:
         a, b = self._rows_needed(1, s1)
         ctx.colour_rows_dev(self.tmp, d_flt_rgb, 0, a, b)
         smo0 = self.smo[nxt]
-        yield ("wait", "smo")
+        yield from self.need_frame(smo0, "smo")
         if d_fflo is not None:
             ctx.warp_rows_dev(self.warp, smo0, d_fflo, d_focc, a, b)
             smo0 = self.warp
@@ -280,6 +471,25 @@ class StripRank:
 
 
 # ---- drivers -----------------------------------------------------------------------------------
+
+def bind_virtual(rank_objs):
+    """peer transport, all ranks in this process: the peers' slabs are plain pointers"""
+    slabs = [o.slab for o in rank_objs]
+    for o in rank_objs:
+        o.bind_peers(slabs)
+
+
+def bind_dist(rank_obj, group=None):
+    """peer transport, one process per GPU: exchange the CUDA IPC handles of the slabs (plumbing
+    over torch.distributed) and map the peers' slabs into this process"""
+    import torch.distributed as dist
+    mine = rank_obj.ctx.peer_ipc_export(rank_obj.slab)
+    handles = [None] * rank_obj.nranks
+    dist.all_gather_object(handles, mine, group=group)
+    slabs = [rank_obj.slab if r == rank_obj.rank else rank_obj.ctx.peer_ipc_import(hd) for r, hd in enumerate(handles)]
+    rank_obj.bind_peers(slabs)
+    dist.barrier(group=group)
+
 
 def _tail(plans, h):
     n, c = len(plans), plans[0].chunk_y
@@ -293,6 +503,8 @@ def run_dist(rank_obj, gen, group=None):
     with torch.cuda.stream(rank_obj.stream):
         for req in gen:
             kind = req[0]
+            if kind == "sync":
+                continue              # peer transport: the waits are on the device
             if kind == "nbr":
                 allgather_chunks(req[1], req[2][0].chunk_g, n, rk, None, group)
             elif kind == "borders":
@@ -333,6 +545,8 @@ def run_virtual(rank_objs, gens):
             continue
         for o in rank_objs:
             o.ctx.sync()
+        if kind == "sync":
+            continue                  # peer transport: everything the coming waits need has run
         plans = reqs[0][2]
         if kind in ("nbr", "gather"):
             for src, p in enumerate(plans):

@@ -14,6 +14,7 @@
 #define NLKALMAN_B200_H
 
 #include "nlkalman.h"
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -133,6 +134,38 @@ int nlk_strip_filter(nlk_ctx *ctx);
 /* stage 3 (after the border rows of the neighbours were added): pixel rows [row0, row1)
  * of the output */
 int nlk_strip_normalize(nlk_ctx *ctx, float *d_out, int row0, int row1);
+
+/* ---- peer-memory exchanges between the strips' GPUs (NVLink / NVSwitch, no collective library) ----
+ * What crosses strips in the reference's patch loop (src/nlkalman.c:586-595 sharded by rows: the
+ * processed-mask bitmaps of :597-600 / :930-931, the aggregation of :913-928 into rows beyond the
+ * strip border, the output rows the next pass reads) is exchanged by the kernels themselves.  Every
+ * rank keeps its exchange buffers in one "slab" (cudaMalloc, the same layout on all ranks, a
+ * header of nlk_peer_header_bytes() first); the peers' slabs are mapped with CUDA IPC (or are plain
+ * pointers when several strips live in one process) and handed to nlk_peer_bind.  All calls are
+ * asynchronous on the context's stream; ranges are byte offsets into the slab.
+ *   nlk_peer_push      copy [off, off+bytes) of the own slab to the same offset of the peers in
+ *                      peer_mask, then store `value` into flag `slot` of those peers (slot < 0: no
+ *                      flag).  side = 1: on a side stream with the copy engines (whole strips),
+ *                      joined again by the next nlk_strip_normalize.
+ *   nlk_peer_push_add  red.global.add the floats of the range into peer `peer` (accumulator halo
+ *                      rows into their owner), then flag it.
+ *   nlk_peer_signal    the flag alone.
+ *   nlk_peer_wait      the stream waits until flag `slot` from every rank in src_mask is >= value
+ *                      (sequence numbers, compared modulo 2^32).  A wait gives up after
+ *                      NLK_PEER_TIMEOUT_MS (default 4000) and raises the error word read by
+ *                      nlk_peer_error instead of hanging the GPU.
+ * Flags: slots 0 .. 63, one word per (slot, source rank) in the receiver's slab. */
+size_t nlk_peer_header_bytes(void);
+int nlk_peer_slab_alloc(nlk_ctx *ctx, size_t bytes, void **d_slab);           /* zero-filled */
+int nlk_peer_ipc_export(nlk_ctx *ctx, void *d_slab, unsigned char *handle64); /* cudaIpcMemHandle_t, 64 bytes */
+int nlk_peer_ipc_import(nlk_ctx *ctx, const unsigned char *handle64, void **d_ptr);
+int nlk_peer_bind(nlk_ctx *ctx, int rank, int nranks, void *const *slabs, size_t slab_bytes);
+int nlk_peer_push(nlk_ctx *ctx, size_t off, size_t bytes, unsigned int peer_mask, int slot,
+                  unsigned int value, int side);
+int nlk_peer_push_add(nlk_ctx *ctx, size_t off, size_t bytes, int peer, int slot, unsigned int value);
+int nlk_peer_signal(nlk_ctx *ctx, int slot, unsigned int value, unsigned int peer_mask);
+int nlk_peer_wait(nlk_ctx *ctx, int slot, unsigned int value, unsigned int src_mask);
+int nlk_peer_error(nlk_ctx *ctx, unsigned int *code);   /* synchronises; 0 = no wait timed out */
 
 /* ---- resident sequence recursion (what scripts/nlkalman-seq.sh does per frame) ------
  * The context keeps the previous frame's first and second filtering outputs in

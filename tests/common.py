@@ -56,3 +56,76 @@ def compare_knn(gpu, cpu):
         gap = float(abs(cpu["knn_d"][g, min(r + 1, k - 1)] - cpu["knn_d"][g, r]))
         details.append((int(g), r, gap))
     return G, len(bad), details
+
+
+# ---- near-tie aware comparison against the unmodified reference ---------------------------------
+# The reference is compiled with -ffast-math (CMakeLists.txt:10): the order in which it sums the
+# psz*psz*ch squared differences of a patch distance is the compiler's.  The GPU (and the
+# restatement it is bit-identical to) use the source order with separately rounded operations.
+# Two candidates whose distances differ by a few fp32 ulps can therefore swap ranks between the two;
+# a swap at the cut of the list (rank k) or of the group (rank tagg) changes that group and, through
+# the processed-pixel mask, the groups after it.  north_star: "k-NN index sets are identical except
+# for documented distance near-ties".  The helpers below document them: for the groups around the
+# pixels that differ, all candidate distances are recomputed in float64 and the smallest relative
+# gap between neighbours in the sorted list is reported.
+
+def neartie_gaps(src, dump, prms, smooth, diff_map, max_groups=600):
+    """-> sorted list of (relative gap, g, px, py, position in the sorted list) over the processed
+    groups whose reference patch lies within reach of a pixel of diff_map (bool, h x w)"""
+    h, w = diff_map.shape
+    psz, step = prms.patch_sz, prms.patch_sz // 2
+    gw, gh = dump["gw"], dump["gh"]
+    src64 = src.astype(np.float64)
+    ys, xs = np.nonzero(diff_map)
+    groups = set()
+    reach = max(prms.search_sz_t, prms.search_sz_x) + psz
+    for y, x in zip(ys[::7], xs[::7]):
+        for gy in range(max(0, (y - reach) // step), min(gh, (y + reach) // step + 1)):
+            for gx in range(max(0, (x - reach) // step), min(gw, (x + reach) // step + 1)):
+                if dump["active"][gy * gw + gx] and dump["nk"][gy * gw + gx] > 1:
+                    groups.add(gy * gw + gx)
+    # nearest groups first, bounded work
+    cy, cx = ys.mean(), xs.mean()
+    groups = sorted(groups, key=lambda g: abs((g // gw) * step - cy) + abs((g % gw) * step - cx))[:max_groups]
+    rows = []
+    for g in groups:
+        gy, gx = divmod(g, gw)
+        px, py = gx * step, gy * step
+        rad = prms.search_sz_t if (smooth or dump["prev_p"][g]) else prms.search_sz_x
+        x0, x1 = max(px - rad, 0), min(px + rad, w - psz)
+        y0, y1 = max(py - rad, 0), min(py + rad, h - psz)
+        refp = src64[py:py + psz, px:px + psz]
+        win = np.lib.stride_tricks.sliding_window_view(src64[y0:y1 + psz, x0:x1 + psz], (psz, psz), axis=(0, 1))
+        d = ((win - np.moveaxis(refp, 2, 0)[None, None]) ** 2).mean(axis=(2, 3, 4)).ravel()
+        d.sort()
+        nk = int(dump["nk"][g])
+        upto = min(nk + 1, d.size)
+        gaps = np.diff(d[:upto]) / np.maximum(d[1:upto], 1e-30)
+        j = int(np.argmin(gaps))
+        rows.append((float(gaps[j]), int(g), px, py, j))
+    rows.sort()
+    return rows
+
+
+def compare_with_reference(name, ours, theirs, src, dump, prms, smooth, clean=None, frac_tol=1e-3, gap_tol=1e-5):
+    """ours (bit-identical k-NN with the restatement, checked by the caller) against the reference's
+    output.  Within 1e-3 everywhere, or: few pixels differ, the PSNR does not move, and a distance
+    near-tie is found among the groups around them.  Returns a printable summary."""
+    d = np.abs(ours.astype(np.float64) - theirs.astype(np.float64))
+    d[np.isnan(d)] = 0
+    e = float(d.max())
+    if e <= TOL_MAXABS:
+        return f"{name}: max-abs {e:.2e}"
+    dm = d.max(axis=2) > TOL_MAXABS
+    frac = float(dm.mean())
+    rows = neartie_gaps(src, dump, prms, smooth, dm)
+    msg = (f"{name}: max-abs {e:.2e} on {int(dm.sum())} pixels ({frac:.1e}); smallest relative distance gaps nearby: "
+           + ", ".join(f"{g:.1e}@({x},{y})#{j}" for g, _, x, y, j in rows[:4]))
+    # a flipped group moves up to tagg patches (and what the processed mask makes of it downstream)
+    assert dm.sum() <= max(frac_tol * dm.size, 40 * prms.patch_sz ** 2), msg
+    assert rows and rows[0][0] <= gap_tol, "no distance near-tie explains the difference -- " + msg
+    if clean is not None:
+        dp = abs(psnr_between(ours, clean) - psnr_between(theirs, clean))
+        assert dp <= TOL_DPSNR, (msg, dp)
+        msg += f"; dPSNR {dp:.1e}"
+    return msg + "  [documented near-tie]"

@@ -23,8 +23,9 @@ def _scene(w, h, ch, sigma, nframes):
     return frames, synth.backward_flow(w, h), synth.forward_flow(w, h), occ
 
 
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
 @pytest.mark.parametrize("shape,nranks", [((101, 150, 3), 3), ((122, 96, 1), 2), ((90, 200, 3), 4)])
-def test_virtual_strips_match_single_context(nlk, shape, nranks):
+def test_virtual_strips_match_single_context(nlk, shape, nranks, transport):
     import torch
     from bwd_nlkalman_b200 import strips
     w, h, ch = shape
@@ -51,7 +52,9 @@ def test_virtual_strips_match_single_context(nlk, shape, nranks):
             ctx.sync()
             refs[t] = o1.cpu().numpy().copy()
 
-    ranks = [strips.StripRank(w, h, ch, r, nranks, 0) for r in range(nranks)]
+    ranks = [strips.StripRank(w, h, ch, r, nranks, 0, transport=transport) for r in range(nranks)]
+    if transport == "peer":
+        strips.bind_virtual(ranks)
     try:
         outs1 = [torch.zeros_like(d_frames[0]) for _ in ranks]
         outs2 = [torch.zeros_like(d_frames[0]) for _ in ranks]
@@ -79,6 +82,8 @@ def test_virtual_strips_match_single_context(nlk, shape, nranks):
             for rk in ranks:
                 rk.ctx.sync()
             assert maxabs(assemble(outs1, pls), refs[t]) <= TOL_MAXABS, f"smoother frame {t}"
+        if transport == "peer":
+            assert all(rk.ctx.peer_error() == 0 for rk in ranks), "a device-side wait timed out"
     finally:
         for rk in ranks:
             rk.close()
@@ -112,14 +117,17 @@ def test_virtual_strips_match_oracle(nlk, port):
             rk.close()
 
 
-def test_nccl_strips_two_gpus(nlk):
-    """the torch.distributed driver over NCCL: needs two GPUs on the box"""
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_strips_two_gpus(nlk, transport):
+    """one process per GPU: slabs mapped across processes with CUDA IPC and the exchanges done by the
+    kernels over NVLink (peer), or torch.distributed over NCCL; needs two GPUs on the box"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("one GPU visible")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29533",
-           os.path.join(ROOT, "tools", "strips_check.py"), "--w", "160", "--h", "200", "--frames", "3"]
+           os.path.join(ROOT, "tools", "strips_check.py"), "--w", "160", "--h", "200", "--frames", "3",
+           "--transport", transport]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "strips_check OK" in res.stdout

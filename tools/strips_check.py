@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU check of the strip-sharded recursion (run under torchrun, one rank per GPU):
-filter + smoother on a small synthetic sequence through strips.run_dist (NCCL) against the
+filter + smoother on a small synthetic sequence through strips.run_dist (peer-memory or NCCL
+transport) against the
 single-context recursion computed on rank 0.  Prints "strips_check OK" on success."""
 import argparse
 import os
@@ -22,6 +23,7 @@ def main():
     ap.add_argument("--ch", type=int, default=3)
     ap.add_argument("--frames", type=int, default=3)
     ap.add_argument("--sigma", type=float, default=20.0)
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"])
     a = ap.parse_args()
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -32,7 +34,9 @@ def main():
     up = lambda x: torch.from_numpy(x).to(dev)
     frames = [up(synth.noisy_frame(w, h, ch, t, sigma)) for t in range(a.frames)]
     bflo, fflo, occ = up(synth.backward_flow(w, h)), up(synth.forward_flow(w, h)), up(synth.occlusion_mask(w, h))
-    rk = strips.StripRank(w, h, ch, rank, world, lr)
+    rk = strips.StripRank(w, h, ch, rank, world, lr, transport=a.transport)
+    if a.transport == "peer":
+        strips.bind_dist(rk)        # CUDA IPC handles of the slabs over torch.distributed, once
     o1, o2 = torch.zeros_like(frames[0]), torch.zeros_like(frames[0])
     p1, p2, ps = rk.plans(0, f1), rk.plans(0, f2), rk.plans(1, s1)
 
@@ -73,6 +77,13 @@ def main():
                 e = float((r1 - gots[t]).abs().max())
                 print(f"frame {t}: smoother max abs {e:.2e}")
                 ok &= e <= 1e-3
+    if a.transport == "peer":
+        err = rk.ctx.peer_error()
+        if err:
+            print(f"rank {rank}: a device-side wait timed out (code {err:#x})")
+        errs = torch.tensor([err], device=dev, dtype=torch.int64)
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        ok &= int(errs.item()) == 0
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     rk.close()
