@@ -79,6 +79,8 @@ def lib():
     L.nlk_ctx_profile.argtypes = [vp, C.c_int]
     L.nlk_ctx_profile_collect.argtypes = [vp, C.POINTER(C.c_double), _ip]
     L.nlk_fp32_peak.argtypes = [vp, C.c_float, C.POINTER(C.c_double)]
+    L.nlk_ctx_profile_alpha.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.nlk_seq_set_mask_mode.argtypes = [vp, C.c_int, C.c_float]
     L.nlk_host_alloc.argtypes = [C.c_size_t]
     L.nlk_host_alloc.restype = vp
     L.nlk_host_free.argtypes = [vp]
@@ -155,7 +157,7 @@ def _vp(a):
     if isinstance(a, int):
         return C.c_void_p(a)
     if isinstance(a, np.ndarray):
-        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+        assert a.dtype in (np.float32, np.uint8) and a.flags["C_CONTIGUOUS"]
         return C.c_void_p(a.ctypes.data)
     if hasattr(a, "data_ptr"):
         assert a.is_contiguous()
@@ -266,6 +268,18 @@ class Context:
                 if cnt[i * npk + j]:
                     out[(kn, pk)] = (ms[i * npk + j], cnt[i * npk + j])
         return out
+
+    def profile_alpha(self):
+        """{pass_kind: (processed patches, grid patches)} summed over the profiled passes"""
+        npk = len(self.PASS_KINDS)
+        a, g = (C.c_double * npk)(), (C.c_double * npk)()
+        _check(lib().nlk_ctx_profile_alpha(self._h, a, g))
+        return {pk: (a[j], g[j]) for j, pk in enumerate(self.PASS_KINDS) if g[j] > 0}
+
+    MASK_FLOAT, MASK_U8, MASK_FROM_FLOW = 0, 1, 2
+
+    def seq_set_mask_mode(self, mode: int, th: float = 0.0):
+        _check(lib().nlk_seq_set_mask_mode(self._h, int(mode), float(th)))
 
     def fp32_peak(self, ms: float = 200.0) -> float:
         v = C.c_double(0)

@@ -168,6 +168,15 @@ struct nlk_ctx {
     struct ProfRec { int kid, kind; cudaEvent_t a, b; };
     std::vector<ProfRec> prof_recs;
     std::vector<cudaEvent_t> prof_pool;
+    // processed / grid patches per pass while profiling (alpha of SURVEY.md section 8(d))
+    struct AlphaRec { int kind, G, idx; };
+    std::vector<AlphaRec> alpha_recs;
+    int *h_alpha = nullptr;
+    static constexpr int ALPHA_CAP = 8192;
+    // how nlk_seq_submit_host reads its mask argument (nlk_seq_set_mask_mode)
+    int mask_mode = NLK_MASK_FLOAT;
+    float mask_th = 0.f;
+    DevBuf p_msk8[PIPE_SETS];
     size_t img_bytes() const { return (size_t)w * h * ch * sizeof(float); }
 };
 
@@ -229,6 +238,28 @@ extern "C" int nlk_ctx_profile_collect(nlk_ctx *c, double *ms_sum, int *count)
         c->prof_pool.push_back(r.b);
     }
     c->prof_recs.clear();
+    return NLK_OK;
+}
+
+extern "C" int nlk_ctx_profile_alpha(nlk_ctx *c, double *active_sum, double *grid_sum)
+{
+    if (int r = nlk_ctx_sync(c)) return r;
+    for (int i = 0; i < NLK_PASS_KINDS; ++i) { active_sum[i] = 0; grid_sum[i] = 0; }
+    for (auto &a : c->alpha_recs) {
+        active_sum[a.kind] += c->h_alpha[a.idx];
+        grid_sum[a.kind] += a.G;
+    }
+    c->alpha_recs.clear();
+    return NLK_OK;
+}
+
+extern "C" int nlk_seq_set_mask_mode(nlk_ctx *c, int mode, float th)
+{
+    if (!c) return set_err(NLK_ERR_PARAM, "null context");
+    if (mode != NLK_MASK_FLOAT && mode != NLK_MASK_U8 && mode != NLK_MASK_FROM_FLOW)
+        return set_err(NLK_ERR_PARAM, "mask mode %d", mode);
+    c->mask_mode = mode;
+    c->mask_th = th;
     return NLK_OK;
 }
 
@@ -299,6 +330,8 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     if (c->ev_side_fork) cudaEventDestroy(c->ev_side_fork);
     if (c->ev_side_done) cudaEventDestroy(c->ev_side_done);
     for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
+    if (c->h_alpha) cudaFreeHost(c->h_alpha);
+    for (int i = 0; i < nlk_ctx::PIPE_SETS; ++i) c->p_msk8[i].release();
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) if (c->lane[i].st) cudaStreamDestroy(c->lane[i].st);
@@ -574,6 +607,14 @@ static int run_pass(nlk_ctx *c, int smooth, float *d_out, const float *d_in1, co
     KindScope ks(c, pass_kind(P));
     if (int r = pass_search(c, P)) return r;
     if (int r = pass_filter(c, P, false)) return r;
+    if (c->prof && P.G > 0) {
+        if (!c->h_alpha) CU_TRY(cudaMallocHost(&c->h_alpha, nlk_ctx::ALPHA_CAP * sizeof(int)));
+        const int idx = (int)c->alpha_recs.size();
+        if (idx < nlk_ctx::ALPHA_CAP) {
+            CU_TRY(cudaMemcpyAsync(c->h_alpha + idx, P.nactive, sizeof(int), cudaMemcpyDeviceToHost, c->L->st));
+            c->alpha_recs.push_back({pass_kind(P), P.G, idx});
+        }
+    }
     return pass_normalize(c, P, 0, P.h);
 }
 
@@ -1074,13 +1115,32 @@ extern "C" int nlk_seq_submit_host(nlk_ctx *c, const float *h_noisy, const float
         CU_TRY(cudaMemcpyAsync(c->p_of[s].p, h_bflo, npix * 2 * 4, cudaMemcpyHostToDevice, c->st_h2d));
         d_of = c->p_of[s].as<float>();
     }
-    if (h_bocc) {
+    // the mask: float samples (the reference's in-memory form, src/main-flt.c:236-262), the bytes of the
+    // 8-bit file it is read from (scripts/nlkalman-seq.sh:70-73 writes a PNG), or none at all -- built
+    // here from the divergence of the flow that was just uploaded (the script's plambda expression)
+    int mask_job = 0;
+    if (c->mask_mode == NLK_MASK_FROM_FLOW) {
+        if (h_bflo) { if (int r = c->p_msk[s].ensure(npix * 4)) return r; d_msk = c->p_msk[s].as<float>(); mask_job = 2; }
+    } else if (h_bocc) {
         if (int r = c->p_msk[s].ensure(npix * 4)) return r;
-        CU_TRY(cudaMemcpyAsync(c->p_msk[s].p, h_bocc, npix * 4, cudaMemcpyHostToDevice, c->st_h2d));
         d_msk = c->p_msk[s].as<float>();
+        if (c->mask_mode == NLK_MASK_U8) {
+            if (int r = c->p_msk8[s].ensure(npix)) return r;
+            CU_TRY(cudaMemcpyAsync(c->p_msk8[s].p, h_bocc, npix, cudaMemcpyHostToDevice, c->st_h2d));
+            mask_job = 1;
+        } else {
+            CU_TRY(cudaMemcpyAsync(c->p_msk[s].p, h_bocc, npix * 4, cudaMemcpyHostToDevice, c->st_h2d));
+        }
     }
     CU_TRY(cudaEventRecord(c->ev_up[s], c->st_h2d));
     CU_TRY(cudaStreamWaitEvent(c->lane[0].st, c->ev_up[s], 0));
+    if (mask_job) {
+        c->L = &c->lane[0];
+        ProfScope ps(c, NLK_K_WARP);
+        const int n = mask_job == 1 ? launch_mask_u8(c->p_msk[s].as<float>(), c->p_msk8[s].as<uint8_t>(), (long)npix, c->lane[0].st)
+                                    : launch_occlusion(c->p_msk[s].as<float>(), d_of, c->w, c->h, c->mask_th, c->lane[0].st);
+        if (int r = check_launch(c, n, "mask")) return r;
+    }
     float *d_o1 = nullptr, *d_o2 = nullptr;
     if (h_flt1_out) { if (int r = c->p_o1[s].ensure(ib)) return r; d_o1 = c->p_o1[s].as<float>(); }
     if (h_flt2_out && f2.patch_sz != 0) { if (int r = c->p_o2[s].ensure(ib)) return r; d_o2 = c->p_o2[s].as<float>(); }

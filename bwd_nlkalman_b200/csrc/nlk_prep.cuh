@@ -149,6 +149,21 @@ inline int launch_occlusion(float *occ, const float *of, int w, int h, float th,
     return 1;
 }
 
+// 8-bit mask samples (as stored in the PNG the script writes) to the float form warp_bicubic takes
+__global__ void k_mask_u8(float *__restrict__ occ, const uint8_t *__restrict__ m8, long n)
+{
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        occ[i] = (float)m8[i];
+}
+
+inline int launch_mask_u8(float *occ, const uint8_t *m8, long n, cudaStream_t st)
+{
+    const int nt = 256;
+    const int nb = (int)((n + nt - 1) / nt < 148 * 8 ? (n + nt - 1) / nt : 148 * 8);
+    k_mask_u8<<<nb, nt, 0, st>>>(occ, m8, n);
+    return 1;
+}
+
 // ---- patch validity of the warped previous frame --------------------------------------------
 // valid(q) <=> no NaN in channel 0 of the psz x psz patch at q (reference
 // src/nlkalman.c:605-609, :725-730).  Separable: row pass then column pass.

@@ -57,6 +57,10 @@ enum { NLK_PASS_FLT1_T = 0, /* filter, previous frame given, no basic estimate *
        NLK_PASS_KINDS };
 int nlk_ctx_profile(nlk_ctx *ctx, int enable);
 int nlk_ctx_profile_collect(nlk_ctx *ctx, double *ms_sum, int *count);
+/* while profiling: per pass kind, the processed patches (those the reference's mask test
+ * src/nlkalman.c:597-600 does not skip) and the grid patches, summed over the passes since the
+ * last call; both [NLK_PASS_KINDS].  alpha = active / grid. */
+int nlk_ctx_profile_alpha(nlk_ctx *ctx, double *active_sum, double *grid_sum);
 
 /* sustained fp32 FMA throughput of the device in TFLOP/s (2 flops per FMA), measured
  * with a register-resident FMA kernel for about `ms` milliseconds: the denominator of
@@ -194,6 +198,15 @@ int nlk_seq_submit_host(nlk_ctx *ctx, const float *h_noisy, const float *h_bflo,
                         const float *h_bocc, float sigma, struct nlkalman_params f1,
                         struct nlkalman_params f2, float *h_flt1_out, float *h_flt2_out);
 int nlk_seq_drain(nlk_ctx *ctx);
+/* How nlk_seq_submit_host / nlk_seq_filter_host read their h_bocc argument:
+ *   NLK_MASK_FLOAT      w*h floats, 0 = valid (the reference's in-memory form, src/main-flt.c:236-262);
+ *   NLK_MASK_U8         w*h bytes, the samples of the 8-bit file the mask is read from
+ *                       (scripts/nlkalman-seq.sh:70-73): a quarter of the upload;
+ *   NLK_MASK_FROM_FLOW  h_bocc is ignored: the mask is built on the device from the divergence of the
+ *                       frame's flow with threshold th, the script's plambda expression
+ *                       (nlk_occlusion_dev) -- no mask upload at all. */
+enum { NLK_MASK_FLOAT = 0, NLK_MASK_U8 = 1, NLK_MASK_FROM_FLOW = 2 };
+int nlk_seq_set_mask_mode(nlk_ctx *ctx, int mode, float th);
 /* The pipelined recursion runs the two filterings of a frame on two streams: the second
  * filtering of frame t (it needs flt1(t) and flt2(t-1)) overlaps the first filtering of frame
  * t+1 (it needs flt1(t) only), so that one pass's single-SM processed-mask replay and its
