@@ -13,16 +13,26 @@ steps are exactly one sequence.  Metric: denoised Mpixel/s = w*h*frames / second
 * value     -- inputs (noisy frame, flow, occlusion mask of every frame) resident in HBM,
                state resident in HBM, CUDA-event timed on the context's stream (nlk_seq_submit_dev
                per frame, nlk_seq_join before the closing event).
-* e2e       -- the same steps through the host-buffer C-ABI call (nlk_seq_filter_host):
-               every step copies its inputs from pinned host memory and both outputs back.
+* e2e       -- the same steps through the host-buffer C-ABI call (nlk_seq_submit_host): every
+               step uploads its inputs from pinned host memory and downloads the frame's result
+               (the second filtering; the first stays on the device as recursion state -- the
+               figure with both outputs downloaded is reported next to it).
 * roofline  -- the kernel with the largest share of the step, algorithmic flops per launch
-                over its CUDA-event duration, against the fp32 FMA
-               peak measured live on the same device.
-* cpu_baseline / --impl reference -- the UNMODIFIED reference numerics (oracle/_ref,
-               OpenMP on all host cores) on a bounded crop of the same workload.
+               (every grid patch counted) over its CUDA-event duration,
+               against the fp32 FMA peak measured live on the same device; alpha = processed /
+               grid patches and the fraction on the work actually done are reported with it.
+* cpu_baseline / --impl reference -- the UNMODIFIED reference numerics (oracle/_ref, OpenMP on
+               all host cores) on full 1920x1080 frames of the same sequence.  Its FFTW calls go
+               to the table-driven stand-in of oracle/fftw_shim (no libfftw3f in this image):
+               read the ratio as an upper bound by the (unmeasured) FFTW-codelet advantage.
+* cli       -- wall time of one nlkalman-flt process on config C1 files, file I/O included:
+               the reference program (all cores) against ours.
 
-N > 1 (torchrun, one rank per GPU): every rank runs its own independent sequence
-(weak scaling, no data-path collective); value = total pixels / max-over-ranks time.
+N > 1 (torchrun, one rank per GPU): the headline is N independent sequences (weak scaling, no
+data-path collective); value = total pixels / max-over-ranks time.  The line also carries
+"strips": one 3840x2160 sequence (config C4, filter + smoother) with every pass split into N
+horizontal strips -- north_star's strong-scaling case -- next to the same sequence on one GPU
+measured in the same run (tools/bench_strips.py).
 """
 from __future__ import annotations
 
@@ -124,10 +134,19 @@ def make_sequence(n_frames, w=W, h=H, ch=CH, sigma=SIGMA, seed_offset=0):
 
 # ---- reference arm (CPU, unmodified reference numerics) -----------------------------------------
 
-def reference_sample(steps, warmup, budget_s=150.0, state=None):
+def bench_config(world):
+    """the `config` object, identical in both arms"""
+    return {"workload": WORKLOAD, "frame_w": W, "frame_h": H, "channels": CH, "sigma": SIGMA,
+            "parallelism": f"{world} independent sequence(s), one per GPU" if world > 1 else "1 GPU",
+            "l2": "inputs larger than L2: 20 distinct frames (noisy + flow + mask = 1.0 GB) cycled"}
+
+
+def reference_sample(steps, warmup, budget_s=240.0, state=None):
     """Times the reference's own CPU path (oracle/_ref: src/nlkalman.c compiled unmodified,
-    OpenMP on all host cores) on a bounded crop of the C2 workload.  One step = one temporal
-    frame step (rgb2opp, 2x warp_bicubic, filter 1, filter 2, opp2rgb) on the crop."""
+    OpenMP on all host cores) on full frames of the C2 workload.  One step = one temporal
+    frame step (rgb2opp, 2x warp_bicubic, filter 1, filter 2, opp2rgb).  state = (flt1, flt2)
+    RGB frames of frame 0 to start from; without it frame 0 is filtered here first (spatial,
+    untimed).  Falls back to a crop only if the full frame does not fit the time budget."""
     from oracle import oracle as O
     from bwd_nlkalman_b200 import synth
     kind = "reference"
@@ -152,13 +171,16 @@ def reference_sample(steps, warmup, budget_s=150.0, state=None):
         dt = time.perf_counter() - t0
         return a, b, out, dt
 
-    crops = [(960, 540), (480, 270), (240, 136)]
+    sizes = [(W, H), (960, 540), (480, 270)]
     total = steps + max(warmup, 1)
-    for ci, (cw, chh) in enumerate(crops):
-        # frame 0 of the crop gives the state (spatial step, untimed), then one temporal probe
-        p1, p2, _, _ = one_step(cw, chh, None, None, 0)
-        p1, p2, _, dt = one_step(cw, chh, p1, p2, 1)
-        if dt * total <= budget_s or ci == len(crops) - 1:
+    for ci, (cw, chh) in enumerate(sizes):
+        if state is not None and (cw, chh) == (W, H):
+            p1, p2 = impl.rgb2opp(state[0].copy()), impl.rgb2opp(state[1].copy())
+        else:
+            # frame 0 gives the state (spatial step, untimed)
+            p1, p2, _, _ = one_step(cw, chh, None, None, 0)
+        p1, p2, _, dt = one_step(cw, chh, p1, p2, 1)      # temporal probe (also the first warm-up step)
+        if dt * total <= budget_s or ci == len(sizes) - 1:
             break
     times = []
     t = 2
@@ -169,11 +191,12 @@ def reference_sample(steps, warmup, budget_s=150.0, state=None):
             times.append(dt)
     sec = sum(times)
     mpix = cw * chh * len(times) / sec / 1e6
+    what = "full 1920x1080 RGB frames" if (cw, chh) == (W, H) else f"a {cw}x{chh} RGB crop (the full frame exceeds the time budget)"
     return {"value": mpix, "unit": "Mpixel/s", "cores": cores, "kind": kind,
-            "sample": f"{len(times)} temporal flt1+flt2 frame steps on a {cw}x{chh} RGB crop of the C2 scene "
-                      f"(state from the preceding frames of the same run), {cores} OpenMP threads, "
-                      "FFTW replaced by the table-driven stand-in of oracle/fftw_shim",
-            "ms_per_step": 1e3 * sec / len(times), "crop": [cw, chh]}
+            "sample": f"{len(times)} temporal flt1+flt2 frame steps on {what} of the C2 sequence, {cores} OpenMP threads; "
+                      "FFTW replaced by the table-driven stand-in of oracle/fftw_shim (no libfftw3f here: an upper "
+                      "bound on the ratio by the FFTW-codelet advantage)",
+            "ms_per_step": 1e3 * sec / len(times), "frame": [cw, chh]}
 
 
 def run_reference(args):
@@ -185,7 +208,7 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": cb["sample"]},
+            "config": bench_config(max(args.gpus, 1)),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -227,6 +250,7 @@ def run_ours(args):
     # pinned host copies for the end-to-end leg
     h_noisy = [torch.from_numpy(f).pin_memory() for f in frames]
     h_flo, h_occ = torch.from_numpy(bflo).pin_memory(), torch.from_numpy(occ).pin_memory()
+    h_occ8 = torch.from_numpy(occ.astype(np.uint8)).pin_memory()   # the samples of the 8-bit mask file
     h_o1 = [torch.empty((H, W, CH), dtype=torch.float32).pin_memory() for _ in range(3)]
     h_o2 = [torch.empty((H, W, CH), dtype=torch.float32).pin_memory() for _ in range(3)]
     torch.cuda.synchronize()
@@ -238,14 +262,20 @@ def run_ours(args):
         # pipelined recursion: the second filtering of a frame overlaps the first of the next one
         ctx.seq_submit_dev(d_noisy[t], d_flo[t] if t else None, d_occ[t] if t else None, SIGMA, f1, f2, d_o1, d_o2)
 
-    def step_host(i, pipelined=True):
-        # the streaming call: frame i's inputs go up and its two outputs come back inside the
-        # timed region; copies overlap the neighbouring frames' kernels (three output sets)
+    def step_host(i, mode):
+        # the streaming call: frame i's inputs go up and its result comes back inside the timed
+        # region; copies overlap the neighbouring frames' kernels (three staging sets)
+        #   "result": mask as the bytes of its 8-bit file, the frame's result (second filtering) back
+        #   "full":   float mask, both filterings back (what the reference driver writes to disk)
+        #   "sync":   "full" through the synchronous call
         t = i % SEQ_LEN
         if t == 0:
             ctx.seq_reset()
-        call = ctx.seq_submit_host if pipelined else ctx.seq_filter_host
-        call(h_noisy[t], h_flo if t else None, h_occ if t else None, SIGMA, f1, f2, h_o1[i % 3], h_o2[i % 3])
+        if mode == "result":
+            ctx.seq_submit_host(h_noisy[t], h_flo if t else None, h_occ8 if t else None, SIGMA, f1, f2, None, h_o2[i % 3])
+        else:
+            call = ctx.seq_submit_host if mode == "full" else ctx.seq_filter_host
+            call(h_noisy[t], h_flo if t else None, h_occ if t else None, SIGMA, f1, f2, h_o1[i % 3], h_o2[i % 3])
 
     def barrier():
         if dist is not None:
@@ -301,31 +331,55 @@ def run_ours(args):
             ctx.seq_reset()
         ctx.seq_filter_dev(d_noisy[t], d_flo[t] if t else None, d_occ[t] if t else None, SIGMA, f1, f2, d_o1, d_o2)
     prof = ctx.profile_collect()
+    alpha = {pk: a / g for pk, (a, g) in ctx.profile_alpha().items()}
     ctx.profile(False)
+    # frame 0's outputs: the state the CPU baseline starts from
+    ctx.seq_reset()
+    ctx.seq_filter_dev(d_noisy[0], None, None, SIGMA, f1, f2, d_o1, d_o2)
+    ctx.sync()
+    state0 = (d_o1.cpu().numpy().copy(), d_o2.cpu().numpy().copy())
 
     # ---- end-to-end leg: host buffers through the C ABI ----------------------------------------
-    def e2e_leg(pipelined):
+    def e2e_leg(mode):
+        ctx.seq_set_mask_mode(ctx.MASK_U8 if mode == "result" else ctx.MASK_FLOAT)
         for i in range(Wm):
-            step_host(i, pipelined)
+            step_host(i, mode)
         ctx.seq_drain()
         barrier()
         t0 = time.perf_counter()
         with torch.cuda.stream(stream):
             e0.record()
         for i in range(Wm, Wm + K):
-            step_host(i, pipelined)
+            step_host(i, mode)
         with torch.cuda.stream(stream):
             e1.record()
         ctx.seq_drain()          # the last frame's outputs are in host memory
         wall = time.perf_counter() - t0
         barrier()
+        ctx.seq_set_mask_mode(ctx.MASK_FLOAT)
         return max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3))
-    e2e_sync_ms = e2e_leg(False)
-    e2e_ms = e2e_leg(True)
-    e2e_value = world * W * H * K / (e2e_ms * 1e-3) / 1e6
-    e2e_sync_value = world * W * H * K / (e2e_sync_ms * 1e-3) / 1e6
-    h2d = W * H * (CH + 3) * 4  # noisy + 2-channel flow + mask (frame 0 of a sequence: noisy only)
-    d2h = 2 * W * H * CH * 4    # both filtering outputs, as the reference driver writes both
+    e2e_sync_ms = e2e_leg("sync")
+    e2e_full_ms = e2e_leg("full")
+    e2e_ms = e2e_leg("result")
+    mpix = lambda ms: world * W * H * K / (ms * 1e-3) / 1e6
+    e2e_value, e2e_full_value, e2e_sync_value = mpix(e2e_ms), mpix(e2e_full_ms), mpix(e2e_sync_ms)
+    h2d = W * H * (CH * 4 + 2 * 4 + 1)  # noisy + 2-channel flow + 8-bit mask (frame 0 of a sequence: noisy only)
+    d2h = W * H * CH * 4                # the frame's result: the second filtering
+    h2d_full, d2h_full = W * H * (CH + 3) * 4, 2 * W * H * CH * 4
+
+    fp32_peak = ctx.fp32_peak(300.0) if rank == 0 else 0.0
+    # ---- strips (N > 1): one 4K sequence split over the N GPUs -----------------------------------
+    strips_res = None
+    if world > 1 and not args.no_strips:
+        ctx.close()
+        del d_noisy, d_flo, d_occ
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_strips
+        try:
+            strips_res = bench_strips.measure(rank, world, local_rank, dist, nf=4, reps=2, warmup=1, transport="peer")
+        except Exception as exc:     # the headline stands on its own
+            strips_res = {"error": repr(exc)}
 
     if rank != 0:
         if dist is not None:
@@ -333,7 +387,6 @@ def run_ours(args):
         return 0
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
-    fp32_peak = ctx.fp32_peak(300.0)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -351,6 +404,10 @@ def run_ours(args):
             ent["algorithmic_gflop"] = gf / 1e9
             ent["tflops"] = gf / (ms / cnt * 1e-3) / 1e12
             ent["frac_fp32_peak"] = ent["tflops"] / fp32_peak
+            if kn == "group_filter" and pk in alpha:
+                # group_filter only runs the processed patches (search_knn runs every grid patch)
+                ent["alpha"] = alpha[pk]
+                ent["frac_fp32_peak_active"] = ent["frac_fp32_peak"] * alpha[pk]
         kernels.append(ent)
     dom = next(k for k in kernels if "tflops" in k)
     # compulsory HBM bytes of a pass: B = 4 w h (ch (n_in + 3) + 2)
@@ -358,55 +415,131 @@ def run_ours(args):
     roofline = {"kernel": f'{dom["kernel"]} ({dom["pass"]})', "bound": "fp32",
                 "achieved": dom["tflops"], "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": dom["tflops"] / fp32_peak,
+                "alpha": dom.get("alpha"), "frac_active": dom.get("frac_fp32_peak_active"),
+                "definition": "algorithmic flops of SURVEY 8(d) with every grid patch counted (alpha = 1) and the "
+                              "matrix-form transform count F_dct = 4 psz^3; alpha = processed / grid patches of the "
+                              "launch, frac_active = frac * alpha (the work the kernel actually ran)",
                 "peak_source": "fp32 FMA micro-benchmark run live on this device (nlk_fp32_peak); "
                                "the path is CUDA-core fp32 work, neither HBM- nor tensor-bound (SURVEY 8(d))",
-                "traffic": None,
+                "traffic": None, "traffic_source": None,
+                "whole_step": {"gflop": sum(fl[k][0] + fl[k][1] for k in ("flt1_temporal", "flt2_temporal")) / 1e9,
+                               "frac": sum(fl[k][0] + fl[k][1] for k in ("flt1_temporal", "flt2_temporal"))
+                                       / (ms_total / K * 1e-3) / 1e12 / fp32_peak},
                 "hbm": {"compulsory_bytes_per_pass": 4 * W * H * (CH * (n_in + 3) + 2), "peak_gbs": hbm_peak,
                         "peak_source": hbm_src}}
     prof_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(prof_path):
         try:
             with open(prof_path) as f:
-                roofline["traffic"] = json.load(f).get(dom["kernel"] + ":" + dom["pass"])
+                tj = json.load(f)
+            roofline["traffic"] = tj.get(dom["kernel"] + ":" + dom["pass"])
+            roofline["traffic_source"] = ("static: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the "
+                                          "committed ncu --set full capture " + str(tj.get("_source", "profiles/ncu_traffic.json"))
+                                          + ", not measured in this run")
         except (OSError, ValueError):
             pass
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cpu = reference_sample(steps=2, warmup=1, budget_s=30.0)
+            cpu = reference_sample(steps=2, warmup=1, budget_s=40.0, state=state0)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as exc:  # the checker is optional for the number itself
             cpu = {"value": None, "unit": "Mpixel/s", "cores": 0, "kind": "unavailable", "sample": repr(exc)}
+    cli = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cli = cli_leg()
+        except Exception as exc:
+            cli = {"error": repr(exc)}
 
+    cfg = bench_config(world)
     line = {"metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frame": [W, H, CH], "sigma": SIGMA,
-                       "params": {"flt1": f1.as_dict(), "flt2": f2.as_dict()},
-                       "parallelism": f"{world} independent sequence(s), one per GPU" if world > 1 else "1 GPU",
-                       "l2": "inputs larger than L2: 20 distinct frames (noisy + flow + mask = 1.0 GB) cycled",
-                       "timed_call": "nlk_seq_submit_dev per frame (two-lane pipelined recursion), nlk_seq_join before the "
-                                     "closing event",
-                       "per_kernel_events": "separate leg over the same K steps, in order on one stream "
-                                            "(nlk_seq_filter_dev), CUDA events around every kernel; the timed leg "
-                                            "carries no per-kernel events"},
+            "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / K,
                     "api": "nlk_seq_submit_host per frame + nlk_seq_drain (pinned host buffers; uploads, kernels and "
                            "downloads of neighbouring frames overlap on three streams)",
+                    "returns": "the frame's result (second filtering, RGB); the first filtering stays on the device as "
+                               "recursion state; mask uploaded as the bytes of its 8-bit file (NLK_MASK_U8)",
+                    "both_outputs_value": e2e_full_value,
+                    "both_outputs": {"value": e2e_full_value, "ms_per_step": e2e_full_ms / K,
+                                     "h2d_bytes_per_step": h2d_full, "d2h_bytes_per_step": d2h_full,
+                                     "what": "float mask up, both filterings down (what the reference driver writes)"},
                     "synchronous": {"value": e2e_sync_value, "ms_per_step": e2e_sync_ms / K,
                                     "api": "nlk_seq_filter_host (returns with both outputs in host memory)"}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels[:12],
-            "in_order_ms_per_step": step_ms,
-            "fp32_peak_tflops": fp32_peak}
+            "alpha": alpha, "in_order_ms_per_step": step_ms, "fp32_peak_tflops": fp32_peak,
+            "details": {"params": {"flt1": f1.as_dict(), "flt2": f2.as_dict()},
+                        "timed_call": "nlk_seq_submit_dev per frame (two-lane pipelined recursion), nlk_seq_join before "
+                                      "the closing event",
+                        "per_kernel_events": "separate leg over the same K steps, in order on one stream "
+                                             "(nlk_seq_filter_dev), CUDA events around every kernel; the timed leg "
+                                             "carries no per-kernel events"}}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if cli is not None:
+        line["cli"] = cli
+    if strips_res is not None:
+        line["strips"] = strips_res
+        if "value" in strips_res:
+            # scalars in the objects the driver keeps
+            line["config"]["strips_mpixel_s"] = strips_res["value"]
+            line["config"]["strips_single_gpu_mpixel_s"] = strips_res.get("single_gpu_value")
+            line["config"]["strips_workload"] = strips_res["workload"]
     print(json.dumps(line))
-    ctx.close()
+    if world == 1:
+        ctx.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+# ---- CLI wall time ----------------------------------------------------
+
+def cli_leg():
+    """One nlkalman-flt process on config C1 (854x480 gray, sigma 20, frame 1 with flow, mask and the
+    previous filtered frames), file I/O and process start included: the unmodified reference program
+    (oracle/_ref/nlkalman-flt-ref, all host cores) against bwd_nlkalman_b200/bin/nlkalman-flt."""
+    import tempfile
+    from bwd_nlkalman_b200 import synth
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "nlkalman-flt-ref")
+    our_exe = os.path.join(ROOT, "bwd_nlkalman_b200", "bin", "nlkalman-flt")
+    if not (os.path.exists(ref_exe) and os.path.exists(our_exe)):
+        return {"error": "programs not built"}
+    w, h, sigma = 854, 480, 20.0
+
+    def pfm(path, a):
+        with open(path, "wb") as f:
+            f.write(f"Pf\n{w} {h}\n-1\n".encode() + np.ascontiguousarray(a, np.float32).tobytes())
+    with tempfile.TemporaryDirectory() as d:
+        for t in range(2):
+            pfm(os.path.join(d, f"n{t}.pfm"), synth.noisy_frame(w, h, 1, t, sigma))
+        with open(os.path.join(d, "bflo.flo"), "wb") as f:
+            f.write(b"PIEH" + np.array([w, h], np.int32).tobytes() + synth.backward_flow(w, h).tobytes())
+        with open(os.path.join(d, "occ.pgm"), "wb") as f:
+            f.write(f"P5\n{w} {h}\n255\n".encode() + synth.occlusion_mask(w, h).astype(np.uint8).tobytes())
+        p = lambda n: os.path.join(d, n)
+        # previous filtered frames (frame 0) with our program, untimed
+        subprocess.run([our_exe, "-i", p("n0.pfm"), "-s", str(sigma), "--flt11", p("a1.pfm"), "--flt21", p("a2.pfm")],
+                       check=True, capture_output=True)
+        args = ["-i", p("n1.pfm"), "-s", str(sigma), "-o", p("bflo.flo"), "-k", p("occ.pgm"), "--flt10", p("a1.pfm"),
+                "--flt20", p("a2.pfm")]
+        out = {}
+        for name, exe in (("reference", ref_exe), ("ours", our_exe)):
+            ts = []
+            for rep in range(3):
+                t0 = time.perf_counter()
+                subprocess.run([exe] + args + ["--flt11", p(f"{name}1.pfm"), "--flt21", p(f"{name}2.pfm")],
+                               check=True, capture_output=True)
+                ts.append(time.perf_counter() - t0)
+            out[name + "_s"] = min(ts)
+        out["workload"] = ("C1: one nlkalman-flt process, 854x480 gray, sigma 20, frame 1 (flow, mask, previous flt1/flt2 "
+                           "from PFM/FLO/PGM files), both filterings written; best of 3, process start, CUDA context "
+                           "creation and file I/O included")
+        out["cores"] = os.cpu_count()
+        return out
 
 
 def main():
@@ -416,6 +549,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strips", action="store_true", help="N > 1: skip the strip-sharded 4K leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

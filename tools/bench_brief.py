@@ -9,3 +9,10 @@ print(f"value {d['value']:.1f} {d['unit']}  e2e {d['e2e']['value']:.1f}  ms/step
 for k in d["kernels"]:
     print(f"  {k['kernel']:14s} {k['pass']:14s} n={k['launches']:3d} avg {k['avg_ms']:.3f} ms  share {k['share_of_step']:.3f}"
           f"  frac_fp32 {k.get('frac_fp32_peak', 0):.3f}")
+r = d["roofline"]
+print(f"roofline {r['kernel']}: frac {r['frac']:.3f} alpha {r.get('alpha')} frac_active {r.get('frac_active')} whole step {r.get('whole_step')}")
+print("e2e both outputs", d["e2e"].get("both_outputs_value"), "sync", d["e2e"]["synchronous"]["value"])
+print("cpu_baseline", d.get("cpu_baseline"))
+print("cli", d.get("cli"))
+if "strips" in d:
+    print("strips", d["strips"])

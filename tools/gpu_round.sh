@@ -11,10 +11,10 @@ for w in $WHAT; do
 case $w in
 tests)   timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; tail -3 $OUT/${TAG}_pytest_gpu.log;;
 bench)   timeout 600 python bench.py > $OUT/${TAG}_bench_ours.json 2> $OUT/${TAG}_bench_ours.err; python tools/bench_brief.py $OUT/${TAG}_bench_ours.json;;
-ref)     timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_reference.json 2>&1; cut -c1-300 $OUT/${TAG}_bench_reference.json;;
+ref)     timeout 900 python bench.py --impl reference --steps 5 --warmup 2 > $OUT/${TAG}_bench_reference.json 2>&1; cut -c1-300 $OUT/${TAG}_bench_reference.json;;
 launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
             --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches.log 2>&1;;
-ncu)     timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_group|k_resolve_blk|k_search_rows' -s 6 -c 6 \
+ncu)     timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_group|k_resolve_sys|k_search_rows' -s 0 -c 14 \
             -f -o $OUT/${TAG}_hot python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu.log 2>&1
          ls -la $OUT/${TAG}_hot.ncu-rep;;
 esac
