@@ -66,6 +66,91 @@ __device__ __forceinline__ void stage_window(float *__restrict__ win, int wrow, 
     }
 }
 
+// ---- separable transforms with one thread per tile LINE ----------------------------------------
+// A chunk holds at most ~100 tiles for 256 threads, and a 12x12 transform by one thread is a chain
+// of ~3,000 dependent-latency instructions: (tile, row) then (tile, column) work items keep every
+// thread busy and cut the serial chain per phase by the patch side.
+template <int PSZ_T, bool INVERSE>
+__device__ __forceinline__ void line_dct(float *r, int psz)
+{
+    if constexpr (PSZ_T != 0) {
+        float (&a)[PSZ_T] = *reinterpret_cast<float (*)[PSZ_T]>(r);
+        if (INVERSE) dct1d_inv<PSZ_T>(a); else dct1d_fwd<PSZ_T>(a);
+    } else {
+        float o[MAX_PSZ];
+        const float *T = c_dct[psz];
+        for (int k = 0; k < psz; ++k) {
+            float acc = 0.f;
+            for (int j = 0; j < psz; ++j) acc = fmaf(INVERSE ? T[j * psz + k] : T[k * psz + j], r[j], acc);
+            o[k] = acc;
+        }
+        for (int k = 0; k < psz; ++k) r[k] = o[k];
+    }
+}
+
+// forward 2-D transform of ntiles patches out of the staged windows into tiles[t * TS]; src_of(t) is
+// the patch's first sample (nullptr: no such tile), samples at src[y * wrow + x * ch].  Ends with
+// a block barrier.
+template <int PSZ_T, class SrcOf>
+__device__ __forceinline__ void block_fwd_tiles(float *tiles, int TS, int ntiles, int psz, int wrow, int ch, SrcOf src_of)
+{
+    constexpr int NR = PSZ_T ? PSZ_T : MAX_PSZ;
+    for (int it = threadIdx.x; it < ntiles * psz; it += GF_THREADS) {
+        const int t = it / psz, y = it - t * psz;
+        const float *src = src_of(t);
+        if (!src) continue;
+        float r[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) if (i < psz) r[i] = src[y * wrow + i * ch];
+        line_dct<PSZ_T, false>(r, psz);
+        float *d = tiles + t * TS + y * psz;
+#pragma unroll
+        for (int i = 0; i < NR; ++i) if (i < psz) d[i] = r[i];
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < ntiles * psz; it += GF_THREADS) {
+        const int t = it / psz, x = it - t * psz;
+        if (!src_of(t)) continue;
+        float *d = tiles + t * TS + x;
+        float r[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) if (i < psz) r[i] = d[i * psz];
+        line_dct<PSZ_T, false>(r, psz);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) if (i < psz) d[i * psz] = r[i];
+    }
+    __syncthreads();
+}
+
+// inverse 2-D transform, in place, of the ntiles tiles tile_of(t) (an index into `tiles`)
+template <int PSZ_T, class TileOf>
+__device__ __forceinline__ void block_inv_tiles(float *tiles, int TS, int ntiles, int psz, TileOf tile_of)
+{
+    constexpr int NR = PSZ_T ? PSZ_T : MAX_PSZ;
+    for (int it = threadIdx.x; it < ntiles * psz; it += GF_THREADS) {
+        const int t = it / psz, x = it - t * psz;
+        float *d = tiles + tile_of(t) * TS + x;
+        float r[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) if (i < psz) r[i] = d[i * psz];
+        line_dct<PSZ_T, true>(r, psz);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) if (i < psz) d[i * psz] = r[i];
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < ntiles * psz; it += GF_THREADS) {
+        const int t = it / psz, y = it - t * psz;
+        float *d = tiles + tile_of(t) * TS + y * psz;
+        float r[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) if (i < psz) r[i] = d[i];
+        line_dct<PSZ_T, true>(r, psz);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) if (i < psz) d[i] = r[i];
+    }
+    __syncthreads();
+}
+
 template <int PSZ_T, int CH_T>
 __global__ void __launch_bounds__(GF_THREADS, 2)
 k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
@@ -162,16 +247,14 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
         for (int c0 = 0; c0 < k; c0 += cc) {
             const int cnt = min(cc, k - c0);
             if (c0) __syncthreads();
-            // one thread per tile: transform straight out of the staged windows
-            for (int t = tid; t < cnt * tpc; t += GF_THREADS) {
+            // transform straight out of the staged windows, one thread per tile line
+            block_fwd_tiles<PSZ_T>(tiles, TS, cnt * tpc, psz, wrow, ch, [&](int t) -> const float * {
                 const int slot = t / tpc, rr = t - slot * tpc;
                 const int s = rr >= ch, c = rr - s * ch;
                 const uint32_t cd = s_cand[c0 + slot];
-                if (s == 1 && !cand_prev(cd)) continue;
-                const float *src = (s ? winP : winS) + (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * ch + c;
-                dct2d_from_window<PSZ_T>(src, wrow, ch, tiles + t * TS, psz);
-            }
-            __syncthreads();
+                if (s == 1 && !cand_prev(cd)) return nullptr;
+                return (s ? winP : winS) + (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * ch + c;
+            });
             // one thread per coefficient, candidates in sorted order
             {
                 const int cstride = tpc * TS;
@@ -260,14 +343,14 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
             const int cnt = min(cc, nagg - m0);
             if (!resident) {
                 __syncthreads();
-                for (int t = tid; t < cnt * nsrc2 * ch; t += GF_THREADS) {
-                    const int ml = t / (nsrc2 * ch), rr = t - ml * nsrc2 * ch;
+                // (tile index ml * tpc + rr: with one source per member the tiles of the second are unused)
+                block_fwd_tiles<PSZ_T>(tiles, TS, cnt * tpc, psz, wrow, ch, [&](int t) -> const float * {
+                    const int ml = t / tpc, rr = t - ml * tpc;
+                    if (rr >= nsrc2 * ch) return nullptr;
                     const int s = rr >= ch, c = rr - s * ch;
                     const uint32_t cd = s_cand[s_grp[m0 + ml]];
-                    const float *src = (s ? winP : winS) + (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * ch + c;
-                    dct2d_from_window<PSZ_T>(src, wrow, ch, tiles + (ml * tpc + rr) * TS, psz);
-                }
-                __syncthreads();
+                    return (s ? winP : winS) + (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * ch + c;
+                });
             }
             // one thread per coefficient over the members of the chunk
 #pragma unroll
@@ -285,12 +368,10 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
                 }
             }
             __syncthreads();
-            for (int t = tid; t < cnt * ch; t += GF_THREADS) {
+            block_inv_tiles<PSZ_T>(tiles, TS, cnt * ch, psz, [&](int t) {
                 const int ml = t / ch, c = t - ml * ch;
-                const int slot = resident ? s_grp[m0 + ml] : ml;
-                dct2d_tile<PSZ_T, true>(tiles + (slot * tpc + c) * TS, psz);
-            }
-            __syncthreads();
+                return (resident ? s_grp[m0 + ml] : ml) * tpc + c;
+            });
             for (int it = tid; it < cnt * pp; it += GF_THREADS) {
                 const int ml = it / pp, e = it - ml * pp;
                 const int hy = e / psz, hx = e - hy * psz;

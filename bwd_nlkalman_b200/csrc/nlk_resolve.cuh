@@ -207,7 +207,7 @@ __host__ __device__ inline int resolve_blocks_per_row(int gw) { return (gw + RB_
 __host__ __device__ inline int resolve_steps(int gw, int gh, int R)
 {
     const int n = gh - 1 + (gw + R * (gh - 1) + RB_C - 1) / RB_C + 12;
-    return (n + RB_Q - 1) / RB_Q * RB_Q;
+    return (n + RB_Q - 1) / RB_Q * RB_Q + 96;     // + pad steps: the replay loop runs whole bodies and fetches ahead
 }
 
 // pk[s][i] (uint4): the block row i handles at step s, or a pad block (all four cells flagged
@@ -260,11 +260,18 @@ __global__ void k_resolve_pack(const PassParams P, unsigned int *__restrict__ pk
 // above by one step plus the ring's visibility latency; a step is a shuffle, the 3-operation
 // recurrence per column and a store: ~100 cycles instead of the ~800 of a barrier-separated step.
 constexpr unsigned int RS_SENT = 0xffffffffu;   // published words only use bits 0..23
+constexpr int RS_Q = 8;                         // steps per unrolled loop body = prefetch distance of the packed blocks
+constexpr int RS_PAD = 2 * RS_Q;                // pad steps behind the last one (straight-line loop, no bounds tests)
 
-__device__ __forceinline__ unsigned int ring_wait(const volatile unsigned int *slot)
+// both words of a ring slot (lanes 31 and 30 of the producer), by every lane of the consumer warp:
+// one broadcast load, a warp-uniform spin, no divergence
+__device__ __forceinline__ uint2 ring_wait2(const volatile uint2 *slot)
 {
-    unsigned int v = *slot;
-    while (v == RS_SENT) v = *slot;
+    uint2 v;
+    do {
+        v.x = slot->x;
+        v.y = slot->y;
+    } while (v.x == RS_SENT || v.y == RS_SENT);
     return v;
 }
 
@@ -273,21 +280,23 @@ __global__ void __launch_bounds__(1024) k_resolve_sys(const PassParams P, int rw
                                                       unsigned int *__restrict__ rec, int *__restrict__ row_off,
                                                       int ring_len)
 {
-    constexpr int C = RB_C, Q = 8;
+    constexpr int C = RB_C, Q = RS_Q;
     extern __shared__ __align__(8) unsigned int s_dyn[];
     const int gw = P.gw, gh = P.gh;
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
-    unsigned int *s_ring = s_dyn;                                       // [nwarps][ring_len][2] words of lanes 31, 30
-    unsigned int *s_act = s_ring + (size_t)nwarps * ring_len * 2;       // [nthr][rw] active bits, bit 4b+c of row i
-    int *s_base = reinterpret_cast<int *>(s_act + (size_t)nthr * rw);  // [gh+1] row offsets
+    // ring w, slot j: what lanes 31 / 30 of warp w published at step first(w) + j.  Ring `nwarps` is the
+    // all-zero input of warp 0.
+    uint2 *s_ring = reinterpret_cast<uint2 *>(s_dyn);                                   // [nwarps + 1][ring_len]
+    unsigned int *s_act = s_dyn + (size_t)(nwarps + 1) * ring_len * 2;                  // [nthr][rw] active bits, bit 4b+c of row i
+    int *s_base = reinterpret_cast<int *>(s_act + (size_t)nthr * rw);                  // [gh+1] row offsets
     __shared__ int s_part[1024];
 
     if (*P.any_nbr == 0) return;   // k_resolve_pack filled the list
     constexpr int FW = C + 2 * R;
     static_assert(FW <= 8 && (C + R) * (R - 1) + FW <= 32 && 1 + C - 1 + R <= 8, "window / field layout");
     constexpr unsigned int fwmask = (1u << FW) - 1u, ownmask = ((1u << (R + C)) - 1u) << 1;
-    const int nsteps = resolve_steps(gw, gh, R);
-    for (int x = tid; x < nwarps * ring_len * 2; x += nthr) s_ring[x] = RS_SENT;
+    for (int x = tid; x < nwarps * ring_len; x += nthr) s_ring[x] = make_uint2(RS_SENT, RS_SENT);
+    for (int x = tid; x < ring_len; x += nthr) s_ring[(size_t)nwarps * ring_len + x] = make_uint2(0u, 0u);
     for (int x = tid; x < nthr * rw; x += nthr) s_act[x] = 0u;
     __syncthreads();
 
@@ -295,44 +304,35 @@ __global__ void __launch_bounds__(1024) k_resolve_sys(const PassParams P, int rw
     const unsigned int m1 = i >= 1 ? fwmask : 0u, m2 = i >= 2 ? fwmask : 0u;
     const int sb = i + (R * i) / C;                     // block b of the row is handled at step sb + b
     // steps in which some row of this warp has work: marks for its first columns arrive at most
-    // three blocks before the row starts, and the last record word closes 8 blocks after its end
+    // three blocks before the row starts, and the last record word closes 8 blocks after its end;
+    // rounded up to whole loop bodies (the extra steps see pad blocks)
     const int i0 = warp * 32, i1 = i0 + 31;
     const int w_first = max(i0 + (R * i0) / C - 3, 0);
-    const int w_last = min(i1 + (R * i1) / C + nb + 9, nsteps - 1);
-    // the band of the warp above (the producer of lane 0's and, for R = 2, lane 1's inputs)
-    const int p0 = i0 - 32, p1 = i0 - 1;
-    const int pw_first = max(p0 + (R * p0) / C - 3, 0);
-    const int pw_last = min(p1 + (R * p1) / C + nb + 9, nsteps - 1);
-    const volatile unsigned int *ring_in = s_ring + (size_t)(warp - 1) * ring_len * 2;
-    volatile unsigned int *ring_out = s_ring + (size_t)warp * ring_len * 2;
-    const uint4 *pcol = pk + i;                         // pk[s][i]
-    const uint4 zero4 = make_uint4(0xf0000000u, 0u, 0u, 0u);   // a pad block
+    const int w_len = (i1 + (R * i1) / C + nb + 9 - w_first + 1 + Q - 1) / Q * Q;
+    const int p0 = i0 - 32;
+    const int pw_first = warp > 0 ? max(p0 + (R * p0) / C - 3, 0) : w_first - 1;   // ring slot of step s-1: s-1-pw_first
+    const volatile uint2 *ring_in = s_ring + (size_t)(warp > 0 ? warp - 1 : nwarps) * ring_len + (w_first - 1 - pw_first);
+    volatile unsigned int *ring_out = reinterpret_cast<unsigned int *>(s_ring + (size_t)warp * ring_len);
+    const uint4 *pcol = pk + (size_t)w_first * nthr + i;     // pk[s][i]
     uint4 q[Q];             // blocks of steps s .. s+Q-1 (fetched Q steps ahead: an L2 round trip)
 #pragma unroll
-    for (int u = 0; u < Q; ++u) q[u] = (w_first + u <= w_last) ? pcol[(size_t)(w_first + u) * nthr] : zero4;
+    for (int u = 0; u < Q; ++u) q[u] = pcol[(size_t)u * nthr];
+    pcol += (size_t)Q * nthr;
     unsigned int wnd = 0u, acc = 0u, mypub = 0u;
     unsigned int *act_row = s_act + (size_t)i * rw;
-    for (int s0 = w_first; s0 <= w_last; s0 += Q) {
+    const bool pub_lane = lane >= 32 - R;
+    const unsigned int sel0 = lane == 0 ? ~0u : 0u, sel1 = lane == 1 ? ~0u : 0u;
+    const int pub_word = 31 - lane;
+    int b = w_first - sb;
+    for (int j0 = 0; j0 < w_len; j0 += Q) {
 #pragma unroll
         for (int u = 0; u < Q; ++u) {
-            const int s = s0 + u;
-            if (s > w_last) break;                       // warp-uniform
-            // what the rows above published at step s-1
+            // what the rows above published at step s-1: lanes 0 (and 1) take the warp above's
+            const uint2 pr = ring_wait2(ring_in + j0 + u);
             unsigned int up1 = __shfl_up_sync(0xffffffffu, mypub, 1);
             unsigned int up2 = R > 1 ? __shfl_up_sync(0xffffffffu, mypub, 2) : 0u;
-            if (warp > 0 && lane < R) {
-                const int sp = s - 1;
-                unsigned int a = 0u, b2 = 0u;
-                if (sp >= pw_first && sp <= pw_last) {
-                    const volatile unsigned int *slot = ring_in + (size_t)(sp - pw_first) * 2;
-                    a = ring_wait(slot);                 // lane 31 of the warp above
-                    if (R > 1) b2 = ring_wait(slot + 1); // lane 30
-                }
-                if (lane == 0) { up1 = a; up2 = b2; }
-                else up2 = a;                            // lane 1 (R = 2): two rows up is lane 31 above
-            }
-            __syncwarp();
-            const int b = s - sb;
+            up1 = (pr.x & sel0) | (up1 & ~sel0);
+            if (R > 1) up2 = (pr.y & sel0) | (pr.x & sel1) | (up2 & ~(sel0 | sel1));
             const uint4 x = q[u];
             wnd |= (up1 >> 8) & m1;
             if (R > 1) wnd |= ((up2 >> 16) & m2) << (C + R);
@@ -347,17 +347,20 @@ __global__ void __launch_bounds__(1024) k_resolve_sys(const PassParams P, int rw
             mypub = ((x.x & ~(unsigned int)((int)(wnd << 31) >> 31)) | (x.y & ~(unsigned int)((int)(wnd << 30) >> 31)) |
                      (x.z & ~(unsigned int)((int)(wnd << 29) >> 31)) | (x.w & ~(unsigned int)((int)(wnd << 28) >> 31))) &
                     0x00ffffffu;
-            if (lane >= 32 - R) ring_out[(size_t)(s - w_first) * 2 + (31 - lane)] = mypub;
+            if (pub_lane) ring_out[(size_t)(j0 + u) * 2 + pub_word] = mypub;
             // record: nibble b of the row (pads and cells outside the row are never active)
             acc |= (~wnd & 0xfu) << (4 * (b & 7));
-            if ((b & 7) == 7) {
-                if (b >= 0 && (b >> 3) < rw) act_row[b >> 3] = acc;
-                acc = 0u;
-            }
+            const bool last = (b & 7) == 7;
+            if (last && (unsigned int)(b >> 3) < (unsigned int)rw) act_row[b >> 3] = acc;
+            acc = last ? 0u : acc;
             wnd >>= C;
-            q[u] = (s + Q <= w_last) ? pcol[(size_t)(s + Q) * nthr] : zero4;
+            b += 1;
+            q[u] = pcol[(size_t)u * nthr];               // step s + Q (pad rows behind the last step)
         }
+        pcol += (size_t)Q * nthr;
     }
+    // the warp below runs a few dozen steps longer than this one: nothing more is published
+    for (int j = w_len + lane; j < ring_len; j += 32) reinterpret_cast<uint2 *>(s_ring)[(size_t)warp * ring_len + j] = make_uint2(0u, 0u);
     __syncthreads();
 
     // active list in raster order: per-row counts, block scan, then one warp per row
@@ -453,8 +456,8 @@ inline int launch_resolve(const PassParams &P, unsigned int *pk, cudaStream_t st
         if (nthr < 64) nthr = 64;
         const int nb = resolve_blocks_per_row(P.gw);
         const int rw8 = (nb + 7) / 8;          // record words per row (8 blocks each)
-        const int ring_len = nb + 32 + 8 * P.R + 16;      // steps of a warp's band (k_resolve_sys)
-        const size_t bb = ((size_t)(nthr / 32) * ring_len * 2 + (size_t)nthr * rw8 + P.gh + 1) * 4;
+        const int ring_len = nb + 2 * (32 + 8 * P.R) + 48;   // a warp's band and the steps the warp below runs beyond it
+        const size_t bb = ((size_t)(nthr / 32 + 1) * ring_len * 2 + (size_t)nthr * rw8 + P.gh + 1) * 4;
         if (bb <= 200 * 1024) {
             const int nsteps = resolve_steps(P.gw, P.gh, P.R);
             const long n = (long)nsteps * nthr * RB_C;
