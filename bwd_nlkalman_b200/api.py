@@ -123,6 +123,10 @@ def lib():
     L.nlk_pass_host_debug.argtypes = [vp, C.c_int, _fp, _fp, _fp, _fp, C.c_float, Params, C.c_int,
                                       _ip, _ip, _ip, _fp, _bp, _bp, _fp]
     L.nlk_dct_host.argtypes = [vp, _fp, C.c_int, C.c_int, C.c_int]
+    L.nlk_tvl1_level_host.argtypes = [vp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                      C.c_int, C.c_float, _ip]
+    L.nlk_tvl1_level_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                     C.c_int, C.c_float, _ip]
     # drop-in entry points
     L.rgb2opp.argtypes = L.opp2rgb.argtypes = [_fp, C.c_int, C.c_int, C.c_int]
     L.warp_bicubic.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int]
@@ -427,6 +431,18 @@ class Context:
             res["knn_xy"].ctypes.data_as(_ip), _p(res["knn_d"]),
             res["prev_p"].ctypes.data_as(_bp), res["active"].ctypes.data_as(_bp), _p(res["vp"])))
         return out, res
+
+    def tvl1_level(self, I0, I1, u1, u2, tau=0.25, lam=0.15, theta=0.3, warps=5, epsilon=0.01):
+        """Dual TV-L1 flow at one scale (reference lib/tvl1flow/tvl1flow_lib.c:93-280): host arrays
+        (ny, nx); returns (u1, u2, iterations per warping step)"""
+        ny, nx = I0.shape
+        a = np.ascontiguousarray(u1, np.float32).copy()
+        b = np.ascontiguousarray(u2, np.float32).copy()
+        its = np.zeros(max(warps, 1), np.int32)
+        _check(lib().nlk_tvl1_level_host(self._h, _p(np.ascontiguousarray(I0, np.float32)),
+                                         _p(np.ascontiguousarray(I1, np.float32)), _p(a), _p(b), nx, ny, float(tau),
+                                         float(lam), float(theta), int(warps), float(epsilon), its.ctypes.data_as(_ip)))
+        return a, b, its[:warps]
 
     def dct(self, tiles: np.ndarray, inverse: bool = False) -> np.ndarray:
         t = np.ascontiguousarray(tiles, dtype=np.float32).copy()

@@ -9,6 +9,7 @@
 #include "nlk_group.cuh"
 #include "nlk_group_warp.cuh"
 #include "nlk_peer.cuh"
+#include "nlk_tvl1.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -135,7 +136,7 @@ struct nlk_ctx {
     bool b_pending = false;      // lane 1 has work that lane 0 has not waited for
     cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr}, ev_join = nullptr;
     long long launches = 0;
-    DevBuf dbg_dist, dbg_vp;
+    DevBuf dbg_dist, dbg_vp, tv_scratch;
     // host-call staging
     DevBuf s_in1, s_prev0, s_bsic, s_out, s_of, s_msk;
     // sequence state (opponent colour space)
@@ -309,7 +310,7 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     for (int i = 0; i < 2; ++i) if (c->lane[i].st) cudaStreamSynchronize(c->lane[i].st);
     if (c->st_d2h) cudaStreamSynchronize(c->st_d2h);
     if (c->st_h2d) cudaStreamSynchronize(c->st_h2d);
-    DevBuf *all[] = {&c->dbg_dist, &c->dbg_vp, &c->s_in1, &c->s_prev0, &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk,
+    DevBuf *all[] = {&c->tv_scratch, &c->dbg_dist, &c->dbg_vp, &c->s_in1, &c->s_prev0, &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk,
                      &c->q_noisy[0], &c->q_noisy[1], &c->q_flt1[0], &c->q_flt1[1], &c->q_flt2[0], &c->q_flt2[1],
                      &c->q_smo[0], &c->q_smo[1], &c->q_tmp};
     for (DevBuf *b : all) b->release();
@@ -395,6 +396,30 @@ extern "C" void nlk_dev_free(nlk_ctx *c, void *d_ptr)
     if (!d_ptr || ctx_use(c)) return;
     cudaStreamSynchronize(c->L->st);
     cudaFree(d_ptr);
+}
+
+// a point of the context's stream another host thread can wait for (file writers, staging reuse)
+extern "C" void *nlk_marker_record(nlk_ctx *c)
+{
+    if (enter(c)) return nullptr;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess ||
+        cudaEventRecord(e, c->L->st) != cudaSuccess) {
+        set_err(NLK_ERR_CUDA, "marker: %s", cudaGetErrorString(cudaGetLastError()));
+        if (e) cudaEventDestroy(e);
+        return nullptr;
+    }
+    return e;
+}
+
+extern "C" int nlk_marker_wait(void *marker)
+{
+    if (!marker) return set_err(NLK_ERR_PARAM, "null marker");
+    cudaEvent_t e = static_cast<cudaEvent_t>(marker);
+    const cudaError_t r = cudaEventSynchronize(e);
+    cudaEventDestroy(e);
+    if (r != cudaSuccess) return set_err(NLK_ERR_CUDA, "marker wait: %s", cudaGetErrorString(r));
+    return NLK_OK;
 }
 
 extern "C" int nlk_upload(nlk_ctx *c, void *d_dst, const void *h_src, size_t bytes)
@@ -953,6 +978,89 @@ extern "C" int nlk_peer_error(nlk_ctx *c, unsigned int *code)
     if (!c->peer_on) return set_err(NLK_ERR_STATE, "nlk_peer_bind must come first");
     if (c->st_side) CU_TRY(cudaStreamSynchronize(c->st_side));
     CU_TRY(cudaMemcpy(code, c->peer.slab[c->peer.rank] + PEER_ERR_OFF, 4, cudaMemcpyDeviceToHost));
+    return NLK_OK;
+}
+
+// ---- Dual TV-L1 optical flow at one scale (nlk_tvl1.cuh; SURVEY 8(f4), first slice) --------------
+
+extern "C" int nlk_tvl1_level_dev(nlk_ctx *c, const float *d_I0, const float *d_I1, float *d_u1, float *d_u2,
+                                  int nx, int ny, float tau, float lambda, float theta, int warps, float epsilon,
+                                  int *iterations)
+{
+    if (int r = enter(c)) return r;
+    if (!d_I0 || !d_I1 || !d_u1 || !d_u2 || nx < 2 || ny < 2 || warps < 0 || warps > 64)
+        return set_err(NLK_ERR_PARAM, "bad TV-L1 request (%dx%d, %d warpings)", nx, ny, warps);
+    const size_t size = (size_t)nx * ny;
+    const int ES = TVL1_MAX_ITERATIONS + 4;        // error slots per warping step
+    const size_t fl = 10 * size + (size_t)warps * ES + 64;
+    if (int r = c->tv_scratch.ensure(fl * 4 + (size_t)warps * 4 + 64)) return r;
+    float *base = c->tv_scratch.as<float>();
+    float *I1x = base, *I1y = I1x + size, *I1wx = I1y + size, *I1wy = I1wx + size, *grad = I1wy + size,
+          *rho_c = grad + size, *p11 = rho_c + size, *p12 = p11 + size, *p21 = p12 + size, *p22 = p21 + size;
+    float *err = p22 + size;
+    int *cnt = reinterpret_cast<int *>(err + (size_t)warps * ES);
+    cudaStream_t st = c->L->st;
+    const float l_t = lambda * theta, taut = tau / theta, eps2 = epsilon * epsilon;
+    const dim3 nt(32, 8), nb((nx + 31) / 32, (ny + 7) / 8);
+    CU_TRY(cudaMemsetAsync(p11, 0, 4 * size * 4, st));                       // p = 0 (:130-134)
+    CU_TRY(cudaMemsetAsync(err, 0, ((size_t)warps * ES) * 4 + (size_t)warps * 4, st));
+    k_tvl1_centered_gradient<<<nb, nt, 0, st>>>(d_I1, I1x, I1y, nx, ny);
+    if (int r = check_launch(c, 1, "tvl1 gradient")) return r;
+    float *h_err = nullptr;
+    CU_TRY(cudaMallocHost(&h_err, 4));
+    int rc = NLK_OK;
+    for (int wi = 0; wi < warps && rc == NLK_OK; ++wi) {
+        float *e = err + (size_t)wi * ES;
+        k_tvl1_warp<<<nb, nt, 0, st>>>(d_I0, d_I1, I1x, I1y, d_u1, d_u2, I1wx, I1wy, grad, rho_c, nx, ny);
+        rc = check_launch(c, 1, "tvl1 warp");
+        // batches of iterations; the kernels themselves stop at the reference's stopping iteration
+        // (:164), the host only learns between batches that nothing is left to queue
+        const int BATCH = 20;
+        for (int n0 = 1; n0 <= TVL1_MAX_ITERATIONS && rc == NLK_OK; n0 += BATCH) {
+            const int n1 = n0 + BATCH - 1 < TVL1_MAX_ITERATIONS ? n0 + BATCH - 1 : TVL1_MAX_ITERATIONS;
+            for (int n = n0; n <= n1; ++n) {
+                k_tvl1_u<<<nb, nt, 0, st>>>(rho_c, I1wx, I1wy, grad, p11, p12, p21, p22, d_u1, d_u2, e, n, nx, ny, l_t, theta, eps2);
+                k_tvl1_p<<<nb, nt, 0, st>>>(d_u1, d_u2, p11, p12, p21, p22, e, n, nx, ny, taut, eps2);
+            }
+            rc = check_launch(c, 2 * (n1 - n0 + 1), "tvl1 iteration");
+            if (rc != NLK_OK || n1 == TVL1_MAX_ITERATIONS) break;
+            if (cudaMemcpyAsync(h_err, e + n1, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess) {
+                rc = set_err(NLK_ERR_CUDA, "tvl1: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+            if (!(*h_err / (float)size > eps2)) break;     // converged inside this batch
+        }
+        k_tvl1_count<<<1, 1, 0, st>>>(e, cnt + wi, (float)size, eps2);
+        if (rc == NLK_OK) rc = check_launch(c, 1, "tvl1 count");
+    }
+    cudaFreeHost(h_err);
+    if (rc != NLK_OK) return rc;
+    if (iterations && warps > 0) {
+        CU_TRY(cudaMemcpyAsync(iterations, cnt, (size_t)warps * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    return NLK_OK;
+}
+
+extern "C" int nlk_tvl1_level_host(nlk_ctx *c, const float *h_I0, const float *h_I1, float *h_u1, float *h_u2,
+                                   int nx, int ny, float tau, float lambda, float theta, int warps, float epsilon,
+                                   int *iterations)
+{
+    if (int r = enter(c)) return r;
+    if (!h_I0 || !h_I1 || !h_u1 || !h_u2 || nx < 2 || ny < 2) return set_err(NLK_ERR_PARAM, "bad TV-L1 request");
+    const size_t pb = (size_t)nx * ny * 4;
+    if (int r = c->q_tmp.ensure(4 * pb)) return r;
+    float *d = c->q_tmp.as<float>();
+    const size_t n = (size_t)nx * ny;
+    CU_TRY(cudaMemcpyAsync(d, h_I0, pb, cudaMemcpyHostToDevice, c->L->st));
+    CU_TRY(cudaMemcpyAsync(d + n, h_I1, pb, cudaMemcpyHostToDevice, c->L->st));
+    CU_TRY(cudaMemcpyAsync(d + 2 * n, h_u1, pb, cudaMemcpyHostToDevice, c->L->st));
+    CU_TRY(cudaMemcpyAsync(d + 3 * n, h_u2, pb, cudaMemcpyHostToDevice, c->L->st));
+    if (int r = nlk_tvl1_level_dev(c, d, d + n, d + 2 * n, d + 3 * n, nx, ny, tau, lambda, theta, warps, epsilon, iterations)) return r;
+    CU_TRY(cudaMemcpyAsync(h_u1, d + 2 * n, pb, cudaMemcpyDeviceToHost, c->L->st));
+    CU_TRY(cudaMemcpyAsync(h_u2, d + 3 * n, pb, cudaMemcpyDeviceToHost, c->L->st));
+    CU_TRY(cudaStreamSynchronize(c->L->st));
     return NLK_OK;
 }
 

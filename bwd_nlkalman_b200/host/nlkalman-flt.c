@@ -6,13 +6,33 @@
  * All frames of one invocation stay in HBM between the stages (colour transform, warp,
  * first filtering, second filtering); only the inputs go up and the outputs come back.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <unistd.h>
 
 #include "nlk_image_io.h"
 #include "nlk_opts.h"
 #include "nlkalman_b200.h"
+
+/* The CUDA runtime, the context and the kernel module take a few hundred milliseconds to come up: more
+ * than everything else a per-frame invocation does.  A helper thread brings them up (a throw-away 8x8
+ * context) while the main thread parses and decodes the input files. */
+static void *gpu_warmup(void *arg)
+{
+    nlk_ctx *t = nlk_ctx_create(8, 8, 1, *(int *)arg);
+    if (t) nlk_ctx_destroy(t);
+    return NULL;
+}
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
 
 static void auto_params(struct nlkalman_params *p)
 {
@@ -124,6 +144,14 @@ int main(int argc, const char *argv[])
         if (apply_filt2) print_params("second filtering parameters:", &f2);
     }
 
+    /* bring the GPU up beside the file decoding */
+    int dev = 0;
+    if (getenv("NLK_DEVICE")) dev = atoi(getenv("NLK_DEVICE"));
+    const int timing = getenv("NLK_CLI_TIMING") != NULL;
+    const double t_start = now_s();
+    pthread_t warm;
+    const int warm_on = pthread_create(&warm, NULL, gpu_warmup, &dev) == 0;
+
     /* load data (reference src/main-flt.c:215-332: same checks, same messages) */
     int w, h, c, w1, h1, c1;
     float *nisy = noisy_path ? nlk_read_image(noisy_path, &w, &h, &c) : NULL;
@@ -158,8 +186,9 @@ int main(int argc, const char *argv[])
     }
 
     /* run on the GPU (reference src/main-flt.c:335-388) */
-    int dev = 0;
-    if (getenv("NLK_DEVICE")) dev = atoi(getenv("NLK_DEVICE"));
+    const double t_read = now_s();
+    if (warm_on) pthread_join(warm, NULL);
+    const double t_warm = now_s();
     nlk_ctx *ctx = nlk_ctx_create(w, h, c, dev);
     if (!ctx) return gpu_fail("no usable CUDA device (there is no CPU fallback)");
     const size_t ib = (size_t)w * h * c * sizeof(float), npix = (size_t)w * h;
@@ -212,10 +241,12 @@ int main(int argc, const char *argv[])
         if (nlk_write_image(flt11_path, out, w, h, c)) return fprintf(stderr, "%s\n", nlk_io_error()), 1;
     }
 
-    free(out);
-    nlk_dev_free(ctx, d_nisy); nlk_dev_free(ctx, d_warp); nlk_dev_free(ctx, d_tmp);
-    nlk_dev_free(ctx, d_flt11); nlk_dev_free(ctx, d_flt21); nlk_dev_free(ctx, d_of); nlk_dev_free(ctx, d_occ);
-    nlk_ctx_destroy(ctx);
-    free(nisy); free(bflo); free(bocc); free(flt10); free(flt20); free(flt11);
-    return EXIT_SUCCESS;
+    if (timing)
+        fprintf(stderr, "nlkalman-flt timing: read+decode %.3f s (GPU bring-up beside it, +%.3f s waited), "
+                        "GPU + output files %.3f s, total %.3f s\n",
+                t_read - t_start, t_warm - t_read, now_s() - t_warm, now_s() - t_start);
+    /* the outputs are on disk: leave without tearing the CUDA context down (tens of milliseconds
+     * that nothing depends on) */
+    fflush(NULL);
+    _exit(EXIT_SUCCESS);
 }

@@ -7,17 +7,27 @@
  * previous first filtering, second filtering (from the second frame on) guided by the
  * warped previous output with the first filtering as basic estimate, then either the
  * one-frame-lag smoother inside the forward loop or the full backward smoother
- * (--s1_full 1).  Differences in mechanism, not in results: frames are read one at a
- * time instead of all up front, and every filtered frame stays on the GPU (opponent
- * colour space) until the smoother has consumed it -- nothing but the inputs goes up
- * and nothing but the requested outputs comes back.
+ * (--s1_full 1).  The recursion is that of the pipeline script and of main-flt.c -- main-seq.c's
+ * DECOUPLE_FILTER2 build (src/nlkalman.h:2, src/main-seq.c:451-467): the first filtering of a
+ * frame is guided by the warped previous FIRST filtering.  Differences in mechanism, not in
+ * results: frames are read one at a time instead of all up front, and every filtered frame
+ * stays on the GPU (opponent colour space) until the smoother has consumed it -- nothing but
+ * the inputs goes up and nothing but the requested outputs comes back.
+ *
+ * File I/O runs beside the GPU: a reader thread decodes the next frame's files into pinned
+ * staging sets while the current frame is filtered, a writer thread encodes each output once
+ * its download has landed (nlk_marker_*); the driving thread only queues uploads, kernels and
+ * downloads and never waits for a file.
  *
  * --first_f2 1 applies the second filtering to the first frame too, which is what the
  * per-frame pipeline script does (reference scripts/nlkalman-seq.sh:39-41).
  */
+#include <pthread.h>
+#include <semaphore.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "nlk_image_io.h"
 #include "nlk_opts.h"
@@ -74,38 +84,118 @@ static float *read_frame(const char *pattern, int f, int want_c, int *err)
     return x;
 }
 
-/* device (opponent space) -> RGB -> file pattern % f */
-static int write_frame(const char *pattern, int f, const float *d_opp, float *d_scratch, float *h_out)
+/* ---- reader thread: the files of the coming requests, decoded into pinned staging sets ------- */
+#define N_IN 3
+#define N_OUT 4
+enum { REQ_FRAME = 0 /* noisy frame f + its backward flow and mask */, REQ_FLOW = 1 /* forward flow and mask of f */ };
+typedef struct { int kind, f, with_flow; } in_req;
+typedef struct {
+    float *img, *flo, *occ;     /* pinned */
+    int has_img, has_flo, has_occ, err;
+    void *consumed;             /* marker: the uploads out of this set have finished */
+} in_set;
+static struct {
+    in_req *req;
+    int nreq;
+    in_set set[N_IN];
+    sem_t free_sets, ready_sets;
+    const char *nisy, *bflo, *bocc, *fflo, *focc;
+} rd;
+
+static void *reader_main(void *arg)
 {
-    char name[1024];
-    snprintf(name, sizeof name, pattern, f);
-    if (nlk_opp2rgb_dev(ctx, d_scratch, d_opp) || nlk_download(ctx, h_out, d_scratch, ib) || nlk_ctx_sync(ctx))
-        return gpu_fail("output");
-    if (nlk_write_image(name, h_out, w, h, c)) return fprintf(stderr, "Error: %s\n", nlk_io_error()), 1;
+    (void)arg;
+    for (int i = 0; i < rd.nreq; ++i) {
+        sem_wait(&rd.free_sets);
+        in_set *s = &rd.set[i % N_IN];
+        if (s->consumed) { nlk_marker_wait(s->consumed); s->consumed = NULL; }
+        const in_req q = rd.req[i];
+        s->has_img = s->has_flo = s->has_occ = 0;
+        int err = 0;
+        if (q.kind == REQ_FRAME) {
+            float *x = read_frame(rd.nisy, q.f, c, &err);
+            if (x) { memcpy(s->img, x, ib); free(x); s->has_img = 1; } else err = 1;
+        }
+        if (!err && q.with_flow) {
+            float *of = read_frame(q.kind == REQ_FRAME ? rd.bflo : rd.fflo, q.f, 2, &err);
+            float *oc = of ? read_frame(q.kind == REQ_FRAME ? rd.bocc : rd.focc, q.f, 1, &err) : NULL;
+            if (of) { memcpy(s->flo, of, npix * 2 * sizeof(float)); s->has_flo = 1; }
+            if (oc) { memcpy(s->occ, oc, npix * sizeof(float)); s->has_occ = 1; }
+            free(of);
+            free(oc);
+        }
+        s->err = err;
+        sem_post(&rd.ready_sets);
+        if (err) break;
+    }
+    return NULL;
+}
+
+static int rd_next;
+/* the next request's set (blocks until the reader has it); release_set after its uploads are queued */
+static in_set *acquire_set(void)
+{
+    sem_wait(&rd.ready_sets);
+    in_set *s = &rd.set[rd_next++ % N_IN];
+    return s->err ? NULL : s;
+}
+static void release_set(in_set *s)
+{
+    s->consumed = nlk_marker_record(ctx);
+    sem_post(&rd.free_sets);
+}
+
+/* flow / occlusion of a staging set -> device; *d_flow_out = NULL when there is no flow */
+static int upload_flow(const in_set *s, float *d_of, float *d_occ, const float **d_flow_out, const float **d_occ_out)
+{
+    *d_flow_out = *d_occ_out = NULL;
+    if (s->has_flo) {
+        if (nlk_upload(ctx, d_of, s->flo, npix * 2 * sizeof(float))) return gpu_fail("upload");
+        *d_flow_out = d_of;
+        if (s->has_occ) {
+            if (nlk_upload(ctx, d_occ, s->occ, npix * sizeof(float))) return gpu_fail("upload");
+            *d_occ_out = d_occ;
+        }
+    }
     return 0;
 }
 
-/* flow / occlusion of frame f -> device; *d_flow_out = NULL when there is no flow */
-static int load_flow(const char *flo_pat, const char *occ_pat, int f, float *d_of, float *d_occ,
-                     const float **d_flow_out, const float **d_occ_out)
+/* ---- writer thread: outputs encoded and written once their download has landed ---------------- */
+typedef struct { void *marker; char name[1024]; int stop; } out_job;
+static struct {
+    float *buf[N_OUT];          /* pinned */
+    out_job job[N_OUT];
+    sem_t free_bufs, ready_jobs;
+    int head, failed;
+} wr;
+
+static void *writer_main(void *arg)
 {
-    int err = 0;
-    *d_flow_out = *d_occ_out = NULL;
-    float *of = read_frame(flo_pat, f, 2, &err);
-    float *oc = of ? read_frame(occ_pat, f, 1, &err) : NULL;
-    if (err) return 1;
-    if (of) {
-        if (nlk_upload(ctx, d_of, of, npix * 2 * sizeof(float))) return gpu_fail("upload");
-        *d_flow_out = d_of;
-        if (oc) {
-            if (nlk_upload(ctx, d_occ, oc, npix * sizeof(float))) return gpu_fail("upload");
-            *d_occ_out = d_occ;
-        }
-        if (nlk_ctx_sync(ctx)) return gpu_fail("upload");   /* the host copies are freed below */
+    (void)arg;
+    for (int i = 0;; ++i) {
+        sem_wait(&wr.ready_jobs);
+        out_job *j = &wr.job[i % N_OUT];
+        if (j->stop) break;
+        if (nlk_marker_wait(j->marker)) { fprintf(stderr, "nlkalman-seq: output: %s\n", nlk_last_error()); wr.failed = 1; }
+        else if (nlk_write_image(j->name, wr.buf[i % N_OUT], w, h, c)) { fprintf(stderr, "Error: %s\n", nlk_io_error()); wr.failed = 1; }
+        sem_post(&wr.free_bufs);
     }
-    free(of);
-    free(oc);
-    return 0;
+    return NULL;
+}
+
+/* device (opponent space) -> RGB -> pinned buffer -> (writer thread) file pattern % f */
+static int write_frame(const char *pattern, int f, const float *d_opp, float *d_scratch)
+{
+    sem_wait(&wr.free_bufs);
+    const int k = wr.head++ % N_OUT;
+    out_job *j = &wr.job[k];
+    snprintf(j->name, sizeof j->name, pattern, f);
+    j->stop = 0;
+    if (nlk_opp2rgb_dev(ctx, d_scratch, d_opp) || nlk_download(ctx, wr.buf[k], d_scratch, ib)) return gpu_fail("output");
+    j->marker = nlk_marker_record(ctx);
+    if (!j->marker) return gpu_fail("output");
+    sem_post(&wr.ready_jobs);
+    return wr.failed;
 }
 
 int main(int argc, const char *argv[])
@@ -232,25 +322,48 @@ int main(int argc, const char *argv[])
     float **d_deno = (float **)calloc((size_t)nslots, sizeof(float *));
     for (int i = 0; i < nslots; ++i) if (!(d_deno[i] = nlk_dev_alloc(ctx, ib))) return gpu_fail("device memory");
     float *d_nisy = nlk_dev_alloc(ctx, ib), *d_warp = nlk_dev_alloc(ctx, ib), *d_tmp = nlk_dev_alloc(ctx, ib);
+    float *d_rgb[2] = {nlk_dev_alloc(ctx, ib), nlk_dev_alloc(ctx, ib)};   /* RGB scratch of the two outputs of a frame */
     float *d_bsic[2] = {nlk_dev_alloc(ctx, ib), nlk_dev_alloc(ctx, ib)};
     float *d_of = nlk_dev_alloc(ctx, npix * 2 * sizeof(float)), *d_occ = nlk_dev_alloc(ctx, npix * sizeof(float));
-    float *h_io = (float *)nlk_host_alloc(ib);
-    if (!d_nisy || !d_warp || !d_tmp || !d_bsic[0] || !d_bsic[1] || !d_of || !d_occ || !h_io)
+    float *d_of2 = nlk_dev_alloc(ctx, npix * 2 * sizeof(float)), *d_occ2 = nlk_dev_alloc(ctx, npix * sizeof(float));
+    if (!d_nisy || !d_warp || !d_tmp || !d_rgb[0] || !d_rgb[1] || !d_bsic[0] || !d_bsic[1] || !d_of || !d_occ || !d_of2 || !d_occ2)
         return gpu_fail("device memory");
 #define SLOT(f) d_deno[keep_all ? (f) - fframe : ((f) - fframe) & 1]
+
+    /* the files, in the order the loops below consume them */
+    rd.nisy = nisy_path; rd.bflo = bflo_path; rd.bocc = bocc_path; rd.fflo = fflo_path; rd.focc = focc_path;
+    rd.req = (in_req *)calloc((size_t)3 * nframes + 1, sizeof(in_req));
+    for (int f = fframe; f <= lframe; ++f) {
+        rd.req[rd.nreq++] = (in_req){REQ_FRAME, f, f > fframe && bflo_path != NULL};
+        if (lag_smoother && f > fframe) rd.req[rd.nreq++] = (in_req){REQ_FLOW, f - 1, fflo_path != NULL};
+    }
+    if (full_smoother)
+        for (int f = lframe - 1; f >= fframe; --f) rd.req[rd.nreq++] = (in_req){REQ_FLOW, f, fflo_path != NULL};
+    for (int i = 0; i < N_IN; ++i) {
+        rd.set[i].img = (float *)nlk_host_alloc(ib);
+        rd.set[i].flo = (float *)nlk_host_alloc(npix * 2 * sizeof(float));
+        rd.set[i].occ = (float *)nlk_host_alloc(npix * sizeof(float));
+        if (!rd.set[i].img || !rd.set[i].flo || !rd.set[i].occ) return gpu_fail("pinned memory");
+    }
+    for (int i = 0; i < N_OUT; ++i) if (!(wr.buf[i] = (float *)nlk_host_alloc(ib))) return gpu_fail("pinned memory");
+    sem_init(&rd.free_sets, 0, N_IN);
+    sem_init(&rd.ready_sets, 0, 0);
+    sem_init(&wr.free_bufs, 0, N_OUT);
+    sem_init(&wr.ready_jobs, 0, 0);
+    pthread_t reader, writer;
+    if (pthread_create(&reader, NULL, reader_main, NULL) || pthread_create(&writer, NULL, writer_main, NULL))
+        return fprintf(stderr, "Error: cannot start the I/O threads\n"), 1;
 
     /* ---- forward: filtering (reference src/main-seq.c:444-550) ---------------------------- */
     for (int f = fframe; f <= lframe; ++f) {
         if (verbose) printf("processing frame %d\n", f);
-        int err = 0;
-        float *x = read_frame(nisy_path, f, c, &err);
-        if (!x) return 1;
-        memcpy(h_io, x, ib);
-        free(x);
-        if (nlk_upload(ctx, d_nisy, h_io, ib) || nlk_rgb2opp_dev(ctx, d_nisy, d_nisy)) return gpu_fail("upload");
+        in_set *in = acquire_set();
+        if (!in) return 1;
+        if (nlk_upload(ctx, d_nisy, in->img, ib) || nlk_rgb2opp_dev(ctx, d_nisy, d_nisy)) return gpu_fail("upload");
         float *bsic1 = d_bsic[(f - fframe) & 1], *bsic0 = d_bsic[(f - fframe + 1) & 1];
         const float *d_flow = NULL, *d_mask = NULL;
-        if (f > fframe && load_flow(bflo_path, bocc_path, f, d_of, d_occ, &d_flow, &d_mask)) return 1;
+        if (upload_flow(in, d_of, d_occ, &d_flow, &d_mask)) return 1;
+        release_set(in);
 
         /* first filtering, guided by the previous first filtering */
         const float *prev = NULL;
@@ -259,7 +372,7 @@ int main(int argc, const char *argv[])
             if (d_flow) { if (nlk_warp_dev(ctx, d_warp, bsic0, d_flow, d_mask)) return gpu_fail("warp"); prev = d_warp; }
         }
         if (nlk_pass_dev(ctx, 0, bsic1, d_nisy, prev, NULL, sigma, f1)) return gpu_fail("first filtering");
-        if (flt1_path && write_frame(flt1_path, f, bsic1, d_tmp, h_io)) return 1;
+        if (flt1_path && write_frame(flt1_path, f, bsic1, d_rgb[0])) return 1;
 
         /* second filtering, guided by the previous output */
         float *deno1 = SLOT(f);
@@ -274,18 +387,21 @@ int main(int argc, const char *argv[])
             /* the output of this frame is its first filtering */
             if (nlk_copy_dev(ctx, deno1, bsic1, ib)) return gpu_fail("copy");
         }
-        if (second_filt && flt2_path && write_frame(flt2_path, f, deno1, d_tmp, h_io)) return 1;
+        if (second_filt && flt2_path && write_frame(flt2_path, f, deno1, d_rgb[1])) return 1;
 
         /* one-frame-lag smoother: frame f-1 smoothed against frame f */
         if (lag_smoother && f > fframe) {
+            in_set *ff = acquire_set();
+            if (!ff) return 1;
             const float *d_ff = NULL, *d_fm = NULL;
-            if (load_flow(fflo_path, focc_path, f - 1, d_of, d_occ, &d_ff, &d_fm)) return 1;
+            if (upload_flow(ff, d_of2, d_occ2, &d_ff, &d_fm)) return 1;
+            release_set(ff);
             const float *smoo0 = deno1;
             if (d_ff) { if (nlk_warp_dev(ctx, d_warp, deno1, d_ff, d_fm)) return gpu_fail("warp"); smoo0 = d_warp; }
             float *filt1 = SLOT(f - 1);
             if (nlk_pass_dev(ctx, 1, d_tmp, filt1, smoo0, NULL, sigma, s1)) return gpu_fail("smoothing");
             if (nlk_copy_dev(ctx, filt1, d_tmp, ib)) return gpu_fail("copy");
-            if (write_frame(smo1_path, f - 1, filt1, d_tmp, h_io)) return 1;
+            if (write_frame(smo1_path, f - 1, filt1, d_rgb[0])) return 1;
         }
     }
 
@@ -293,23 +409,26 @@ int main(int argc, const char *argv[])
     if (full_smoother) {
         for (int f = lframe - 1; f >= fframe; --f) {
             if (verbose) printf("processing frame %d\n", f);
+            in_set *ff = acquire_set();
+            if (!ff) return 1;
             const float *d_ff = NULL, *d_fm = NULL;
-            if (load_flow(fflo_path, focc_path, f, d_of, d_occ, &d_ff, &d_fm)) return 1;
+            if (upload_flow(ff, d_of, d_occ, &d_ff, &d_fm)) return 1;
+            release_set(ff);
             const float *smoo0 = SLOT(f + 1);
             if (d_ff) { if (nlk_warp_dev(ctx, d_warp, smoo0, d_ff, d_fm)) return gpu_fail("warp"); smoo0 = d_warp; }
             float *filt1 = SLOT(f);
             if (nlk_pass_dev(ctx, 1, d_nisy, filt1, smoo0, NULL, sigma, s1)) return gpu_fail("smoothing");
             if (nlk_copy_dev(ctx, filt1, d_nisy, ib)) return gpu_fail("copy");
-            if (write_frame(smo1_path, f, filt1, d_tmp, h_io)) return 1;
+            if (write_frame(smo1_path, f, filt1, d_rgb[(f - fframe) & 1])) return 1;
         }
     }
 
+    /* drain the writer, then leave without tearing the CUDA context down (the files are on disk) */
+    sem_wait(&wr.free_bufs);
+    wr.job[wr.head++ % N_OUT].stop = 1;
+    sem_post(&wr.ready_jobs);
+    pthread_join(writer, NULL);
     if (nlk_ctx_sync(ctx)) return gpu_fail("sync");
-    for (int i = 0; i < nslots; ++i) nlk_dev_free(ctx, d_deno[i]);
-    free(d_deno);
-    nlk_dev_free(ctx, d_nisy); nlk_dev_free(ctx, d_warp); nlk_dev_free(ctx, d_tmp);
-    nlk_dev_free(ctx, d_bsic[0]); nlk_dev_free(ctx, d_bsic[1]); nlk_dev_free(ctx, d_of); nlk_dev_free(ctx, d_occ);
-    nlk_host_free(h_io);
-    nlk_ctx_destroy(ctx);
-    return EXIT_SUCCESS;
+    fflush(NULL);
+    _exit(wr.failed ? 1 : EXIT_SUCCESS);
 }

@@ -78,6 +78,12 @@ void nlk_dev_free(nlk_ctx *ctx, void *d_ptr);
 int nlk_upload(nlk_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int nlk_download(nlk_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 int nlk_copy_dev(nlk_ctx *ctx, void *d_dst, const void *d_src, size_t bytes);
+/* A point of the context's stream (everything queued so far) that ANOTHER host thread may wait for:
+ * nlk_marker_record is called by the thread that drives the context, nlk_marker_wait (blocking, frees
+ * the marker) by any thread -- how a file writer learns that a download has landed while the driving
+ * thread goes on queueing the next frame. */
+void *nlk_marker_record(nlk_ctx *ctx);
+int nlk_marker_wait(void *marker);
 
 /* ---- single operations on device buffers (asynchronous on the context's stream) ---- */
 int nlk_rgb2opp_dev(nlk_ctx *ctx, float *d_dst, const float *d_src);   /* src may equal dst */
@@ -232,6 +238,22 @@ int nlk_seq_smooth_start_host(nlk_ctx *ctx, const float *h_last_rgb);
 int nlk_seq_smooth_host(nlk_ctx *ctx, const float *h_flt_rgb, const float *h_fflo,
                         const float *h_focc, float sigma, struct nlkalman_params s1,
                         float *h_smo_out);
+
+/* ---- Dual TV-L1 optical flow at one scale (first slice of SURVEY.md 8(f4)) ---------------------
+ * What the reference's Dual_TVL1_optic_flow does (lib/tvl1flow/tvl1flow_lib.c:93-280; called per
+ * pyramid level by Dual_TVL1_optic_flow_multiscale, :345-477, the flow estimator in front of the
+ * filter in scripts/nlkalman-seq.sh:60-65): `warps` times { bicubic warp of I1 and its centred
+ * gradient by the current flow, then the thresholding / Chambolle dual iterations until the mean
+ * squared update falls to epsilon^2 or 300 iterations }.  I0, I1: nx x ny single-channel images
+ * (the level's, already normalised and smoothed); u1, u2: the flow, initial value in, result out.
+ * iterations (host, [warps], may be NULL): iterations run by each warping step.  The pyramid around
+ * it (normalisation, Gaussian pre-smoothing, zoom) is not built yet. */
+int nlk_tvl1_level_dev(nlk_ctx *ctx, const float *d_I0, const float *d_I1, float *d_u1, float *d_u2,
+                       int nx, int ny, float tau, float lambda, float theta, int warps, float epsilon,
+                       int *iterations);
+int nlk_tvl1_level_host(nlk_ctx *ctx, const float *h_I0, const float *h_I1, float *h_u1, float *h_u2,
+                        int nx, int ny, float tau, float lambda, float theta, int warps, float epsilon,
+                        int *iterations);
 
 /* ---- stage dumps for the parity tests (host arrays, any may be NULL) ------------------
  * Runs one pass on host images like nlkalman_filter_frame / nlkalman_smooth_frame and

@@ -56,6 +56,54 @@ def build(ref: bool = True):
                    stdout=subprocess.DEVNULL)
 
 
+TVL1_SO = os.path.join(HERE, "_ref", "libtvl1_ref.so")
+
+
+class Tvl1Ref:
+    """The reference's TV-L1 flow library (lib/tvl1flow/tvl1flow_lib.c compiled unmodified)."""
+
+    def __init__(self, threads: int | None = None):
+        if not os.path.exists(TVL1_SO):
+            raise FileNotFoundError(f"{TVL1_SO} missing: run `make -C oracle ref` where /root/reference exists")
+        self.lib = C.CDLL(TVL1_SO)
+        f = self.lib.Dual_TVL1_optic_flow          # tvl1flow_lib.c:93
+        f.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_bool]
+        f.restype = None
+        if threads is not None:
+            try:
+                C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL).omp_set_num_threads(int(threads))
+            except OSError:
+                pass
+
+    def level(self, I0, I1, u1, u2, tau=0.25, lam=0.15, theta=0.3, warps=5, epsilon=0.01):
+        ny, nx = I0.shape
+        a = np.ascontiguousarray(u1, np.float32).copy()
+        b = np.ascontiguousarray(u2, np.float32).copy()
+        self.lib.Dual_TVL1_optic_flow(_p(np.ascontiguousarray(I0, np.float32)), _p(np.ascontiguousarray(I1, np.float32)),
+                                      _p(a), _p(b), nx, ny, tau, lam, theta, warps, epsilon, False)
+        return a, b
+
+
+def tvl1_pair(nx, ny, shift=(1.5, -0.75), seed=3):
+    """a smooth textured image pair, I1(x) = I0(x - shift) up to a little noise, in 0..255 like a
+    normalised, pre-smoothed pyramid level (tvl1flow_lib.c:379-384)"""
+    rng = np.random.default_rng(seed)
+    xs, ys = np.meshgrid(np.arange(nx, dtype=np.float64), np.arange(ny, dtype=np.float64))
+
+    def img(dx, dy):
+        r = np.random.default_rng(seed + 1)
+        out = np.zeros((ny, nx))
+        for _ in range(12):
+            a, fx, fy, ph = r.uniform(8, 30), r.uniform(-0.25, 0.25), r.uniform(-0.25, 0.25), r.uniform(0, 6.28)
+            out += a * np.sin(fx * (xs - dx) + fy * (ys - dy) + ph)
+        return out
+    I0 = img(0, 0) + rng.normal(0, 0.5, (ny, nx))
+    I1 = img(*shift) + rng.normal(0, 0.5, (ny, nx))
+    lo, hi = min(I0.min(), I1.min()), max(I0.max(), I1.max())
+    sc = 255.0 / (hi - lo)
+    return ((I0 - lo) * sc).astype(np.float32), ((I1 - lo) * sc).astype(np.float32)
+
+
 class Ref:
     """The reference's own six entry points (reference src/nlkalman.h:14-53)."""
 

@@ -393,3 +393,38 @@ def test_smoother_single_patch_branch_is_rejected(nlk):
                 ctx.pass_host_debug(1, n0, prev, None, sigma, s1)
             out, _ = ctx.pass_host_debug(1, n0, None, None, sigma, s1)     # no next frame: copy
             assert maxabs(out, n0) <= TOL_MAXABS
+
+
+def test_mask_modes_of_the_streaming_recursion(nlk):
+    """nlk_seq_set_mask_mode: the mask as the bytes of its 8-bit file, or built on the device from the
+    divergence of the uploaded flow (the script's plambda expression), against the float mask"""
+    import torch
+    from bwd_nlkalman_b200 import synth
+    from oracle import oracle as O
+    w, h, ch, sigma, nf, th = 140, 100, 3, 20.0, 4, 0.75
+    f1, f2 = nlk.default_params(sigma, nlk.FLT1), nlk.default_params(sigma, nlk.FLT2)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    frames = [pin(synth.noisy_frame(w, h, ch, t, sigma)) for t in range(nf)]
+    # a flow with a divergent region, so that the divergence mask is not empty
+    rng = np.random.default_rng(5)
+    of = synth.backward_flow(w, h).copy()
+    of[30:50, 60:90] += rng.normal(0, 1.5, (20, 30, 2)).astype(np.float32)
+    occ = O.occlusion_from_flow(of, th)
+    assert 0 < int((occ > 0).sum()) < occ.size
+    flo, occ_f, occ_8 = pin(of), pin(occ), pin(occ.astype(np.uint8))
+    outs = {}
+    with nlk.Context(w, h, ch) as ctx:
+        for name, mode, mask in (("float", ctx.MASK_FLOAT, occ_f), ("u8", ctx.MASK_U8, occ_8), ("flow", ctx.MASK_FROM_FLOW, None)):
+            ctx.seq_reset()
+            ctx.seq_set_mask_mode(mode, th)
+            o2 = [torch.empty((h, w, ch)).pin_memory() for _ in range(nf)]
+            for t in range(nf):
+                ctx.seq_submit_host(frames[t], flo if t else None, mask if t else None, sigma, f1, f2, None, o2[t])
+            ctx.seq_drain()
+            outs[name] = [x.numpy().copy() for x in o2]
+        ctx.seq_set_mask_mode(ctx.MASK_FLOAT)
+    for t in range(nf):
+        # same mask samples, same kernels; only the reduction order of the aggregation differs between runs
+        assert maxabs(outs["u8"][t], outs["float"][t]) <= TOL_MAXABS, t
+        assert maxabs(outs["flow"][t], outs["float"][t]) <= TOL_MAXABS, t
+    assert float(np.abs(outs["float"][-1] - frames[-1].numpy()).mean()) > 1.0
