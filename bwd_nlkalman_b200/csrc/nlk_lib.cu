@@ -1390,13 +1390,14 @@ extern "C" int nlk_pass_host_debug(nlk_ctx *c, int smooth, float *h_out, const f
     std::vector<uint32_t> cand((size_t)G * ks);
     std::vector<float> dist((size_t)G * ks), vps(G);
     std::vector<int> act(G);
-    int counters[2];
+    int counters[5];
     CU_TRY(cudaMemcpy(hdr.data(), c->L->hdr.p, (size_t)G * sizeof(GroupHdr), cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(cand.data(), c->L->cand.p, (size_t)G * ks * 4, cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(dist.data(), c->dbg_dist.p, (size_t)G * ks * 4, cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(vps.data(), c->dbg_vp.p, (size_t)G * 4, cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(act.data(), c->L->active.p, (size_t)G * 4, cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(counters, c->L->counters.p, 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(counters, c->L->counters.p, sizeof counters, cudaMemcpyDeviceToHost));
+    if (counters[4]) return set_err(NLK_ERR_CUDA, "mask_resolve: a ring slot never arrived (internal error)");
     if (active) memset(active, 0, G);
     for (int i = 0; i < counters[0] && i < G; ++i)
         if (active && act[i] >= 0 && act[i] < G) active[act[i]] = 1;

@@ -263,14 +263,22 @@ constexpr unsigned int RS_SENT = 0xffffffffu;   // published words only use bits
 constexpr int RS_Q = 8;                         // steps per unrolled loop body = prefetch distance of the packed blocks
 constexpr int RS_PAD = 2 * RS_Q;                // pad steps behind the last one (straight-line loop, no bounds tests)
 
-// both words of a ring slot (lanes 31 and 30 of the producer), by every lane of the consumer warp:
-// one broadcast load, a warp-uniform spin, no divergence
-__device__ __forceinline__ uint2 ring_wait2(const volatile uint2 *slot)
+// both words of a ring slot (lanes 31 and, for R = 2, 30 of the producer), by every lane of the
+// consumer warp: one broadcast load, a warp-uniform spin, no divergence.  The spin is bounded: a
+// slot that never comes (a bug, not a state of the algorithm) raises *timeout and reads as zero
+// instead of hanging the GPU.
+template <int R>
+__device__ __forceinline__ uint2 ring_wait2(const volatile uint2 *slot, int *timeout)
 {
     uint2 v;
+    int spins = 0;
     do {
         v.x = slot->x;
-        v.y = slot->y;
+        v.y = R > 1 ? slot->y : 0u;
+        if (++spins > (1 << 22)) {
+            *timeout = 1;
+            return make_uint2(v.x == RS_SENT ? 0u : v.x, v.y == RS_SENT ? 0u : v.y);
+        }
     } while (v.x == RS_SENT || v.y == RS_SENT);
     return v;
 }
@@ -328,7 +336,7 @@ __global__ void __launch_bounds__(1024) k_resolve_sys(const PassParams P, int rw
 #pragma unroll
         for (int u = 0; u < Q; ++u) {
             // what the rows above published at step s-1: lanes 0 (and 1) take the warp above's
-            const uint2 pr = ring_wait2(ring_in + j0 + u);
+            const uint2 pr = ring_wait2<R>(ring_in + j0 + u, P.work + 2);   // (counters[4]: replay timeout flag)
             unsigned int up1 = __shfl_up_sync(0xffffffffu, mypub, 1);
             unsigned int up2 = R > 1 ? __shfl_up_sync(0xffffffffu, mypub, 2) : 0u;
             up1 = (pr.x & sel0) | (up1 & ~sel0);

@@ -52,6 +52,29 @@ def noisy_frame(w: int, h: int, ch: int, t: int, sigma: float,
     return clean_frame(w, h, ch, t, seed) + np.float32(sigma) * noise
 
 
+def noisy_frame_cuda(w: int, h: int, ch: int, t: int, sigma: float, device, seed: int = SCENE_SEED,
+                     noise_seed: int = NOISE_SEED):
+    """noisy_frame evaluated with torch on `device` (float64 scene, the same NumPy noise stream): the
+    4K frames of the strip benchmark without seconds of host trigonometry.  Returns a float32 tensor."""
+    import torch
+    amp, fx, fy, ph, gain = _scene_params(ch, seed)
+    xs = torch.arange(w, dtype=torch.float64, device=device)[None, :] - t * MOTION[0]
+    ys = torch.arange(h, dtype=torch.float64, device=device)[:, None] - t * MOTION[1]
+    out = torch.zeros((h, w, ch), dtype=torch.float64, device=device)
+    g = torch.from_numpy(np.ascontiguousarray(gain)).to(device)
+    for i in range(len(amp)):
+        s = amp[i] * torch.sin(fx[i] * xs + fy[i] * ys + ph[i])
+        out += s[:, :, None] * g[i][None, None, :]
+    cx = torch.floor(xs / 37.0).to(torch.int64)
+    cy = torch.floor(ys / 29.0).to(torch.int64)
+    out += (20.0 * ((cx + cy) & 1))[:, :, None]
+    out += 128.0
+    clean = torch.clamp(out, 0.0, 255.0).to(torch.float32)
+    rng = np.random.default_rng(noise_seed + 7919 * t)
+    noise = torch.from_numpy(rng.standard_normal((h, w, ch), dtype=np.float32)).to(device)
+    return clean + np.float32(sigma) * noise
+
+
 def backward_flow(w: int, h: int) -> np.ndarray:
     """Flow from frame t to frame t-1, float32 (h, w, 2), [..., 0] = dx."""
     f = np.empty((h, w, 2), dtype=np.float32)

@@ -37,7 +37,7 @@ def measure(rank, world, lr, dist, w=3840, h=2160, sigma=10.0, nf=4, reps=2, war
     f1, f2, s1 = (nlk.default_params(sigma, m) for m in (nlk.FLT1, nlk.FLT2, nlk.SMO1))
     up = lambda x: torch.from_numpy(x).to(dev)
     # two distinct noisy frames are enough to exercise the recursion; they alternate
-    base = [up(synth.noisy_frame(w, h, ch, t, sigma)) for t in range(2)]
+    base = [synth.noisy_frame_cuda(w, h, ch, t, sigma, dev) for t in range(2)]
     frames = [base[t & 1] for t in range(nf)]
     bflo, fflo, occ = up(synth.backward_flow(w, h)), up(synth.forward_flow(w, h)), up(synth.occlusion_mask(w, h))
     flt_rgb = [torch.empty_like(base[0]) for _ in range(nf)]
