@@ -417,14 +417,20 @@ def test_mask_modes_of_the_streaming_recursion(nlk):
         for name, mode, mask in (("float", ctx.MASK_FLOAT, occ_f), ("u8", ctx.MASK_U8, occ_8), ("flow", ctx.MASK_FROM_FLOW, None)):
             ctx.seq_reset()
             ctx.seq_set_mask_mode(mode, th)
+            o1 = [torch.empty((h, w, ch)).pin_memory() for _ in range(nf)]
             o2 = [torch.empty((h, w, ch)).pin_memory() for _ in range(nf)]
             for t in range(nf):
-                ctx.seq_submit_host(frames[t], flo if t else None, mask if t else None, sigma, f1, f2, None, o2[t])
+                ctx.seq_submit_host(frames[t], flo if t else None, mask if t else None, sigma, f1, f2, o1[t], o2[t])
             ctx.seq_drain()
-            outs[name] = [x.numpy().copy() for x in o2]
+            outs[name] = ([x.numpy().copy() for x in o1], [x.numpy().copy() for x in o2])
         ctx.seq_set_mask_mode(ctx.MASK_FLOAT)
     for t in range(nf):
-        # same mask samples, same kernels; only the reduction order of the aggregation differs between runs
-        assert maxabs(outs["u8"][t], outs["float"][t]) <= TOL_MAXABS, t
-        assert maxabs(outs["flow"][t], outs["float"][t]) <= TOL_MAXABS, t
-    assert float(np.abs(outs["float"][-1] - frames[-1].numpy()).mean()) > 1.0
+        for name in ("u8", "flow"):
+            # first filtering: searched on the noisy frame -- the same lists in every run, only the
+            # reduction order of the aggregation differs
+            assert maxabs(outs[name][0][t], outs["float"][0][t]) <= TOL_MAXABS, (name, t)
+            # second filtering: searched on the run's own first filtering, whose last bits differ from run
+            # to run, so a distance near-tie may flip a group (also between two runs of one mode)
+            d = np.abs(outs[name][1][t].astype(np.float64) - outs["float"][1][t])
+            assert (d > TOL_MAXABS).mean() <= 2e-2 and d.mean() <= 1e-3, (name, t, d.max(), (d > TOL_MAXABS).mean())
+    assert float(np.abs(outs["float"][1][-1] - frames[-1].numpy()).mean()) > 1.0
