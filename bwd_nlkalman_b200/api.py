@@ -254,7 +254,7 @@ class Context:
 
     # per-kernel CUDA-event timing (include/nlkalman_b200.h)
     KERNELS = ["colour", "warp_bicubic", "valid_map", "search_knn", "mask_resolve", "group_filter",
-               "normalize", "memset"]
+               "normalize", "memset", "peer_wait", "peer_push"]
     PASS_KINDS = ["flt1_temporal", "flt1_spatial", "flt2_temporal", "flt2_spatial", "smoother", "other"]
 
     def profile(self, enable: bool):

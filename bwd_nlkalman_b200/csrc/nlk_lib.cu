@@ -894,6 +894,7 @@ extern "C" int nlk_peer_signal(nlk_ctx *c, int slot, unsigned int value, unsigne
     if (int r = peer_ok(c, 0, 0, peer_mask)) return r;
     if (slot < 0 || slot >= PEER_SLOTS) return set_err(NLK_ERR_PARAM, "flag slot %d", slot);
     if (!peer_mask) return NLK_OK;
+    ProfScope ps(c, NLK_K_PEER_PUSH);
     k_peer_signal<<<1, 32, 0, c->L->st>>>(c->peer, slot, value, peer_mask);
     return check_launch(c, 1, "peer_signal");
 }
@@ -906,6 +907,7 @@ extern "C" int nlk_peer_wait(nlk_ctx *c, int slot, unsigned int value, unsigned 
     if (!src_mask) return NLK_OK;
     static const unsigned long long tmo = getenv("NLK_PEER_TIMEOUT_MS") ? strtoull(getenv("NLK_PEER_TIMEOUT_MS"), nullptr, 10) * 1000000ull
                                                                          : 4000000000ull;
+    ProfScope ps(c, NLK_K_PEER_WAIT);
     k_peer_wait<<<1, 32, 0, c->L->st>>>(c->peer, slot, value, src_mask, tmo);
     return check_launch(c, 1, "peer_wait");
 }
@@ -941,6 +943,7 @@ extern "C" int nlk_peer_push(nlk_ctx *c, size_t off, size_t bytes, unsigned int 
         c->side_pending = true;
         return NLK_OK;
     }
+    ProfScope ps(c, NLK_K_PEER_PUSH);
     const int cnt = (int)(c->cnt_rot++ & 7);
     const bool v16 = (off % 16 == 0) && (bytes % 16 == 0);
     const size_t n = v16 ? bytes / 16 : bytes / 4;
@@ -960,6 +963,7 @@ extern "C" int nlk_peer_push_add(nlk_ctx *c, size_t off, size_t bytes, int peer,
     if (int r = peer_ok(c, off, bytes, 1u << peer)) return r;
     if (slot >= PEER_SLOTS || bytes % 4) return set_err(NLK_ERR_PARAM, "bad push_add request");
     if (peer == c->peer.rank) return set_err(NLK_ERR_PARAM, "push_add to oneself");
+    ProfScope ps(c, NLK_K_PEER_PUSH);
     const int cnt = (int)(c->cnt_rot++ & 7);
     const size_t n = bytes / 4;
     const bool v4 = (off % 16 == 0) && (n % 4 == 0);

@@ -190,6 +190,12 @@ static float *read_png(const buf_t *b, int *w, int *h, int *c)
     case 6: spp = 4; break;
     default: free(z); fail("bad PNG colour type %d", ctype); return NULL;
     }
+    /* bit depths of the PNG specification per colour type (palette indices need <= 8 bits) */
+    const int depth_ok = ctype == 0 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)
+                       : ctype == 3 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8)
+                                    : (depth == 8 || depth == 16);
+    if (!depth_ok) { free(z); fail("bad PNG bit depth %d for colour type %d", depth, ctype); return NULL; }
+    if (W > 65535u || H > 65535u) { free(z); fail("PNG larger than 65535 pixels a side"); return NULL; }
     const size_t bits = (size_t)spp * depth, stride = (W * bits + 7) / 8, bpp = bits >= 8 ? bits / 8 : 1;
     uLongf rawn = (uLongf)((stride + 1) * H);
     uint8_t *raw = (uint8_t *)malloc(rawn);
@@ -383,8 +389,9 @@ static float *read_tiff(const buf_t *b, int *w, int *h, int *c)
         return NULL;
     }
     if (!(bits == 8 || bits == 16 || bits == 32 || bits == 64) || (bits == 64 && fmt != 3) || pred > 2 ||
-        (pred == 2 && fmt == 3)) {
-        fail("unsupported TIFF sample type (%u bits, format %u, predictor %u)", bits, fmt, pred);
+        (pred == 2 && fmt == 3) || (fmt == 3 && bits < 32) || (pred == 2 && spp > 16) || rps == 0 ||
+        spp == 0 || spp > 64 || W > 65535u || H > 65535u) {
+        fail("unsupported TIFF sample type or geometry (%u bits, format %u, predictor %u, %u samples, %u rows per strip)", bits, fmt, pred, spp, rps);
         return NULL;
     }
     if (rps > H) rps = H;
@@ -424,7 +431,7 @@ static float *read_tiff(const buf_t *b, int *w, int *h, int *c)
                 continue;
             }
             uint32_t u = (uint32_t)v;
-            if (pred == 2 && spp <= 16) {   /* horizontal differencing, per sample, modulo 2^bits */
+            if (pred == 2) {   /* horizontal differencing, per sample, modulo 2^bits (spp <= 16 checked above) */
                 const uint32_t ch = i % spp;
                 if (i >= spp) u += acc[ch];
                 if (bits < 32) u &= (1u << bits) - 1u;

@@ -47,7 +47,7 @@ void *nlk_ctx_stream(nlk_ctx *ctx);
  * the stream, then fills ms_sum / count, both [NLK_KERNEL_COUNT][NLK_PASS_KINDS], with
  * the summed durations and the launch-group counts since the last collection. */
 enum { NLK_K_COLOUR = 0, NLK_K_WARP, NLK_K_VALID, NLK_K_SEARCH, NLK_K_RESOLVE, NLK_K_GROUP,
-       NLK_K_NORMALIZE, NLK_K_MEMSET, NLK_KERNEL_COUNT };
+       NLK_K_NORMALIZE, NLK_K_MEMSET, NLK_K_PEER_WAIT, NLK_K_PEER_PUSH, NLK_KERNEL_COUNT };
 enum { NLK_PASS_FLT1_T = 0, /* filter, previous frame given, no basic estimate */
        NLK_PASS_FLT1_X,     /* filter, no previous frame, no basic estimate  */
        NLK_PASS_FLT2_T,     /* filter with basic estimate, previous frame given */

@@ -198,3 +198,52 @@ def test_smo_and_seq_option_tables():
         assert opt in r.stdout, opt
     r = _run("nlkalman-seq", "--f1_p", "0")
     assert r.returncode == 1 and "f1_p == 0" in r.stderr
+
+
+def test_decoders_reject_malformed_headers(io, tmp_path):
+    """header fields are not trusted: zero rows per strip, float samples narrower than 32 bits, PNG bit
+    depths outside the specification (a 16-bit "palette" image would index past the palette)"""
+    import zlib
+    from PIL import Image
+    a = (np.arange(12 * 9, dtype=np.uint8).reshape(9, 12) * 2)
+    tif = tmp_path / "ok.tif"
+    Image.fromarray(a).save(tif)
+    assert np.array_equal(io.read(tif)[..., 0], a.astype(np.float32))
+    raw = bytearray(open(tif, "rb").read())
+    assert raw[:2] == b"II"
+    ifd = struct.unpack_from("<I", raw, 4)[0]
+    n = struct.unpack_from("<H", raw, ifd)[0]
+
+    def patched(tag, value):
+        out = bytearray(raw)
+        for k in range(n):
+            off = ifd + 2 + 12 * k
+            if struct.unpack_from("<H", out, off)[0] == tag:
+                typ = struct.unpack_from("<H", out, off + 2)[0]
+                struct.pack_into("<H" if typ == 3 else "<I", out, off + 8, value)
+                return out
+        # tag absent: overwrite the last entry (a resolution tag nobody reads)
+        off = ifd + 2 + 12 * (n - 1)
+        struct.pack_into("<HHII", out, off, tag, 3, 1, value)
+        return out
+    for tag, value in ((278, 0), (339, 3)):          # RowsPerStrip = 0; SampleFormat = float with 8-bit samples
+        bad = tmp_path / f"bad{tag}.tif"
+        open(bad, "wb").write(patched(tag, value))
+        with pytest.raises(IOError):
+            io.read(bad)
+
+    def png(depth, ctype, w=4, h=2):
+        def chunk(t, d):
+            return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+        rowb = (w * depth * {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[ctype] + 7) // 8
+        body = zlib.compress(b"".join(b"\x00" + bytes(rowb) for _ in range(h)))
+        return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0)) +
+                (chunk(b"PLTE", bytes(6)) if ctype == 3 else b"") + chunk(b"IDAT", body) + chunk(b"IEND", b""))
+    good = tmp_path / "g.png"
+    open(good, "wb").write(png(8, 0))
+    assert io.read(good).shape == (2, 4, 1)
+    for depth, ctype in ((16, 3), (3, 0), (4, 2), (32, 0)):
+        bad = tmp_path / f"bad_{depth}_{ctype}.png"
+        open(bad, "wb").write(png(depth, ctype))
+        with pytest.raises(IOError):
+            io.read(bad)

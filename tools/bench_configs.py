@@ -50,9 +50,6 @@ def run_config(name, w, h, ch, sigma, over, smooth, nseq, nframes, reps):
 
     sequence()
     torch.cuda.synchronize()
-    for c in ctxs:
-        c.profile(True)
-        c.profile_collect()
     l0 = sum(c.launches for c in ctxs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -63,20 +60,30 @@ def run_config(name, w, h, ch, sigma, over, smooth, nseq, nframes, reps):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    prof = {}
-    for c in ctxs:
-        for k, (t, n) in c.profile_collect().items():
-            a = prof.setdefault(k, [0.0, 0])
-            a[0] += t
-            a[1] += n
+    launches = sum(c.launches for c in ctxs) - l0
+    # per-kernel durations: ONE sequence, IN ORDER on one stream (nlk_seq_filter_dev), CUDA events around
+    # every kernel -- in the timed leg above the lanes / sequences overlap, and an event pair around a
+    # kernel would also time whatever shares the GPU with it
+    c = ctxs[0]
+    c.profile(True)
+    c.profile_collect()
+    c.seq_reset()
+    for t in range(nframes):
+        c.seq_filter_dev(frames[t], bflo if t else None, occ if t else None, sigma, f1, f2, None, flt[0][t])
+    if smooth:
+        c.seq_smooth_start_dev(flt[0][-1])
+        for t in range(nframes - 2, -1, -1):
+            c.seq_smooth_dev(flt[0][t], fflo, occ, sigma, s1, out[0])
+    prof = {k: [t, n] for k, (t, n) in c.profile_collect().items()}
+    c.profile(False)
     kern = [{"kernel": k[0], "pass": k[1], "launches": n, "avg_ms": t / n} for k, (t, n) in
-            sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]]
+            sorted(prof.items(), key=lambda kv: -kv[1][0])[:10]]
     nfr = nframes * reps * nseq
     print(json.dumps({"config": name, "metric": "denoised Mpixel/s", "value": w * h * nfr / (ms * 1e-3) / 1e6,
                       "ms_per_frame": ms / nfr, "frame": [w, h, ch], "sigma": sigma, "sequences": nseq,
                       "frames_per_sequence": nframes, "smoother": bool(smooth),
                       "params": {"flt1": f1.as_dict(), "flt2": f2.as_dict(), "smo1": s1.as_dict()},
-                      "gpu_launches": sum(c.launches for c in ctxs) - l0, "kernels": kern}), flush=True)
+                      "gpu_launches": launches, "kernels_in_order": kern}), flush=True)
     for c in ctxs:
         c.close()
 

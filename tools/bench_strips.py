@@ -113,6 +113,23 @@ def measure(rank, world, lr, dist, w=3840, h=2160, sigma=10.0, nf=4, reps=2, war
     t = torch.tensor([ms, wall_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, wall_ms = float(t[0].item()), float(t[1].item())
+    # where a frame's time goes on this rank: one more sequence with CUDA events around every kernel of the
+    # context's stream (a device-side wait shows as its own duration: time spent waiting for a peer)
+    rk.ctx.profile(True)
+    rk.ctx.profile_collect()
+    barrier()
+    sequence()
+    prof = rk.ctx.profile_collect()
+    rk.ctx.profile(False)
+    phases = {}
+    for (kn, pk), (pms, cnt) in prof.items():
+        phases[kn] = phases.get(kn, 0.0) + pms / nf
+    ph = torch.tensor([phases.get(k, 0.0) for k in rk.ctx.KERNELS], dtype=torch.float64, device=dev)
+    ph_max, ph_min = ph.clone(), ph.clone()
+    dist.all_reduce(ph_max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ph_min, op=dist.ReduceOp.MIN)
+    res["phases_ms_per_frame_max_over_ranks"] = {k: round(float(v), 4) for k, v in zip(rk.ctx.KERNELS, ph_max.tolist())}
+    res["phases_ms_per_frame_min_over_ranks"] = {k: round(float(v), 4) for k, v in zip(rk.ctx.KERNELS, ph_min.tolist())}
     err = rk.ctx.peer_error() if transport == "peer" else 0
     e = torch.tensor([err], dtype=torch.int64, device=dev)
     dist.all_reduce(e, op=dist.ReduceOp.MAX)
