@@ -39,6 +39,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # lanes, copy streams and NCCL on their own hardware queues
 import statistics
 import subprocess
 import sys

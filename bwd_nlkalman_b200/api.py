@@ -96,6 +96,9 @@ def lib():
     L.nlk_warp_rows_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int]
     L.nlk_strip_search.argtypes = [vp, C.c_int, vp, vp, vp, C.c_float, Params, C.c_int, C.c_int, vp, vp]
     L.nlk_strip_filter.argtypes = [vp]
+    L.nlk_strip_lane.argtypes = [vp, C.c_int, C.c_int]
+    L.nlk_lane_record.argtypes = [vp, C.c_int]
+    L.nlk_lane_wait.argtypes = [vp, C.c_int]
     L.nlk_strip_normalize.argtypes = [vp, vp, C.c_int, C.c_int]
     L.nlk_peer_header_bytes.restype = C.c_size_t
     L.nlk_peer_slab_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
@@ -328,6 +331,15 @@ class Context:
 
     def strip_filter(self):
         _check(lib().nlk_strip_filter(self._h))
+
+    def strip_lane(self, lane: int, reserve_sm: int = 0):
+        _check(lib().nlk_strip_lane(self._h, int(lane), int(reserve_sm)))
+
+    def lane_record(self, idx: int):
+        _check(lib().nlk_lane_record(self._h, int(idx)))
+
+    def lane_wait(self, idx: int):
+        _check(lib().nlk_lane_wait(self._h, int(idx)))
 
     def strip_normalize(self, out, row0, row1):
         _check(lib().nlk_strip_normalize(self._h, _vp(out), int(row0), int(row1)))

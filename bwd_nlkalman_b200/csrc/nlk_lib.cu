@@ -152,16 +152,19 @@ struct nlk_ctx {
     cudaEvent_t ev_up[PIPE_SETS] = {}, ev_o1[PIPE_SETS] = {}, ev_o2[PIPE_SETS] = {}, ev_done[PIPE_SETS] = {};
     long long p_frames = 0;
     // strip-sharded pass in flight (nlk_strip_search .. nlk_strip_normalize)
-    PassParams strip_P;
-    bool strip_open = false;
+    PassParams strip_Ps[2];
+    bool strip_opens[2] = {false, false};
+    int strip_lane = 0;                        // lane the strip / peer / row-range calls queue on (nlk_strip_lane)
+    int strip_reserve = 0;                     // SMs group_filter leaves to the other lane's mask_resolve
+    cudaEvent_t ev_lane[8] = {};               // cross-lane dependencies of the caller's schedule
     // peer-memory exchanges between the strips' GPUs (nlk_peer_*)
     PeerTable peer;
     bool peer_on = false;
     size_t slab_bytes = 0;
     std::vector<void *> ipc_opened;
-    cudaStream_t st_side = nullptr;            // whole-strip pushes (copy engines) beside the next pass
-    cudaEvent_t ev_side_fork = nullptr, ev_side_done = nullptr;
-    bool side_pending = false;
+    cudaStream_t st_sides[2] = {nullptr, nullptr};   // whole-strip pushes (copy engines) beside the next pass, per lane
+    cudaEvent_t ev_side_forks[2] = {nullptr, nullptr}, ev_side_dones[2] = {nullptr, nullptr};
+    bool side_pendings[2] = {false, false};
     unsigned int cnt_rot = 0;
     // optional per-kernel timing with CUDA events on the stream of the lane in use
     bool prof = false;
@@ -327,9 +330,12 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     }
     if (c->st_h2d) cudaStreamDestroy(c->st_h2d);
     if (c->st_d2h) cudaStreamDestroy(c->st_d2h);
-    if (c->st_side) { cudaStreamSynchronize(c->st_side); cudaStreamDestroy(c->st_side); }
-    if (c->ev_side_fork) cudaEventDestroy(c->ev_side_fork);
-    if (c->ev_side_done) cudaEventDestroy(c->ev_side_done);
+    for (int i = 0; i < 2; ++i) {
+        if (c->st_sides[i]) { cudaStreamSynchronize(c->st_sides[i]); cudaStreamDestroy(c->st_sides[i]); }
+        if (c->ev_side_forks[i]) cudaEventDestroy(c->ev_side_forks[i]);
+        if (c->ev_side_dones[i]) cudaEventDestroy(c->ev_side_dones[i]);
+    }
+    for (cudaEvent_t e : c->ev_lane) if (e) cudaEventDestroy(e);
     for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
     if (c->h_alpha) cudaFreeHost(c->h_alpha);
     for (int i = 0; i < nlk_ctx::PIPE_SETS; ++i) c->p_msk8[i].release();
@@ -356,13 +362,52 @@ static int enter(nlk_ctx *c)   // public entry points outside the pipelined recu
     return lanes_join(c);
 }
 
+// entry points of the strip-sharded pass: queued on the lane chosen with nlk_strip_lane.  Lane 1 is
+// used by callers that run the two filterings of a frame as two pipelines (as the single-GPU
+// recursion does); their cross-lane order is the caller's (nlk_lane_record / nlk_lane_wait).
+static int enter_strip(nlk_ctx *c)
+{
+    if (!c) return set_err(NLK_ERR_PARAM, "null context");
+    if (c->strip_lane == 0) return enter(c);
+    if (int r = ctx_use(c)) return r;
+    c->L = &c->lane[1];
+    return NLK_OK;
+}
+
+extern "C" int nlk_strip_lane(nlk_ctx *c, int lane, int reserve_sm)
+{
+    if (!c || lane < 0 || lane > 1 || reserve_sm < 0 || reserve_sm > 8) return set_err(NLK_ERR_PARAM, "bad lane request");
+    c->strip_lane = lane;
+    c->strip_reserve = reserve_sm;
+    return NLK_OK;
+}
+
+extern "C" int nlk_lane_record(nlk_ctx *c, int idx)
+{
+    if (int r = enter_strip(c)) return r;
+    if (idx < 0 || idx >= 8) return set_err(NLK_ERR_PARAM, "lane event %d", idx);
+    if (!c->ev_lane[idx]) CU_TRY(cudaEventCreateWithFlags(&c->ev_lane[idx], cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(c->ev_lane[idx], c->L->st));
+    return NLK_OK;
+}
+
+extern "C" int nlk_lane_wait(nlk_ctx *c, int idx)
+{
+    if (int r = enter_strip(c)) return r;
+    if (idx < 0 || idx >= 8) return set_err(NLK_ERR_PARAM, "lane event %d", idx);
+    if (!c->ev_lane[idx]) return NLK_OK;       // never recorded: nothing to wait for
+    CU_TRY(cudaStreamWaitEvent(c->L->st, c->ev_lane[idx], 0));
+    return NLK_OK;
+}
+
 extern "C" int nlk_ctx_sync(nlk_ctx *c)
 {
     if (int r = ctx_use(c)) return r;
     if (int r = lanes_join(c)) return r;
     CU_TRY(cudaStreamSynchronize(c->lane[0].st));
+    CU_TRY(cudaStreamSynchronize(c->lane[1].st));
     if (c->st_d2h) CU_TRY(cudaStreamSynchronize(c->st_d2h));
-    if (c->st_side) CU_TRY(cudaStreamSynchronize(c->st_side));
+    for (int i = 0; i < 2; ++i) if (c->st_sides[i]) CU_TRY(cudaStreamSynchronize(c->st_sides[i]));
     return NLK_OK;
 }
 
@@ -728,7 +773,7 @@ static int rows_ok(nlk_ctx *c, int row0, int row1)
 
 extern "C" int nlk_colour_rows_dev(nlk_ctx *c, float *d_dst, const float *d_src, int inverse, int row0, int row1)
 {
-    if (int r = enter(c)) return r;
+    if (int r = enter_strip(c)) return r;
     if (int r = rows_ok(c, row0, row1)) return r;
     const size_t off = (size_t)row0 * c->w * c->ch;
     const long npix = (long)(row1 - row0) * c->w;
@@ -744,7 +789,7 @@ extern "C" int nlk_colour_rows_dev(nlk_ctx *c, float *d_dst, const float *d_src,
 extern "C" int nlk_warp_rows_dev(nlk_ctx *c, float *d_imw, const float *d_im, const float *d_of,
                                  const float *d_msk, int row0, int row1)
 {
-    if (int r = enter(c)) return r;
+    if (int r = enter_strip(c)) return r;
     if (int r = rows_ok(c, row0, row1)) return r;
     ProfScope ps(c, NLK_K_WARP);
     return check_launch(c, launch_warp(d_imw, d_im, d_of, d_msk, c->w, c->h, c->ch, row0, row1, c->L->st), "warp_rows");
@@ -786,39 +831,44 @@ extern "C" int nlk_strip_search(nlk_ctx *c, int smooth, const float *d_in1, cons
                                 const float *d_bsic1, float sigma, struct nlkalman_params prms,
                                 int gy0, int gy1, unsigned int *d_nbr, float *d_accw)
 {
-    if (int r = enter(c)) return r;
+    if (int r = enter_strip(c)) return r;
     if (!d_nbr || !d_accw) return set_err(NLK_ERR_PARAM, "the strip pass needs the caller's bitmap and accumulator buffers");
-    PassParams &P = c->strip_P;
-    c->strip_open = false;
+    PassParams &P = c->strip_Ps[c->strip_lane];
+    c->strip_opens[c->strip_lane] = false;
     if (int r = pass_setup(c, P, smooth, nullptr, d_in1, d_prev0, d_bsic1, sigma, prms, false, d_nbr, d_accw)) return r;
     if (gy0 < 0 || gy1 > P.gh || gy1 < gy0) return set_err(NLK_ERR_PARAM, "grid rows [%d,%d) outside 0..%d", gy0, gy1, P.gh);
     P.gy0 = gy0; P.gy1 = gy1;
     KindScope ks(c, pass_kind(P));
     if (int r = pass_search(c, P)) return r;
-    c->strip_open = true;
+    c->strip_opens[c->strip_lane] = true;
     return NLK_OK;
 }
 
 extern "C" int nlk_strip_filter(nlk_ctx *c)
 {
-    if (int r = enter(c)) return r;
-    if (!c->strip_open) return set_err(NLK_ERR_STATE, "nlk_strip_search must come first");
-    KindScope ks(c, pass_kind(c->strip_P));
-    return pass_filter(c, c->strip_P, true);
+    if (int r = enter_strip(c)) return r;
+    if (!c->strip_opens[c->strip_lane]) return set_err(NLK_ERR_STATE, "nlk_strip_search must come first");
+    PassParams &P = c->strip_Ps[c->strip_lane];
+    KindScope ks(c, pass_kind(P));
+    c->reserve_sm = c->strip_reserve;
+    const int r = pass_filter(c, P, true);
+    c->reserve_sm = 0;
+    return r;
 }
 
 extern "C" int nlk_strip_normalize(nlk_ctx *c, float *d_out, int row0, int row1)
 {
-    if (int r = enter(c)) return r;
-    if (!c->strip_open) return set_err(NLK_ERR_STATE, "nlk_strip_search must come first");
+    if (int r = enter_strip(c)) return r;
+    const int ln = c->strip_lane;
+    if (!c->strip_opens[ln]) return set_err(NLK_ERR_STATE, "nlk_strip_search must come first");
     if (int r = rows_ok(c, row0, row1)) return r;
-    c->strip_P.out = d_out;
-    if (c->side_pending) {      // the previous frame buffer's whole-strip push reads what this may overwrite
-        CU_TRY(cudaStreamWaitEvent(c->L->st, c->ev_side_done, 0));
-        c->side_pending = false;
+    c->strip_Ps[ln].out = d_out;
+    if (c->side_pendings[ln]) {      // the previous frame buffer's whole-strip push reads what this may overwrite
+        CU_TRY(cudaStreamWaitEvent(c->L->st, c->ev_side_dones[ln], 0));
+        c->side_pendings[ln] = false;
     }
-    KindScope ks(c, pass_kind(c->strip_P));
-    return pass_normalize(c, c->strip_P, row0, row1);
+    KindScope ks(c, pass_kind(c->strip_Ps[ln]));
+    return pass_normalize(c, c->strip_Ps[ln], row0, row1);
 }
 
 // ---- peer-memory exchanges between strips (nlk_peer.cuh) ---------------------------------------
@@ -871,10 +921,11 @@ extern "C" int nlk_peer_bind(nlk_ctx *c, int rank, int nranks, void *const *slab
     }
     c->peer.rank = rank; c->peer.nranks = nranks;
     c->slab_bytes = slab_bytes;
-    if (!c->st_side) {
-        CU_TRY(cudaStreamCreateWithFlags(&c->st_side, cudaStreamNonBlocking));
-        CU_TRY(cudaEventCreateWithFlags(&c->ev_side_fork, cudaEventDisableTiming));
-        CU_TRY(cudaEventCreateWithFlags(&c->ev_side_done, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        if (c->st_sides[i]) continue;
+        CU_TRY(cudaStreamCreateWithFlags(&c->st_sides[i], cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_side_forks[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_side_dones[i], cudaEventDisableTiming));
     }
     c->peer_on = true;
     return NLK_OK;
@@ -890,7 +941,7 @@ static int peer_ok(nlk_ctx *c, size_t off, size_t bytes, unsigned int mask)
 
 extern "C" int nlk_peer_signal(nlk_ctx *c, int slot, unsigned int value, unsigned int peer_mask)
 {
-    if (int r = enter(c)) return r;
+    if (int r = enter_strip(c)) return r;
     if (int r = peer_ok(c, 0, 0, peer_mask)) return r;
     if (slot < 0 || slot >= PEER_SLOTS) return set_err(NLK_ERR_PARAM, "flag slot %d", slot);
     if (!peer_mask) return NLK_OK;
@@ -901,7 +952,7 @@ extern "C" int nlk_peer_signal(nlk_ctx *c, int slot, unsigned int value, unsigne
 
 extern "C" int nlk_peer_wait(nlk_ctx *c, int slot, unsigned int value, unsigned int src_mask)
 {
-    if (int r = enter(c)) return r;
+    if (int r = enter_strip(c)) return r;
     if (int r = peer_ok(c, 0, 0, src_mask)) return r;
     if (slot < 0 || slot >= PEER_SLOTS) return set_err(NLK_ERR_PARAM, "flag slot %d", slot);
     if (!src_mask) return NLK_OK;
@@ -919,32 +970,34 @@ extern "C" int nlk_peer_wait(nlk_ctx *c, int slot, unsigned int value, unsigned 
 extern "C" int nlk_peer_push(nlk_ctx *c, size_t off, size_t bytes, unsigned int peer_mask, int slot,
                              unsigned int value, int side)
 {
-    if (int r = enter(c)) return r;
+    if (int r = enter_strip(c)) return r;
     if (int r = peer_ok(c, off, bytes, peer_mask)) return r;
     if (slot >= PEER_SLOTS) return set_err(NLK_ERR_PARAM, "flag slot %d", slot);
     peer_mask &= ~(1u << c->peer.rank);
     if (!peer_mask) return NLK_OK;
     if (side) {
-        CU_TRY(cudaEventRecord(c->ev_side_fork, c->L->st));
-        CU_TRY(cudaStreamWaitEvent(c->st_side, c->ev_side_fork, 0));
+        const int ln = c->strip_lane;
+        cudaStream_t st_side = c->st_sides[ln];
+        CU_TRY(cudaEventRecord(c->ev_side_forks[ln], c->L->st));
+        CU_TRY(cudaStreamWaitEvent(st_side, c->ev_side_forks[ln], 0));
         const char *src = c->peer.slab[c->peer.rank] + off;
         // nearest ranks first: they read the rows soonest
         for (int d = 1; d < c->peer.nranks; ++d)
             for (int sgn = -1; sgn <= 1; sgn += 2) {
                 const int p = c->peer.rank + sgn * d;
                 if (p < 0 || p >= c->peer.nranks || !((peer_mask >> p) & 1u)) continue;
-                if (bytes) CU_TRY(cudaMemcpyAsync(c->peer.slab[p] + off, src, bytes, cudaMemcpyDeviceToDevice, c->st_side));
+                if (bytes) CU_TRY(cudaMemcpyAsync(c->peer.slab[p] + off, src, bytes, cudaMemcpyDeviceToDevice, st_side));
             }
         if (slot >= 0) {
-            k_peer_signal<<<1, 32, 0, c->st_side>>>(c->peer, slot, value, peer_mask);
+            k_peer_signal<<<1, 32, 0, st_side>>>(c->peer, slot, value, peer_mask);
             if (int r = check_launch(c, 1, "peer_signal")) return r;
         }
-        CU_TRY(cudaEventRecord(c->ev_side_done, c->st_side));
-        c->side_pending = true;
+        CU_TRY(cudaEventRecord(c->ev_side_dones[ln], st_side));
+        c->side_pendings[ln] = true;
         return NLK_OK;
     }
     ProfScope ps(c, NLK_K_PEER_PUSH);
-    const int cnt = (int)(c->cnt_rot++ & 7);
+    const int cnt = (int)(c->cnt_rot++ & 3) + 4 * c->strip_lane;
     const bool v16 = (off % 16 == 0) && (bytes % 16 == 0);
     const size_t n = v16 ? bytes / 16 : bytes / 4;
     if (bytes % 4) return set_err(NLK_ERR_PARAM, "push of %zu bytes: not a multiple of 4", bytes);
@@ -958,13 +1011,13 @@ extern "C" int nlk_peer_push(nlk_ctx *c, size_t off, size_t bytes, unsigned int 
 
 extern "C" int nlk_peer_push_add(nlk_ctx *c, size_t off, size_t bytes, int peer, int slot, unsigned int value)
 {
-    if (int r = enter(c)) return r;
+    if (int r = enter_strip(c)) return r;
     if (peer < 0 || peer >= PEER_MAX) return set_err(NLK_ERR_PARAM, "peer %d", peer);
     if (int r = peer_ok(c, off, bytes, 1u << peer)) return r;
     if (slot >= PEER_SLOTS || bytes % 4) return set_err(NLK_ERR_PARAM, "bad push_add request");
     if (peer == c->peer.rank) return set_err(NLK_ERR_PARAM, "push_add to oneself");
     ProfScope ps(c, NLK_K_PEER_PUSH);
-    const int cnt = (int)(c->cnt_rot++ & 7);
+    const int cnt = (int)(c->cnt_rot++ & 3) + 4 * c->strip_lane;
     const size_t n = bytes / 4;
     const bool v4 = (off % 16 == 0) && (n % 4 == 0);
     int nb = (int)(((v4 ? n / 4 : n) + 255) / 256);
@@ -980,7 +1033,6 @@ extern "C" int nlk_peer_error(nlk_ctx *c, unsigned int *code)
 {
     if (int r = nlk_ctx_sync(c)) return r;
     if (!c->peer_on) return set_err(NLK_ERR_STATE, "nlk_peer_bind must come first");
-    if (c->st_side) CU_TRY(cudaStreamSynchronize(c->st_side));
     CU_TRY(cudaMemcpy(code, c->peer.slab[c->peer.rank] + PEER_ERR_OFF, 4, cudaMemcpyDeviceToHost));
     return NLK_OK;
 }

@@ -148,13 +148,18 @@ class StripRank:
     """
 
     # flag slots of the peer transport (include/nlkalman_b200.h: nlk_peer_wait)
-    SLOT_SEARCH, SLOT_ACC, SLOT_HALO, SLOT_FRAME = 0, 1, 8, 16      # HALO + b, FRAME + b for frame buffer b
+    SLOT_SEARCH, SLOT_ACC, SLOT_HALO, SLOT_FRAME = 0, 1, 8, 16      # SEARCH / ACC + 2 * lane; HALO + b, FRAME + b for frame buffer b
 
-    def __init__(self, w, h, ch, rank, nranks, device=0, transport="nccl"):
+    def __init__(self, w, h, ch, rank, nranks, device=0, transport="nccl", lanes=1):
         import torch
         self.torch = torch
         self.w, self.h, self.ch, self.rank, self.nranks = w, h, ch, rank, nranks
         self.transport = transport
+        # lanes = 2 (peer transport): the two filterings of a frame as two pipelines on two streams, the
+        # second filtering of frame t beside the first of frame t+1 -- what nlk_seq_submit_dev does on
+        # one GPU; a lane that waits for a peer's flag leaves the GPU to the other lane
+        self.lanes, self.lane = lanes, 0
+        assert lanes == 1 or (lanes == 2 and transport == "peer"), "two lanes need the peer transport"
         self.ctx = api.Context(w, h, ch, device)
         self.dev = torch.device("cuda", device)
         self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
@@ -166,11 +171,14 @@ class StripRank:
         elif transport != "nccl":
             raise ValueError(transport)
         self.noisy, self.warp, self.tmp = self.frame(local=True), self.frame(local=True), self.frame(local=True)
+        self.noisy_l = [self.noisy, self.frame(local=True)] if lanes == 2 else [self.noisy, self.noisy]
+        self.warp_l = [self.warp, self.frame(local=True)] if lanes == 2 else [self.warp, self.warp]
         self.flt1, self.flt2 = [self.frame(), self.frame()], [self.frame(), self.frame()]
         self.smo = [self.frame(), self.frame()]
         if transport == "peer":
-            self.accw = self._view(self.off_accw, (h, w, ch + 1), "<f4")
-            self.nbr = self._view(self.off_nbr, (self.nbr_words,), "<i4")
+            self.accw_l = [self._view(o, (h, w, ch + 1), "<f4") for o in self.off_accw_l]
+            self.nbr_l = [self._view(o, (self.nbr_words,), "<i4") for o in self.off_nbr_l]
+            self.accw, self.nbr = self.accw_l[0], self.nbr_l[0]
         else:
             self.accw = torch.empty((h, w, ch + 1), dtype=torch.float32, device=self.dev)
             self.nbr = None
@@ -188,10 +196,13 @@ class StripRank:
         # bitmaps: one word per grid patch for any patch side >= 4 (step >= 2), whole chunks per rank
         self.nbr_words = (self.w // 2 + 1) * (self.h // 2 + 1 + self.nranks)
         off = al(api.lib().nlk_peer_header_bytes())
-        self.off_nbr = off
-        off = al(off + self.nbr_words * 4)
-        self.off_accw = off
-        off = al(off + self.h * self.w * (self.ch + 1) * 4)
+        self.off_nbr_l, self.off_accw_l = [], []
+        for _ in range(self.lanes):              # bitmaps and accumulator per lane
+            self.off_nbr_l.append(off)
+            off = al(off + self.nbr_words * 4)
+            self.off_accw_l.append(off)
+            off = al(off + self.h * self.w * (self.ch + 1) * 4)
+        self.off_nbr, self.off_accw = self.off_nbr_l[0], self.off_accw_l[0]
         self.off_frames = off
         self.n_slab_frames = 6
         self.slab_bytes = off + self.n_slab_frames * self.frame_bytes
@@ -236,11 +247,25 @@ class StripRank:
 
     def reset(self):
         self.cur, self.have_prev, self.have_flt2, self.smo_cur, self.have_smo = 0, False, False, 0, False
+        self.frames_done = 0
+        self._join_lanes()
+
+    def _set_lane(self, lane):
+        if self.lanes == 2:
+            self.lane = lane
+            self.ctx.strip_lane(lane, 1)       # group_filter leaves an SM to the other lane's mask_resolve
+
+    def _join_lanes(self):
+        """everything queued on lane 1 (second filterings) before what lane 0 queues next"""
+        if self.lanes == 2:
+            self._set_lane(0)
+            self.ctx.lane_wait(2)
+            self.ctx.lane_wait(3)
 
     def close(self):
         if self.slab:
             self.ctx.sync()
-            self.accw = self.nbr = None
+            self.accw = self.nbr = self.accw_l = self.nbr_l = None
             self.flt1 = self.flt2 = self.smo = None
             self._full.clear()
             self.ctx.dev_free(self.slab)
@@ -266,11 +291,11 @@ class StripRank:
     def _await(self, slot, mask):
         """queue a device-side wait for the latest sequence number of `slot` from `mask` (once)"""
         v = self.seq.get(slot, 0)
-        if v == 0 or mask == 0 or self.waited.get((slot, mask), 0) >= v:
+        if v == 0 or mask == 0 or self.waited.get((self.lane, slot, mask), 0) >= v:
             return
         yield ("sync",)
         self.ctx.peer_wait(slot, v, mask)
-        self.waited[(slot, mask)] = v
+        self.waited[(self.lane, slot, mask)] = v
 
     def need_frame(self, buf, key):
         """before reading rows of `buf` that OTHER strips produced, anywhere in the frame"""
@@ -336,24 +361,27 @@ class StripRank:
         words = n * p.chunk_g * p.gw * p.nbw
         if words > self.nbr_words:
             raise api.NlkError(f"peer transport: {words} bitmap words exceed the slab's {self.nbr_words}")
-        ctx.strip_search(smooth, in1, prev0, bsic1, sigma, prms, p.gy0, p.gy1, self.nbr, self.accw)
+        ln = self.lane
+        off_nbr, off_accw = self.off_nbr_l[ln], self.off_accw_l[ln]
+        SLOT_SEARCH, SLOT_ACC = self.SLOT_SEARCH + 2 * ln, self.SLOT_ACC + 2 * ln
+        ctx.strip_search(smooth, in1, prev0, bsic1, sigma, prms, p.gy0, p.gy1, self.nbr_l[ln], self.accw_l[ln])
         if n > 1:
             # (A) every rank has searched: its bitmap rows are here (when groups can mark other grid
             # cells), its accumulator rows are zeroed, and it is done reading the frame buffers that
             # the peers overwrite after this pass
             rmax = prms.search_sz_t if smooth else max(prms.search_sz_t, prms.search_sz_x)
-            v = self._next_seq(self.SLOT_SEARCH)
+            v = self._next_seq(SLOT_SEARCH)
             if prms.npatches_tagg > 1 and rmax // (prms.patch_sz // 2) >= 1:
                 rowb = p.gw * p.nbw * 4
-                ctx.peer_push(self.off_nbr + p.gy0 * rowb, (p.gy1 - p.gy0) * rowb, self._mask_all(), self.SLOT_SEARCH, v, 0)
+                ctx.peer_push(off_nbr + p.gy0 * rowb, (p.gy1 - p.gy0) * rowb, self._mask_all(), SLOT_SEARCH, v, 0)
             else:
-                ctx.peer_signal(self.SLOT_SEARCH, v, self._mask_all())
-            yield from self._await(self.SLOT_SEARCH, self._mask_all())
+                ctx.peer_signal(SLOT_SEARCH, v, self._mask_all())
+            yield from self._await(SLOT_SEARCH, self._mask_all())
         ctx.strip_filter()
         if n > 1:
             # (B) overlap-add: the rows this strip's groups aggregated into beyond its border go
             # straight into the owner's accumulator
-            v = self._next_seq(self.SLOT_ACC)
+            v = self._next_seq(SLOT_ACC)
             br = border_ranges(plans, rk)
             rowb = self.w * (self.ch + 1) * 4
             for key, peer in (("up_send", rk - 1), ("dn_send", rk + 1)):
@@ -361,10 +389,10 @@ class StripRank:
                     continue
                 if br[key]:
                     a, b = br[key]
-                    ctx.peer_push_add(self.off_accw + a * rowb, (b - a) * rowb, peer, self.SLOT_ACC, v)
+                    ctx.peer_push_add(off_accw + a * rowb, (b - a) * rowb, peer, SLOT_ACC, v)
                 else:
-                    ctx.peer_signal(self.SLOT_ACC, v, 1 << peer)
-            yield from self._await(self.SLOT_ACC, self._mask_nb())
+                    ctx.peer_signal(SLOT_ACC, v, 1 << peer)
+            yield from self._await(SLOT_ACC, self._mask_nb())
         ctx.strip_normalize(out, p.oy0, p.oy1)
         if n > 1:
             # (C) publish the strip: border rows to the neighbours at once (what the next pass of
@@ -398,34 +426,45 @@ class StripRank:
         ctx = self.ctx
         cur, prv = self.cur, self.cur ^ 1
         do2 = f2.patch_sz != 0
+        two = self.lanes == 2
+        noisy = self.noisy_l[cur if two else 0]
+        self._set_lane(0)
+        if two:
+            # lane 1 is done with this parity's noisy frame and first filtering (frame t-2)
+            ctx.lane_wait(2 + cur)
         e0, e1 = self._rows_needed(0, *([f1, f2] if do2 else [f1]))
-        ctx.colour_rows_dev(self.noisy, d_noisy, 0, e0, e1)
+        ctx.colour_rows_dev(noisy, d_noisy, 0, e0, e1)
         prev1 = None
         if self.have_prev:
             prev1 = self.flt1[prv]
             yield from self.need_frame(prev1, "flt1")   # the other strips of the previous frame (warp reads anywhere)
             if d_bflo is not None:
                 a, b = self._rows_needed(0, f1)
-                ctx.warp_rows_dev(self.warp, prev1, d_bflo, d_bocc, a, b)
-                prev1 = self.warp
-        plans = yield from self.strip_pass(0, self.flt1[cur], self.noisy, prev1, None, sigma, f1, key="flt1",
+                ctx.warp_rows_dev(self.warp_l[0], prev1, d_bflo, d_bocc, a, b)
+                prev1 = self.warp_l[0]
+        plans = yield from self.strip_pass(0, self.flt1[cur], noisy, prev1, None, sigma, f1, key="flt1",
                                            next_plans=self.plans(0, f2) if do2 else None)
         p = plans[self.rank]
         if d_out1 is not None:
             ctx.colour_rows_dev(d_out1, self.flt1[cur], 1, p.oy0, p.oy1)
+        if two:
+            ctx.lane_record(cur)                # first filtering of this frame queued: lane 1 may follow
         if do2:
+            if two:
+                self._set_lane(1)
+                ctx.lane_wait(cur)
             prev2 = None
             if self.have_prev and self.have_flt2:
                 prev2 = self.flt2[prv]
                 yield from self.need_frame(prev2, "flt2")
                 if d_bflo is not None:
                     a, b = self._rows_needed(0, f2)
-                    ctx.warp_rows_dev(self.warp, prev2, d_bflo, d_bocc, a, b)
-                    prev2 = self.warp
+                    ctx.warp_rows_dev(self.warp_l[1], prev2, d_bflo, d_bocc, a, b)
+                    prev2 = self.warp_l[1]
             nxt = self.plans(1, out2_for) if (out2_for is not None and d_out2 is not None) else None
             # the basic estimate on the rows beyond the strip
             yield from self.need_halo(self.flt1[cur], self._same_rows(plans, self.plans(0, f2)))
-            plans = yield from self.strip_pass(0, self.flt2[cur], self.noisy, prev2, self.flt1[cur], sigma, f2,
+            plans = yield from self.strip_pass(0, self.flt2[cur], noisy, prev2, self.flt1[cur], sigma, f2,
                                                key="flt2", next_plans=nxt)
             p = plans[self.rank]
             if d_out2 is not None:
@@ -433,10 +472,14 @@ class StripRank:
                 if nxt is not None:
                     yield from self.need_halo(self.flt2[cur], self._same_rows(plans, nxt))
                 ctx.colour_rows_dev(d_out2, self.flt2[cur], 1, min(a, p.oy0), max(b, p.oy1))
+        if two:
+            ctx.lane_record(2 + cur)            # this parity's buffers are free again once this has run
+            self._set_lane(0)
         self.have_prev, self.have_flt2, self.cur = True, do2, prv
 
     def last_filtered(self, d_out_rgb, second=True):
         """RGB of the whole most recent filtered frame on this rank (waits for its gather)."""
+        self._join_lanes()
         src = (self.flt2 if second else self.flt1)[self.cur ^ 1]
         yield from self.need_frame(src, "flt2" if second else "flt1")
         self.ctx.colour_rows_dev(d_out_rgb, src, 1, 0, self.h)
@@ -444,6 +487,7 @@ class StripRank:
     def smooth_start(self, d_last_rgb):
         """The last frame of a sequence is its own smoothed version (scripts/nlkalman-seq.sh:122-124).
         d_last_rgb: full frame, valid everywhere (see last_filtered)."""
+        self._join_lanes()
         self.ctx.colour_rows_dev(self.smo[0], d_last_rgb, 0, 0, self.h)
         self.smo_cur, self.have_smo = 0, True
         self.pending.pop("smo", None)
@@ -455,6 +499,7 @@ class StripRank:
         the filtered frame, valid on this rank's rows [ey0, ey1) of the smoothing plan."""
         ctx = self.ctx
         assert self.have_smo, "smooth_start must come first"
+        self._join_lanes()
         nxt, cur = self.smo_cur, self.smo_cur ^ 1
         a, b = self._rows_needed(1, s1)
         ctx.colour_rows_dev(self.tmp, d_flt_rgb, 0, a, b)

@@ -134,6 +134,16 @@ int nlk_strip_plan(int w, int h, int smooth, struct nlkalman_params prms, int nr
 int nlk_colour_rows_dev(nlk_ctx *ctx, float *d_dst, const float *d_src, int inverse, int row0, int row1);
 int nlk_warp_rows_dev(nlk_ctx *ctx, float *d_imw, const float *d_im, const float *d_of,
                       const float *d_msk, int row0, int row1);
+/* The strip calls, the row-range calls and the nlk_peer_* calls queue on lane 0 (the context's stream)
+ * or, after nlk_strip_lane(ctx, 1, ...), on lane 1 (second stream, own pass scratch): a caller can run
+ * the two filterings of a frame as two pipelines, the second filtering of frame t beside the first of
+ * frame t+1, as the single-GPU recursion does.  reserve_sm: SMs the persistent group_filter launch
+ * leaves free for the other lane's one-block mask_resolve.  Cross-lane order is the caller's:
+ * nlk_lane_record(ctx, i) records event i (0..7) on the current lane, nlk_lane_wait(ctx, i) makes the
+ * current lane wait for it.  nlk_ctx_sync waits for both lanes. */
+int nlk_strip_lane(nlk_ctx *ctx, int lane, int reserve_sm);
+int nlk_lane_record(nlk_ctx *ctx, int idx);
+int nlk_lane_wait(nlk_ctx *ctx, int idx);
 /* stage 1: zero accumulator rows, patch validity, block matching + k-NN for [gy0, gy1) */
 int nlk_strip_search(nlk_ctx *ctx, int smooth, const float *d_in1, const float *d_prev0,
                      const float *d_bsic1, float sigma, struct nlkalman_params prms,

@@ -23,13 +23,16 @@ def _scene(w, h, ch, sigma, nframes):
     return frames, synth.backward_flow(w, h), synth.forward_flow(w, h), occ
 
 
-@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("transport", ["peer2", "peer", "nccl"])
 @pytest.mark.parametrize("shape,nranks", [((101, 150, 3), 3), ((122, 96, 1), 2), ((90, 200, 3), 4)])
 def test_virtual_strips_match_single_context(nlk, shape, nranks, transport):
+    """peer2 = peer transport with the two filterings of a frame on two lanes (streams)"""
     import torch
     from bwd_nlkalman_b200 import strips
     w, h, ch = shape
-    sigma, nframes = 20.0, 3
+    lanes = 2 if transport == "peer2" else 1
+    transport = "peer" if transport == "peer2" else transport
+    sigma, nframes = 20.0, 5 if lanes == 2 else 3
     frames, bflo, fflo, occ = _scene(w, h, ch, sigma, nframes)
     f1, f2, s1 = (nlk.default_params(sigma, m) for m in (nlk.FLT1, nlk.FLT2, nlk.SMO1))
     dev = torch.device("cuda", 0)
@@ -52,10 +55,12 @@ def test_virtual_strips_match_single_context(nlk, shape, nranks, transport):
             ctx.sync()
             refs[t] = o1.cpu().numpy().copy()
 
-    ranks = [strips.StripRank(w, h, ch, r, nranks, 0, transport=transport) for r in range(nranks)]
+    ranks = [strips.StripRank(w, h, ch, r, nranks, 0, transport=transport, lanes=lanes) for r in range(nranks)]
     if transport == "peer":
         strips.bind_virtual(ranks)
     try:
+        # (distinct output buffers per frame: with two lanes the second filtering of a frame is still
+        # running when the next frame is queued)
         outs1 = [torch.zeros_like(d_frames[0]) for _ in ranks]
         outs2 = [torch.zeros_like(d_frames[0]) for _ in ranks]
 

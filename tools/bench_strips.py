@@ -21,6 +21,8 @@ import os
 import sys
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # lanes, side streams and NCCL on their own hardware queues
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 WORKLOAD = ("C4: 3840x2160 RGB sequence sigma=10, flt1+flt2 forward then RTS smoother backward, every pass in "
@@ -28,7 +30,7 @@ WORKLOAD = ("C4: 3840x2160 RGB sequence sigma=10, flt1+flt2 forward then RTS smo
 
 
 def measure(rank, world, lr, dist, w=3840, h=2160, sigma=10.0, nf=4, reps=2, warmup=1, transport="peer",
-            single_gpu_baseline=True):
+            single_gpu_baseline=True, lanes=None):
     import torch
     import bwd_nlkalman_b200 as nlk
     from bwd_nlkalman_b200 import strips, synth
@@ -90,7 +92,10 @@ def measure(rank, world, lr, dist, w=3840, h=2160, sigma=10.0, nf=4, reps=2, war
         return res
 
     # ---- N strips ---------------------------------------------------------------------------------
-    rk = strips.StripRank(w, h, ch, rank, world, lr, transport=transport)
+    if lanes is None:
+        lanes = 2 if transport == "peer" else 1
+    res["lanes"] = lanes
+    rk = strips.StripRank(w, h, ch, rank, world, lr, transport=transport, lanes=lanes)
     if transport == "peer":
         strips.bind_dist(rk)
 
@@ -152,12 +157,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--lanes", type=int, default=0, help="0: two for the peer transport, one for NCCL")
     a = ap.parse_args()
     rank, world, lr = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(lr)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    res = measure(rank, world, lr, dist, a.w, a.h, a.sigma, a.frames, a.reps, a.warmup, a.transport, not a.no_single)
+    res = measure(rank, world, lr, dist, a.w, a.h, a.sigma, a.frames, a.reps, a.warmup, a.transport, not a.no_single,
+                  a.lanes or None)
     if rank == 0:
         print(json.dumps(res))
     if world > 1:

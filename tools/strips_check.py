@@ -7,6 +7,7 @@ import argparse
 import os
 import sys
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # lanes, side streams and NCCL on their own hardware queues
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -24,6 +25,7 @@ def main():
     ap.add_argument("--frames", type=int, default=3)
     ap.add_argument("--sigma", type=float, default=20.0)
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--lanes", type=int, default=1, help="2: the two filterings of a frame on two streams (peer transport)")
     a = ap.parse_args()
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -34,10 +36,12 @@ def main():
     up = lambda x: torch.from_numpy(x).to(dev)
     frames = [up(synth.noisy_frame(w, h, ch, t, sigma)) for t in range(a.frames)]
     bflo, fflo, occ = up(synth.backward_flow(w, h)), up(synth.forward_flow(w, h)), up(synth.occlusion_mask(w, h))
-    rk = strips.StripRank(w, h, ch, rank, world, lr, transport=a.transport)
+    rk = strips.StripRank(w, h, ch, rank, world, lr, transport=a.transport, lanes=a.lanes)
     if a.transport == "peer":
         strips.bind_dist(rk)        # CUDA IPC handles of the slabs over torch.distributed, once
     o1, o2 = torch.zeros_like(frames[0]), torch.zeros_like(frames[0])
+    o1s = [torch.zeros_like(frames[0]) for _ in frames]
+    o2s = [torch.zeros_like(frames[0]) for _ in frames]
     p1, p2, ps = rk.plans(0, f1), rk.plans(0, f2), rk.plans(1, s1)
 
     def gathered(t, plans):
@@ -47,11 +51,14 @@ def main():
         rk.ctx.sync()
         return g
     got1, got2, gots = [], [], [None] * a.frames
+    # all frames queued back to back (no host synchronisation in between: with two lanes the second
+    # filtering of a frame runs beside the first of the next), then compared
     for t in range(a.frames):
-        strips.run_dist(rk, rk.filter_step(frames[t], bflo if t else None, occ if t else None, sigma, f1, f2, o1, o2))
-        rk.ctx.sync()
-        got1.append(gathered(o1, p1))
-        got2.append(gathered(o2, p2))
+        strips.run_dist(rk, rk.filter_step(frames[t], bflo if t else None, occ if t else None, sigma, f1, f2, o1s[t], o2s[t]))
+    rk.ctx.sync()
+    for t in range(a.frames):
+        got1.append(gathered(o1s[t], p1))
+        got2.append(gathered(o2s[t], p2))
     strips.run_dist(rk, rk.smooth_start(got2[-1]))
     gots[-1] = got2[-1]
     for t in range(a.frames - 2, -1, -1):
