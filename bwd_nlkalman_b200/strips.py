@@ -150,7 +150,7 @@ class StripRank:
     # flag slots of the peer transport (include/nlkalman_b200.h: nlk_peer_wait)
     SLOT_SEARCH, SLOT_ACC, SLOT_HALO, SLOT_FRAME = 0, 1, 8, 16      # SEARCH / ACC + 2 * lane; HALO + b, FRAME + b for frame buffer b
 
-    def __init__(self, w, h, ch, rank, nranks, device=0, transport="nccl", lanes=1):
+    def __init__(self, w, h, ch, rank, nranks, device=0, transport="nccl", lanes=1, ctx=None):
         import torch
         self.torch = torch
         self.w, self.h, self.ch, self.rank, self.nranks = w, h, ch, rank, nranks
@@ -160,9 +160,11 @@ class StripRank:
         # one GPU; a lane that waits for a peer's flag leaves the GPU to the other lane
         self.lanes, self.lane = lanes, 0
         assert lanes == 1 or (lanes == 2 and transport == "peer"), "two lanes need the peer transport"
-        self.ctx = api.Context(w, h, ch, device)
-        self.dev = torch.device("cuda", device)
-        self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
+        # ctx: a stand-in context that only records the calls (CPU tests of the schedule itself)
+        self.dry = ctx is not None
+        self.ctx = ctx if self.dry else api.Context(w, h, ch, device)
+        self.dev = torch.device("cpu") if self.dry else torch.device("cuda", device)
+        self.stream = None if self.dry else torch.cuda.ExternalStream(self.ctx.stream, device=self.dev)
         self._full = {}
         self._buf = {}                   # data_ptr of an exchanged frame buffer -> (index, slab offset)
         self.slab = 0
@@ -211,6 +213,9 @@ class StripRank:
 
     def _view(self, off, shape, typestr):
         """torch tensor over a range of the slab (CUDA array interface, no copy)"""
+        if self.dry:
+            return self.torch.empty(tuple(shape), dtype=self.torch.float32 if typestr == "<f4" else self.torch.int32)
+
         class _Mem:
             pass
         m = _Mem()

@@ -145,3 +145,150 @@ def test_border_ranges_are_mutually_consistent(nlk):
     assert b - a == rr + psz - step                      # rows below the last reference patch row
     a, b = strips.border_ranges(plans, 3)["up_send"]
     assert b - a == rr
+
+
+# ---- the peer-transport schedule itself, without a GPU ------------------------------------------
+# StripRank issues its exchanges as calls of the nlk_peer_* C ABI (asynchronous on a stream, waits on
+# the device).  With a stand-in context that only records the calls, the schedules of N ranks can be
+# replayed on the CPU as N x lanes in-order streams whose wait entries block until the flag they name
+# has been stored by the source rank: the test checks that the replay never dead-locks, that every
+# wait is matched by a push / signal of the same slot and sequence number addressed to the waiter,
+# and that the accumulator and frame ranges pushed are the ones the row plan prescribes.
+
+class _DryCtx:
+    KERNELS = []
+
+    def __init__(self, rank, log):
+        self.rank, self.log, self.lane = rank, log, 0
+
+    def _op(self, kind, **kw):
+        self.log.append(dict(kind=kind, rank=self.rank, lane=self.lane, **kw))
+
+    def peer_slab_alloc(self, nbytes):
+        return 0x10000
+
+    def peer_bind(self, rank, nranks, slabs, nbytes):
+        pass
+
+    def strip_lane(self, lane, reserve_sm=0):
+        self.lane = lane
+
+    def lane_record(self, idx):
+        self._op("record", idx=idx)
+
+    def lane_wait(self, idx):
+        self._op("lwait", idx=idx)
+
+    def peer_push(self, off, nbytes, mask, slot, value, side=0):
+        self._op("push", off=off, nbytes=nbytes, mask=mask, slot=slot, value=value, side=side)
+
+    def peer_push_add(self, off, nbytes, peer, slot, value):
+        self._op("push_add", off=off, nbytes=nbytes, mask=1 << peer, slot=slot, value=value)
+
+    def peer_signal(self, slot, value, mask):
+        self._op("signal", mask=mask, slot=slot, value=value)
+
+    def peer_wait(self, slot, value, mask):
+        self._op("wait", mask=mask, slot=slot, value=value)
+
+    def __getattr__(self, name):            # kernels and copies: recorded, nothing else
+        def f(*a, **k):
+            self._op(name)
+        return f
+
+
+def _replay(logs, nranks):
+    """in-order streams (rank, lane) with device-side waits; returns the number of executed ops"""
+    queues = {}
+    for r, log in enumerate(logs):
+        for op in log:
+            queues.setdefault((r, op["lane"]), []).append(op)
+    flags, events, done = {}, {}, 0
+    heads = {k: 0 for k in queues}
+    progress = True
+    while progress:
+        progress = False
+        for k, q in queues.items():
+            while heads[k] < len(q):
+                op = q[heads[k]]
+                if op["kind"] == "wait":
+                    if not all(flags.get((op["rank"], op["slot"], s), 0) >= op["value"]
+                               for s in range(nranks) if (op["mask"] >> s) & 1):
+                        break
+                elif op["kind"] == "lwait":
+                    want = op.get("need")          # the record this wait saw at issue time (None: never recorded)
+                    if want is not None and events.get((op["rank"], op["idx"]), 0) < want:
+                        break
+                elif op["kind"] == "record":
+                    events[(op["rank"], op["idx"])] = op["serial"]
+                elif op["kind"] in ("push", "push_add", "signal") and op["slot"] >= 0:
+                    for d in range(nranks):
+                        if (op["mask"] >> d) & 1 and d != op["rank"]:
+                            flags[(d, op["slot"], op["rank"])] = max(flags.get((d, op["slot"], op["rank"]), 0), op["value"])
+                heads[k] += 1
+                done += 1
+                progress = True
+    stuck = {k: q[heads[k]] for k, q in queues.items() if heads[k] < len(q)}
+    assert not stuck, f"dead-lock: {stuck}"
+    return done
+
+
+@pytest.mark.parametrize("nranks,lanes", [(2, 1), (3, 2), (8, 2), (8, 1)])
+def test_peer_schedule_replays_without_deadlock(nlk, nranks, lanes):
+    from bwd_nlkalman_b200 import strips
+    w, h, ch, sigma, nframes = 3840, 2160, 3, 10.0, 4
+    f1, f2, s1 = (nlk.default_params(sigma, m) for m in (nlk.FLT1, nlk.FLT2, nlk.SMO1))
+    logs = [[] for _ in range(nranks)]
+    ranks = [strips.StripRank(w, h, ch, r, nranks, transport="peer", lanes=lanes, ctx=_DryCtx(r, logs[r]))
+             for r in range(nranks)]
+    x = torch.empty(1)
+
+    def drive(gens):
+        gens = list(gens)
+        alive = [True] * len(gens)
+        while any(alive):
+            for i, g in enumerate(gens):
+                if alive[i]:
+                    try:
+                        assert next(g) == ("sync",)
+                    except StopIteration:
+                        alive[i] = False
+    for t in range(nframes):
+        drive(rk.filter_step(x, x if t else None, x if t else None, sigma, f1, f2, None, x, out2_for=s1) for rk in ranks)
+    drive(rk.last_filtered(x) for rk in ranks)
+    drive(rk.smooth_start(x) for rk in ranks)
+    for t in range(nframes - 2, -1, -1):
+        drive(rk.smooth_step(x, x, x, sigma, s1, x) for rk in ranks)
+    # cross-lane events: a wait refers to the latest record of that event issued before it on the rank
+    for log in logs:
+        serial, last = 0, {}
+        for op in log:
+            if op["kind"] == "record":
+                serial += 1
+                op["serial"] = serial
+                last[op["idx"]] = serial
+            elif op["kind"] == "lwait":
+                op["need"] = last.get(op["idx"])
+    n = _replay(logs, nranks)
+    assert n == sum(len(g) for g in logs)
+    # every wait has its producers: same slot, same sequence number, addressed to the waiter
+    for r, log in enumerate(logs):
+        for op in (o for o in log if o["kind"] == "wait"):
+            for s in range(nranks):
+                if (op["mask"] >> s) & 1:
+                    assert any(o["kind"] in ("push", "push_add", "signal") and o["slot"] == op["slot"] and
+                               o["value"] == op["value"] and (o["mask"] >> r) & 1 for o in logs[s]), (r, s, op)
+    # the overlap-add pushes are exactly the halo rows of the plan, into the two neighbours
+    p1 = ranks[0].plans(0, f1)
+    rowb = w * (ch + 1) * 4
+    for r, log in enumerate(logs):
+        adds = [o for o in log if o["kind"] == "push_add" and o["lane"] == 0]
+        want = set()
+        if r > 0 and p1[r].ey0 < p1[r].oy0:
+            want.add((1 << (r - 1), (p1[r].oy0 - p1[r].ey0) * rowb))
+        if r + 1 < nranks and p1[r].ey1 > p1[r].oy1:
+            want.add((1 << (r + 1), (p1[r].ey1 - p1[r].oy1) * rowb))
+        assert want <= {(o["mask"], o["nbytes"]) for o in adds}, (r, want)
+    # with two lanes the second filterings are queued on lane 1
+    if lanes == 2:
+        assert any(o["lane"] == 1 and o["kind"] == "strip_search" for o in logs[0])
