@@ -263,24 +263,18 @@ constexpr unsigned int RS_SENT = 0xffffffffu;   // published words only use bits
 constexpr int RS_Q = 8;                         // steps per unrolled loop body = prefetch distance of the packed blocks
 constexpr int RS_PAD = 2 * RS_Q;                // pad steps behind the last one (straight-line loop, no bounds tests)
 
-// both words of a ring slot (lanes 31 and, for R = 2, 30 of the producer), by every lane of the
-// consumer warp: one broadcast load, a warp-uniform spin, no divergence.  The spin is bounded: a
-// slot that never comes (a bug, not a state of the algorithm) raises *timeout and reads as zero
-// instead of hanging the GPU.
-template <int R>
-__device__ __forceinline__ uint2 ring_wait2(const volatile uint2 *slot, int *timeout)
+// A warp publishes its progress (ring slots written so far) every RS_G steps; the warp below checks it
+// once per RS_G steps -- a warp-uniform spin on one shared-memory word, bounded: a count that never
+// comes (a bug, not a state of the algorithm) raises *timeout instead of hanging the GPU -- and then
+// reads the slots with plain loads.
+constexpr int RS_G = 4;
+
+__device__ __forceinline__ void prog_wait(const volatile int *prog, int need, int *timeout)
 {
-    uint2 v;
     int spins = 0;
-    do {
-        v.x = slot->x;
-        v.y = R > 1 ? slot->y : 0u;
-        if (++spins > (1 << 22)) {
-            *timeout = 1;
-            return make_uint2(v.x == RS_SENT ? 0u : v.x, v.y == RS_SENT ? 0u : v.y);
-        }
-    } while (v.x == RS_SENT || v.y == RS_SENT);
-    return v;
+    while (*prog < need) {
+        if (++spins > (1 << 22)) { *timeout = 1; break; }
+    }
 }
 
 template <int R>
@@ -289,6 +283,7 @@ __global__ void __launch_bounds__(1024) k_resolve_sys(const PassParams P, int rw
                                                       int ring_len)
 {
     constexpr int C = RB_C, Q = RS_Q;
+    static_assert(Q % RS_G == 0, "progress granularity divides the loop body");
     extern __shared__ __align__(8) unsigned int s_dyn[];
     const int gw = P.gw, gh = P.gh;
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
@@ -298,14 +293,15 @@ __global__ void __launch_bounds__(1024) k_resolve_sys(const PassParams P, int rw
     unsigned int *s_act = s_dyn + (size_t)(nwarps + 1) * ring_len * 2;                  // [nthr][rw] active bits, bit 4b+c of row i
     int *s_base = reinterpret_cast<int *>(s_act + (size_t)nthr * rw);                  // [gh+1] row offsets
     __shared__ int s_part[1024];
+    __shared__ int s_prog[33];                                                          // slots published per warp
 
     if (*P.any_nbr == 0) return;   // k_resolve_pack filled the list
     constexpr int FW = C + 2 * R;
     static_assert(FW <= 8 && (C + R) * (R - 1) + FW <= 32 && 1 + C - 1 + R <= 8, "window / field layout");
     constexpr unsigned int fwmask = (1u << FW) - 1u, ownmask = ((1u << (R + C)) - 1u) << 1;
-    for (int x = tid; x < nwarps * ring_len; x += nthr) s_ring[x] = make_uint2(RS_SENT, RS_SENT);
-    for (int x = tid; x < ring_len; x += nthr) s_ring[(size_t)nwarps * ring_len + x] = make_uint2(0u, 0u);
+    for (int x = tid; x < (nwarps + 1) * ring_len; x += nthr) s_ring[x] = make_uint2(0u, 0u);
     for (int x = tid; x < nthr * rw; x += nthr) s_act[x] = 0u;
+    if (tid <= nwarps) s_prog[tid] = tid == nwarps ? 0x7fffffff : 0;
     __syncthreads();
 
     const int i = tid;                                  // lanes past the last row only see pad blocks
@@ -319,28 +315,35 @@ __global__ void __launch_bounds__(1024) k_resolve_sys(const PassParams P, int rw
     const int w_len = (i1 + (R * i1) / C + nb + 9 - w_first + 1 + Q - 1) / Q * Q;
     const int p0 = i0 - 32;
     const int pw_first = warp > 0 ? max(p0 + (R * p0) / C - 3, 0) : w_first - 1;   // ring slot of step s-1: s-1-pw_first
-    const volatile uint2 *ring_in = s_ring + (size_t)(warp > 0 ? warp - 1 : nwarps) * ring_len + (w_first - 1 - pw_first);
-    volatile unsigned int *ring_out = reinterpret_cast<unsigned int *>(s_ring + (size_t)warp * ring_len);
+    const int in_off = w_first - 1 - pw_first;
+    const int src_w = warp > 0 ? warp - 1 : nwarps;
+    const volatile uint2 *ring_in = s_ring + (size_t)src_w * ring_len + in_off;
+    const volatile int *prog_in = s_prog + src_w;
+    volatile unsigned int *ring_out = reinterpret_cast<unsigned int *>(s_ring + (size_t)warp * ring_len) + (31 - lane);
     const uint4 *pcol = pk + (size_t)w_first * nthr + i;     // pk[s][i]
     uint4 q[Q];             // blocks of steps s .. s+Q-1 (fetched Q steps ahead: an L2 round trip)
 #pragma unroll
-    for (int u = 0; u < Q; ++u) q[u] = pcol[(size_t)u * nthr];
-    pcol += (size_t)Q * nthr;
+    for (int u = 0; u < Q; ++u) { q[u] = *pcol; pcol += nthr; }
     unsigned int wnd = 0u, acc = 0u, mypub = 0u;
     unsigned int *act_row = s_act + (size_t)i * rw;
     const bool pub_lane = lane >= 32 - R;
-    const unsigned int sel0 = lane == 0 ? ~0u : 0u, sel1 = lane == 1 ? ~0u : 0u;
-    const int pub_word = 31 - lane;
+    const bool is0 = lane == 0, is1 = lane == 1;
     int b = w_first - sb;
     for (int j0 = 0; j0 < w_len; j0 += Q) {
 #pragma unroll
         for (int u = 0; u < Q; ++u) {
+            if (u % RS_G == 0) {
+                // the warp above has published the slots of the next RS_G steps (or is done: its
+                // remaining slots are zero, the initial value)
+                prog_wait(prog_in, in_off + j0 + u + RS_G, P.work + 2);   // (counters[4]: replay timeout flag)
+                __threadfence_block();
+            }
             // what the rows above published at step s-1: lanes 0 (and 1) take the warp above's
-            const uint2 pr = ring_wait2<R>(ring_in + j0 + u, P.work + 2);   // (counters[4]: replay timeout flag)
+            const uint2 pr = make_uint2(ring_in[j0 + u].x, R > 1 ? ring_in[j0 + u].y : 0u);
             unsigned int up1 = __shfl_up_sync(0xffffffffu, mypub, 1);
             unsigned int up2 = R > 1 ? __shfl_up_sync(0xffffffffu, mypub, 2) : 0u;
-            up1 = (pr.x & sel0) | (up1 & ~sel0);
-            if (R > 1) up2 = (pr.y & sel0) | (pr.x & sel1) | (up2 & ~(sel0 | sel1));
+            up1 = is0 ? pr.x : up1;
+            if (R > 1) { up2 = is1 ? pr.x : up2; up2 = is0 ? pr.y : up2; }
             const uint4 x = q[u];
             wnd |= (up1 >> 8) & m1;
             if (R > 1) wnd |= ((up2 >> 16) & m2) << (C + R);
@@ -355,20 +358,26 @@ __global__ void __launch_bounds__(1024) k_resolve_sys(const PassParams P, int rw
             mypub = ((x.x & ~(unsigned int)((int)(wnd << 31) >> 31)) | (x.y & ~(unsigned int)((int)(wnd << 30) >> 31)) |
                      (x.z & ~(unsigned int)((int)(wnd << 29) >> 31)) | (x.w & ~(unsigned int)((int)(wnd << 28) >> 31))) &
                     0x00ffffffu;
-            if (pub_lane) ring_out[(size_t)(j0 + u) * 2 + pub_word] = mypub;
-            // record: nibble b of the row (pads and cells outside the row are never active)
-            acc |= (~wnd & 0xfu) << (4 * (b & 7));
-            const bool last = (b & 7) == 7;
-            if (last && (unsigned int)(b >> 3) < (unsigned int)rw) act_row[b >> 3] = acc;
-            acc = last ? 0u : acc;
+            if (pub_lane) ring_out[(j0 + u) * 2] = mypub;
+            if (u % RS_G == RS_G - 1) {
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 31) *reinterpret_cast<volatile int *>(s_prog + warp) = j0 + u + 1;
+            }
+            // record: nibble b of the row (pads and cells outside the row are never active); the word of
+            // eight blocks fills from the top and is complete when b & 7 == 7
+            acc = __funnelshift_r(acc, ~wnd & 0xfu, 4);
+            if ((b & 7) == 7 && (unsigned int)(b >> 3) < (unsigned int)rw) act_row[b >> 3] = acc;
             wnd >>= C;
             b += 1;
-            q[u] = pcol[(size_t)u * nthr];               // step s + Q (pad rows behind the last step)
+            q[u] = *pcol;                                // step s + Q (pad rows behind the last step)
+            pcol += nthr;
         }
-        pcol += (size_t)Q * nthr;
     }
-    // the warp below runs a few dozen steps longer than this one: nothing more is published
-    for (int j = w_len + lane; j < ring_len; j += 32) reinterpret_cast<uint2 *>(s_ring)[(size_t)warp * ring_len + j] = make_uint2(0u, 0u);
+    // the warp below runs a few dozen steps longer than this one: the rest of the ring stays zero
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 31) *reinterpret_cast<volatile int *>(s_prog + warp) = 0x7fffffff;
     __syncthreads();
 
     // active list in raster order: per-row counts, block scan, then one warp per row

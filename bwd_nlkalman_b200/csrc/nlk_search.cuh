@@ -125,14 +125,16 @@ __device__ __forceinline__ void warp_top32_of_128(unsigned long long (&key)[4], 
 // warp-level: sort npad keys (ascending), keep the first k, write the candidate
 // records, the header and the grid-neighbour bitmap of patch g.  bm: 2*nbw words of
 // shared scratch private to the warp.
-template <bool TOP32 = false>
+template <bool TOP32 = false, bool PRESORTED = false>
 __device__ __forceinline__ void sort_and_emit(const PassParams &P, int g, int px, int py, int prev_p, int k,
                                               unsigned long long *keys, int n, int npad, int nx, int x0,
                                               int y0, int lane, unsigned int *bm)
 {
     const int nbw = P.nbw;
     uint32_t *nbr_out = P.nbr + (long)g * nbw;
-    if (npad <= 128) {
+    if (PRESORTED) {
+        // the caller sorted `keys` (ascending) already
+    } else if (npad <= 128) {
         // the usual temporal window (121 candidates): sort in registers
         unsigned long long key[4];
 #pragma unroll
@@ -323,9 +325,9 @@ __device__ __forceinline__ void search_rows_block(const PassParams &P, int gy, i
         const int r = P.smooth ? P.r_t : (prev_p ? P.r_t : P.r_x);
         s_prev[s] = (r == RAD) ? prev_p : -1;
         if (r != RAD && feed_worklist) {
-            // a patch of the other radius: queue its run of the other launch (once per pass)
-            const int run2 = gy * P.x_runs + (gx0 + s) / P.x_np_cta;
-            if (atomicExch(&P.xflag[run2], P.epoch) != P.epoch) P.xlist[atomicAdd(P.xcount, 1)] = run2;
+            // a patch of the other radius (no valid previous patch: occlusions, the warp's border rows and
+            // columns): queued for k_search_patch_list, one block per patch
+            P.xlist[atomicAdd(P.xcount, 1)] = gy * P.gw + gx0 + s;
         }
     }
     __syncthreads();
@@ -448,17 +450,73 @@ k_search_rows(const PassParams P, int np_cta, int runs_per_row, int wrow, int wh
     search_rows_block<PSZ, CH, RAD, TOP32>(P, P.gy0 + gyl, run, np_cta, wrow, wh_max, npad, feed != 0);
 }
 
-// only the runs queued by the launch of the other radius (few: occluded or border patches)
-template <int PSZ, int CH, int RAD>
+// The patches queued by the launch of the other radius (few and scattered: occluded patches, the
+// warp's border rows and columns): ONE BLOCK PER PATCH, thread = candidate, so that a handful of
+// patches costs a handful of microseconds instead of the latency of whole runs.  Each distance is
+// still the reference's sequential (hy, hx, c) sum with separately rounded operations; the keys are
+// sorted by the whole block (bitonic network in shared memory), then one warp emits.
+template <int PSZ_T, int CH_T>
 __global__ void __launch_bounds__(256)
-k_search_rows_list(const PassParams P, int np_cta, int runs_per_row, int wrow, int wh_max, int npad)
+k_search_patch_list(const PassParams P, int r, int npad, int wrow)
 {
-    const int n = *P.xcount;
-    for (int wi = blockIdx.x; wi < n; wi += gridDim.x) {
-        const int run2 = P.xlist[wi];
-        const int gy = run2 / runs_per_row;
-        search_rows_block<PSZ, CH, RAD, false>(P, gy, run2 - gy * runs_per_row, np_cta, wrow, wh_max, npad, false);
-        __syncthreads();   // shared memory is reused by the next run
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);       // [npad]
+    float *win = reinterpret_cast<float *>(keys + npad);                                 // [2r + psz][wrow]
+    const int psz = PSZ_T ? PSZ_T : P.psz, ch = CH_T ? CH_T : P.ch;
+    unsigned int *bm = reinterpret_cast<unsigned int *>(win + (size_t)(2 * r + psz) * wrow);   // [2][nbw]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nq = *P.xcount;
+    for (int wi = blockIdx.x; wi < nq; wi += gridDim.x) {
+        const int g = P.xlist[wi];
+        const int gy = g / P.gw, gx = g - gy * P.gw;
+        const int px = gx * P.step, py = gy * P.step;
+        const int prev_p = (P.valid != nullptr) ? (int)P.valid[(long)py * P.vw + px] : 0;
+        const int k = prev_p ? P.k_t : P.k_x;
+        if (k <= 1) {          // no search (reference :631): header only
+            if (tid == 0) {
+                GroupHdr hd;
+                hd.nk = 0; hd.np0 = 0; hd.flags = prev_p ? HDR_PREV_P : 0; hd.pxy = (int)cand_pack(px, py, 0);
+                P.hdr[g] = hd;
+            }
+            for (int i = tid; i < P.nbw; i += blockDim.x) P.nbr[(long)g * P.nbw + i] = 0u;
+            continue;
+        }
+        const int x0 = max(px - r, 0), x1 = min(px + r, P.w - psz);
+        const int y0 = max(py - r, 0), y1 = min(py + r, P.h - psz);
+        const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, n = nx * ny;
+        const int wlen = (nx + psz - 1) * ch, wh = ny + psz - 1;
+        for (int row = tid >> 5; row < wh; row += 8) {
+            const float *srow = P.src + ((long)(y0 + row) * P.w + x0) * ch;
+            for (int j = lane; j < wlen; j += 32) win[row * wrow + j] = srow[j];
+        }
+        __syncthreads();
+        const float *cp = win + (py - y0) * wrow + (px - x0) * ch;
+        const float npix = (float)psz * (float)psz * (float)ch;
+        int np2 = 32;
+        while (np2 < n) np2 <<= 1;
+        for (int ci = tid; ci < np2; ci += blockDim.x) {
+            unsigned long long key = ~0ull;
+            if (ci < n) {
+                const int cy = ci / nx, cx = ci - cy * nx;
+                const float ww = patch_dist<PSZ_T, CH_T>(win + cy * wrow + cx * ch, cp, wrow, psz, ch);
+                const float d = fmaxf(__fdiv_rn(ww, npix), 0.f);
+                key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)ci;
+            }
+            keys[ci] = key;
+        }
+        __syncthreads();
+        for (int size = 2; size <= np2; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int t = tid; t < (np2 >> 1); t += blockDim.x) {
+                    const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1)), hi = lo + stride;
+                    const bool asc = (lo & size) == 0;
+                    const unsigned long long a = keys[lo], b = keys[hi];
+                    if ((a > b) == asc) { keys[lo] = b; keys[hi] = a; }
+                }
+                __syncthreads();
+            }
+        if (tid < 32) sort_and_emit<false, true>(P, g, px, py, prev_p, k, keys, n, np2, nx, x0, y0, lane, bm);
+        __syncthreads();   // shared memory is reused by the next patch
     }
 }
 
@@ -475,7 +533,7 @@ inline void search_rows_geom(const PassParams &P, int PSZ, int CH, int *np_cta, 
     *smem = (size_t)*np_cta * *npad * 8 + (size_t)*wh_max * *wrow * 4 + 8 * 2 * P.nbw * 4 + *np_cta * 4;
 }
 
-// mode 0: all runs of the strip; 1: all runs, queueing the runs of the other radius; 2: queued runs only
+// mode 0: all runs of the strip; 1: all runs, queueing the patches of the other radius for k_search_patch_list
 template <int PSZ, int CH, int RAD>
 inline int launch_search_rows(const PassParams &P, int mode, cudaStream_t st)
 {
@@ -484,12 +542,7 @@ inline int launch_search_rows(const PassParams &P, int mode, cudaStream_t st)
     search_rows_geom<RAD>(P, PSZ, CH, &np_cta, &npad, &wrow, &wh_max, &smem);
     if (smem > 220 * 1024) return -1;
     const int runs = (P.gw + np_cta - 1) / np_cta;
-    if (mode == 2) {
-        cudaFuncSetAttribute(k_search_rows_list<PSZ, CH, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        // one queued run per block when they fit one wave (a run is ~50 us of latency, the
-        // queue is a few hundred runs: occlusions and the warp's border rows / columns)
-        k_search_rows_list<PSZ, CH, RAD><<<6 * 148, 256, smem, st>>>(P, np_cta, runs, wrow, wh_max, npad);
-    } else {
+    {
         // what the patches of this launch keep: those with a valid previous patch k_t, the others k_x
         // (reference :631-707); with one radius for both, or in the smoother, a launch holds both kinds
         int kmax = P.k_t > P.k_x ? P.k_t : P.k_x;
@@ -560,22 +613,42 @@ inline int launch_search_radius(const PassParams &P, int r, int mode, cudaStream
     return launch_search_generic(P, r, r, st);
 }
 
+// the queued patches of radius r (see k_search_patch_list)
+inline int launch_search_patch_list(const PassParams &P, int r, cudaStream_t st)
+{
+    const int side = 2 * r + 1;
+    int npad = 32;
+    while (npad < side * side) npad <<= 1;
+    const int wrow = ((2 * r + P.psz) * P.ch) | 1;        // odd stride: candidate rows fall in different banks
+    const size_t smem = (size_t)npad * 8 + (size_t)(2 * r + P.psz) * wrow * 4 + 2 * P.nbw * 4;
+    if (smem > 200 * 1024) return -1;
+    const int nb = 148 * 4;
+#define NLK_LAUNCH_PL(PS, CHN)                                                                        \
+    do {                                                                                              \
+        cudaFuncSetAttribute(k_search_patch_list<PS, CHN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        k_search_patch_list<PS, CHN><<<nb, 256, smem, st>>>(P, r, npad, wrow);                        \
+    } while (0)
+    if (P.psz == 8 && P.ch == 3) NLK_LAUNCH_PL(8, 3);
+    else if (P.psz == 8 && P.ch == 1) NLK_LAUNCH_PL(8, 1);
+    else if (P.psz == 12 && P.ch == 3) NLK_LAUNCH_PL(12, 3);
+    else NLK_LAUNCH_PL(0, 0);
+#undef NLK_LAUNCH_PL
+    return 1;
+}
+
 inline int launch_search(PassParams &P, cudaStream_t st)
 {
     // a patch searches with radius r_t (it has a valid previous patch, or the pass is the
     // smoother) or r_x (reference :637, :1527)
     if (P.smooth || P.r_x == P.r_t) return launch_search_radius(P, P.r_t, 0, st);
     if (!P.has_prev) return launch_search_radius(P, P.r_x, 0, st);   // no previous frame: all spatial
-    // temporal pass: the r_t launch covers the frame and queues the runs that hold patches
-    // without a valid previous patch (occlusions, warp borders) for a small r_x launch
-    int np2 = 0;
-    const int runs2 = search_rows_runs(P, P.r_x, &np2);
+    // temporal pass: the r_t launch covers the frame and queues the patches without a valid previous
+    // patch (occlusions, warp borders) for the one-block-per-patch launch of radius r_x
     int np1 = 0;
-    const bool listed = runs2 > 0 && search_rows_runs(P, P.r_t, &np1) > 0 && P.xlist != nullptr;
-    if (listed) { P.x_runs = runs2; P.x_np_cta = np2; }
+    const bool listed = search_rows_runs(P, P.r_t, &np1) > 0 && P.xlist != nullptr;
     int n = launch_search_radius(P, P.r_t, listed ? 1 : 0, st);
     if (n < 0) return n;
-    const int m = launch_search_radius(P, P.r_x, listed ? 2 : 0, st);
+    const int m = listed ? launch_search_patch_list(P, P.r_x, st) : launch_search_radius(P, P.r_x, 0, st);
     return m < 0 ? m : n + m;
 }
 

@@ -9,7 +9,13 @@ mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
 for w in $WHAT; do
 case $w in
-tests)   timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; tail -3 $OUT/${TAG}_pytest_gpu.log;;
+tests)   timeout 900 python -m pytest tests -m gpu -q -s --timeout 240 > $OUT/${TAG}_pytest_gpu.log 2>&1; grep -E "passed|failed|FAILED|rror:" $OUT/${TAG}_pytest_gpu.log | tail -8;;
+configs) timeout 400 python tools/bench_configs.py > $OUT/${TAG}_configs.jsonl 2> $OUT/${TAG}_configs.err; python - <<PYEOF
+import json
+for l in open("$OUT/${TAG}_configs.jsonl"):
+    d = json.loads(l); print(d["config"], round(d["value"], 1), "Mpixel/s", [(k["kernel"], k["pass"], round(k["avg_ms"], 3)) for k in d["kernels_in_order"][:6]])
+PYEOF
+;;
 bench)   timeout 600 python bench.py > $OUT/${TAG}_bench_ours.json 2> $OUT/${TAG}_bench_ours.err; python tools/bench_brief.py $OUT/${TAG}_bench_ours.json;;
 ref)     timeout 900 python bench.py --impl reference --steps 5 --warmup 2 > $OUT/${TAG}_bench_reference.json 2>&1; cut -c1-300 $OUT/${TAG}_bench_reference.json;;
 launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
