@@ -379,7 +379,7 @@ def run_ours(args):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_strips
         try:
-            strips_res = bench_strips.measure(rank, world, local_rank, dist, nf=4, reps=2, warmup=1, transport="peer")
+            strips_res = bench_strips.measure(rank, world, local_rank, dist, nf=6, reps=2, warmup=1, transport="peer")
         except Exception as exc:     # the headline stands on its own
             strips_res = {"error": repr(exc)}
 
@@ -529,12 +529,13 @@ def cli_leg():
         args = ["-i", p("n1.pfm"), "-s", str(sigma), "-o", p("bflo.flo"), "-k", p("occ.pgm"), "--flt10", p("a1.pfm"),
                 "--flt20", p("a2.pfm")]
         out = {}
+        env = {k: v for k, v in os.environ.items() if k != "CUDA_DEVICE_MAX_CONNECTIONS"}   # (this process asks for 32 hardware queues: slower context creation)
         for name, exe in (("reference", ref_exe), ("ours", our_exe)):
             ts = []
             for rep in range(3):
                 t0 = time.perf_counter()
                 subprocess.run([exe] + args + ["--flt11", p(f"{name}1.pfm"), "--flt21", p(f"{name}2.pfm")],
-                               check=True, capture_output=True)
+                               check=True, capture_output=True, env=env)
                 ts.append(time.perf_counter() - t0)
             out[name + "_s"] = min(ts)
         out["workload"] = ("C1: one nlkalman-flt process, 854x480 gray, sigma 20, frame 1 (flow, mask, previous flt1/flt2 "
