@@ -57,16 +57,14 @@ struct PassParams {
     int nbw, R;
     float *dbg_dist;        // [G][kstride] distances of the kept candidates, or nullptr
     int *any_nbr;           // set to 1 if some group marks a grid patch other than its own
-    // runs of the spatial-radius launch that hold a patch without a valid previous patch, queued
-    // by the temporal-radius launch: xflag[run] == epoch marks a queued run (no clearing per pass)
-    int *xlist, *xflag, *xcount;
-    int epoch, x_runs, x_np_cta;
+    // grid patches of the other search radius (no valid previous patch in a temporal pass), queued by
+    // the main search launch for k_search_patch_list
+    int *xlist, *xcount;
     // resolve output
     uint8_t *actflag;       // [G] 1 = processed (written by mask_resolve)
     int *active;            // [G] indices of processed patches, raster order
     int *nactive;
     int *work;              // ticket counter of group_filter (zeroed at the start of a pass)
-    uint8_t *gmask;         // [G] processed mask (global-memory fallback of mask_resolve)
     // aggregation
     float *accw;            // [h*w][ch+1]: weighted sums, then the weight
     float *out;             // [h*w][ch]

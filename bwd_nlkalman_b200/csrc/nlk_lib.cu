@@ -118,11 +118,10 @@ struct DevBuf {
 // recursions only meet through flt1(t) -> flt2(t)).
 struct Lane {
     cudaStream_t st = nullptr;
-    DevBuf accw, valid, valid_tmp, cand, hdr, nbr, active, actflag, counters, gmask, xlist, rpack, q_warp;
-    int epoch = 0;
+    DevBuf accw, valid, valid_tmp, cand, hdr, nbr, active, actflag, counters, xlist, rpack, q_warp;
     void release()
     {
-        DevBuf *all[] = {&accw, &valid, &valid_tmp, &cand, &hdr, &nbr, &active, &actflag, &counters, &gmask, &xlist,
+        DevBuf *all[] = {&accw, &valid, &valid_tmp, &cand, &hdr, &nbr, &active, &actflag, &counters, &xlist,
                          &rpack, &q_warp};
         for (DevBuf *b : all) b->release();
     }
@@ -554,7 +553,6 @@ static int pass_setup(nlk_ctx *c, PassParams &P, int smooth, float *d_out, const
     if (int r = c->L->hdr.ensure(G * sizeof(GroupHdr))) return r;
     if (!d_nbr_ext) if (int r = c->L->nbr.ensure(G * P.nbw * 4)) return r;
     if (int r = c->L->active.ensure(G * 4)) return r;
-    if (int r = c->L->gmask.ensure(G)) return r;
     if (int r = c->L->actflag.ensure(G)) return r;
     if (d_prev0 && P.G > 0) {
         if (int r = c->L->valid.ensure((size_t)P.vw * P.vh)) return r;
@@ -566,22 +564,14 @@ static int pass_setup(nlk_ctx *c, PassParams &P, int smooth, float *d_out, const
     P.hdr = c->L->hdr.as<GroupHdr>();
     P.nbr = d_nbr_ext ? d_nbr_ext : c->L->nbr.as<uint32_t>();
     P.active = c->L->active.as<int>();
-    P.gmask = c->L->gmask.as<uint8_t>();
     P.actflag = c->L->actflag.as<uint8_t>();
     P.nactive = c->L->counters.as<int>();
     P.any_nbr = c->L->counters.as<int>() + 1;
     P.work = c->L->counters.as<int>() + 2;
     P.xcount = c->L->counters.as<int>() + 3;
-    {
-        // worklist of the second search launch: at most one run per 256/(2*r_x+1) patches
-        const size_t cap = G + 16;
-        const bool fresh = c->L->xlist.cap < 2 * cap * 4;
-        if (int r = c->L->xlist.ensure(2 * cap * 4)) return r;
-        if (fresh) { CU_TRY(cudaMemsetAsync(c->L->xlist.p, 0, 2 * cap * 4, c->L->st)); c->L->epoch = 0; }
-        P.xlist = c->L->xlist.as<int>();
-        P.xflag = c->L->xlist.as<int>() + cap;
-        P.epoch = ++c->L->epoch;
-    }
+    // worklist of the one-block-per-patch search launch: at most every grid patch
+    if (int r = c->L->xlist.ensure((G + 16) * 4)) return r;
+    P.xlist = c->L->xlist.as<int>();
     P.out = d_out;
     if (debug) {
         if (int r = c->dbg_dist.ensure(G * kmax * 4)) return r;
