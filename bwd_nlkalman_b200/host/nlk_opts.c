@@ -99,3 +99,13 @@ int nlk_opts_parse(const struct nlk_opt *opts, const char *usage_line, const cha
     }
     return nrest;
 }
+
+int nlk_pick_device(void)
+{
+    const char *d = getenv("NLK_DEVICE");
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        setenv("CUDA_VISIBLE_DEVICES", (d && *d) ? d : "0", 1);
+        return 0;
+    }
+    return (d && *d) ? atoi(d) : 0;
+}

@@ -25,4 +25,10 @@ struct nlk_opt {
 int nlk_opts_parse(const struct nlk_opt *opts, const char *usage, const char *descr,
                    int argc, const char **argv);
 
+/* The device of this process: NLK_DEVICE (default 0).  Unless the caller has restricted the visible
+ * devices already, the others are hidden before the CUDA runtime comes up -- it initialises every
+ * visible GPU, which on an 8-GPU box is most of the wall time of a per-frame invocation.  Returns the
+ * device index to pass to nlk_ctx_create. */
+int nlk_pick_device(void);
+
 #endif

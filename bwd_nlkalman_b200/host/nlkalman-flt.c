@@ -145,8 +145,8 @@ int main(int argc, const char *argv[])
     }
 
     /* bring the GPU up beside the file decoding */
-    int dev = 0;
-    if (getenv("NLK_DEVICE")) dev = atoi(getenv("NLK_DEVICE"));
+    const int dev_pick = nlk_pick_device();
+    int dev = dev_pick;
     const int timing = getenv("NLK_CLI_TIMING") != NULL;
     const double t_start = now_s();
     pthread_t warm;

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include "nlk_image_io.h"
+#include "nlk_opts.h"
 #include "nlkalman_b200.h"
 
 int main(int argc, const char *argv[])
@@ -20,7 +21,7 @@ int main(int argc, const char *argv[])
     if (!of) return fprintf(stderr, "nlkalman-occ: cannot read %s: %s\n", argv[1], nlk_io_error()), 1;
     if (c != 2) return fprintf(stderr, "nlkalman-occ: %s has %d channels, a flow has 2\n", argv[1], c), 1;
     const float th = (float)atof(argv[2]);
-    nlk_ctx *ctx = nlk_ctx_create(w, h, 1, getenv("NLK_DEVICE") ? atoi(getenv("NLK_DEVICE")) : 0);
+    nlk_ctx *ctx = nlk_ctx_create(w, h, 1, nlk_pick_device());
     if (!ctx) return fprintf(stderr, "nlkalman-occ: %s\n", nlk_last_error()), 2;
     float *occ = malloc((size_t)w * h * sizeof(float));
     if (!occ || nlk_occlusion_host(ctx, occ, of, th))

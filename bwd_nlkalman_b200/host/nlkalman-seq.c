@@ -309,8 +309,8 @@ int main(int argc, const char *argv[])
     }
     ib = (size_t)w * h * c * sizeof(float);
     npix = (size_t)w * h;
-    int dev = 0;
-    if (getenv("NLK_DEVICE")) dev = atoi(getenv("NLK_DEVICE"));
+    const int dev_pick = nlk_pick_device();
+    int dev = dev_pick;
     ctx = nlk_ctx_create(w, h, c, dev);
     if (!ctx) return gpu_fail("no usable CUDA device (there is no CPU fallback)");
 

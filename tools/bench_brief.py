@@ -3,7 +3,7 @@
 import json
 import sys
 
-d = json.load(open(sys.argv[1]))
+d = json.loads([l for l in open(sys.argv[1]).read().splitlines() if l.startswith('{')][-1])
 print(f"value {d['value']:.1f} {d['unit']}  e2e {d['e2e']['value']:.1f}  ms/step {d['ms_per_step']:.3f}  "
       f"launches {d['gpu_launches']}  clocks {d.get('clocks')}")
 for k in d["kernels"]:
