@@ -91,8 +91,10 @@ __device__ __forceinline__ void line_dct(float *r, int psz)
 // forward 2-D transform of ntiles patches out of the staged windows into tiles[t * TS]; src_of(t) is
 // the patch's first sample (nullptr: no such tile), samples at src[y * wrow + x * ch].  Ends with
 // a block barrier.
+// sub_off != 0: the transform of src - (src + sub_off), two windows at a fixed distance
 template <int PSZ_T, class SrcOf>
-__device__ __forceinline__ void block_fwd_tiles(float *tiles, int TS, int ntiles, int psz, int wrow, int ch, SrcOf src_of)
+__device__ __forceinline__ void block_fwd_tiles(float *tiles, int TS, int ntiles, int psz, int wrow, int ch, SrcOf src_of,
+                                                long sub_off = 0)
 {
     constexpr int NR = PSZ_T ? PSZ_T : MAX_PSZ;
     for (int it = threadIdx.x; it < ntiles * psz; it += GF_THREADS) {
@@ -101,7 +103,8 @@ __device__ __forceinline__ void block_fwd_tiles(float *tiles, int TS, int ntiles
         if (!src) continue;
         float r[NR];
 #pragma unroll
-        for (int i = 0; i < NR; ++i) if (i < psz) r[i] = src[y * wrow + i * ch];
+        for (int i = 0; i < NR; ++i)
+            if (i < psz) r[i] = sub_off ? src[y * wrow + i * ch] - src[sub_off + y * wrow + i * ch] : src[y * wrow + i * ch];
         line_dct<PSZ_T, false>(r, psz);
         float *d = tiles + t * TS + y * psz;
 #pragma unroll
@@ -338,19 +341,20 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
         // ---- pass 2: update, inverse transform and aggregation of the group ------------
         // resident: every candidate's transform is still in `tiles`, members are updated in
         // place; otherwise members are transformed again, a chunk at a time
-        const int nsrc2 = P.smooth ? 2 : 1;
+        // smoother, not resident: by linearity T^-1((1-a) Y1 + a Y0) = x1 + T^-1(a T(x0 - x1)) -- one forward
+        // transform per member and channel (of the difference of the two windows) instead of two
+        const bool diff = P.smooth && !resident;
         for (int m0 = 0; m0 < nagg; m0 += cc) {
             const int cnt = min(cc, nagg - m0);
             if (!resident) {
                 __syncthreads();
-                // (tile index ml * tpc + rr: with one source per member the tiles of the second are unused)
+                // (tile index ml * tpc + c: the tiles of a second source stay unused)
                 block_fwd_tiles<PSZ_T>(tiles, TS, cnt * tpc, psz, wrow, ch, [&](int t) -> const float * {
                     const int ml = t / tpc, rr = t - ml * tpc;
-                    if (rr >= nsrc2 * ch) return nullptr;
-                    const int s = rr >= ch, c = rr - s * ch;
+                    if (rr >= ch) return nullptr;
                     const uint32_t cd = s_cand[s_grp[m0 + ml]];
-                    return (s ? winP : winS) + (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * ch + c;
-                });
+                    return (diff ? winP : winS) + (cand_y(cd) - y0) * wrow + (cand_x(cd) - x0) * ch + rr;
+                }, diff ? (long)(winS - winP) : 0L);
             }
             // one thread per coefficient over the members of the chunk
 #pragma unroll
@@ -363,8 +367,9 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
                 for (int ml = 0; ml < cnt; ++ml) {
                     const int slot = resident ? s_grp[m0 + ml] : ml;
                     float *y = yb + slot * tpc * TS;
-                    if (P.smooth) *y = oma * (*y) + a * y[ch * TS];     // :1775
-                    else *y = a * (*y) + oma * mj;                      // :878 / :901
+                    if (diff) *y = a * (*y);                                 // :1775, difference form
+                    else if (P.smooth) *y = oma * (*y) + a * y[ch * TS];     // :1775
+                    else *y = a * (*y) + oma * mj;                           // :878 / :901
                 }
             }
             __syncthreads();
@@ -380,9 +385,13 @@ k_group_filter(const PassParams P, int CT, int kcap, int wrow, int win_floats)
                 const uint32_t cd = s_cand[gi];
                 const long pix = (long)(cand_y(cd) + hy) * P.w + cand_x(cd) + hx;
                 const float wW = __fmul_rn(wgt, W[e]);                  // :923
+                const float *x1 = winS + (cand_y(cd) - y0 + hy) * wrow + (cand_x(cd) - x0 + hx) * ch;
                 float v[MAX_CH];
-                for (int c = 0; c < ch; ++c)
-                    v[c] = __fmul_rn(wW, tiles[(slot * tpc + c) * TS + e]); // :926
+                for (int c = 0; c < ch; ++c) {
+                    float px_val = tiles[(slot * tpc + c) * TS + e];
+                    if (diff) px_val += x1[c];
+                    v[c] = __fmul_rn(wW, px_val);                       // :926
+                }
                 accumulate_pixel<CH_T>(P.accw + pix * (ch + 1), v, wW, ch);
             }
         }
@@ -403,7 +412,9 @@ inline int launch_group_filter(const PassParams &P, int num_sms, cudaStream_t st
     // about 64 KB), else chunks
     int CT = kcap * tpc;
     if (CT > GF_THREADS) CT = (GF_THREADS / tpc) * tpc;
-    const int by_smem = (64 * 1024 / (TS * 4)) / tpc * tpc;
+    // tile area: 64 KB by default (two blocks per SM beside the windows at 12x12); NLK_GF_TILE_KB overrides it
+    static const int tile_kb = getenv("NLK_GF_TILE_KB") ? atoi(getenv("NLK_GF_TILE_KB")) : 64;
+    const int by_smem = ((tile_kb > 4 ? tile_kb : 4) * 1024 / (TS * 4)) / tpc * tpc;
     if (CT > by_smem) CT = by_smem;
     if (CT < tpc) CT = tpc;
     const int r = P.smooth ? P.r_t : (P.r_t > P.r_x ? P.r_t : P.r_x);
@@ -411,7 +422,8 @@ inline int launch_group_filter(const PassParams &P, int num_sms, cudaStream_t st
     const int win_floats = (2 * r + P.psz) * wrow;
     const size_t smem = ((size_t)CT * TS + (size_t)win_floats * (P.has_prev ? 2 : 1) + 2 * cpp + kcap +
                          (P.tagg > 1 ? P.tagg : 1) + 8 + P.psz * P.psz) * 4;
-    const int nb = num_sms * 2;
+    static const int blocks_per_sm = getenv("NLK_GF_BLOCKS") ? atoi(getenv("NLK_GF_BLOCKS")) : 2;
+    const int nb = num_sms * (blocks_per_sm > 0 ? blocks_per_sm : 2);
 #define NLK_LAUNCH_GF(PS, CHN)                                                                        \
     do {                                                                                              \
         cudaFuncSetAttribute(k_group_filter<PS, CHN>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
