@@ -110,6 +110,7 @@ def lib():
     L.nlk_peer_signal.argtypes = [vp, C.c_int, C.c_uint, C.c_uint]
     L.nlk_peer_wait.argtypes = [vp, C.c_int, C.c_uint, C.c_uint]
     L.nlk_peer_error.argtypes = [vp, C.POINTER(C.c_uint)]
+    L.nlk_warp_rows_peer_dev.argtypes = [vp, vp, C.c_size_t, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.nlk_dev_free.argtypes = [vp, vp]
     L.nlk_dev_free.restype = None
     L.nlk_seq_reset.argtypes = [vp]
@@ -375,6 +376,10 @@ class Context:
 
     def peer_wait(self, slot, value, src_mask):
         _check(lib().nlk_peer_wait(self._h, int(slot), int(value) & 0xffffffff, int(src_mask)))
+
+    def warp_rows_peer_dev(self, imw, frame_off, of, msk, row0, row1, lo, hi, chunk_y):
+        _check(lib().nlk_warp_rows_peer_dev(self._h, _vp(imw), int(frame_off), _vp(of), _vp(msk), int(row0), int(row1),
+                                            int(lo), int(hi), int(chunk_y)))
 
     def peer_error(self) -> int:
         v = C.c_uint(0)

@@ -1018,6 +1018,24 @@ extern "C" int nlk_peer_push_add(nlk_ctx *c, size_t off, size_t bytes, int peer,
     return check_launch(c, 1, "peer_push_add");
 }
 
+// warp of rows [row0, row1) of the frame at frame_off of the slabs; rows [lo, hi) are read locally, any
+// other row from its owner's slab (see k_warp_peer)
+extern "C" int nlk_warp_rows_peer_dev(nlk_ctx *c, float *d_imw, size_t frame_off, const float *d_of, const float *d_msk,
+                                      int row0, int row1, int lo, int hi, int chunk_y)
+{
+    if (int r = enter_strip(c)) return r;
+    if (int r = rows_ok(c, row0, row1)) return r;
+    if (int r = peer_ok(c, frame_off, c->img_bytes(), 0)) return r;
+    if (chunk_y < 1 || lo > hi) return set_err(NLK_ERR_PARAM, "bad row ownership (chunk %d, local [%d, %d))", chunk_y, lo, hi);
+    if (row1 <= row0) return NLK_OK;
+    ProfScope ps(c, NLK_K_WARP);
+    const dim3 nt(32, 8), nb((c->w + 31) / 32, (row1 - row0 + 7) / 8);
+    if (c->ch == 3) k_warp_peer<3><<<nb, nt, 0, c->L->st>>>(d_imw, c->peer, frame_off, d_of, d_msk, c->w, c->h, c->ch, row0, row1, lo, hi, chunk_y);
+    else if (c->ch == 1) k_warp_peer<1><<<nb, nt, 0, c->L->st>>>(d_imw, c->peer, frame_off, d_of, d_msk, c->w, c->h, c->ch, row0, row1, lo, hi, chunk_y);
+    else k_warp_peer<0><<<nb, nt, 0, c->L->st>>>(d_imw, c->peer, frame_off, d_of, d_msk, c->w, c->h, c->ch, row0, row1, lo, hi, chunk_y);
+    return check_launch(c, 1, "warp_rows_peer");
+}
+
 // nonzero once a wait has timed out (the flag never came): (0x10000 | slot << 8 | source rank)
 extern "C" int nlk_peer_error(nlk_ctx *c, unsigned int *code)
 {

@@ -16,6 +16,7 @@
 // A wait gives up after a timeout and raises the slab's error word instead of hanging the GPU.
 #pragma once
 #include "nlk_common.cuh"
+#include "nlk_prep.cuh"   // cubic1
 
 namespace nlk {
 
@@ -133,6 +134,60 @@ __global__ void __launch_bounds__(256) k_peer_push_add(const PeerTable T, size_t
         for (size_t i = i0; i < n; i += stride) atomicAdd(dst + i, src[i]);
     }
     peer_last_block_signal(T, slot, value, 1u << p, cnt_idx);
+}
+
+// ---- warp with remote rows ----------------------------------------------------------------------
+// The bicubic warp of a strip (reference src/nlkalman.c:66-88) reads the previous output at
+// flow-displaced positions: almost always inside the rows the rank holds (its own and the halo rows its
+// neighbours pushed), occasionally anywhere.  Instead of every rank pushing its whole strip to everybody
+// after every pass, a tap row outside [lo, hi) is loaded straight from its owner's slab over NVLink
+// (rows [k * chunk_y, (k+1) * chunk_y) belong to rank k, the rest to the last rank); the frame sits at the
+// same offset in every slab.  Same arithmetic as k_warp.
+template <int CH>
+__global__ void k_warp_peer(float *__restrict__ imw, const PeerTable T, size_t frame_off,
+                            const float *__restrict__ of, const float *__restrict__ msk, int w, int h, int ch_rt,
+                            int row0, int row1, int lo, int hi, int chunk_y)
+{
+    const int ch = CH ? CH : ch_rt;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = row0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= row1) return;
+    const long pix = (long)y * w + x;
+    float *o = imw + pix * ch;
+    const float nanv = __int_as_float(0x7fc00000);
+    if (msk != nullptr && msk[pix] != 0.f) {
+        for (int c = 0; c < ch; ++c) o[c] = nanv;
+        return;
+    }
+    float xw = __fadd_rn((float)x, of[pix * 2 + 0]);
+    float yw = __fadd_rn((float)y, of[pix * 2 + 1]);
+    xw = __fsub_rn(xw, 1.f);
+    yw = __fsub_rn(yw, 1.f);
+    const int ix = (int)floorf(xw), iy = (int)floorf(yw);
+    const float fx = __fsub_rn(xw, (float)ix), fy = __fsub_rn(yw, (float)iy);
+    const bool inside = (ix >= 0) && (ix + 3 < w) && (iy >= 0) && (iy + 3 < h) && (xw == xw) && (yw == yw);
+    if (!inside) {
+        for (int c = 0; c < ch; ++c) o[c] = nanv;
+        return;
+    }
+    const float *rowp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int yy = iy + k;
+        int owner = T.rank;
+        if (yy < lo || yy >= hi) {
+            owner = yy / chunk_y;
+            if (owner > T.nranks - 1) owner = T.nranks - 1;
+        }
+        rowp[k] = reinterpret_cast<const float *>(T.slab[owner] + frame_off) + ((long)yy * w + ix) * ch;
+    }
+    for (int c = 0; c < ch; ++c) {
+        float col[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            col[i] = cubic1(rowp[0][i * ch + c], rowp[1][i * ch + c], rowp[2][i * ch + c], rowp[3][i * ch + c], fy);
+        o[c] = cubic1(col[0], col[1], col[2], col[3], fx);
+    }
 }
 
 } // namespace nlk

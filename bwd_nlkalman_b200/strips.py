@@ -187,6 +187,8 @@ class StripRank:
         self.pending = {}
         self.seq = {}                    # flag slot -> last sequence number used (same on every rank)
         self.waited = {}
+        self.local_rows = {}             # exchanged frame buffer -> rows of it this rank holds (peer transport)
+        self._chunk_prms, self._last_rows = None, None
         self.reset()
 
     # ---- peer transport: the slab ---------------------------------------------------------------
@@ -315,6 +317,8 @@ class StripRank:
         """before reading the halo rows of `buf` (the neighbours' border rows); when the reading
         pass cuts the frame into other strips than the pass that wrote `buf`, the whole frame"""
         if self.nranks > 1 and self.transport == "peer":
+            if not same_rows:
+                raise api.NlkError("peer transport: the passes of a frame must cut it into the same strips (one patch size)")
             if same_rows:
                 yield from self._await(self.SLOT_HALO + self._buf[buf.data_ptr()][0], self._mask_nb())
             else:
@@ -363,6 +367,7 @@ class StripRank:
         """The pass with the exchanges done by the kernels themselves over peer memory."""
         ctx, rk, n = self.ctx, self.rank, self.nranks
         p = plans[rk]
+        self._chunk_prms = prms
         words = n * p.chunk_g * p.gw * p.nbw
         if words > self.nbr_words:
             raise api.NlkError(f"peer transport: {words} bitmap words exceed the slab's {self.nbr_words}")
@@ -400,24 +405,47 @@ class StripRank:
             yield from self._await(SLOT_ACC, self._mask_nb())
         ctx.strip_normalize(out, p.oy0, p.oy1)
         if n > 1:
-            # (C) publish the strip: border rows to the neighbours at once (what the next pass of
-            # this frame searches), the whole strip to everybody beside the next pass (the next
-            # frame's warp reads at flow-displaced positions)
+            # (C) publish the strip: its border rows (the reader's halo plus a margin for the warp's
+            # flow-displaced taps) go to the two neighbours at once; everybody else only learns that the
+            # rows are final -- the next frame's warp pulls the few rows it may need beyond that straight
+            # from the owner's slab (nlk_warp_rows_peer_dev), no strip is broadcast
             idx, off = self._buf[out.data_ptr()]
             v = self._next_seq(self.SLOT_HALO + idx)
             self.seq[self.SLOT_FRAME + idx] = v
             rowb = self.w * self.ch * 4
-            br = border_ranges(next_plans if next_plans is not None else plans, rk)
-            for key, peer in (("up_recv", rk - 1), ("dn_recv", rk + 1)):
+            rp = next_plans if next_plans is not None else plans
+            lo, hi = self._local_rows(plans, rp, rk)
+            self.local_rows[idx] = (lo, hi)
+            for peer in (rk - 1, rk + 1):
                 if not 0 <= peer < n:
                     continue
-                a, b = br[key] if br[key] else (0, 0)
-                a, b = max(a, p.oy0), min(b, p.oy1)
+                plo, phi = self._local_rows(plans, rp, peer)        # what the neighbour keeps of the frame
+                a, b = max(plo, p.oy0), min(phi, p.oy1)             # ... of which these rows are mine
                 if b > a:
                     ctx.peer_push(off + a * rowb, (b - a) * rowb, 1 << peer, self.SLOT_HALO + idx, v, 0)
                 else:
                     ctx.peer_signal(self.SLOT_HALO + idx, v, 1 << peer)
-            ctx.peer_push(off + p.oy0 * rowb, (p.oy1 - p.oy0) * rowb, self._mask_all(), self.SLOT_FRAME + idx, v, 1)
+            ctx.peer_signal(self.SLOT_FRAME + idx, v, self._mask_all())
+
+    WARP_MARGIN = 8      # rows beyond a pass's halo that a rank keeps of a frame (the warp's reach for small flows)
+
+    def _local_rows(self, plans, reader_plans, r):
+        """rows of a frame that rank r holds after the pass cut by `plans` produced it: its own, and the
+        neighbours' rows within the halo of the pass that reads it next plus the margin"""
+        lo = max(reader_plans[r].ey0 - self.WARP_MARGIN, plans[r - 1].oy0) if r > 0 else 0
+        hi = min(reader_plans[r].ey1 + self.WARP_MARGIN, plans[r + 1].oy1) if r + 1 < len(plans) else self.h
+        return min(lo, plans[r].oy0), max(hi, plans[r].oy1)
+
+    def _warp(self, dst, src, flo, occ, a, b):
+        """warp rows [a, b) of `src` (reference src/nlkalman.c:66-88); with the peer transport the rows this
+        rank does not hold come from their owners"""
+        if self.transport == "peer" and self.nranks > 1 and src.data_ptr() in self._buf:
+            idx, off = self._buf[src.data_ptr()]
+            lo, hi = self.local_rows.get(idx, (0, self.h))
+            chunk_y = api.strip_plan(self.w, self.h, 0, self._chunk_prms, self.nranks, 0).chunk_y
+            self.ctx.warp_rows_peer_dev(dst, off, flo, occ, a, b, lo, hi, chunk_y)
+        else:
+            self.ctx.warp_rows_dev(dst, src, flo, occ, a, b)
 
     def _rows_needed(self, smooth, *prms_list):
         ps = [api.strip_plan(self.w, self.h, smooth, q, self.nranks, self.rank) for q in prms_list]
@@ -445,7 +473,7 @@ class StripRank:
             yield from self.need_frame(prev1, "flt1")   # the other strips of the previous frame (warp reads anywhere)
             if d_bflo is not None:
                 a, b = self._rows_needed(0, f1)
-                ctx.warp_rows_dev(self.warp_l[0], prev1, d_bflo, d_bocc, a, b)
+                self._warp(self.warp_l[0], prev1, d_bflo, d_bocc, a, b)
                 prev1 = self.warp_l[0]
         plans = yield from self.strip_pass(0, self.flt1[cur], noisy, prev1, None, sigma, f1, key="flt1",
                                            next_plans=self.plans(0, f2) if do2 else None)
@@ -464,7 +492,7 @@ class StripRank:
                 yield from self.need_frame(prev2, "flt2")
                 if d_bflo is not None:
                     a, b = self._rows_needed(0, f2)
-                    ctx.warp_rows_dev(self.warp_l[1], prev2, d_bflo, d_bocc, a, b)
+                    self._warp(self.warp_l[1], prev2, d_bflo, d_bocc, a, b)
                     prev2 = self.warp_l[1]
             nxt = self.plans(1, out2_for) if (out2_for is not None and d_out2 is not None) else None
             # the basic estimate on the rows beyond the strip
@@ -483,19 +511,38 @@ class StripRank:
         self.have_prev, self.have_flt2, self.cur = True, do2, prv
 
     def last_filtered(self, d_out_rgb, second=True):
-        """RGB of the whole most recent filtered frame on this rank (waits for its gather)."""
+        """RGB of the most recent filtered frame on this rank: the whole frame with the NCCL transport
+        (waits for its gather), the rows this rank holds with the peer transport."""
         self._join_lanes()
         src = (self.flt2 if second else self.flt1)[self.cur ^ 1]
+        if self.transport == "peer" and self.nranks > 1:
+            yield from self.need_halo(src)
+            lo, hi = self.local_rows.get(self._buf[src.data_ptr()][0], (0, self.h))
+            self._last_rows = (lo, hi)
+            self.ctx.colour_rows_dev(d_out_rgb, src, 1, lo, hi)
+            return
         yield from self.need_frame(src, "flt2" if second else "flt1")
         self.ctx.colour_rows_dev(d_out_rgb, src, 1, 0, self.h)
 
     def smooth_start(self, d_last_rgb):
         """The last frame of a sequence is its own smoothed version (scripts/nlkalman-seq.sh:122-124).
-        d_last_rgb: full frame, valid everywhere (see last_filtered)."""
+        d_last_rgb: valid on the whole frame, or (peer transport, after last_filtered) on the rows this
+        rank holds."""
         self._join_lanes()
-        self.ctx.colour_rows_dev(self.smo[0], d_last_rgb, 0, 0, self.h)
+        lo, hi = self._last_rows if (self.transport == "peer" and self._last_rows) else (0, self.h)
+        self._last_rows = None
+        self.ctx.colour_rows_dev(self.smo[0], d_last_rgb, 0, lo, hi)
         self.smo_cur, self.have_smo = 0, True
         self.pending.pop("smo", None)
+        if self.transport == "peer" and self.nranks > 1:
+            # the rows are final: the smoothing pass of the frame before warps from them (and pulls what it
+            # lacks from the owners)
+            idx, _ = self._buf[self.smo[0].data_ptr()]
+            v = self._next_seq(self.SLOT_HALO + idx)
+            self.seq[self.SLOT_FRAME + idx] = v
+            self.local_rows[idx] = (lo, hi)
+            self.ctx.peer_signal(self.SLOT_HALO + idx, v, self._mask_nb())
+            self.ctx.peer_signal(self.SLOT_FRAME + idx, v, self._mask_all())
         return
         yield  # noqa: makes this a generator like the other steps
 
@@ -511,7 +558,7 @@ class StripRank:
         smo0 = self.smo[nxt]
         yield from self.need_frame(smo0, "smo")
         if d_fflo is not None:
-            ctx.warp_rows_dev(self.warp, smo0, d_fflo, d_focc, a, b)
+            self._warp(self.warp, smo0, d_fflo, d_focc, a, b)
             smo0 = self.warp
         plans = yield from self.strip_pass(1, self.smo[cur], self.tmp, smo0, None, sigma, s1, key="smo")
         p = plans[self.rank]

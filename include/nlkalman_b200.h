@@ -170,6 +170,7 @@ int nlk_strip_normalize(nlk_ctx *ctx, float *d_out, int row0, int row1);
  *   nlk_peer_push_add  red.global.add the floats of the range into peer `peer` (accumulator halo
  *                      rows into their owner), then flag it.
  *   nlk_peer_signal    the flag alone.
+ *   nlk_warp_rows_peer_dev  the bicubic warp with the rows it does not hold pulled from their owners.
  *   nlk_peer_wait      the stream waits until flag `slot` from every rank in src_mask is >= value
  *                      (sequence numbers, compared modulo 2^32).  A wait gives up after
  *                      NLK_PEER_TIMEOUT_MS (default 4000) and raises the error word read by
@@ -185,6 +186,12 @@ int nlk_peer_push(nlk_ctx *ctx, size_t off, size_t bytes, unsigned int peer_mask
 int nlk_peer_push_add(nlk_ctx *ctx, size_t off, size_t bytes, int peer, int slot, unsigned int value);
 int nlk_peer_signal(nlk_ctx *ctx, int slot, unsigned int value, unsigned int peer_mask);
 int nlk_peer_wait(nlk_ctx *ctx, int slot, unsigned int value, unsigned int src_mask);
+/* warp_bicubic of pixel rows [row0, row1) of the frame that sits at byte offset frame_off of every slab:
+ * tap rows inside [local_lo, local_hi) are read from the own slab, any other row straight from its
+ * owner's slab over NVLink (rank k owns rows [k * chunk_y, (k+1) * chunk_y), the last rank the rest).  The
+ * caller has waited for the owners' "rows final" flags. */
+int nlk_warp_rows_peer_dev(nlk_ctx *ctx, float *d_imw, size_t frame_off, const float *d_of, const float *d_msk,
+                           int row0, int row1, int local_lo, int local_hi, int chunk_y);
 int nlk_peer_error(nlk_ctx *ctx, unsigned int *code);   /* synchronises; 0 = no wait timed out */
 
 /* ---- resident sequence recursion (what scripts/nlkalman-seq.sh does per frame) ------

@@ -23,10 +23,13 @@ def _scene(w, h, ch, sigma, nframes):
     return frames, synth.backward_flow(w, h), synth.forward_flow(w, h), occ
 
 
-@pytest.mark.parametrize("transport", ["peer2", "peer", "nccl"])
+@pytest.mark.parametrize("transport", ["peer2", "peer", "nccl", "peer2-bigflow"])
 @pytest.mark.parametrize("shape,nranks", [((101, 150, 3), 3), ((122, 96, 1), 2), ((90, 200, 3), 4)])
 def test_virtual_strips_match_single_context(nlk, shape, nranks, transport):
-    """peer2 = peer transport with the two filterings of a frame on two lanes (streams)"""
+    """peer2 = peer transport with the two filterings of a frame on two lanes (streams); bigflow = a flow
+    that reaches far beyond a strip's halo, so that the warp pulls rows from other strips' slabs"""
+    bigflow = transport.endswith("-bigflow")
+    transport = transport.replace("-bigflow", "")
     import torch
     from bwd_nlkalman_b200 import strips
     w, h, ch = shape
@@ -34,6 +37,10 @@ def test_virtual_strips_match_single_context(nlk, shape, nranks, transport):
     transport = "peer" if transport == "peer2" else transport
     sigma, nframes = 20.0, 5 if lanes == 2 else 3
     frames, bflo, fflo, occ = _scene(w, h, ch, sigma, nframes)
+    if bigflow:
+        bflo, fflo = bflo.copy(), fflo.copy()
+        bflo[h // 4:h // 2, :, 1] += 0.45 * h        # these rows look two strips further down
+        fflo[h // 2:3 * h // 4, :, 1] -= 0.4 * h     # ... and these two strips up
     f1, f2, s1 = (nlk.default_params(sigma, m) for m in (nlk.FLT1, nlk.FLT2, nlk.SMO1))
     dev = torch.device("cuda", 0)
     up = lambda a: torch.from_numpy(a).to(dev)
