@@ -1030,9 +1030,9 @@ extern "C" int nlk_warp_rows_peer_dev(nlk_ctx *c, float *d_imw, size_t frame_off
     if (row1 <= row0) return NLK_OK;
     ProfScope ps(c, NLK_K_WARP);
     const dim3 nt(32, 8), nb((c->w + 31) / 32, (row1 - row0 + 7) / 8);
-    if (c->ch == 3) k_warp_peer<3><<<nb, nt, 0, c->L->st>>>(d_imw, c->peer, frame_off, d_of, d_msk, c->w, c->h, c->ch, row0, row1, lo, hi, chunk_y);
-    else if (c->ch == 1) k_warp_peer<1><<<nb, nt, 0, c->L->st>>>(d_imw, c->peer, frame_off, d_of, d_msk, c->w, c->h, c->ch, row0, row1, lo, hi, chunk_y);
-    else k_warp_peer<0><<<nb, nt, 0, c->L->st>>>(d_imw, c->peer, frame_off, d_of, d_msk, c->w, c->h, c->ch, row0, row1, lo, hi, chunk_y);
+    if (c->ch == 3) k_warp_peer<3><<<nb, nt, 0, c->L->st>>>(d_imw, c->peer, c->peer.slab[c->peer.rank], frame_off, d_of, d_msk, c->w, c->h, c->ch, row0, row1, lo, hi, chunk_y);
+    else if (c->ch == 1) k_warp_peer<1><<<nb, nt, 0, c->L->st>>>(d_imw, c->peer, c->peer.slab[c->peer.rank], frame_off, d_of, d_msk, c->w, c->h, c->ch, row0, row1, lo, hi, chunk_y);
+    else k_warp_peer<0><<<nb, nt, 0, c->L->st>>>(d_imw, c->peer, c->peer.slab[c->peer.rank], frame_off, d_of, d_msk, c->w, c->h, c->ch, row0, row1, lo, hi, chunk_y);
     return check_launch(c, 1, "warp_rows_peer");
 }
 

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) k_peer_push_add(const PeerTable T, size_t
 // (rows [k * chunk_y, (k+1) * chunk_y) belong to rank k, the rest to the last rank); the frame sits at the
 // same offset in every slab.  Same arithmetic as k_warp.
 template <int CH>
-__global__ void k_warp_peer(float *__restrict__ imw, const PeerTable T, size_t frame_off,
+__global__ void k_warp_peer(float *__restrict__ imw, const PeerTable T, const char *__restrict__ local_base, size_t frame_off,
                             const float *__restrict__ of, const float *__restrict__ msk, int w, int h, int ch_rt,
                             int row0, int row1, int lo, int hi, int chunk_y)
 {
@@ -170,16 +170,20 @@ __global__ void k_warp_peer(float *__restrict__ imw, const PeerTable T, size_t f
         for (int c = 0; c < ch; ++c) o[c] = nanv;
         return;
     }
+    // (kernel parameters are only ever indexed with compile-time constants: a run-time index into the
+    // table would make the compiler keep a copy of it in local memory)
     const float *rowp[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int yy = iy + k;
-        int owner = T.rank;
+        const char *base = local_base;
         if (yy < lo || yy >= hi) {
-            owner = yy / chunk_y;
+            int owner = yy / chunk_y;
             if (owner > T.nranks - 1) owner = T.nranks - 1;
+#pragma unroll
+            for (int q = 0; q < PEER_MAX; ++q) if (q == owner) base = T.slab[q];
         }
-        rowp[k] = reinterpret_cast<const float *>(T.slab[owner] + frame_off) + ((long)yy * w + ix) * ch;
+        rowp[k] = reinterpret_cast<const float *>(base + frame_off) + ((long)yy * w + ix) * ch;
     }
     for (int c = 0; c < ch; ++c) {
         float col[4];
