@@ -622,7 +622,7 @@ inline int launch_search_patch_list(const PassParams &P, int r, cudaStream_t st)
     const int wrow = ((2 * r + P.psz) * P.ch) | 1;        // odd stride: candidate rows fall in different banks
     const size_t smem = (size_t)npad * 8 + (size_t)(2 * r + P.psz) * wrow * 4 + 2 * P.nbw * 4;
     if (smem > 200 * 1024) return -1;
-    const int nb = 148 * 4;
+    const int nb = 148 * 8;      // ~14 KB of shared memory a block: a thousand queued patches in one wave
 #define NLK_LAUNCH_PL(PS, CHN)                                                                        \
     do {                                                                                              \
         cudaFuncSetAttribute(k_search_patch_list<PS, CHN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

@@ -20,7 +20,7 @@ bench)   timeout 600 python bench.py > $OUT/${TAG}_bench_ours.json 2> $OUT/${TAG
 ref)     timeout 900 python bench.py --impl reference --steps 5 --warmup 2 > $OUT/${TAG}_bench_reference.json 2>&1; cut -c1-300 $OUT/${TAG}_bench_reference.json;;
 launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
             --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_launches.log 2>&1;;
-ncu)     timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_group|k_resolve_sys|k_search_rows' -s 0 -c 14 \
+ncu)     timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_group_team8|k_resolve_sys|k_search_rows|k_search_patch' -s 0 -c 16 \
             -f -o $OUT/${TAG}_hot python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu.log 2>&1
          ls -la $OUT/${TAG}_hot.ncu-rep;;
 esac
