@@ -131,6 +131,11 @@ def lib():
                                       C.c_int, C.c_float, _ip]
     L.nlk_tvl1_level_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                      C.c_int, C.c_float, _ip]
+    L.nlk_tvl1_scales.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int]
+    L.nlk_tvl1_flow_host.argtypes = [vp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                     C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, _ip]
+    L.nlk_tvl1_flow_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                    C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, _ip]
     # drop-in entry points
     L.rgb2opp.argtypes = L.opp2rgb.argtypes = [_fp, C.c_int, C.c_int, C.c_int]
     L.warp_bicubic.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int]
@@ -461,11 +466,40 @@ class Context:
                                          float(lam), float(theta), int(warps), float(epsilon), its.ctypes.data_as(_ip)))
         return a, b, its[:warps]
 
+    def tvl1_flow(self, I0, I1, tau=0.25, lam=0.15, theta=0.3, nscales=100, fscale=0, zfactor=0.5, warps=5,
+                  epsilon=0.01):
+        """Dual TV-L1 flow, pyramid and all (reference lib/tvl1flow/tvl1flow_lib.c:345-477 with the scale
+        cap of its driver, main.c:159-163): host images (ny, nx); returns (flow (2, ny, nx): u then v,
+        iterations (nscales, warps))"""
+        ny, nx = I0.shape
+        nscales = tvl1_scales(nx, ny, zfactor, nscales)
+        fscale = min(fscale, nscales)
+        flow = np.empty((2, ny, nx), np.float32)
+        its = np.zeros((nscales, max(warps, 1)), np.int32)
+        _check(lib().nlk_tvl1_flow_host(self._h, _p(np.ascontiguousarray(I0, np.float32)),
+                                        _p(np.ascontiguousarray(I1, np.float32)), _p(flow), nx, ny, float(tau), float(lam),
+                                        float(theta), int(nscales), int(fscale), float(zfactor), int(warps),
+                                        float(epsilon), its.ctypes.data_as(_ip) if warps > 0 else None))
+        return flow, its[:, :warps]
+
+    def tvl1_flow_dev(self, I0, I1, u1, u2, nx, ny, tau=0.25, lam=0.15, theta=0.3, nscales=100, fscale=0, zfactor=0.5,
+                      warps=5, epsilon=0.01):
+        """the same on device buffers (pointers or objects with data_ptr()), queued on the context's stream"""
+        nscales = tvl1_scales(nx, ny, zfactor, nscales)
+        _check(lib().nlk_tvl1_flow_dev(self._h, _vp(I0), _vp(I1), _vp(u1), _vp(u2), int(nx), int(ny), float(tau),
+                                       float(lam), float(theta), int(nscales), int(min(fscale, nscales)), float(zfactor),
+                                       int(warps), float(epsilon), None))
+
     def dct(self, tiles: np.ndarray, inverse: bool = False) -> np.ndarray:
         t = np.ascontiguousarray(tiles, dtype=np.float32).copy()
         n, psz, _ = t.shape
         _check(lib().nlk_dct_host(self._h, _p(t), psz, n, 1 if inverse else 0))
         return t
+
+
+def tvl1_scales(nx: int, ny: int, zfactor: float = 0.5, nscales: int = 100) -> int:
+    """nscales as the reference's tvl1flow driver caps it (lib/tvl1flow/main.c:159-161); host arithmetic"""
+    return int(lib().nlk_tvl1_scales(int(nx), int(ny), float(zfactor), int(nscales)))
 
 
 def strip_plan(w: int, h: int, smooth: int, prms: Params, nranks: int, rank: int) -> StripPlan:

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -135,7 +136,8 @@ struct nlk_ctx {
     bool b_pending = false;      // lane 1 has work that lane 0 has not waited for
     cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr}, ev_join = nullptr;
     long long launches = 0;
-    DevBuf dbg_dist, dbg_vp, tv_scratch;
+    DevBuf dbg_dist, dbg_vp, tv_scratch, tv_pyr;
+    float *tv_herr = nullptr;       // pinned word the TV-L1 level solver reads its stopping error back into
     // host-call staging
     DevBuf s_in1, s_prev0, s_bsic, s_out, s_of, s_msk;
     // sequence state (opponent colour space)
@@ -312,7 +314,7 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     for (int i = 0; i < 2; ++i) if (c->lane[i].st) cudaStreamSynchronize(c->lane[i].st);
     if (c->st_d2h) cudaStreamSynchronize(c->st_d2h);
     if (c->st_h2d) cudaStreamSynchronize(c->st_h2d);
-    DevBuf *all[] = {&c->tv_scratch, &c->dbg_dist, &c->dbg_vp, &c->s_in1, &c->s_prev0, &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk,
+    DevBuf *all[] = {&c->tv_scratch, &c->tv_pyr, &c->dbg_dist, &c->dbg_vp, &c->s_in1, &c->s_prev0, &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk,
                      &c->q_noisy[0], &c->q_noisy[1], &c->q_flt1[0], &c->q_flt1[1], &c->q_flt2[0], &c->q_flt2[1],
                      &c->q_smo[0], &c->q_smo[1], &c->q_tmp};
     for (DevBuf *b : all) b->release();
@@ -337,6 +339,7 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     for (cudaEvent_t e : c->ev_lane) if (e) cudaEventDestroy(e);
     for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
     if (c->h_alpha) cudaFreeHost(c->h_alpha);
+    if (c->tv_herr) cudaFreeHost(c->tv_herr);
     for (int i = 0; i < nlk_ctx::PIPE_SETS; ++i) c->p_msk8[i].release();
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
@@ -1070,8 +1073,8 @@ extern "C" int nlk_tvl1_level_dev(nlk_ctx *c, const float *d_I0, const float *d_
     CU_TRY(cudaMemsetAsync(err, 0, ((size_t)warps * ES) * 4 + (size_t)warps * 4, st));
     k_tvl1_centered_gradient<<<nb, nt, 0, st>>>(d_I1, I1x, I1y, nx, ny);
     if (int r = check_launch(c, 1, "tvl1 gradient")) return r;
-    float *h_err = nullptr;
-    CU_TRY(cudaMallocHost(&h_err, 4));
+    if (!c->tv_herr) CU_TRY(cudaMallocHost(&c->tv_herr, 64));
+    float *h_err = c->tv_herr;
     int rc = NLK_OK;
     for (int wi = 0; wi < warps && rc == NLK_OK; ++wi) {
         float *e = err + (size_t)wi * ES;
@@ -1098,7 +1101,6 @@ extern "C" int nlk_tvl1_level_dev(nlk_ctx *c, const float *d_I0, const float *d_
         k_tvl1_count<<<1, 1, 0, st>>>(e, cnt + wi, (float)size, eps2);
         if (rc == NLK_OK) rc = check_launch(c, 1, "tvl1 count");
     }
-    cudaFreeHost(h_err);
     if (rc != NLK_OK) return rc;
     if (iterations && warps > 0) {
         CU_TRY(cudaMemcpyAsync(iterations, cnt, (size_t)warps * 4, cudaMemcpyDeviceToHost, st));
@@ -1124,6 +1126,88 @@ extern "C" int nlk_tvl1_level_host(nlk_ctx *c, const float *h_I0, const float *h
     if (int r = nlk_tvl1_level_dev(c, d, d + n, d + 2 * n, d + 3 * n, nx, ny, tau, lambda, theta, warps, epsilon, iterations)) return r;
     CU_TRY(cudaMemcpyAsync(h_u1, d + 2 * n, pb, cudaMemcpyDeviceToHost, c->L->st));
     CU_TRY(cudaMemcpyAsync(h_u2, d + 3 * n, pb, cudaMemcpyDeviceToHost, c->L->st));
+    CU_TRY(cudaStreamSynchronize(c->L->st));
+    return NLK_OK;
+}
+
+// ---- the whole estimator: pyramid + levels (Dual_TVL1_optic_flow_multiscale, tvl1flow_lib.c:345-477) ----
+
+extern "C" int nlk_tvl1_scales(int nx, int ny, float zfactor, int nscales)
+{
+    return tvl1_scales_cap(nx, ny, zfactor, nscales);
+}
+
+namespace {
+// the steps of Tvl1Pyramid::run as kernel launches on the context's stream
+struct Tvl1Cuda {
+    nlk_ctx *c;
+    cudaStream_t st;
+    float tau, lambda, theta, epsilon;
+    int warps, launches = 0;
+    static dim3 grid(int w, int h) { return dim3((w + 31) / 32, (h + 7) / 8); }
+    void upload(double *dB, const std::vector<double> &B)
+    {   // (pageable source: staged before the call returns)
+        cudaMemcpyAsync(dB, B.data(), B.size() * 8, cudaMemcpyHostToDevice, st);
+    }
+    void zero(float *p, size_t n) { cudaMemsetAsync(p, 0, n * 4, st); }
+    void normalize(const float *I0, const float *I1, float *O0, float *O1, size_t n, float *part)
+    {
+        const int nparts = (int)std::min<size_t>(TVL1_MINMAX_BLOCKS, (n + 255) / 256);
+        k_tvl1_minmax<<<nparts, 256, 0, st>>>(I0, I1, n, part);
+        k_tvl1_normalize<<<nparts, 256, 0, st>>>(I0, I1, O0, O1, n, part, nparts);
+        launches += 2;
+    }
+    void gauss(const float *in, float *tmp, float *out, int w, int h, const double *B, int taps)
+    {
+        k_tvl1_gauss<true><<<grid(w, h), dim3(32, 8), 0, st>>>(in, tmp, w, h, B, taps);
+        k_tvl1_gauss<false><<<grid(w, h), dim3(32, 8), 0, st>>>(tmp, out, w, h, B, taps);
+        launches += 2;
+    }
+    void zoom(const float *in, float *out, int w, int h, int ww, int hh, float fx, float fy, float scale, int scaled)
+    {
+        k_tvl1_zoom<<<grid(ww, hh), dim3(32, 8), 0, st>>>(in, out, w, h, ww, hh, fx, fy, scale, scaled);
+        launches += 1;
+    }
+    int level(const float *I0, const float *I1, float *u1, float *u2, int w, int h, int *iterations)
+    {
+        if (int r = check_launch(c, launches, "tvl1 pyramid")) return r;
+        launches = 0;
+        return nlk_tvl1_level_dev(c, I0, I1, u1, u2, w, h, tau, lambda, theta, warps, epsilon, iterations);
+    }
+};
+}
+
+extern "C" int nlk_tvl1_flow_dev(nlk_ctx *c, const float *d_I0, const float *d_I1, float *d_u1, float *d_u2,
+                                 int nxx, int nyy, float tau, float lambda, float theta, int nscales, int fscale,
+                                 float zfactor, int warps, float epsilon, int *iterations)
+{
+    if (int r = enter(c)) return r;
+    if (!d_I0 || !d_I1 || !d_u1 || !d_u2) return set_err(NLK_ERR_PARAM, "bad TV-L1 request (null image)");
+    Tvl1Pyramid P;
+    if (!P.plan(nxx, nyy, nscales, fscale, zfactor, warps))
+        return set_err(NLK_ERR_PARAM, "%s (%dx%d, %d scales from %d, zoom %g, %d warpings)", P.error, nxx, nyy, nscales,
+                       fscale, (double)zfactor, warps);
+    if (int r = c->tv_pyr.ensure(P.floats * 4)) return r;
+    Tvl1Cuda ex{c, c->L->st, tau, lambda, theta, epsilon, warps};
+    if (int r = P.run(ex, c->tv_pyr.as<float>(), d_I0, d_I1, d_u1, d_u2, iterations)) return r;
+    return check_launch(c, ex.launches, "tvl1 pyramid");
+}
+
+extern "C" int nlk_tvl1_flow_host(nlk_ctx *c, const float *h_I0, const float *h_I1, float *h_flow, int nx, int ny,
+                                  float tau, float lambda, float theta, int nscales, int fscale, float zfactor,
+                                  int warps, float epsilon, int *iterations)
+{
+    if (int r = enter(c)) return r;
+    if (!h_I0 || !h_I1 || !h_flow || nx < 2 || ny < 2) return set_err(NLK_ERR_PARAM, "bad TV-L1 request");
+    const size_t n = (size_t)nx * ny, pb = n * 4;
+    if (int r = c->q_tmp.ensure(4 * pb)) return r;
+    float *d = c->q_tmp.as<float>();
+    CU_TRY(cudaMemcpyAsync(d, h_I0, pb, cudaMemcpyHostToDevice, c->L->st));
+    CU_TRY(cudaMemcpyAsync(d + n, h_I1, pb, cudaMemcpyHostToDevice, c->L->st));
+    if (int r = nlk_tvl1_flow_dev(c, d, d + n, d + 2 * n, d + 3 * n, nx, ny, tau, lambda, theta, nscales, fscale, zfactor,
+                                  warps, epsilon, iterations)) return r;
+    // two planes, u then v: what the reference's driver hands to iio_write_image_float_split (main.c:177)
+    CU_TRY(cudaMemcpyAsync(h_flow, d + 2 * n, 2 * pb, cudaMemcpyDeviceToHost, c->L->st));
     CU_TRY(cudaStreamSynchronize(c->L->st));
     return NLK_OK;
 }

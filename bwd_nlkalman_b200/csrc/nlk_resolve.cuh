@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(1024) k_resolve_sys(const PassParams P, int rw
     constexpr int C = RB_C, Q = RS_Q;
     static_assert(Q % RS_G == 0, "progress granularity divides the loop body");
     extern __shared__ __align__(8) unsigned int s_dyn[];
-    const int gw = P.gw, gh = P.gh;
+    const int gh = P.gh;
     const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
     // ring w, slot j: what lanes 31 / 30 of warp w published at step first(w) + j.  Ring `nwarps` is the
     // all-zero input of warp 0.

@@ -1,4 +1,4 @@
-// Dual TV-L1 optical flow at one scale (first slice): what the reference's
+// Dual TV-L1 optical flow.  One scale: what the reference's
 // Dual_TVL1_optic_flow computes (lib/tvl1flow/tvl1flow_lib.c:93-280, Zach-Pock-Bischof with
 // Chambolle's dual update), the heavy per-frame step in front of the filter in
 // scripts/nlkalman-seq.sh:60-65.  All of it is per-pixel / 5-point-stencil work on ~14 float planes:
@@ -13,8 +13,22 @@
 // ON THE DEVICE: an iteration's kernels look at the error of the previous one and return at once when
 // it is below the threshold, so a batch of iterations can be queued without a host round trip and
 // the result is that of the exact stopping iteration.
+//
+// Around the level solver, the pyramid of Dual_TVL1_optic_flow_multiscale (:345-477): joint
+// normalisation, separable Gaussian, zoom out / zoom in (kernels at the end of this file; the sequence of
+// steps is in nlk_tvl1_pyramid.h).
+//
+// All arithmetic is written with explicit roundings (__fmul_rn, __dadd_rn ...): the reference is built
+// without FMA contraction (x86-64 baseline, no -ffast-math: lib/tvl1flow/CMakeLists.txt:18), so a * b + c
+// must round twice here as well for the flow to come out bit for bit.  The per-pixel device functions
+// are also compiled for the HOST by tests/models/tvl1_host_model.cpp (NLK_HOST_MODEL: the intrinsics
+// become plain operators, a kernel becomes a loop over its grid) and checked there against the
+// reference's library without a GPU.
 #pragma once
+#ifndef NLK_HOST_MODEL
 #include "nlk_common.cuh"
+#endif
+#include "nlk_tvl1_pyramid.h"
 
 namespace nlk {
 
@@ -44,7 +58,11 @@ __device__ __forceinline__ int tvl1_neumann(int x, int n, bool &out)
 // cubic_interpolation_cell, in double like the reference (bicubic_interpolation.c:102-110)
 __device__ __forceinline__ double tvl1_cubic(double v0, double v1, double v2, double v3, double x)
 {
-    return v1 + 0.5 * x * (v2 - v0 + x * (2.0 * v0 - 5.0 * v1 + 4.0 * v2 - v3 + x * (3.0 * (v1 - v2) + v3 - v0)));
+    const double c3 = __dsub_rn(__dadd_rn(__dmul_rn(3.0, __dsub_rn(v1, v2)), v3), v0);
+    const double c2 = __dadd_rn(__dsub_rn(__dadd_rn(__dsub_rn(__dmul_rn(2.0, v0), __dmul_rn(5.0, v1)), __dmul_rn(4.0, v2)), v3),
+                                __dmul_rn(x, c3));
+    const double c1 = __dadd_rn(__dsub_rn(v2, v0), __dmul_rn(x, c2));
+    return __dadd_rn(v1, __dmul_rn(__dmul_rn(0.5, x), c1));
 }
 
 // bicubic_interpolation_at with border_out = true (bicubic_interpolation.c:138-233), Neumann
@@ -69,9 +87,10 @@ __device__ __forceinline__ Tvl1Taps tvl1_taps(float uu, float vv, int nx, int ny
     t.out = out;
     return t;
 }
+template <bool BORDER_OUT = true>
 __device__ __forceinline__ float tvl1_bicubic(const float *__restrict__ img, const Tvl1Taps &t, int nx)
 {
-    if (t.out) return 0.f;
+    if (BORDER_OUT && t.out) return 0.f;
     double col[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a)   // pol[a][b] = input[xs[a] + nx * ys[b]], interpolated along y first
@@ -104,9 +123,12 @@ __device__ __forceinline__ float tvl1_div(const float *__restrict__ v1, const fl
                                           int nx, int ny)
 {
     const int p = i * nx + j;
-    const float a = j == 0 ? v1[p] : (j == nx - 1 ? -v1[p - 1] : v1[p] - v1[p - 1]);
-    const float b = i == 0 ? v2[p] : (i == ny - 1 ? -v2[p - nx] : v2[p] - v2[p - nx]);
-    return a + b;
+    // (the first and last columns sum left to right in the reference, mask.c:81-82: keep its association)
+    if ((j == 0 || j == nx - 1) && i > 0 && i < ny - 1)
+        return __fsub_rn(__fadd_rn(j == 0 ? v1[p] : -v1[p - 1], v2[p]), v2[p - nx]);
+    const float a = j == 0 ? v1[p] : (j == nx - 1 ? -v1[p - 1] : __fsub_rn(v1[p], v1[p - 1]));
+    const float b = i == 0 ? v2[p] : (i == ny - 1 ? -v2[p - nx] : __fsub_rn(v2[p], v2[p - nx]));
+    return __fadd_rn(a, b);
 }
 
 // err[n]: sum over the pixels of the squared update of iteration n (n = 1 ..); err[0] unused.
@@ -116,6 +138,32 @@ __device__ __forceinline__ bool tvl1_runs(const float *err, int n, float size, f
     return n == 1 || __fdiv_rn(err[n - 1], size) > eps2;
 }
 
+// thresholding step, divergence and flow update of one pixel; returns its squared update
+__device__ __forceinline__ float tvl1_u_pixel(const float *__restrict__ rho_c, const float *__restrict__ I1wx,
+                                              const float *__restrict__ I1wy, const float *__restrict__ grad,
+                                              const float *__restrict__ p11, const float *__restrict__ p12,
+                                              const float *__restrict__ p21, const float *__restrict__ p22,
+                                              float *__restrict__ u1, float *__restrict__ u2, int i, int j, int nx, int ny,
+                                              float l_t, float theta)
+{
+    const int p = i * nx + j;
+    const float wx = I1wx[p], wy = I1wy[p], g = grad[p], a = u1[p], b = u2[p];
+    const float rho = __fadd_rn(rho_c[p], __fadd_rn(__fmul_rn(wx, a), __fmul_rn(wy, b)));
+    const float lg = __fmul_rn(l_t, g);
+    float d1, d2;
+    if (rho < -lg) { d1 = __fmul_rn(l_t, wx); d2 = __fmul_rn(l_t, wy); }
+    else if (rho > lg) { d1 = __fmul_rn(-l_t, wx); d2 = __fmul_rn(-l_t, wy); }
+    else if (g < TVL1_GRAD_IS_ZERO) { d1 = d2 = 0.f; }
+    else { const float fi = __fdiv_rn(-rho, g); d1 = __fmul_rn(fi, wx); d2 = __fmul_rn(fi, wy); }
+    const float na = __fadd_rn(__fadd_rn(a, d1), __fmul_rn(theta, tvl1_div(p11, p12, i, j, nx, ny)));
+    const float nb = __fadd_rn(__fadd_rn(b, d2), __fmul_rn(theta, tvl1_div(p21, p22, i, j, nx, ny)));
+    u1[p] = na;
+    u2[p] = nb;
+    const float da = __fsub_rn(na, a), db = __fsub_rn(nb, b);
+    return __fadd_rn(__fmul_rn(da, da), __fmul_rn(db, db));
+}
+
+#ifndef NLK_HOST_MODEL
 __global__ void __launch_bounds__(256) k_tvl1_u(const float *__restrict__ rho_c, const float *__restrict__ I1wx,
                                                 const float *__restrict__ I1wy, const float *__restrict__ grad,
                                                 const float *__restrict__ p11, const float *__restrict__ p12,
@@ -126,21 +174,7 @@ __global__ void __launch_bounds__(256) k_tvl1_u(const float *__restrict__ rho_c,
     if (!tvl1_runs(err, n, (float)(nx * ny), eps2)) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
     float e = 0.f;
-    if (j < nx && i < ny) {
-        const int p = i * nx + j;
-        const float wx = I1wx[p], wy = I1wy[p], g = grad[p], a = u1[p], b = u2[p];
-        const float rho = rho_c[p] + (wx * a + wy * b);
-        float d1, d2;
-        if (rho < -l_t * g) { d1 = l_t * wx; d2 = l_t * wy; }
-        else if (rho > l_t * g) { d1 = -l_t * wx; d2 = -l_t * wy; }
-        else if (g < TVL1_GRAD_IS_ZERO) { d1 = d2 = 0.f; }
-        else { const float fi = -rho / g; d1 = fi * wx; d2 = fi * wy; }
-        const float na = (a + d1) + theta * tvl1_div(p11, p12, i, j, nx, ny);
-        const float nb = (b + d2) + theta * tvl1_div(p21, p22, i, j, nx, ny);
-        u1[p] = na;
-        u2[p] = nb;
-        e = (na - a) * (na - a) + (nb - b) * (nb - b);
-    }
+    if (j < nx && i < ny) e = tvl1_u_pixel(rho_c, I1wx, I1wy, grad, p11, p12, p21, p22, u1, u2, i, j, nx, ny, l_t, theta);
     // block sum, one atomic per block
     __shared__ float s_red[8];
 #pragma unroll
@@ -155,6 +189,7 @@ __global__ void __launch_bounds__(256) k_tvl1_u(const float *__restrict__ rho_c,
         if (t == 0) atomicAdd(err + n, e);
     }
 }
+#endif
 
 __global__ void __launch_bounds__(256) k_tvl1_p(const float *__restrict__ u1, const float *__restrict__ u2,
                                                 float *__restrict__ p11, float *__restrict__ p12,
@@ -171,11 +206,12 @@ __global__ void __launch_bounds__(256) k_tvl1_p(const float *__restrict__ u1, co
     const float u2x = j < nx - 1 ? u2[p + 1] - b : 0.f, u2y = i < ny - 1 ? u2[p + nx] - b : 0.f;
     // (the reference's hypot and `1.0 +` are double: :239-242)
     const double g1 = hypot((double)u1x, (double)u1y), g2 = hypot((double)u2x, (double)u2y);
-    const float ng1 = (float)(1.0 + (double)(taut * (float)g1)), ng2 = (float)(1.0 + (double)(taut * (float)g2));
-    p11[p] = (p11[p] + taut * u1x) / ng1;
-    p12[p] = (p12[p] + taut * u1y) / ng1;
-    p21[p] = (p21[p] + taut * u2x) / ng2;
-    p22[p] = (p22[p] + taut * u2y) / ng2;
+    const float ng1 = (float)__dadd_rn(1.0, (double)__fmul_rn(taut, (float)g1));
+    const float ng2 = (float)__dadd_rn(1.0, (double)__fmul_rn(taut, (float)g2));
+    p11[p] = __fdiv_rn(__fadd_rn(p11[p], __fmul_rn(taut, u1x)), ng1);
+    p12[p] = __fdiv_rn(__fadd_rn(p12[p], __fmul_rn(taut, u1y)), ng1);
+    p21[p] = __fdiv_rn(__fadd_rn(p21[p], __fmul_rn(taut, u2x)), ng2);
+    p22[p] = __fdiv_rn(__fadd_rn(p22[p], __fmul_rn(taut, u2y)), ng2);
 }
 
 // iterations run by a warping step = the last n that passed the test
@@ -184,6 +220,102 @@ __global__ void k_tvl1_count(const float *err, int *count, float size, float eps
     int n = 1;
     while (n < TVL1_MAX_ITERATIONS && __fdiv_rn(err[n], size) > eps2) ++n;
     *count = n;
+}
+
+// ---- the pyramid around the level solver (Dual_TVL1_optic_flow_multiscale, tvl1flow_lib.c:345-477) ----
+
+// image_normalization (tvl1flow_lib.c:305-337): 255 (I - min) / (max - min) in double, or a copy
+__device__ __forceinline__ float tvl1_norm_pixel(float a, float mn, float den)
+{
+    return den > 0.f ? (float)__ddiv_rn(__dmul_rn(255.0, (double)__fsub_rn(a, mn)), (double)den) : a;
+}
+
+#ifndef NLK_HOST_MODEL
+// joint extrema of the two images, stage 1 (getminmax, tvl1flow_lib.c:283-298): part[2b] = min, part[2b+1] = max
+__global__ void __launch_bounds__(256) k_tvl1_minmax(const float *__restrict__ I0, const float *__restrict__ I1, size_t size,
+                                                     float *__restrict__ part)
+{
+    float mn = I0[0], mx = mn;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < size; i += (size_t)gridDim.x * blockDim.x) {
+        const float a = I0[i], b = I1[i];
+        if (a < mn) mn = a;
+        if (a > mx) mx = a;
+        if (b < mn) mn = b;
+        if (b > mx) mx = b;
+    }
+    __shared__ float s_mn[8], s_mx[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) { mn = fminf(mn, s_mn[k]); mx = fmaxf(mx, s_mx[k]); }
+        part[2 * blockIdx.x] = mn;
+        part[2 * blockIdx.x + 1] = mx;
+    }
+}
+
+// stage 2 + image_normalization (tvl1flow_lib.c:305-337): 255 (I - min) / (max - min) in double, or a copy
+__global__ void __launch_bounds__(256) k_tvl1_normalize(const float *__restrict__ I0, const float *__restrict__ I1,
+                                                        float *__restrict__ O0, float *__restrict__ O1, size_t size,
+                                                        const float *__restrict__ part, int nparts)
+{
+    __shared__ float s_mn[8], s_mx[8];
+    float mn = part[0], mx = part[1];
+    for (int k = threadIdx.x; k < nparts; k += blockDim.x) { mn = fminf(mn, part[2 * k]); mx = fmaxf(mx, part[2 * k + 1]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    mn = s_mn[0]; mx = s_mx[0];
+    for (int k = 1; k < 8; ++k) { mn = fminf(mn, s_mn[k]); mx = fmaxf(mx, s_mx[k]); }
+    const float den = __fsub_rn(mx, mn);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < size; i += (size_t)gridDim.x * blockDim.x) {
+        const float a = I0[i], b = I1[i];
+        O0[i] = tvl1_norm_pixel(a, mn, den);
+        O1[i] = tvl1_norm_pixel(b, mn, den);
+    }
+}
+#endif
+
+// One direction of the separable Gaussian (mask.c:216-330): double accumulation in the reference's order,
+// its boundary rule (the left / top side mirrors about the border sample, the right / bottom side
+// repeats it: R[-m] = I[m], R[n + m] = I[n - 1 - m]), float result.  B: the normalised half kernel.
+template <bool ROWS>
+__global__ void __launch_bounds__(256) k_tvl1_gauss(const float *__restrict__ in, float *__restrict__ out, int nx, int ny,
+                                                    const double *__restrict__ B, int taps)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (j >= nx || i >= ny) return;
+    const int n = ROWS ? nx : ny, q = ROWS ? j : i;
+    const float *line = ROWS ? in + (size_t)i * nx : in + j;
+    const int step = ROWS ? 1 : nx;
+    double sum = __dmul_rn(B[0], (double)line[(size_t)q * step]);
+    for (int k = 1; k < taps; ++k) {
+        int a = q - k, b = q + k;
+        if (a < 0) a = -a;
+        if (b >= n) b = 2 * n - 1 - b;
+        sum = __dadd_rn(sum, __dmul_rn(B[k], __dadd_rn((double)line[(size_t)a * step], (double)line[(size_t)b * step])));
+    }
+    out[(size_t)i * nx + j] = (float)sum;
+}
+
+// zoom_out's resampling and zoom_in (zoom.c:70-79, :104-112): bicubic at (j1 / fx, i1 / fy), samples
+// beyond the border clamped (border_out = false); `scale` is the 1 / zfactor of the flow (1 for images)
+__global__ void k_tvl1_zoom(const float *__restrict__ in, float *__restrict__ out, int nx, int ny, int nxx, int nyy,
+                            float fx, float fy, float scale, int scaled)
+{
+    const int j1 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y * blockDim.y + threadIdx.y;
+    if (j1 >= nxx || i1 >= nyy) return;
+    const Tvl1Taps t = tvl1_taps(__fdiv_rn((float)j1, fx), __fdiv_rn((float)i1, fy), nx, ny);
+    const float g = tvl1_bicubic<false>(in, t, nx);
+    out[(size_t)i1 * nxx + j1] = scaled ? __fmul_rn(g, scale) : g;
 }
 
 } // namespace nlk

@@ -11,6 +11,8 @@
 #include <zlib.h>
 
 static char g_err[512];
+/* sample type of the file read last: 8 / 16 = unsigned integers of that width, 0 = anything else */
+static int g_sample_bits;
 
 static int fail(const char *fmt, ...)
 {
@@ -243,6 +245,7 @@ static float *read_png(const buf_t *b, int *w, int *h, int *c)
         }
     }
     free(raw);
+    g_sample_bits = depth == 16 ? 16 : 8;
     *w = (int)W; *h = (int)H; *c = outc;
     return x;
 }
@@ -442,6 +445,7 @@ static float *read_tiff(const buf_t *b, int *w, int *h, int *c)
         }
     }
     free(raw);
+    g_sample_bits = (fmt == 1 && (bits == 8 || bits == 16)) ? (int)bits : 0;
     *w = (int)W; *h = (int)H; *c = (int)spp;
     return x;
 }
@@ -451,6 +455,7 @@ static float *read_tiff(const buf_t *b, int *w, int *h, int *c)
 float *nlk_read_image(const char *path, int *w, int *h, int *c)
 {
     g_err[0] = 0;
+    g_sample_bits = 0;
     if (!path) { fail("no path"); return NULL; }
     buf_t b;
     if (slurp(path, &b)) return NULL;
@@ -469,6 +474,26 @@ float *nlk_read_image(const char *path, int *w, int *h, int *c)
         snprintf(g_err, sizeof g_err, "%s", tmp);
     }
     return x;
+}
+
+/* Single-channel read as iio_read_image_float does it (reference lib/iio/iio.c:3984-4003): 3 or 4
+ * channels become .299 R + .587 G + .114 B (alpha dropped), computed in double and stored in the
+ * sample type iio holds the file in before the conversion to float -- so 8 and 16 bit PNG / TIFF
+ * truncate to an integer (:1021-1093); PNM samples are floats in iio from the start -- any other
+ * channel count is an error. */
+float *nlk_read_image_gray(const char *path, int *w, int *h)
+{
+    int c;
+    float *x = nlk_read_image(path, w, h, &c);
+    if (!x || c == 1) return x;
+    if (c != 3 && c != 4) { free(x); fail("%s: %d channels cannot be read as a scalar image", path, c); return NULL; }
+    const size_t n = (size_t)*w * *h;
+    for (size_t i = 0; i < n; ++i) {
+        const double y = .299 * x[i * c] + .587 * x[i * c + 1] + .114 * x[i * c + 2];
+        x[i] = g_sample_bits == 8 ? (float)(uint8_t)y : (g_sample_bits == 16 ? (float)(uint16_t)y : (float)y);
+    }
+    float *g = (float *)realloc(x, n * sizeof(float));
+    return g ? g : x;
 }
 
 /* ---- writers ------------------------------------------------------------------------------ */

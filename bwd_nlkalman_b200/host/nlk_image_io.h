@@ -24,6 +24,9 @@ extern "C" {
 
 /* Returns a malloc'd w*h*c float array, or NULL (message in nlk_io_error()). */
 float *nlk_read_image(const char *path, int *w, int *h, int *c);
+/* The same as one channel, the way the reference's scalar read does it (iio_read_image_float, reference
+ * lib/iio/iio.c:3984: .299 R + .587 G + .114 B in the file's sample type): the flow estimator's input. */
+float *nlk_read_image_gray(const char *path, int *w, int *h);
 /* Returns 0 on success, nonzero on failure (message in nlk_io_error()). */
 int nlk_write_image(const char *path, const float *x, int w, int h, int c);
 const char *nlk_io_error(void);

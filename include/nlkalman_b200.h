@@ -256,21 +256,44 @@ int nlk_seq_smooth_host(nlk_ctx *ctx, const float *h_flt_rgb, const float *h_ffl
                         const float *h_focc, float sigma, struct nlkalman_params s1,
                         float *h_smo_out);
 
-/* ---- Dual TV-L1 optical flow at one scale (first slice of SURVEY.md 8(f4)) ---------------------
+/* ---- Dual TV-L1 optical flow, one scale ---------------------------------------
  * What the reference's Dual_TVL1_optic_flow does (lib/tvl1flow/tvl1flow_lib.c:93-280; called per
  * pyramid level by Dual_TVL1_optic_flow_multiscale, :345-477, the flow estimator in front of the
  * filter in scripts/nlkalman-seq.sh:60-65): `warps` times { bicubic warp of I1 and its centred
  * gradient by the current flow, then the thresholding / Chambolle dual iterations until the mean
  * squared update falls to epsilon^2 or 300 iterations }.  I0, I1: nx x ny single-channel images
  * (the level's, already normalised and smoothed); u1, u2: the flow, initial value in, result out.
- * iterations (host, [warps], may be NULL): iterations run by each warping step.  The pyramid around
- * it (normalisation, Gaussian pre-smoothing, zoom) is not built yet. */
+ * iterations (host, [warps], may be NULL): iterations run by each warping step.  The arithmetic is
+ * written with the reference's roundings (no fused multiply-add), so a level's flow is the
+ * reference's bit for bit unless the float sum behind the stopping test lands on the other side of
+ * epsilon^2 (its order differs; the reference's own OpenMP reduction is not ordered either). */
 int nlk_tvl1_level_dev(nlk_ctx *ctx, const float *d_I0, const float *d_I1, float *d_u1, float *d_u2,
                        int nx, int ny, float tau, float lambda, float theta, int warps, float epsilon,
                        int *iterations);
 int nlk_tvl1_level_host(nlk_ctx *ctx, const float *h_I0, const float *h_I1, float *h_u1, float *h_u2,
                         int nx, int ny, float tau, float lambda, float theta, int warps, float epsilon,
                         int *iterations);
+
+/* ---- Dual TV-L1 optical flow, the whole estimator ----------------------------
+ * What the reference's Dual_TVL1_optic_flow_multiscale does (lib/tvl1flow/tvl1flow_lib.c:345-477),
+ * the library call behind the `tvl1flow` program of scripts/nlkalman-seq.sh:60-65, :124-129:
+ * normalise both images to [0, 255] over their joint range (:305-337), Gaussian pre-smoothing
+ * sigma 0.8 (:385-386, lib/tvl1flow/mask.c:216-330), `nscales` levels each zoomed out by `zfactor`
+ * (Gaussian 0.6 sqrt(1/zfactor^2 - 1) + bicubic resampling, lib/tvl1flow/zoom.c:44-83), then from
+ * the coarsest level down to `fscale` the level solver above, the flow zoomed in and multiplied by
+ * 1 / zfactor between levels (zoom.c:91-113); levels finer than `fscale` only upsample.
+ * I0, I1: nx x ny single-channel images; the flow u1, u2 (x and y displacement, nx x ny each) is
+ * output only.  iterations (host, [nscales * warps], may be NULL): [s * warps + k] = iterations of
+ * warping k at scale s (0 where a scale was skipped).  nlk_tvl1_flow_host returns the flow as two
+ * planes, u1 then u2: the buffer the reference's driver writes (lib/tvl1flow/main.c:177).
+ * nlk_tvl1_scales: the reference driver's cap on nscales (main.c:159-161), no level much below 16 px. */
+int nlk_tvl1_scales(int nx, int ny, float zfactor, int nscales);
+int nlk_tvl1_flow_dev(nlk_ctx *ctx, const float *d_I0, const float *d_I1, float *d_u1, float *d_u2,
+                      int nx, int ny, float tau, float lambda, float theta, int nscales, int fscale,
+                      float zfactor, int warps, float epsilon, int *iterations);
+int nlk_tvl1_flow_host(nlk_ctx *ctx, const float *h_I0, const float *h_I1, float *h_flow, int nx, int ny,
+                       float tau, float lambda, float theta, int nscales, int fscale, float zfactor,
+                       int warps, float epsilon, int *iterations);
 
 /* ---- stage dumps for the parity tests (host arrays, any may be NULL) ------------------
  * Runs one pass on host images like nlkalman_filter_frame / nlkalman_smooth_frame and

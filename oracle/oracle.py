@@ -83,6 +83,82 @@ class Tvl1Ref:
                                       _p(a), _p(b), nx, ny, tau, lam, theta, warps, epsilon, False)
         return a, b
 
+    def flow(self, I0, I1, tau=0.25, lam=0.15, theta=0.3, nscales=100, fscale=0, zfactor=0.5, warps=5, epsilon=0.01):
+        """Dual_TVL1_optic_flow_multiscale (tvl1flow_lib.c:345) with the scale cap of the reference's driver
+        (lib/tvl1flow/main.c:159-163); returns the flow as (2, ny, nx): u then v"""
+        ny, nx = I0.shape
+        N = np.float32(1 + np.log(np.hypot(nx, ny) / 16.0) / np.log(float(np.float32(1) / np.float32(zfactor))))
+        if N < nscales:
+            nscales = int(N)
+        fscale = min(fscale, nscales)
+        f = self.lib.Dual_TVL1_optic_flow_multiscale
+        f.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float,
+                      C.c_int, C.c_float, C.c_bool]
+        f.restype = None
+        out = np.zeros((2, ny, nx), np.float32)
+        f(_p(np.ascontiguousarray(I0, np.float32)), _p(np.ascontiguousarray(I1, np.float32)), _p(out[0]), _p(out[1]),
+          nx, ny, tau, lam, theta, nscales, fscale, zfactor, warps, epsilon, False)
+        return out, nscales
+
+    def gaussian(self, I, sigma):
+        """gaussian() of lib/tvl1flow/mask.c:216, in place there, a copy here"""
+        a = np.ascontiguousarray(I, np.float32).copy()
+        f = self.lib.gaussian
+        f.argtypes = [_fp, C.c_int, C.c_int, C.c_double]
+        f.restype = None
+        f(_p(a), a.shape[1], a.shape[0], float(sigma))
+        return a
+
+    def zoom_out(self, I, factor):
+        """zoom_out of lib/tvl1flow/zoom.c:44"""
+        ny, nx = I.shape
+        nxx, nyy = C.c_int(), C.c_int()
+        self.lib.zoom_size.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_float]
+        self.lib.zoom_size(nx, ny, C.byref(nxx), C.byref(nyy), factor)
+        out = np.zeros((nyy.value, nxx.value), np.float32)
+        f = self.lib.zoom_out
+        f.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_float]
+        f.restype = None
+        f(_p(np.ascontiguousarray(I, np.float32)), _p(out), nx, ny, factor)
+        return out
+
+    def zoom_in(self, I, nxx, nyy):
+        """zoom_in of lib/tvl1flow/zoom.c:91"""
+        ny, nx = I.shape
+        out = np.zeros((nyy, nxx), np.float32)
+        f = self.lib.zoom_in
+        f.argtypes = [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int]
+        f.restype = None
+        f(_p(np.ascontiguousarray(I, np.float32)), _p(out), nx, ny, nxx, nyy)
+        return out
+
+
+def tvl1_truth(nx, ny):
+    """the motion of tvl1_frames: I1(x) = I0(x - d(x)), a smooth field of a few pixels"""
+    xs, ys = np.meshgrid(np.arange(nx, dtype=np.float64), np.arange(ny, dtype=np.float64))
+    return 2.5 + 1.5 * np.sin(ys / ny * 3.0), -1.25 + 1.0 * np.cos(xs / nx * 2.0)
+
+
+def tvl1_frames(nx, ny, seed=5, noise=4.0):
+    """two frames of a moving textured scene in arbitrary units (not normalised, not smoothed): the input
+    of the whole estimator.  Band-limited texture (below 0.3 rad / px) so that the coarse scales see it
+    and the estimator converges to the motion (tvl1_truth) instead of aliasing."""
+    rng = np.random.default_rng(seed)
+    xs, ys = np.meshgrid(np.arange(nx, dtype=np.float64), np.arange(ny, dtype=np.float64))
+    r = np.random.default_rng(seed + 1)
+    comps = [(r.uniform(0.03, 0.3) * r.choice([-1, 1]), r.uniform(0.03, 0.3) * r.choice([-1, 1]), r.uniform(0, 6.28))
+             for _ in range(24)]
+
+    def img(x, y):
+        out = np.zeros_like(x)
+        for fx, fy, ph in comps:
+            out += 1.0 / (abs(fx) + abs(fy)) ** 0.5 * np.sin(fx * x + fy * y + ph)
+        return out
+    dx, dy = tvl1_truth(nx, ny)
+    I0 = img(xs, ys) + rng.normal(0, noise / 255.0, (ny, nx))
+    I1 = img(xs - dx, ys - dy) + rng.normal(0, noise / 255.0, (ny, nx))
+    return (I0 * 20 + 40).astype(np.float32), (I1 * 20 + 40).astype(np.float32)
+
 
 def tvl1_pair(nx, ny, shift=(1.5, -0.75), seed=3):
     """a smooth textured image pair, I1(x) = I0(x - shift) up to a little noise, in 0..255 like a

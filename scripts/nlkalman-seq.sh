@@ -18,9 +18,9 @@
 # occlusion masks bflo1-%03d.flo bocc1-%03d.png fflo-%03d.flo focc-%03d.png (kept and
 # reused on a re-run, so a sequence can be resumed at any frame).
 #
-# Optical flow (tvl1flow) and the mask arithmetic (plambda) are not part of this
-# package: they are looked up next to this script, then in PATH, or given through the
-# TVL1FLOW / PLAMBDA environment variables.
+# The optical flow estimator (tvl1flow) and the occlusion mask (nlkalman-occ, standing in for the
+# reference's plambda expression) are the package's GPU programs, installed next to this script;
+# other builds can be given through the TVL1FLOW / PLAMBDA / NLKALMAN_OCC environment variables.
 
 set -u
 SEQ=$1; FFR=$2; LFR=$3; SIG=$4; OUT=$5

@@ -189,3 +189,50 @@ def test_seq_driver_matches_per_frame_chain(scene):
         close(d / f"q2_{t}.pfm", d / f"c2_{t}.pfm")
     for t in (0, 1):
         close(d / f"qs_{t}.pfm", d / f"cs_{t}.pfm")
+
+
+def _read_flo(path):
+    raw = open(path, "rb").read()
+    assert raw[:4] == b"PIEH"
+    w, h = np.frombuffer(raw[4:12], np.int32)
+    return np.frombuffer(raw[12:], np.float32).reshape(h, w, 2)
+
+
+def test_tvl1flow_against_reference_program(tmp_path):
+    """bin/tvl1flow against the reference's own program (oracle/_ref/tvl1flow-ref: lib/tvl1flow/main.c
+    unmodified) with the command lines of the pipeline script (scripts/nlkalman-seq.sh:51, :111:
+    "NPROC 0 DW 0 0 FSCALE": zeros mean defaults) and with every argument given."""
+    from oracle import oracle as O
+    ref = os.path.join(REF, "tvl1flow-ref")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/tvl1flow-ref not built (needs /root/reference)")
+    nx, ny = 240, 176
+    I0, I1 = O.tvl1_frames(nx, ny, seed=21)
+    # a colour pair as well: both programs read it as luminance
+    rgb = lambda g: np.stack([g, 0.7 * g + 30, 200 - 0.5 * g], -1).astype(np.float32)
+    _write_pfm(tmp_path / "a.pfm", I0); _write_pfm(tmp_path / "b.pfm", I1)
+    _write_pfm(tmp_path / "ca.pfm", rgb(I0)); _write_pfm(tmp_path / "cb.pfm", rgb(I1))
+    cases = [("script", ("a.pfm", "b.pfm"), ("8", "0", "0.25", "0", "0", "1")),
+             ("colour", ("ca.pfm", "cb.pfm"), ("2", "0", "0.40", "0", "0", "1")),
+             ("explicit", ("a.pfm", "b.pfm"), ("1", "0.2", "0.3", "0.25", "4", "0", "0.6", "3", "0.02", "1")),
+             ("defaults", ("a.pfm", "b.pfm"), ())]
+    for name, (f0, f1), args in cases:
+        ours, theirs = tmp_path / f"ours-{name}.flo", tmp_path / f"ref-{name}.flo"
+        if args:
+            _run(os.path.join(BIN, "tvl1flow"), tmp_path / f0, tmp_path / f1, ours, *args)
+            _run(ref, tmp_path / f0, tmp_path / f1, theirs, *args)
+        else:   # default output name, in the working directory
+            for exe, dst in ((os.path.join(BIN, "tvl1flow"), ours), (ref, theirs)):
+                r = subprocess.run([exe, str(tmp_path / f0), str(tmp_path / f1)], cwd=tmp_path, capture_output=True, text=True)
+                assert r.returncode == 0, r.stderr
+                os.replace(tmp_path / "flow.flo", dst)
+        a, b = _read_flo(ours), _read_flo(theirs)
+        e = maxabs(a, b)
+        print(f"tvl1flow {name}: max |du| = {e:.2e} px, identical pixels {float(np.mean(a == b)):.4f}")
+        assert a.shape == (ny, nx, 2) and np.abs(b).max() > 2.0
+        assert e <= 5e-2
+    r = _run(os.path.join(BIN, "tvl1flow"), ok=(1,))
+    assert "Usage" in r.stderr
+    _write_pfm(tmp_path / "small.pfm", I0[:50, :60])
+    r = _run(os.path.join(BIN, "tvl1flow"), tmp_path / "a.pfm", tmp_path / "small.pfm", tmp_path / "x.flo", ok=(1,))
+    assert "size mismatch" in r.stderr

@@ -1,11 +1,14 @@
-"""Dual TV-L1 optical flow at one scale on the GPU (first slice) against the
-reference's own library (lib/tvl1flow/tvl1flow_lib.c:93-280 compiled unmodified as
+"""Dual TV-L1 optical flow on the GPU: one scale (lib/tvl1flow/tvl1flow_lib.c:93-280)
+and the whole pyramid (:345-477) against the reference's own library (compiled unmodified as
 oracle/_ref/libtvl1_ref.so) and against golden vectors it produced.
 
-Floating point, iterative: the tolerance is 2e-3 px on the flow when both sides run the same
-iterations (epsilon = 0: all 300 of every warping step), and with the data-dependent stopping rule
-(:164) the iteration counts may differ by one near the threshold, where one update moves the flow
-by about epsilon = 0.01 px."""
+The kernels round like the reference (no fused multiply-add; tests/test_tvl1_model.py checks the same
+device functions bit for bit on the CPU), so with the same iterations the flows are expected to be
+IDENTICAL; what can differ is the float sum behind the stopping rule (:164, another order here and in
+the reference's own OpenMP reduction): when it lands on the other side of epsilon^2 one side runs one
+more iteration, which moves the flow by about epsilon = 0.01 px.  Tolerances: 1e-4 px when both
+sides run all iterations (epsilon = 0), 5e-2 px with the stopping rule; the fraction of bit-identical
+pixels is printed."""
 import os
 
 import numpy as np
@@ -28,7 +31,7 @@ def test_tvl1_level_against_golden(nlk):
         assert list(its) == [300, 300]
         e = max(_err(u1, g["full_u1"]), _err(u2, g["full_u2"]))
         print(f"tvl1 96x72, 2 x 300 iterations: max |du| = {e:.2e} px")
-        assert e <= 2e-3
+        assert e <= 1e-4
         v1, v2, its = ctx.tvl1_level(g["I0"], g["I1"], z, z, tau, lam, theta, warps=5, epsilon=0.01)
         e = max(_err(v1, g["dflt_u1"]), _err(v2, g["dflt_u2"]))
         print(f"tvl1 96x72, default stopping rule: iterations {list(its)}, max |du| = {e:.2e} px")
@@ -54,9 +57,72 @@ def test_tvl1_level_against_reference_library(nlk, shape):
         r1, r2 = ref.level(I0, I1, u0, v0, warps=3, epsilon=0.0)
         e = max(_err(a1, r1), _err(a2, r2))
         print(f"tvl1 {nx}x{ny}, 3 x 300 iterations: max |du| = {e:.2e} px")
-        assert list(its) == [300, 300, 300] and e <= 2e-3
+        assert list(its) == [300, 300, 300] and e <= 1e-4
         b1, b2, its = ctx.tvl1_level(I0, I1, u0, v0, warps=5, epsilon=0.01)
         q1, q2 = ref.level(I0, I1, u0, v0, warps=5, epsilon=0.01)
         e = max(_err(b1, q1), _err(b2, q2))
         print(f"tvl1 {nx}x{ny}, default stopping rule: iterations {list(its)}, max |du| = {e:.2e} px")
         assert e <= 5e-2
+
+
+def _same(a, b):
+    return float(np.mean(a == b))
+
+
+def test_tvl1_flow_against_golden(nlk):
+    g = np.load(os.path.join(os.path.dirname(GOLD), "flow_160x120.npz"))
+    I0, I1 = g["I0"], g["I1"]
+    ny, nx = I0.shape
+    assert nlk.tvl1_scales(nx, ny, 0.5, 100) == int(g["nscales"][0])
+    with nlk.Context(nx, ny, 1) as ctx:
+        for key, kw in (("flow_default", {}), ("flow_script", dict(lam=0.4, fscale=1))):
+            flow, its = ctx.tvl1_flow(I0, I1, **kw)
+            e = _err(flow, g[key])
+            print(f"tvl1 pyramid {nx}x{ny} {key}: max |du| = {e:.2e} px, identical pixels {_same(flow, g[key]):.4f}, "
+                  f"iterations per scale {its.sum(1).tolist()}")
+            assert e <= 5e-2
+            assert (its[kw.get("fscale", 0):] >= 1).all() and (its[:kw.get("fscale", 0)] == 0).all()
+    from oracle import oracle as O
+    dx, dy = O.tvl1_truth(nx, ny)     # it is the motion of the scene
+    assert np.median(np.abs(flow[0] - dx)) < 0.1 and np.median(np.abs(flow[1] - dy)) < 0.1
+
+
+@pytest.mark.parametrize("nx,ny,kw", [(320, 240, {}), (200, 150, dict(lam=0.4, fscale=1)), (131, 97, dict(zfactor=0.7)),
+                                      (96, 72, dict(nscales=1)), (640, 360, dict(lam=0.25, fscale=1, epsilon=0.0, warps=2))])
+def test_tvl1_flow_against_reference_library(nlk, nx, ny, kw):
+    from oracle import oracle as O
+    if not os.path.exists(O.TVL1_SO):
+        pytest.skip("oracle/_ref/libtvl1_ref.so not built (needs /root/reference)")
+    ref = O.Tvl1Ref()
+    I0, I1 = O.tvl1_frames(nx, ny, seed=nx)
+    want, nscales = ref.flow(I0, I1, **kw)
+    with nlk.Context(nx, ny, 1) as ctx:
+        flow, its = ctx.tvl1_flow(I0, I1, **kw)
+    assert its.shape[0] == nscales
+    e = _err(flow, want)
+    print(f"tvl1 pyramid {nx}x{ny} {kw}: {nscales} scales, max |du| = {e:.2e} px, identical pixels {_same(flow, want):.4f}, "
+          f"iterations per scale {its.sum(1).tolist()}")
+    assert np.isfinite(flow).all() and np.abs(want).max() > 2.0
+    assert e <= (1e-4 if kw.get("epsilon", 0.01) == 0.0 else 5e-2)
+
+
+def test_tvl1_flow_on_device_buffers(nlk):
+    import torch
+    from oracle import oracle as O
+    nx, ny = 256, 192
+    I0, I1 = O.tvl1_frames(nx, ny, seed=9)
+    with nlk.Context(nx, ny, 1) as ctx:
+        host, _ = ctx.tvl1_flow(I0, I1, lam=0.4, fscale=1)
+        d0, d1 = torch.from_numpy(I0).cuda(), torch.from_numpy(I1).cuda()
+        u = torch.full((2, ny, nx), float("nan"), device="cuda")
+        ctx.tvl1_flow_dev(d0, d1, u[0], u[1], nx, ny, lam=0.4, fscale=1)
+        ctx.sync()
+        e = _err(u.cpu().numpy(), host)
+        print(f"tvl1 pyramid on device buffers vs host entry: max |du| = {e:.2e}")
+        assert e <= 5e-2
+        # requests the reference would abort on or index out of its pyramid for
+        with pytest.raises(nlk.NlkError):
+            ctx.tvl1_flow(I0[:4, :4], I1[:4, :4], nscales=1)       # Gaussian window larger than the image
+        with pytest.raises(nlk.NlkError):
+            nlk.api._check(nlk.lib().nlk_tvl1_flow_dev(ctx._h, nlk.api._vp(d0), nlk.api._vp(d1), nlk.api._vp(u[0]),
+                                                       nlk.api._vp(u[1]), nx, ny, 0.25, 0.15, 0.3, 3, 0, 1.5, 5, 0.01, None))

@@ -26,6 +26,8 @@ def io():
     L.nlk_read_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.nlk_write_image.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int]
     L.nlk_io_error.restype = C.c_char_p
+    L.nlk_read_image_gray.restype = C.POINTER(C.c_float)
+    L.nlk_read_image_gray.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     libc = C.CDLL(None)
     libc.free.argtypes = [C.c_void_p]
 
@@ -36,6 +38,15 @@ def io():
             if not p:
                 raise IOError(L.nlk_io_error().decode())
             a = np.ctypeslib.as_array(p, shape=(h.value, w.value, c.value)).copy()
+            libc.free(p)
+            return a
+
+        def read_gray(self, path):
+            w, h = C.c_int(), C.c_int()
+            p = L.nlk_read_image_gray(str(path).encode(), C.byref(w), C.byref(h))
+            if not p:
+                raise IOError(L.nlk_io_error().decode())
+            a = np.ctypeslib.as_array(p, shape=(h.value, w.value)).copy()
             libc.free(p)
             return a
 
@@ -247,3 +258,48 @@ def test_decoders_reject_malformed_headers(io, tmp_path):
         open(bad, "wb").write(png(depth, ctype))
         with pytest.raises(IOError):
             io.read(bad)
+
+
+def test_scalar_read_follows_iio(io, tmp_path):
+    """the flow estimator reads its images as one channel the way iio_read_image_float does (reference
+    lib/iio/iio.c:3984-4003, :1021-1060): luminance computed in the file's sample type.  Checked through
+    the reference's own program where it is built: tvl1flow-ref gives the same flow for a colour pair as
+    for the grey pair our reader makes of it."""
+    rng = np.random.default_rng(5)
+    ys, xs = np.mgrid[0:48, 0:64]
+    def frame(dx):
+        base = 120 + 60 * np.sin((xs - dx) * 0.3) * np.cos(ys * 0.23) + 30 * np.sin((xs - dx) * 0.11 + ys * 0.17)
+        rgb = np.stack([base, 0.8 * base + 20, 255 - base], -1) + rng.normal(0, 2, (48, 64, 3))
+        return np.clip(rgb, 0, 255)
+    a, b = frame(0), frame(1.5)
+    lum = lambda x: .299 * x[..., 0] + .587 * x[..., 1] + .114 * x[..., 2]
+    for ext, conv in ((".ppm", lambda x: np.floor(x)), (".pfm", lambda x: x.astype(np.float32)), (".png", np.floor)):
+        for name, img in (("a", a), ("b", b)):
+            io.write(tmp_path / (name + ext), conv(img).astype(np.float32))
+    a8 = np.floor(a)
+    # PNM and float files: iio holds float samples, the luminance is rounded to float;
+    # 8 bit PNG (and 8 / 16 bit TIFF): iio holds integers, the luminance is truncated
+    assert np.array_equal(io.read_gray(tmp_path / "a.ppm"), lum(a8).astype(np.float32))
+    assert np.array_equal(io.read_gray(tmp_path / "a.png"), np.floor(lum(a8)).astype(np.float32))
+    af = a.astype(np.float32).astype(np.float64)
+    assert np.array_equal(io.read_gray(tmp_path / "a.pfm"), lum(af).astype(np.float32))
+    one = tmp_path / "one.pgm"
+    io.write(one, np.floor(lum(a8)).astype(np.float32))
+    assert np.array_equal(io.read_gray(one), np.floor(lum(a8)).astype(np.float32))
+    two = tmp_path / "two.flo"
+    io.write(two, np.zeros((4, 5, 2), np.float32))
+    with pytest.raises(IOError):
+        io.read_gray(two)
+    ref = os.path.join(ROOT, "oracle", "_ref", "tvl1flow-ref")
+    if not os.path.exists(ref):
+        return
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    for ext in (".ppm", ".pfm"):
+        for name in ("a", "b"):
+            io.write(tmp_path / ("g" + name + ".pfm"), io.read_gray(tmp_path / (name + ext)))
+        for src, dst in (((f"a{ext}", f"b{ext}"), "colour.flo"), (("ga.pfm", "gb.pfm"), "grey.flo")):
+            r = subprocess.run([ref, tmp_path / src[0], tmp_path / src[1], tmp_path / dst, "1"], capture_output=True,
+                               text=True, env=env)
+            assert r.returncode == 0, r.stderr
+        assert np.array_equal(io.read(tmp_path / "colour.flo"), io.read(tmp_path / "grey.flo")), ext
+        assert np.abs(io.read(tmp_path / "colour.flo")).max() > 0.5

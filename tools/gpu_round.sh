@@ -1,7 +1,8 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, bench (both arms), ncu launch list and full captures of
 # the hot kernels.  Usage (from the repo root, under gpurun):  bash tools/gpu_round.sh <tag> [what...]
-# what: tests bench ref launches ncu   (default: all)
+# what: tests tvl1 bench ref configs launches ncu   (default: tests bench ref launches ncu)
+# tvl1tests: only the flow estimator's tests (fast check of a new build before the whole suite)
 TAG=${1:-rX}; shift
 WHAT=${@:-tests bench ref launches ncu}
 OUT=gpurun_out
@@ -10,6 +11,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 for w in $WHAT; do
 case $w in
 tests)   timeout 900 python -m pytest tests -m gpu -q -s --timeout 240 > $OUT/${TAG}_pytest_gpu.log 2>&1; grep -E "passed|failed|FAILED|rror:" $OUT/${TAG}_pytest_gpu.log | tail -8;;
+tvl1tests) timeout 300 python -m pytest tests/test_gpu_tvl1.py tests/test_gpu_cli.py -m gpu -q -s --timeout 120 -k tvl1 > $OUT/${TAG}_pytest_tvl1.log 2>&1; grep -E "tvl1|passed|failed|FAILED|rror:" $OUT/${TAG}_pytest_tvl1.log | tail -30;;
+tvl1)    timeout 300 python tools/bench_tvl1.py > $OUT/${TAG}_tvl1.json 2> $OUT/${TAG}_tvl1.err; cat $OUT/${TAG}_tvl1.json; tail -3 $OUT/${TAG}_tvl1.err;;
 configs) timeout 400 python tools/bench_configs.py > $OUT/${TAG}_configs.jsonl 2> $OUT/${TAG}_configs.err; python - <<PYEOF
 import json
 for l in open("$OUT/${TAG}_configs.jsonl"):
