@@ -40,6 +40,18 @@ class Params(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class Tvl1Params(C.Structure):
+    """struct nlk_tvl1_params (include/nlkalman_b200.h): the arguments of the reference's tvl1flow program
+    after nproc (lib/tvl1flow/main.c:95-104); zeros mean "default" like on its command line."""
+    _fields_ = [("tau", C.c_float), ("lam", C.c_float), ("theta", C.c_float), ("nscales", C.c_int),
+                ("fscale", C.c_int), ("zfactor", C.c_float), ("warps", C.c_int), ("epsilon", C.c_float)]
+
+    @classmethod
+    def script(cls, dw=0.25, fscale=1):
+        """what scripts/nlkalman-seq.sh:51 passes: "NPROC 0 DW 0 0 FSCALE" """
+        return cls(0.0, dw, 0.0, 0, fscale, 0.0, 0, 0.0)
+
+
 class StripPlan(C.Structure):
     """struct nlk_strip_plan (include/nlkalman_b200.h): rows of one rank in a strip-sharded pass."""
     _fields_ = [("gw", C.c_int), ("gh", C.c_int), ("nbw", C.c_int), ("gy0", C.c_int), ("gy1", C.c_int),
@@ -131,6 +143,9 @@ def lib():
                                       C.c_int, C.c_float, _ip]
     L.nlk_tvl1_level_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                      C.c_int, C.c_float, _ip]
+    L.nlk_flow_mask_dev.argtypes = [vp, vp, vp, vp, vp, Tvl1Params, C.c_float]
+    L.nlk_tvl1_default_params.argtypes = [C.POINTER(Tvl1Params)]
+    L.nlk_tvl1_default_params.restype = None
     L.nlk_tvl1_scales.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int]
     L.nlk_tvl1_flow_host.argtypes = [vp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                      C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, _ip]
@@ -315,6 +330,11 @@ class Context:
 
     def occlusion_dev(self, occ, of, th):
         _check(lib().nlk_occlusion_dev(self._h, _vp(occ), _vp(of), float(th)))
+
+    def flow_mask_dev(self, of, occ, from_rgb, to_rgb, prms: "Tvl1Params", th: float):
+        """flow (interleaved, like a .flo) and occlusion mask between two resident RGB frames: the
+        tvl1flow + plambda step of the pipeline script (reference scripts/nlkalman-seq.sh:60-72)"""
+        _check(lib().nlk_flow_mask_dev(self._h, _vp(of), _vp(occ), _vp(from_rgb), _vp(to_rgb), prms, float(th)))
 
     def occlusion(self, of: np.ndarray, th: float) -> np.ndarray:
         """0 / 255 mask from the divergence of the flow (reference scripts/nlkalman-seq.sh:70-72)"""

@@ -136,7 +136,7 @@ struct nlk_ctx {
     bool b_pending = false;      // lane 1 has work that lane 0 has not waited for
     cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr}, ev_join = nullptr;
     long long launches = 0;
-    DevBuf dbg_dist, dbg_vp, tv_scratch, tv_pyr;
+    DevBuf dbg_dist, dbg_vp, tv_scratch, tv_pyr, tv_frames;
     float *tv_herr = nullptr;       // pinned word the TV-L1 level solver reads its stopping error back into
     // host-call staging
     DevBuf s_in1, s_prev0, s_bsic, s_out, s_of, s_msk;
@@ -314,7 +314,7 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     for (int i = 0; i < 2; ++i) if (c->lane[i].st) cudaStreamSynchronize(c->lane[i].st);
     if (c->st_d2h) cudaStreamSynchronize(c->st_d2h);
     if (c->st_h2d) cudaStreamSynchronize(c->st_h2d);
-    DevBuf *all[] = {&c->tv_scratch, &c->tv_pyr, &c->dbg_dist, &c->dbg_vp, &c->s_in1, &c->s_prev0, &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk,
+    DevBuf *all[] = {&c->tv_scratch, &c->tv_pyr, &c->tv_frames, &c->dbg_dist, &c->dbg_vp, &c->s_in1, &c->s_prev0, &c->s_bsic, &c->s_out, &c->s_of, &c->s_msk,
                      &c->q_noisy[0], &c->q_noisy[1], &c->q_flt1[0], &c->q_flt1[1], &c->q_flt2[0], &c->q_flt2[1],
                      &c->q_smo[0], &c->q_smo[1], &c->q_tmp};
     for (DevBuf *b : all) b->release();
@@ -1209,6 +1209,51 @@ extern "C" int nlk_tvl1_flow_host(nlk_ctx *c, const float *h_I0, const float *h_
     // two planes, u then v: what the reference's driver hands to iio_write_image_float_split (main.c:177)
     CU_TRY(cudaMemcpyAsync(h_flow, d + 2 * n, 2 * pb, cudaMemcpyDeviceToHost, c->L->st));
     CU_TRY(cudaStreamSynchronize(c->L->st));
+    return NLK_OK;
+}
+
+// ---- flow + mask of two resident frames (scripts/nlkalman-seq.sh:60-72) -----------------------------
+
+extern "C" void nlk_tvl1_default_params(struct nlk_tvl1_params *p)
+{
+    if (!p) return;
+    // lib/tvl1flow/main.c:26-35
+    p->tau = 0.25f; p->lambda = 0.15f; p->theta = 0.3f; p->nscales = 100; p->fscale = 0; p->zfactor = 0.5f;
+    p->warps = 5; p->epsilon = 0.01f;
+}
+
+extern "C" int nlk_flow_mask_dev(nlk_ctx *c, float *d_of, float *d_occ, const float *d_from_rgb, const float *d_to_rgb,
+                                 struct nlk_tvl1_params p, float th)
+{
+    if (int r = enter(c)) return r;
+    if (!d_of || !d_from_rgb || !d_to_rgb) return set_err(NLK_ERR_PARAM, "flow: null frame or flow buffer");
+    if (c->ch == 2) return set_err(NLK_ERR_PARAM, "flow: a 2-channel frame has no luminance");
+    // out-of-range values fall back to the defaults like in the reference's program (main.c:108-148)
+    struct nlk_tvl1_params d;
+    nlk_tvl1_default_params(&d);
+    if (!(p.tau > 0.f && p.tau <= 0.25f)) p.tau = d.tau;
+    if (!(p.lambda > 0.f)) p.lambda = d.lambda;
+    if (!(p.theta > 0.f)) p.theta = d.theta;
+    if (p.nscales <= 0) p.nscales = d.nscales;
+    if (!(p.zfactor > 0.f && p.zfactor < 1.f)) p.zfactor = d.zfactor;
+    if (p.warps <= 0) p.warps = d.warps;
+    if (!(p.epsilon > 0.f)) p.epsilon = d.epsilon;
+    if (p.fscale < 0) p.fscale = 0;
+    p.nscales = tvl1_scales_cap(c->w, c->h, p.zfactor, p.nscales);
+    if (p.nscales < p.fscale) p.fscale = p.nscales;
+    const size_t npix = (size_t)c->w * c->h;
+    if (int r = c->tv_frames.ensure(4 * npix * 4)) return r;
+    float *l0 = c->tv_frames.as<float>(), *l1 = l0 + npix, *u1 = l1 + npix, *u2 = u1 + npix;
+    cudaStream_t st = c->L->st;
+    const int nb = (int)std::min<size_t>((npix + 255) / 256, 148 * 8);
+    k_tvl1_luma<<<nb, 256, 0, st>>>(d_from_rgb, l0, npix, c->ch);
+    k_tvl1_luma<<<nb, 256, 0, st>>>(d_to_rgb, l1, npix, c->ch);
+    if (int r = check_launch(c, 2, "luminance")) return r;
+    if (int r = nlk_tvl1_flow_dev(c, l0, l1, u1, u2, c->w, c->h, p.tau, p.lambda, p.theta, p.nscales, p.fscale, p.zfactor,
+                                  p.warps, p.epsilon, nullptr)) return r;
+    k_tvl1_interleave<<<nb, 256, 0, st>>>(u1, u2, d_of, npix);
+    if (int r = check_launch(c, 1, "flow interleave")) return r;
+    if (d_occ) return check_launch(c, launch_occlusion(d_occ, d_of, c->w, c->h, th, st), "occlusion");
     return NLK_OK;
 }
 

@@ -318,4 +318,28 @@ __global__ void k_tvl1_zoom(const float *__restrict__ in, float *__restrict__ ou
     out[(size_t)i1 * nxx + j1] = scaled ? __fmul_rn(g, scale) : g;
 }
 
+// ---- between the frames of the filter and the estimator (the pipeline script's file interfaces, kept on
+// the device): luminance the way the reference's program reads a colour file (iio_read_image_float,
+// lib/iio/iio.c:1048-1055: .299 R + .587 G + .114 B in double, rounded to float), and the flow's two
+// planes interleaved as the warp and the occlusion mask take them (.flo layout)
+__device__ __forceinline__ float tvl1_luma(float r, float g, float b)
+{
+    return (float)__dadd_rn(__dadd_rn(__dmul_rn(.299, (double)r), __dmul_rn(.587, (double)g)), __dmul_rn(.114, (double)b));
+}
+
+#ifndef NLK_HOST_MODEL
+__global__ void __launch_bounds__(256) k_tvl1_luma(const float *__restrict__ img, float *__restrict__ lum, size_t npix, int ch)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x)
+        lum[i] = ch == 1 ? img[i] : tvl1_luma(img[i * ch], img[i * ch + 1], img[i * ch + 2]);
+}
+
+__global__ void __launch_bounds__(256) k_tvl1_interleave(const float *__restrict__ u1, const float *__restrict__ u2,
+                                                         float *__restrict__ of, size_t npix)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x)
+        reinterpret_cast<float2 *>(of)[i] = make_float2(u1[i], u2[i]);
+}
+#endif
+
 } // namespace nlk

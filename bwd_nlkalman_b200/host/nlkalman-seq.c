@@ -21,6 +21,13 @@
  *
  * --first_f2 1 applies the second filtering to the first frame too, which is what the
  * per-frame pipeline script does (reference scripts/nlkalman-seq.sh:39-41).
+ *
+ * --tvl1 1 makes the program the WHOLE pipeline of that script: the backward flow of a frame
+ * (TV-L1 between the noisy frame and the previous output, scripts/nlkalman-seq.sh:60-65), its
+ * occlusion mask (:68-72), and for the smoother the forward flow and mask (:124-137) are computed
+ * on the GPU from the resident frames instead of being read from files -- no tvl1flow / plambda
+ * processes, no flow or mask files (the -o / -k / --fflow / --foccl patterns then name optional
+ * OUTPUT files).  --of_prms "FSCALE1 DW1 TH1 FSCALE2 DW2 TH2" are the script's OPM values.
  */
 #include <pthread.h>
 #include <semaphore.h>
@@ -161,7 +168,7 @@ static int upload_flow(const in_set *s, float *d_of, float *d_occ, const float *
 }
 
 /* ---- writer thread: outputs encoded and written once their download has landed ---------------- */
-typedef struct { void *marker; char name[1024]; int stop; } out_job;
+typedef struct { void *marker; char name[1024]; int stop, ch; } out_job;
 static struct {
     float *buf[N_OUT];          /* pinned */
     out_job job[N_OUT];
@@ -177,7 +184,7 @@ static void *writer_main(void *arg)
         out_job *j = &wr.job[i % N_OUT];
         if (j->stop) break;
         if (nlk_marker_wait(j->marker)) { fprintf(stderr, "nlkalman-seq: output: %s\n", nlk_last_error()); wr.failed = 1; }
-        else if (nlk_write_image(j->name, wr.buf[i % N_OUT], w, h, c)) { fprintf(stderr, "Error: %s\n", nlk_io_error()); wr.failed = 1; }
+        else if (nlk_write_image(j->name, wr.buf[i % N_OUT], w, h, j->ch)) { fprintf(stderr, "Error: %s\n", nlk_io_error()); wr.failed = 1; }
         sem_post(&wr.free_bufs);
     }
     return NULL;
@@ -191,7 +198,25 @@ static int write_frame(const char *pattern, int f, const float *d_opp, float *d_
     out_job *j = &wr.job[k];
     snprintf(j->name, sizeof j->name, pattern, f);
     j->stop = 0;
+    j->ch = c;
     if (nlk_opp2rgb_dev(ctx, d_scratch, d_opp) || nlk_download(ctx, wr.buf[k], d_scratch, ib)) return gpu_fail("output");
+    j->marker = nlk_marker_record(ctx);
+    if (!j->marker) return gpu_fail("output");
+    sem_post(&wr.ready_jobs);
+    return wr.failed;
+}
+
+/* a computed flow (ch = 2) or mask (ch = 1) -> pinned buffer -> (writer thread) file pattern % f */
+static int write_plane(const char *pattern, int f, const float *d_src, int ch)
+{
+    if (!pattern) return 0;
+    sem_wait(&wr.free_bufs);
+    const int k = wr.head++ % N_OUT;
+    out_job *j = &wr.job[k];
+    snprintf(j->name, sizeof j->name, pattern, f);
+    j->stop = 0;
+    j->ch = ch;
+    if (nlk_download(ctx, wr.buf[k], d_src, npix * ch * sizeof(float))) return gpu_fail("output");
     j->marker = nlk_marker_record(ctx);
     if (!j->marker) return gpu_fail("output");
     sem_post(&wr.ready_jobs);
@@ -202,7 +227,8 @@ int main(int argc, const char *argv[])
 {
     const char *nisy_path = NULL, *bflo_path = NULL, *bocc_path = NULL, *fflo_path = NULL, *focc_path = NULL;
     const char *flt1_path = NULL, *flt2_path = NULL, *smo1_path = NULL;
-    int fframe = 0, lframe = -1, verbose = 0, full = 1, first_f2 = 0;
+    int fframe = 0, lframe = -1, verbose = 0, full = 1, first_f2 = 0, tvl1 = 0;
+    const char *of_prms = "1 0.25 0.75 1 0.25 0.75";   /* the script's OPM default (scripts/nlkalman-seq.sh:17) */
     float sigma = 0.f;
     struct nlkalman_params f1, f2, s1;
     auto_params(&f1, -1);
@@ -251,6 +277,9 @@ int main(int argc, const char *argv[])
         {NLK_OPT_FLOAT, 0, "s1_bt", &s1.beta_t, "noise multiplier in kalman filtering"},
         {NLK_OPT_FLOAT, 0, "s1_l", &s1.dista_lambda, "noisy patch weight in patch distance"},
         {NLK_OPT_INT, 0, "s1_full", &full, "0: next frame smoothing, 1: full video smoothing (default)"},
+        {NLK_OPT_GROUP, 0, "Optical flow options", NULL, NULL},
+        {NLK_OPT_INT, 0, "tvl1", &tvl1, "1: flows and occlusion masks computed on the GPU (the flow / mask paths become outputs)"},
+        {NLK_OPT_STRING, 0, "of_prms", &of_prms, "\"FSCALE1 DW1 TH1 FSCALE2 DW2 TH2\" (filtering, smoothing), as nlkalman-seq.sh"},
         {NLK_OPT_GROUP, 0, "Program options", NULL, NULL},
         {NLK_OPT_INT, 'v', "verbose", &verbose, "verbose output"},
         {NLK_OPT_END, 0, NULL, NULL, NULL},
@@ -273,6 +302,24 @@ int main(int argc, const char *argv[])
         fprintf(stderr, "Warning: s1_p == 0 - no output files will be stored in %s\n", smo1_path);
     if (!nisy_path || lframe < fframe) return fprintf(stderr, "Error: no input frames (-i, -f, -l)\n"), 1;
 
+    /* flow parameters: "NPROC 0 DW 0 0 FSCALE" on tvl1flow's command line (scripts/nlkalman-seq.sh:51, :111) */
+    struct nlk_tvl1_params of1, of2;
+    float th1 = 0.75f, th2 = 0.75f;
+    nlk_tvl1_default_params(&of1);
+    nlk_tvl1_default_params(&of2);
+    if (tvl1) {
+        int fs1, fs2;
+        float dw1, dw2;
+        if (sscanf(of_prms, "%d %f %f %d %f %f", &fs1, &dw1, &th1, &fs2, &dw2, &th2) != 6)
+            return fprintf(stderr, "Error: --of_prms wants six values \"FSCALE1 DW1 TH1 FSCALE2 DW2 TH2\"\n"), 1;
+        of1.fscale = fs1; of1.lambda = dw1;
+        of2.fscale = fs2; of2.lambda = dw2;
+    }
+    /* with --tvl1 the flow / mask patterns are outputs; nothing is read from them */
+    const char *bflo_out = tvl1 ? bflo_path : NULL, *bocc_out = tvl1 ? bocc_path : NULL;
+    const char *fflo_out = tvl1 ? fflo_path : NULL, *focc_out = tvl1 ? focc_path : NULL;
+    if (tvl1) bflo_path = bocc_path = fflo_path = focc_path = NULL;
+
     nlkalman_default_params(&f1, sigma, FLT1);
     nlkalman_default_params(&f2, sigma, FLT2);
     nlkalman_default_params(&s1, sigma, SMO1);
@@ -283,10 +330,11 @@ int main(int argc, const char *argv[])
         printf("\tfirst frame   %d\n", fframe);
         printf("\tlast frame    %d\n", lframe);
         printf("\tnoisy frames  %s\n", nisy_path);
-        printf("\tbwd flows     %s\n", bflo_path);
-        printf("\tfwd flows     %s\n", fflo_path);
-        printf("\tbwd occlus.   %s\n", bocc_path);
-        printf("\tfwd occlus.   %s\n", focc_path);
+        if (tvl1) printf("\tflows         TV-L1 on the GPU, \"%s\"\n", of_prms);
+        printf("\tbwd flows     %s\n", tvl1 ? bflo_out : bflo_path);
+        printf("\tfwd flows     %s\n", tvl1 ? fflo_out : fflo_path);
+        printf("\tbwd occlus.   %s\n", tvl1 ? bocc_out : bocc_path);
+        printf("\tfwd occlus.   %s\n", tvl1 ? focc_out : focc_path);
         printf("\n");
         printf("data output:\n");
         printf("\tfiltering 1   %s\n", flt1_path);
@@ -326,6 +374,9 @@ int main(int argc, const char *argv[])
     float *d_bsic[2] = {nlk_dev_alloc(ctx, ib), nlk_dev_alloc(ctx, ib)};
     float *d_of = nlk_dev_alloc(ctx, npix * 2 * sizeof(float)), *d_occ = nlk_dev_alloc(ctx, npix * sizeof(float));
     float *d_of2 = nlk_dev_alloc(ctx, npix * 2 * sizeof(float)), *d_occ2 = nlk_dev_alloc(ctx, npix * sizeof(float));
+    /* RGB copies of the two frames a flow is estimated between */
+    float *d_from = tvl1 ? nlk_dev_alloc(ctx, ib) : NULL, *d_to = tvl1 ? nlk_dev_alloc(ctx, ib) : NULL;
+    if (tvl1 && (!d_from || !d_to)) return gpu_fail("device memory");
     if (!d_nisy || !d_warp || !d_tmp || !d_rgb[0] || !d_rgb[1] || !d_bsic[0] || !d_bsic[1] || !d_of || !d_occ || !d_of2 || !d_occ2)
         return gpu_fail("device memory");
 #define SLOT(f) d_deno[keep_all ? (f) - fframe : ((f) - fframe) & 1]
@@ -345,7 +396,8 @@ int main(int argc, const char *argv[])
         rd.set[i].occ = (float *)nlk_host_alloc(npix * sizeof(float));
         if (!rd.set[i].img || !rd.set[i].flo || !rd.set[i].occ) return gpu_fail("pinned memory");
     }
-    for (int i = 0; i < N_OUT; ++i) if (!(wr.buf[i] = (float *)nlk_host_alloc(ib))) return gpu_fail("pinned memory");
+    const size_t ob = ib > npix * 2 * sizeof(float) ? ib : npix * 2 * sizeof(float);   /* a frame or a flow */
+    for (int i = 0; i < N_OUT; ++i) if (!(wr.buf[i] = (float *)nlk_host_alloc(ob))) return gpu_fail("pinned memory");
     sem_init(&rd.free_sets, 0, N_IN);
     sem_init(&rd.ready_sets, 0, 0);
     sem_init(&wr.free_bufs, 0, N_OUT);
@@ -359,11 +411,20 @@ int main(int argc, const char *argv[])
         if (verbose) printf("processing frame %d\n", f);
         in_set *in = acquire_set();
         if (!in) return 1;
-        if (nlk_upload(ctx, d_nisy, in->img, ib) || nlk_rgb2opp_dev(ctx, d_nisy, d_nisy)) return gpu_fail("upload");
+        if (nlk_upload(ctx, d_nisy, in->img, ib)) return gpu_fail("upload");
         float *bsic1 = d_bsic[(f - fframe) & 1], *bsic0 = d_bsic[(f - fframe + 1) & 1];
         const float *d_flow = NULL, *d_mask = NULL;
         if (upload_flow(in, d_of, d_occ, &d_flow, &d_mask)) return 1;
         release_set(in);
+        if (tvl1 && f > fframe) {
+            /* backward flow: from the noisy frame to the previous output, both as the script's files hold
+             * them (RGB) (scripts/nlkalman-seq.sh:60-72) */
+            if (nlk_opp2rgb_dev(ctx, d_to, SLOT(f - 1)) || nlk_flow_mask_dev(ctx, d_of, d_occ, d_nisy, d_to, of1, th1))
+                return gpu_fail("optical flow");
+            d_flow = d_of; d_mask = d_occ;
+            if (write_plane(bflo_out, f, d_of, 2) || write_plane(bocc_out, f, d_occ, 1)) return 1;
+        }
+        if (nlk_rgb2opp_dev(ctx, d_nisy, d_nisy)) return gpu_fail("colour transform");
 
         /* first filtering, guided by the previous first filtering */
         const float *prev = NULL;
@@ -396,6 +457,12 @@ int main(int argc, const char *argv[])
             const float *d_ff = NULL, *d_fm = NULL;
             if (upload_flow(ff, d_of2, d_occ2, &d_ff, &d_fm)) return 1;
             release_set(ff);
+            if (tvl1) {   /* forward flow of frame f-1: from its filtered output to the next frame's (:124-137) */
+                if (nlk_opp2rgb_dev(ctx, d_from, SLOT(f - 1)) || nlk_opp2rgb_dev(ctx, d_to, deno1) ||
+                    nlk_flow_mask_dev(ctx, d_of2, d_occ2, d_from, d_to, of2, th2)) return gpu_fail("optical flow");
+                d_ff = d_of2; d_fm = d_occ2;
+                if (write_plane(fflo_out, f - 1, d_of2, 2) || write_plane(focc_out, f - 1, d_occ2, 1)) return 1;
+            }
             const float *smoo0 = deno1;
             if (d_ff) { if (nlk_warp_dev(ctx, d_warp, deno1, d_ff, d_fm)) return gpu_fail("warp"); smoo0 = d_warp; }
             float *filt1 = SLOT(f - 1);
@@ -414,6 +481,12 @@ int main(int argc, const char *argv[])
             const float *d_ff = NULL, *d_fm = NULL;
             if (upload_flow(ff, d_of, d_occ, &d_ff, &d_fm)) return 1;
             release_set(ff);
+            if (tvl1) {   /* forward flow: from the filtered frame to the smoothed next one (:124-137) */
+                if (nlk_opp2rgb_dev(ctx, d_from, SLOT(f)) || nlk_opp2rgb_dev(ctx, d_to, SLOT(f + 1)) ||
+                    nlk_flow_mask_dev(ctx, d_of, d_occ, d_from, d_to, of2, th2)) return gpu_fail("optical flow");
+                d_ff = d_of; d_fm = d_occ;
+                if (write_plane(fflo_out, f, d_of, 2) || write_plane(focc_out, f, d_occ, 1)) return 1;
+            }
             const float *smoo0 = SLOT(f + 1);
             if (d_ff) { if (nlk_warp_dev(ctx, d_warp, smoo0, d_ff, d_fm)) return gpu_fail("warp"); smoo0 = d_warp; }
             float *filt1 = SLOT(f);

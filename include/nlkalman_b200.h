@@ -295,6 +295,26 @@ int nlk_tvl1_flow_host(nlk_ctx *ctx, const float *h_I0, const float *h_I1, float
                        float tau, float lambda, float theta, int nscales, int fscale, float zfactor,
                        int warps, float epsilon, int *iterations);
 
+/* ---- the flow + mask step of the pipeline script, on frames resident in HBM --------------------
+ * What scripts/nlkalman-seq.sh:60-72 (:124-137 for the smoother) does through files between two
+ * filter invocations -- `tvl1flow FROM TO flow.flo NPROC 0 DW 0 0 FSCALE`, then the plambda mask
+ * expression with threshold TH -- for two frames of the context's size and channel count, RGB,
+ * interleaved, already on the device: luminance as the reference's program reads a colour file
+ * (lib/iio/iio.c:3984-4003 on float samples), the estimator above, the flow interleaved [h][w][2]
+ * as nlk_warp_dev takes it, the occlusion mask of nlk_occlusion_dev (d_occ may be NULL).
+ * nlk_tvl1_default_params: the defaults of the reference's program (lib/tvl1flow/main.c:26-35), which
+ * also replace out-of-range values there (:108-148); nscales is capped for the frame size inside. */
+struct nlk_tvl1_params {
+    float tau, lambda, theta;
+    int nscales, fscale;
+    float zfactor;
+    int warps;
+    float epsilon;
+};
+void nlk_tvl1_default_params(struct nlk_tvl1_params *p);
+int nlk_flow_mask_dev(nlk_ctx *ctx, float *d_of, float *d_occ, const float *d_from_rgb, const float *d_to_rgb,
+                      struct nlk_tvl1_params prms, float th);
+
 /* ---- stage dumps for the parity tests (host arrays, any may be NULL) ------------------
  * Runs one pass on host images like nlkalman_filter_frame / nlkalman_smooth_frame and
  * also returns, per grid patch g = gy*gw + gx (gw = (w-psz)/step+1, step = psz/2):

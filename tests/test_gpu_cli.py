@@ -236,3 +236,57 @@ def test_tvl1flow_against_reference_program(tmp_path):
     _write_pfm(tmp_path / "small.pfm", I0[:50, :60])
     r = _run(os.path.join(BIN, "tvl1flow"), tmp_path / "a.pfm", tmp_path / "small.pfm", tmp_path / "x.flo", ok=(1,))
     assert "size mismatch" in r.stderr
+
+
+def _read_image(path):
+    """any format the drivers write, through the drivers' own codec (libnlk_image_io.so)"""
+    import ctypes as C
+    L = C.CDLL(os.path.join(ROOT, "bwd_nlkalman_b200", "libnlk_image_io.so"))
+    L.nlk_read_image.restype = C.POINTER(C.c_float)
+    L.nlk_read_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    w, h, c = C.c_int(), C.c_int(), C.c_int()
+    p = L.nlk_read_image(str(path).encode(), C.byref(w), C.byref(h), C.byref(c))
+    assert p, path
+    a = np.ctypeslib.as_array(p, shape=(h.value, w.value, c.value)).copy()
+    C.CDLL(None).free(C.cast(p, C.c_void_p))
+    return a
+
+
+def test_seq_driver_whole_pipeline_matches_the_script(tmp_path):
+    """nlkalman-seq --tvl1 1 is the pipeline script in one process: flows (TV-L1) and occlusion masks
+    computed on the GPU between resident frames.  Against bin/nlkalman-seq.sh driving the per-frame
+    programs (tvl1flow, nlkalman-occ, nlkalman-flt, nlkalman-smo) through files: same flows, same
+    masks, same frames, up to the effects of the RGB round trip of the state (see above)."""
+    from bwd_nlkalman_b200 import synth
+    w, h, ch, sigma, nf = 192, 144, 3, 10.0, 4
+    for t in range(nf):
+        _write_pfm(tmp_path / f"n{t}.pfm", synth.noisy_frame(w, h, ch, t, sigma))
+    a, b = tmp_path / "script", tmp_path / "seq"
+    os.makedirs(b)
+    r = subprocess.run(["bash", os.path.join(BIN, "nlkalman-seq.sh"), str(tmp_path / "n%d.pfm"), "0", str(nf - 1), str(sigma), str(a)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    _run(os.path.join(BIN, "nlkalman-seq"), "-i", tmp_path / "n%d.pfm", "-f", 0, "-l", nf - 1, "-s", sigma, "--first_f2", 1,
+         "--s1_p", 8, "--tvl1", 1, "-o", b / "bflo1-%03d.flo", "-k", b / "bocc1-%03d.png", "--fflow", b / "fflo-%03d.flo",
+         "--foccl", b / "focc-%03d.png", "--filt1", b / "flt1-%03d.tif", "--filt2", b / "flt2-%03d.tif",
+         "--smoo1", b / "smo1-%03d.tif")
+    mot = np.array(synth.MOTION, np.float64)
+    for t in range(1, nf):
+        fa, fb = _read_flo(a / f"bflo1-{t:03d}.flo"), _read_flo(b / f"bflo1-{t:03d}.flo")
+        d = np.abs(fa.astype(np.float64) - fb)
+        print(f"backward flow {t}: median |d| {np.median(d):.2e}, max {d.max():.2e}; median flow {np.median(fb, (0, 1))}")
+        assert np.median(d) <= 1e-3 and (d > 0.05).mean() <= 0.02
+        # it is the motion of the scene (frame t to frame t-1)
+        assert np.abs(np.median(fb, (0, 1)) + mot).max() < 0.4
+        ma, mb = _read_image(a / f"bocc1-{t:03d}.png"), _read_image(b / f"bocc1-{t:03d}.png")
+        assert (ma != mb).mean() <= 0.01
+    for t in range(nf - 1):
+        fa, fb = _read_flo(a / f"fflo-{t:03d}.flo"), _read_flo(b / f"fflo-{t:03d}.flo")
+        d = np.abs(fa.astype(np.float64) - fb)
+        assert np.median(d) <= 1e-3 and (d > 0.05).mean() <= 0.02
+    for t in range(nf):
+        for name in ("flt1", "flt2", "smo1"):
+            x, y = _read_image(a / f"{name}-{t:03d}.tif"), _read_image(b / f"{name}-{t:03d}.tif")
+            diff = np.abs(x.astype(np.float64) - y)
+            print(f"{name} {t}: mean |d| {diff.mean():.2e}, max {diff.max():.2e}, > 1e-2: {(diff > 1e-2).mean():.2e}")
+            assert diff.mean() <= 2e-3 and (diff > 0.1).mean() <= 1e-2, (name, t)

@@ -126,3 +126,30 @@ def test_tvl1_flow_on_device_buffers(nlk):
         with pytest.raises(nlk.NlkError):
             nlk.api._check(nlk.lib().nlk_tvl1_flow_dev(ctx._h, nlk.api._vp(d0), nlk.api._vp(d1), nlk.api._vp(u[0]),
                                                        nlk.api._vp(u[1]), nx, ny, 0.25, 0.15, 0.3, 3, 0, 1.5, 5, 0.01, None))
+
+
+def test_flow_mask_between_resident_frames(nlk):
+    """nlk_flow_mask_dev = luminance of both frames (as the reference's program reads a colour float file),
+    the estimator with the script's parameters, the flow interleaved, the plambda mask"""
+    import torch
+    from oracle import oracle as O
+    nx, ny = 224, 160
+    g0, g1 = O.tvl1_frames(nx, ny, seed=13)
+    rgb = lambda g: np.stack([g, 0.6 * g + 25, 180 - 0.4 * g], -1).astype(np.float32)
+    a, b = rgb(g0), rgb(g1)
+    lum = lambda x: (.299 * x[..., 0].astype(np.float64) + .587 * x[..., 1] + .114 * x[..., 2]).astype(np.float32)
+    with nlk.Context(nx, ny, 3) as ctx:
+        want, _ = ctx.tvl1_flow(lum(a), lum(b), lam=0.25, fscale=1)
+        of = torch.empty((ny, nx, 2), device="cuda")
+        occ = torch.empty((ny, nx), device="cuda")
+        ctx.flow_mask_dev(of, occ, torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), nlk.Tvl1Params.script(0.25, 1), 0.02)
+        ctx.sync()
+        got = of.cpu().numpy()
+        assert np.array_equal(got[..., 0], want[0]) and np.array_equal(got[..., 1], want[1])
+        m = occ.cpu().numpy()
+        assert np.array_equal(m, ctx.occlusion(got, 0.02)) and 0 < (m > 0).mean() < 1
+    with nlk.Context(nx, ny, 1) as ctx:    # single-channel frames go in as they are
+        of = torch.empty((ny, nx, 2), device="cuda")
+        ctx.flow_mask_dev(of, None, torch.from_numpy(lum(a)).cuda(), torch.from_numpy(lum(b)).cuda(), nlk.Tvl1Params.script(0.25, 1), 0.75)
+        ctx.sync()
+        assert np.array_equal(of.cpu().numpy()[..., 0], want[0])

@@ -11,8 +11,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 for w in $WHAT; do
 case $w in
 tests)   timeout 900 python -m pytest tests -m gpu -q -s --timeout 240 > $OUT/${TAG}_pytest_gpu.log 2>&1; grep -E "passed|failed|FAILED|rror:" $OUT/${TAG}_pytest_gpu.log | tail -8;;
-tvl1tests) timeout 300 python -m pytest tests/test_gpu_tvl1.py tests/test_gpu_cli.py -m gpu -q -s --timeout 120 -k tvl1 > $OUT/${TAG}_pytest_tvl1.log 2>&1; grep -E "tvl1|passed|failed|FAILED|rror:" $OUT/${TAG}_pytest_tvl1.log | tail -30;;
+tvl1tests) timeout 300 python -m pytest tests/test_gpu_tvl1.py tests/test_gpu_cli.py -m gpu -q -s --timeout 120 -k "tvl1 or pipeline or flow_mask" > $OUT/${TAG}_pytest_tvl1.log 2>&1; grep -E "tvl1|passed|failed|FAILED|rror:" $OUT/${TAG}_pytest_tvl1.log | tail -30;;
 tvl1)    timeout 300 python tools/bench_tvl1.py > $OUT/${TAG}_tvl1.json 2> $OUT/${TAG}_tvl1.err; cat $OUT/${TAG}_tvl1.json; tail -3 $OUT/${TAG}_tvl1.err;;
+tvl1launches) timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv \
+            --log-file $OUT/${TAG}_tvl1_launches.csv python tools/bench_tvl1.py --reps 1 > $OUT/${TAG}_tvl1_launches.log 2>&1; wc -l $OUT/${TAG}_tvl1_launches.csv;;
 configs) timeout 400 python tools/bench_configs.py > $OUT/${TAG}_configs.jsonl 2> $OUT/${TAG}_configs.err; python - <<PYEOF
 import json
 for l in open("$OUT/${TAG}_configs.jsonl"):
