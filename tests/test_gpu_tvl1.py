@@ -137,7 +137,7 @@ def test_flow_mask_between_resident_frames(nlk):
     g0, g1 = O.tvl1_frames(nx, ny, seed=13)
     rgb = lambda g: np.stack([g, 0.6 * g + 25, 180 - 0.4 * g], -1).astype(np.float32)
     a, b = rgb(g0), rgb(g1)
-    lum = lambda x: (.299 * x[..., 0].astype(np.float64) + .587 * x[..., 1] + .114 * x[..., 2]).astype(np.float32)
+    lum = lambda x: (lambda d: (.299 * d[..., 0] + .587 * d[..., 1] + .114 * d[..., 2]).astype(np.float32))(x.astype(np.float64))
     with nlk.Context(nx, ny, 3) as ctx:
         want, _ = ctx.tvl1_flow(lum(a), lum(b), lam=0.25, fscale=1)
         of = torch.empty((ny, nx, 2), device="cuda")
