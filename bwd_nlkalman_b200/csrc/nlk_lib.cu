@@ -128,6 +128,17 @@ struct Lane {
     }
 };
 
+// an instantiated CUDA graph of one TV-L1 level (tvl1_level_graph) and what it was built for
+struct Tvl1GraphEntry {
+    const float *I0, *I1;
+    float *u1, *u2, *base;
+    int nx, ny, warps;
+    float tau, lambda, theta, epsilon;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    unsigned long long stamp;
+};
+
 struct nlk_ctx {
     int w = 0, h = 0, ch = 0, device = 0, num_sms = 148;
     Lane lane[2];
@@ -138,6 +149,10 @@ struct nlk_ctx {
     long long launches = 0;
     DevBuf dbg_dist, dbg_vp, tv_scratch, tv_pyr, tv_frames;
     float *tv_herr = nullptr;       // pinned word the TV-L1 level solver reads its stopping error back into
+    std::vector<Tvl1GraphEntry> tv_graphs;         // instantiated level graphs (tvl1_level_graph)
+    cudaStream_t tv_st2 = nullptr;  // captures the loop bodies
+    int tv_graph_state = 0;         // 0: not decided, 1: graphs, -1: stream launches
+    unsigned long long tv_stamp = 0;
     // host-call staging
     DevBuf s_in1, s_prev0, s_bsic, s_out, s_of, s_msk;
     // sequence state (opponent colour space)
@@ -307,6 +322,16 @@ extern "C" nlk_ctx *nlk_ctx_create(int w, int h, int ch, int device)
     return c;
 }
 
+static void tvl1_graphs_release(nlk_ctx *c)
+{
+    for (Tvl1GraphEntry &E : c->tv_graphs) {
+        if (E.exec) cudaGraphExecDestroy(E.exec);
+        if (E.graph) cudaGraphDestroy(E.graph);
+    }
+    c->tv_graphs.clear();
+    if (c->tv_st2) { cudaStreamDestroy(c->tv_st2); c->tv_st2 = nullptr; }
+}
+
 extern "C" void nlk_ctx_destroy(nlk_ctx *c)
 {
     if (!c) return;
@@ -340,6 +365,7 @@ extern "C" void nlk_ctx_destroy(nlk_ctx *c)
     for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
     if (c->h_alpha) cudaFreeHost(c->h_alpha);
     if (c->tv_herr) cudaFreeHost(c->tv_herr);
+    tvl1_graphs_release(c);
     for (int i = 0; i < nlk_ctx::PIPE_SETS; ++i) c->p_msk8[i].release();
     for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
@@ -1048,7 +1074,133 @@ extern "C" int nlk_peer_error(nlk_ctx *c, unsigned int *code)
     return NLK_OK;
 }
 
-// ---- Dual TV-L1 optical flow at one scale (nlk_tvl1.cuh; SURVEY 8(f4), first slice) --------------
+// ---- Dual TV-L1 optical flow at one scale (nlk_tvl1.cuh) ---------------------------
+
+namespace {
+// where a level's work planes sit in tv_scratch
+struct Tvl1Level {
+    int nx, ny, warps;
+    size_t size;
+    float *I1x, *I1y, *I1wx, *I1wy, *grad, *rho_c, *p11, *p12, *p21, *p22, *err;
+    int *cnt, *nloop;
+    static constexpr int ES = TVL1_MAX_ITERATIONS + 4;        // error slots per warping step
+    static size_t bytes(size_t size, int warps) { return (10 * size + (size_t)warps * ES + 64) * 4 + (size_t)warps * 8 + 64; }
+    Tvl1Level(float *base, int nx_, int ny_, int warps_) : nx(nx_), ny(ny_), warps(warps_), size((size_t)nx_ * ny_)
+    {
+        I1x = base; I1y = I1x + size; I1wx = I1y + size; I1wy = I1wx + size; grad = I1wy + size; rho_c = grad + size;
+        p11 = rho_c + size; p12 = p11 + size; p21 = p12 + size; p22 = p21 + size;
+        err = p22 + size;
+        cnt = reinterpret_cast<int *>(err + (size_t)warps * ES);
+        nloop = cnt + warps;
+    }
+    size_t zero_bytes() const { return ((size_t)warps * ES) * 4 + (size_t)warps * 8; }     // err, cnt, nloop
+    dim3 grid() const { return dim3((nx + 31) / 32, (ny + 7) / 8); }
+};
+}
+
+// One level as ONE graph launch: the loop of every warping step is a WHILE node whose body is
+// { k_tvl1_u, k_tvl1_p, k_tvl1_next } (nlk_tvl1.cuh), so the stopping rule needs neither a host round
+// trip nor launches past the stopping iteration.  Built by stream capture (the conditional nodes are
+// added to the capturing graph by hand), instantiated once per (buffers, size, parameters) and kept.
+static cudaError_t tvl1_build_graph(nlk_ctx *c, Tvl1GraphEntry &E)
+{
+    cudaStream_t st = c->L->st;
+    if (!c->tv_st2) { cudaError_t e = cudaStreamCreateWithFlags(&c->tv_st2, cudaStreamNonBlocking); if (e != cudaSuccess) return e; }
+    const Tvl1Level L(E.base, E.nx, E.ny, E.warps);
+    const float l_t = E.lambda * E.theta, taut = E.tau / E.theta, eps2 = E.epsilon * E.epsilon;
+    const dim3 nt(32, 8), nb = L.grid();
+    cudaError_t err = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (err != cudaSuccess) return err;
+    auto CK = [&](cudaError_t x) { if (x != cudaSuccess && err == cudaSuccess) err = x; };
+    cudaGraphConditionalHandle loops[64];
+    cudaGraph_t bodies[64];
+    CK(cudaMemsetAsync(L.p11, 0, 4 * L.size * 4, st));                       // p = 0 (:130-134)
+    CK(cudaMemsetAsync(L.err, 0, L.zero_bytes(), st));
+    k_tvl1_loop_init<<<1, 64, 0, st>>>(L.nloop, L.warps);
+    k_tvl1_centered_gradient<<<nb, nt, 0, st>>>(E.I1, L.I1x, L.I1y, L.nx, L.ny);
+    for (int wi = 0; wi < L.warps && err == cudaSuccess; ++wi) {
+        k_tvl1_warp<<<nb, nt, 0, st>>>(E.I0, E.I1, L.I1x, L.I1y, E.u1, E.u2, L.I1wx, L.I1wy, L.grad, L.rho_c, L.nx, L.ny);
+        // the WHILE node goes after everything captured so far
+        cudaStreamCaptureStatus status;
+        cudaGraph_t g = nullptr;
+        const cudaGraphNode_t *deps = nullptr;
+        size_t ndeps = 0;
+        CK(cudaStreamGetCaptureInfo(st, &status, nullptr, &g, &deps, &ndeps));
+        if (err != cudaSuccess) break;
+        cudaGraphConditionalHandle loop;
+        CK(cudaGraphConditionalHandleCreate(&loop, g, 1, cudaGraphCondAssignDefault));     // iteration 1 always runs
+        cudaGraphNodeParams np = {};       // (reserved fields must be zero)
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = loop;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        CK(cudaGraphAddNode(&node, g, deps, ndeps, &np));
+        if (err != cudaSuccess) break;
+        CK(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
+        loops[wi] = loop;
+        bodies[wi] = np.conditional.phGraph_out[0];
+    }
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamEndCapture(st, &graph));          // (also leaves capture mode after a failure)
+    CK(cudaGetLastError());
+    // the loop bodies, captured into the graphs the WHILE nodes own
+    for (int wi = 0; wi < L.warps && err == cudaSuccess; ++wi) {
+        float *e = L.err + (size_t)wi * Tvl1Level::ES;
+        CK(cudaStreamBeginCaptureToGraph(c->tv_st2, bodies[wi], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        if (err != cudaSuccess) break;
+        k_tvl1_u<<<nb, nt, 0, c->tv_st2>>>(L.rho_c, L.I1wx, L.I1wy, L.grad, L.p11, L.p12, L.p21, L.p22, E.u1, E.u2, e, 0,
+                                           L.nloop + wi, L.nx, L.ny, l_t, E.theta, eps2);
+        k_tvl1_p<<<nb, nt, 0, c->tv_st2>>>(E.u1, E.u2, L.p11, L.p12, L.p21, L.p22, e, 0, L.nx, L.ny, taut, eps2);
+        k_tvl1_next<<<1, 1, 0, c->tv_st2>>>(loops[wi], e, L.nloop + wi, L.cnt + wi, (float)L.size, eps2);
+        CK(cudaStreamEndCapture(c->tv_st2, nullptr));
+        CK(cudaGetLastError());
+    }
+    if (err == cudaSuccess) err = cudaGraphInstantiate(&E.exec, graph, 0);
+    if (err != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return err;
+    }
+    E.graph = graph;
+    return cudaSuccess;
+}
+
+// the cached graph of this level, built on first use; nullptr: graphs are off (NLK_TVL1_GRAPH=0) or not
+// available on this driver (said once on stderr), the caller queues the kernels itself
+static cudaGraphExec_t tvl1_level_graph(nlk_ctx *c, const float *I0, const float *I1, float *u1, float *u2, float *base,
+                                        int nx, int ny, float tau, float lambda, float theta, int warps, float epsilon)
+{
+    if (c->tv_graph_state == 0) {
+        const char *env = getenv("NLK_TVL1_GRAPH");
+        c->tv_graph_state = (env && atoi(env) == 0) ? -1 : 1;
+    }
+    if (c->tv_graph_state < 0 || warps < 1 || warps > 64) return nullptr;
+    for (Tvl1GraphEntry &E : c->tv_graphs)
+        if (E.I0 == I0 && E.I1 == I1 && E.u1 == u1 && E.u2 == u2 && E.base == base && E.nx == nx && E.ny == ny &&
+            E.warps == warps && E.tau == tau && E.lambda == lambda && E.theta == theta && E.epsilon == epsilon) {
+            E.stamp = ++c->tv_stamp;
+            return E.exec;
+        }
+    Tvl1GraphEntry E{I0, I1, u1, u2, base, nx, ny, warps, tau, lambda, theta, epsilon, nullptr, nullptr, ++c->tv_stamp};
+    const cudaError_t e = tvl1_build_graph(c, E);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "[nlkalman_b200] TV-L1: CUDA graph loop not available (%s); queueing the iterations from the host\n",
+                cudaGetErrorString(e));
+        c->tv_graph_state = -1;
+        return nullptr;
+    }
+    if (c->tv_graphs.size() >= 48) {      // evict the least recently used
+        size_t lru = 0;
+        for (size_t i = 1; i < c->tv_graphs.size(); ++i) if (c->tv_graphs[i].stamp < c->tv_graphs[lru].stamp) lru = i;
+        cudaGraphExecDestroy(c->tv_graphs[lru].exec);
+        cudaGraphDestroy(c->tv_graphs[lru].graph);
+        c->tv_graphs[lru] = E;
+    } else {
+        c->tv_graphs.push_back(E);
+    }
+    return E.exec;
+}
 
 extern "C" int nlk_tvl1_level_dev(nlk_ctx *c, const float *d_I0, const float *d_I1, float *d_u1, float *d_u2,
                                   int nx, int ny, float tau, float lambda, float theta, int warps, float epsilon,
@@ -1058,52 +1210,55 @@ extern "C" int nlk_tvl1_level_dev(nlk_ctx *c, const float *d_I0, const float *d_
     if (!d_I0 || !d_I1 || !d_u1 || !d_u2 || nx < 2 || ny < 2 || warps < 0 || warps > 64)
         return set_err(NLK_ERR_PARAM, "bad TV-L1 request (%dx%d, %d warpings)", nx, ny, warps);
     const size_t size = (size_t)nx * ny;
-    const int ES = TVL1_MAX_ITERATIONS + 4;        // error slots per warping step
-    const size_t fl = 10 * size + (size_t)warps * ES + 64;
-    if (int r = c->tv_scratch.ensure(fl * 4 + (size_t)warps * 4 + 64)) return r;
-    float *base = c->tv_scratch.as<float>();
-    float *I1x = base, *I1y = I1x + size, *I1wx = I1y + size, *I1wy = I1wx + size, *grad = I1wy + size,
-          *rho_c = grad + size, *p11 = rho_c + size, *p12 = p11 + size, *p21 = p12 + size, *p22 = p21 + size;
-    float *err = p22 + size;
-    int *cnt = reinterpret_cast<int *>(err + (size_t)warps * ES);
+    if (int r = c->tv_scratch.ensure(Tvl1Level::bytes(size, warps))) return r;
+    const Tvl1Level L(c->tv_scratch.as<float>(), nx, ny, warps);
     cudaStream_t st = c->L->st;
-    const float l_t = lambda * theta, taut = tau / theta, eps2 = epsilon * epsilon;
-    const dim3 nt(32, 8), nb((nx + 31) / 32, (ny + 7) / 8);
-    CU_TRY(cudaMemsetAsync(p11, 0, 4 * size * 4, st));                       // p = 0 (:130-134)
-    CU_TRY(cudaMemsetAsync(err, 0, ((size_t)warps * ES) * 4 + (size_t)warps * 4, st));
-    k_tvl1_centered_gradient<<<nb, nt, 0, st>>>(d_I1, I1x, I1y, nx, ny);
-    if (int r = check_launch(c, 1, "tvl1 gradient")) return r;
-    if (!c->tv_herr) CU_TRY(cudaMallocHost(&c->tv_herr, 64));
-    float *h_err = c->tv_herr;
     int rc = NLK_OK;
-    for (int wi = 0; wi < warps && rc == NLK_OK; ++wi) {
-        float *e = err + (size_t)wi * ES;
-        k_tvl1_warp<<<nb, nt, 0, st>>>(d_I0, d_I1, I1x, I1y, d_u1, d_u2, I1wx, I1wy, grad, rho_c, nx, ny);
-        rc = check_launch(c, 1, "tvl1 warp");
-        // batches of iterations; the kernels themselves stop at the reference's stopping iteration
-        // (:164), the host only learns between batches that nothing is left to queue
-        const int BATCH = 20;
-        for (int n0 = 1; n0 <= TVL1_MAX_ITERATIONS && rc == NLK_OK; n0 += BATCH) {
-            const int n1 = n0 + BATCH - 1 < TVL1_MAX_ITERATIONS ? n0 + BATCH - 1 : TVL1_MAX_ITERATIONS;
-            for (int n = n0; n <= n1; ++n) {
-                k_tvl1_u<<<nb, nt, 0, st>>>(rho_c, I1wx, I1wy, grad, p11, p12, p21, p22, d_u1, d_u2, e, n, nx, ny, l_t, theta, eps2);
-                k_tvl1_p<<<nb, nt, 0, st>>>(d_u1, d_u2, p11, p12, p21, p22, e, n, nx, ny, taut, eps2);
+    if (cudaGraphExec_t exec = tvl1_level_graph(c, d_I0, d_I1, d_u1, d_u2, c->tv_scratch.as<float>(), nx, ny, tau, lambda,
+                                                theta, warps, epsilon)) {
+        CU_TRY(cudaGraphLaunch(exec, st));
+        c->launches += 1;
+    } else {
+        const float l_t = lambda * theta, taut = tau / theta, eps2 = epsilon * epsilon;
+        const dim3 nt(32, 8), nb = L.grid();
+        CU_TRY(cudaMemsetAsync(L.p11, 0, 4 * size * 4, st));                       // p = 0 (:130-134)
+        CU_TRY(cudaMemsetAsync(L.err, 0, L.zero_bytes(), st));
+        k_tvl1_centered_gradient<<<nb, nt, 0, st>>>(d_I1, L.I1x, L.I1y, nx, ny);
+        if (int r = check_launch(c, 1, "tvl1 gradient")) return r;
+        if (!c->tv_herr) CU_TRY(cudaMallocHost(&c->tv_herr, 64));
+        float *h_err = c->tv_herr;
+        for (int wi = 0; wi < warps && rc == NLK_OK; ++wi) {
+            float *e = L.err + (size_t)wi * Tvl1Level::ES;
+            k_tvl1_warp<<<nb, nt, 0, st>>>(d_I0, d_I1, L.I1x, L.I1y, d_u1, d_u2, L.I1wx, L.I1wy, L.grad, L.rho_c, nx, ny);
+            rc = check_launch(c, 1, "tvl1 warp");
+            // batches of iterations; the kernels themselves stop at the reference's stopping iteration
+            // (:164), the host only learns between batches that nothing is left to queue.  Batches grow
+            // 4, 8, 16, 32, 32 ...: most warping steps after the first of a scale stop within a few iterations,
+            // and every queued iteration past the stop is two (empty) launches.
+            int batch = 4;
+            for (int n0 = 1; n0 <= TVL1_MAX_ITERATIONS && rc == NLK_OK; n0 += batch, batch = batch < 32 ? 2 * batch : 32) {
+                const int n1 = n0 + batch - 1 < TVL1_MAX_ITERATIONS ? n0 + batch - 1 : TVL1_MAX_ITERATIONS;
+                for (int n = n0; n <= n1; ++n) {
+                    k_tvl1_u<<<nb, nt, 0, st>>>(L.rho_c, L.I1wx, L.I1wy, L.grad, L.p11, L.p12, L.p21, L.p22, d_u1, d_u2, e, n,
+                                                nullptr, nx, ny, l_t, theta, eps2);
+                    k_tvl1_p<<<nb, nt, 0, st>>>(d_u1, d_u2, L.p11, L.p12, L.p21, L.p22, e, n, nx, ny, taut, eps2);
+                }
+                rc = check_launch(c, 2 * (n1 - n0 + 1), "tvl1 iteration");
+                if (rc != NLK_OK || n1 == TVL1_MAX_ITERATIONS) break;
+                if (cudaMemcpyAsync(h_err, e + n1, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                    cudaStreamSynchronize(st) != cudaSuccess) {
+                    rc = set_err(NLK_ERR_CUDA, "tvl1: %s", cudaGetErrorString(cudaGetLastError()));
+                    break;
+                }
+                if (!(*h_err / (float)size > eps2)) break;     // converged inside this batch
             }
-            rc = check_launch(c, 2 * (n1 - n0 + 1), "tvl1 iteration");
-            if (rc != NLK_OK || n1 == TVL1_MAX_ITERATIONS) break;
-            if (cudaMemcpyAsync(h_err, e + n1, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-                cudaStreamSynchronize(st) != cudaSuccess) {
-                rc = set_err(NLK_ERR_CUDA, "tvl1: %s", cudaGetErrorString(cudaGetLastError()));
-                break;
-            }
-            if (!(*h_err / (float)size > eps2)) break;     // converged inside this batch
+            k_tvl1_count<<<1, 1, 0, st>>>(e, L.cnt + wi, (float)size, eps2);
+            if (rc == NLK_OK) rc = check_launch(c, 1, "tvl1 count");
         }
-        k_tvl1_count<<<1, 1, 0, st>>>(e, cnt + wi, (float)size, eps2);
-        if (rc == NLK_OK) rc = check_launch(c, 1, "tvl1 count");
     }
     if (rc != NLK_OK) return rc;
     if (iterations && warps > 0) {
-        CU_TRY(cudaMemcpyAsync(iterations, cnt, (size_t)warps * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(iterations, L.cnt, (size_t)warps * 4, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
     }
     return NLK_OK;

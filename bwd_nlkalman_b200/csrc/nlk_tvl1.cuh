@@ -169,9 +169,13 @@ __global__ void __launch_bounds__(256) k_tvl1_u(const float *__restrict__ rho_c,
                                                 const float *__restrict__ p11, const float *__restrict__ p12,
                                                 const float *__restrict__ p21, const float *__restrict__ p22,
                                                 float *__restrict__ u1, float *__restrict__ u2, float *err, int n,
-                                                int nx, int ny, float l_t, float theta, float eps2)
+                                                const int *__restrict__ n_loop, int nx, int ny, float l_t, float theta,
+                                                float eps2)
 {
-    if (!tvl1_runs(err, n, (float)(nx * ny), eps2)) return;
+    // stream path: iteration n, skipped when the previous one met the stopping rule; graph path (n_loop):
+    // the loop counter in device memory, the loop condition has already decided that it runs
+    if (n_loop) n = *n_loop;
+    else if (!tvl1_runs(err, n, (float)(nx * ny), eps2)) return;
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
     float e = 0.f;
     if (j < nx && i < ny) e = tvl1_u_pixel(rho_c, I1wx, I1wy, grad, p11, p12, p21, p22, u1, u2, i, j, nx, ny, l_t, theta);
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(256) k_tvl1_p(const float *__restrict__ u1, co
                                                 float *__restrict__ p21, float *__restrict__ p22, const float *err, int n,
                                                 int nx, int ny, float taut, float eps2)
 {
-    if (!tvl1_runs(err, n, (float)(nx * ny), eps2)) return;
+    if (n > 0 && !tvl1_runs(err, n, (float)(nx * ny), eps2)) return;      // (n = 0: inside the graph's loop)
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
     if (j >= nx || i >= ny) return;
     const int p = i * nx + j;
@@ -213,6 +217,26 @@ __global__ void __launch_bounds__(256) k_tvl1_p(const float *__restrict__ u1, co
     p21[p] = __fdiv_rn(__fadd_rn(p21[p], __fmul_rn(taut, u2x)), ng2);
     p22[p] = __fdiv_rn(__fadd_rn(p22[p], __fmul_rn(taut, u2y)), ng2);
 }
+
+#ifndef NLK_HOST_MODEL
+// The loop of a warping step as a CUDA graph WHILE node (nlk_lib.cu: tvl1_build_graph): the body is
+// { k_tvl1_u, k_tvl1_p, k_tvl1_next }; this kernel closes iteration n = *n_loop -- records it as the count
+// of the step, advances the counter and sets the loop condition to the reference's
+// `error > eps^2 && n < MAX_ITERATIONS` (:164).  No host round trip, no launch past the stopping iteration.
+__global__ void k_tvl1_next(cudaGraphConditionalHandle loop, const float *err, int *n_loop, int *count, float size,
+                            float eps2)
+{
+    const int n = *n_loop;
+    *count = n;
+    *n_loop = n + 1;
+    cudaGraphSetConditional(loop, (n < TVL1_MAX_ITERATIONS && __fdiv_rn(err[n], size) > eps2) ? 1u : 0u);
+}
+
+__global__ void k_tvl1_loop_init(int *n_loop, int warps)
+{
+    if ((int)threadIdx.x < warps) n_loop[threadIdx.x] = 1;
+}
+#endif
 
 // iterations run by a warping step = the last n that passed the test
 __global__ void k_tvl1_count(const float *err, int *count, float size, float eps2)

@@ -71,7 +71,7 @@ static void model_level(const float *I0, const float *I1, float *u1, float *u2, 
                 for (int j = 0; j < nx; ++j)
                     e += tvl1_u_pixel(rho_c, I1wx, I1wy, grad, p11, p12, p21, p22, u1, u2, i, j, nx, ny, l_t, theta);
             err[n] = e;
-            launch2d(nx, ny, [&] { k_tvl1_p(u1, u2, p11, p12, p21, p22, err.data(), n, nx, ny, taut, eps2); });
+            launch2d(nx, ny, [&] { k_tvl1_p(u1, u2, p11, p12, p21, p22, err.data(), 0, nx, ny, taut, eps2); });
         }
         if (iterations) iterations[wi] = n - 1;
     }
