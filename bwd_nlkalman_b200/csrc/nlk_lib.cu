@@ -1153,7 +1153,8 @@ static cudaError_t tvl1_build_graph(nlk_ctx *c, Tvl1GraphEntry &E)
                                            L.nloop + wi, L.nx, L.ny, l_t, E.theta, eps2);
         k_tvl1_p<<<nb, nt, 0, c->tv_st2>>>(E.u1, E.u2, L.p11, L.p12, L.p21, L.p22, e, 0, L.nx, L.ny, taut, eps2);
         k_tvl1_next<<<1, 1, 0, c->tv_st2>>>(loops[wi], e, L.nloop + wi, L.cnt + wi, (float)L.size, eps2);
-        CK(cudaStreamEndCapture(c->tv_st2, nullptr));
+        cudaGraph_t same = nullptr;                 // (the body graph again)
+        CK(cudaStreamEndCapture(c->tv_st2, &same));
         CK(cudaGetLastError());
     }
     if (err == cudaSuccess) err = cudaGraphInstantiate(&E.exec, graph, 0);
