@@ -455,6 +455,16 @@ def run_ours(args):
         except Exception as exc:
             cli = {"error": repr(exc)}
 
+    # the flow estimator in front of the filter: its own small leg, outside the timed region
+    tvl1 = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_tvl1
+            tvl1 = bench_tvl1.measure(W, H, reps=5, device=local_rank)
+        except Exception as exc:
+            tvl1 = {"error": repr(exc)}
+
     cfg = bench_config(world)
     line = {"metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -483,6 +493,8 @@ def run_ours(args):
         line["cpu_baseline"] = cpu
     if cli is not None:
         line["cli"] = cli
+    if tvl1 is not None:
+        line["tvl1"] = tvl1
     if strips_res is not None:
         line["strips"] = strips_res
         if "value" in strips_res:

@@ -1099,7 +1099,7 @@ struct Tvl1Level {
 }
 
 // One level as ONE graph launch: the loop of every warping step is a WHILE node whose body is
-// { k_tvl1_u, k_tvl1_p, k_tvl1_next } (nlk_tvl1.cuh), so the stopping rule needs neither a host round
+// { k_tvl1_u, k_tvl1_p } (nlk_tvl1.cuh; k_tvl1_p also sets the loop condition), so the stopping rule needs neither a host round
 // trip nor launches past the stopping iteration.  Built by stream capture (the conditional nodes are
 // added to the capturing graph by hand), instantiated once per (buffers, size, parameters) and kept.
 static cudaError_t tvl1_build_graph(nlk_ctx *c, Tvl1GraphEntry &E)
@@ -1151,8 +1151,8 @@ static cudaError_t tvl1_build_graph(nlk_ctx *c, Tvl1GraphEntry &E)
         if (err != cudaSuccess) break;
         k_tvl1_u<<<nb, nt, 0, c->tv_st2>>>(L.rho_c, L.I1wx, L.I1wy, L.grad, L.p11, L.p12, L.p21, L.p22, E.u1, E.u2, e, 0,
                                            L.nloop + wi, L.nx, L.ny, l_t, E.theta, eps2);
-        k_tvl1_p<<<nb, nt, 0, c->tv_st2>>>(E.u1, E.u2, L.p11, L.p12, L.p21, L.p22, e, 0, L.nx, L.ny, taut, eps2);
-        k_tvl1_next<<<1, 1, 0, c->tv_st2>>>(loops[wi], e, L.nloop + wi, L.cnt + wi, (float)L.size, eps2);
+        k_tvl1_p<<<nb, nt, 0, c->tv_st2>>>(E.u1, E.u2, L.p11, L.p12, L.p21, L.p22, e, 0, L.nx, L.ny, taut, eps2,
+                                           (unsigned long long)loops[wi], L.nloop + wi, L.cnt + wi);
         cudaGraph_t same = nullptr;                 // (the body graph again)
         CK(cudaStreamEndCapture(c->tv_st2, &same));
         CK(cudaGetLastError());
@@ -1242,7 +1242,7 @@ extern "C" int nlk_tvl1_level_dev(nlk_ctx *c, const float *d_I0, const float *d_
                 for (int n = n0; n <= n1; ++n) {
                     k_tvl1_u<<<nb, nt, 0, st>>>(L.rho_c, L.I1wx, L.I1wy, L.grad, L.p11, L.p12, L.p21, L.p22, d_u1, d_u2, e, n,
                                                 nullptr, nx, ny, l_t, theta, eps2);
-                    k_tvl1_p<<<nb, nt, 0, st>>>(d_u1, d_u2, L.p11, L.p12, L.p21, L.p22, e, n, nx, ny, taut, eps2);
+                    k_tvl1_p<<<nb, nt, 0, st>>>(d_u1, d_u2, L.p11, L.p12, L.p21, L.p22, e, n, nx, ny, taut, eps2, 0ull, nullptr, nullptr);
                 }
                 rc = check_launch(c, 2 * (n1 - n0 + 1), "tvl1 iteration");
                 if (rc != NLK_OK || n1 == TVL1_MAX_ITERATIONS) break;

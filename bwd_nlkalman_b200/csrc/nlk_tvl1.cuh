@@ -198,9 +198,27 @@ __global__ void __launch_bounds__(256) k_tvl1_u(const float *__restrict__ rho_c,
 __global__ void __launch_bounds__(256) k_tvl1_p(const float *__restrict__ u1, const float *__restrict__ u2,
                                                 float *__restrict__ p11, float *__restrict__ p12,
                                                 float *__restrict__ p21, float *__restrict__ p22, const float *err, int n,
-                                                int nx, int ny, float taut, float eps2)
+                                                int nx, int ny, float taut, float eps2, unsigned long long loop,
+                                                int *n_loop, int *count)
 {
-    if (n > 0 && !tvl1_runs(err, n, (float)(nx * ny), eps2)) return;      // (n = 0: inside the graph's loop)
+    // stream path (n_loop == nullptr): iteration n, skipped when the previous one met the stopping rule.
+    // Graph path: the loop of a warping step is a CUDA graph WHILE node whose body is { k_tvl1_u, k_tvl1_p }
+    // (nlk_lib.cu: tvl1_build_graph); the error of this iteration is complete (k_tvl1_u has finished), so
+    // one thread closes it here: records the count, advances the counter (nobody reads it before the
+    // next k_tvl1_u) and sets the loop condition to the reference's `error > eps^2 && n < MAX_ITERATIONS`
+    // (:164) -- no host round trip, no launch past the stopping iteration.
+    if (n_loop == nullptr) {
+        if (!tvl1_runs(err, n, (float)(nx * ny), eps2)) return;
+    }
+#ifndef NLK_HOST_MODEL
+    else if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) {
+        const int m = *n_loop;
+        *count = m;
+        *n_loop = m + 1;
+        cudaGraphSetConditional((cudaGraphConditionalHandle)loop,
+                                (m < TVL1_MAX_ITERATIONS && __fdiv_rn(err[m], (float)(nx * ny)) > eps2) ? 1u : 0u);
+    }
+#endif
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
     if (j >= nx || i >= ny) return;
     const int p = i * nx + j;
@@ -219,19 +237,6 @@ __global__ void __launch_bounds__(256) k_tvl1_p(const float *__restrict__ u1, co
 }
 
 #ifndef NLK_HOST_MODEL
-// The loop of a warping step as a CUDA graph WHILE node (nlk_lib.cu: tvl1_build_graph): the body is
-// { k_tvl1_u, k_tvl1_p, k_tvl1_next }; this kernel closes iteration n = *n_loop -- records it as the count
-// of the step, advances the counter and sets the loop condition to the reference's
-// `error > eps^2 && n < MAX_ITERATIONS` (:164).  No host round trip, no launch past the stopping iteration.
-__global__ void k_tvl1_next(cudaGraphConditionalHandle loop, const float *err, int *n_loop, int *count, float size,
-                            float eps2)
-{
-    const int n = *n_loop;
-    *count = n;
-    *n_loop = n + 1;
-    cudaGraphSetConditional(loop, (n < TVL1_MAX_ITERATIONS && __fdiv_rn(err[n], size) > eps2) ? 1u : 0u);
-}
-
 __global__ void k_tvl1_loop_init(int *n_loop, int warps)
 {
     if ((int)threadIdx.x < warps) n_loop[threadIdx.x] = 1;

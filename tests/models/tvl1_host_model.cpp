@@ -56,6 +56,7 @@ static void model_level(const float *I0, const float *I1, float *u1, float *u2, 
 {
     const size_t size = (size_t)nx * ny;
     std::vector<float> buf(10 * size, 0.f), err(TVL1_MAX_ITERATIONS + 4);
+    int loop_state = 0;      // (any non-null loop counter: the host model decides about the next iteration itself)
     float *I1x = buf.data(), *I1y = I1x + size, *I1wx = I1y + size, *I1wy = I1wx + size, *grad = I1wy + size,
           *rho_c = grad + size, *p11 = rho_c + size, *p12 = p11 + size, *p21 = p12 + size, *p22 = p21 + size;
     const float l_t = lambda * theta, taut = tau / theta, eps2 = epsilon * epsilon;
@@ -71,7 +72,7 @@ static void model_level(const float *I0, const float *I1, float *u1, float *u2, 
                 for (int j = 0; j < nx; ++j)
                     e += tvl1_u_pixel(rho_c, I1wx, I1wy, grad, p11, p12, p21, p22, u1, u2, i, j, nx, ny, l_t, theta);
             err[n] = e;
-            launch2d(nx, ny, [&] { k_tvl1_p(u1, u2, p11, p12, p21, p22, err.data(), 0, nx, ny, taut, eps2); });
+            launch2d(nx, ny, [&] { k_tvl1_p(u1, u2, p11, p12, p21, p22, err.data(), 0, nx, ny, taut, eps2, 0ull, &loop_state, &loop_state); });
         }
         if (iterations) iterations[wi] = n - 1;
     }

@@ -16,3 +16,5 @@ print("cpu_baseline", d.get("cpu_baseline"))
 print("cli", d.get("cli"))
 if "strips" in d:
     print("strips", d["strips"])
+if "tvl1" in d:
+    print("tvl1", d["tvl1"])
