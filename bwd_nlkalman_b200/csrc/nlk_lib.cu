@@ -1,6 +1,7 @@
 // libnlkalman_b200.so: the C ABI (include/nlkalman.h, include/nlkalman_b200.h) over the
 // sm_100a kernels.  Single translation unit: the kernel headers are included here.
 #include "../../include/nlkalman_b200.h"
+#include "../../include/tvl1flow.h"
 
 #include "nlk_common.cuh"
 #include "nlk_prep.cuh"
@@ -1972,4 +1973,44 @@ extern "C" int nlk_fp32_peak(nlk_ctx *c, float ms, double *tflops)
     cudaEventDestroy(b);
     *tflops = best;
     return NLK_OK;
+}
+
+// ---- the two entry points of the reference's TV-L1 library (include/tvl1flow.h) ----------------------
+
+extern "C" void Dual_TVL1_optic_flow(float *I0, float *I1, float *u1, float *u2, const int nx, const int ny,
+                                     const float tau, const float lambda, const float theta, const int warps,
+                                     const float epsilon, const bool verbose)
+{
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    nlk_ctx *c = legacy_ctx(nx, ny, 1);
+    std::vector<int> its(warps > 0 ? warps : 1, 0);
+    if (nlk_tvl1_level_host(c, I0, I1, u1, u2, nx, ny, tau, lambda, theta, warps, epsilon, its.data()))
+        legacy_die("Dual_TVL1_optic_flow");
+    if (verbose)     // (reference tvl1flow_lib.c:251-254, without the error value, which stays on the device)
+        for (int k = 0; k < warps; ++k) fprintf(stderr, "Warping: %d, Iterations: %d\n", k, its[k]);
+}
+
+extern "C" void Dual_TVL1_optic_flow_multiscale(float *I0, float *I1, float *u1, float *u2, const int nxx, const int nyy,
+                                                const float tau, const float lambda, const float theta, const int nscales,
+                                                const int fscale, const float zfactor, const int warps,
+                                                const float epsilon, const bool verbose)
+{
+    std::lock_guard<std::mutex> lk(g_legacy_mu);
+    nlk_ctx *c = legacy_ctx(nxx, nyy, 1);
+    const size_t n = (size_t)nxx * nyy;
+    std::vector<float> flow(2 * n);
+    std::vector<int> its((size_t)(nscales > 0 ? nscales : 1) * (warps > 0 ? warps : 1), 0);
+    if (nlk_tvl1_flow_host(c, I0, I1, flow.data(), nxx, nyy, tau, lambda, theta, nscales, fscale, zfactor, warps, epsilon,
+                           its.data()))
+        legacy_die("Dual_TVL1_optic_flow_multiscale");
+    memcpy(u1, flow.data(), n * 4);
+    memcpy(u2, flow.data() + n, n * 4);
+    if (verbose) {   // (reference tvl1flow_lib.c:413-414, :251-254)
+        Tvl1Pyramid P;
+        P.plan(nxx, nyy, nscales, fscale, zfactor, warps);
+        for (int s = nscales - 1; s >= fscale; --s) {
+            fprintf(stderr, "Scale %d: %dx%d\n", s, P.nx[s], P.ny[s]);
+            for (int k = 0; k < warps; ++k) fprintf(stderr, "Warping: %d, Iterations: %d\n", k, its[(size_t)s * warps + k]);
+        }
+    }
 }

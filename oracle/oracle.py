@@ -62,10 +62,13 @@ TVL1_SO = os.path.join(HERE, "_ref", "libtvl1_ref.so")
 class Tvl1Ref:
     """The reference's TV-L1 flow library (lib/tvl1flow/tvl1flow_lib.c compiled unmodified)."""
 
-    def __init__(self, threads: int | None = None):
-        if not os.path.exists(TVL1_SO):
-            raise FileNotFoundError(f"{TVL1_SO} missing: run `make -C oracle ref` where /root/reference exists")
-        self.lib = C.CDLL(TVL1_SO)
+    def __init__(self, threads: int | None = None, so: str | None = None):
+        """so: another library exporting the same two entry points (the tests bind the PRODUCT's
+        include/tvl1flow.h symbols through this very wrapper to compare like with like)"""
+        so = so or TVL1_SO
+        if not os.path.exists(so):
+            raise FileNotFoundError(f"{so} missing: run `make -C oracle ref` where /root/reference exists")
+        self.lib = C.CDLL(so)
         f = self.lib.Dual_TVL1_optic_flow          # tvl1flow_lib.c:93
         f.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_bool]
         f.restype = None

@@ -229,6 +229,14 @@ def test_tvl1flow_against_reference_program(tmp_path):
         a, b = _read_flo(ours), _read_flo(theirs)
         e = maxabs(a, b)
         print(f"tvl1flow {name}: max |du| = {e:.2e} px, identical pixels {float(np.mean(a == b)):.4f}")
+        # and the reference's OWN program (main.c unmodified) on top of the product library (include/tvl1flow.h)
+        dropin = os.path.join(REF, "tvl1flow-dropin")
+        if args and os.path.exists(dropin):
+            mine = tmp_path / f"dropin-{name}.flo"
+            _run(dropin, tmp_path / f0, tmp_path / f1, mine, *args)
+            d = _read_flo(mine)
+            print(f"tvl1flow-dropin {name}: max |du| = {maxabs(d, b):.2e} px, identical pixels {float(np.mean(d == b)):.4f}")
+            assert maxabs(d, b) <= 5e-2
         assert a.shape == (ny, nx, 2) and np.abs(b).max() > 2.0
         assert e <= 5e-2
     r = _run(os.path.join(BIN, "tvl1flow"), ok=(1,))

@@ -175,3 +175,24 @@ def test_tvl1_graph_loop_and_host_queued_iterations_agree(nlk, monkeypatch):
     assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
     print(f"launches for two flows: graph loop {out['1'][2]}, host-queued {out['0'][2]}; iterations {out['1'][1].sum(1).tolist()}")
     assert out["1"][2] * 4 < out["0"][2]
+
+
+def test_reference_entry_points_of_the_flow_library(nlk):
+    """include/tvl1flow.h: Dual_TVL1_optic_flow and Dual_TVL1_optic_flow_multiscale with the reference's
+    names and argument lists, exported by the product library -- bound here through the same ctypes
+    wrapper as the reference's library and compared with it"""
+    from oracle import oracle as O
+    if not os.path.exists(O.TVL1_SO):
+        pytest.skip("oracle/_ref/libtvl1_ref.so not built (needs /root/reference)")
+    so = os.path.join(os.path.dirname(os.path.abspath(nlk.__file__)), "libnlkalman_b200.so")
+    ours, ref = O.Tvl1Ref(so=so), O.Tvl1Ref()
+    nx, ny = 200, 150
+    I0, I1 = O.tvl1_frames(nx, ny, seed=8)
+    a, ns = ours.flow(I0, I1, lam=0.4, fscale=1)
+    b, _ = ref.flow(I0, I1, lam=0.4, fscale=1)
+    print(f"Dual_TVL1_optic_flow_multiscale {nx}x{ny}: max |du| = {_err(a, b):.2e}, identical {_same(a, b):.4f}")
+    assert _err(a, b) <= 5e-2
+    J0, J1 = O.tvl1_pair(96, 72)
+    z = np.zeros((72, 96), np.float32)
+    p, q = ours.level(J0, J1, z, z), ref.level(J0, J1, z, z)
+    assert max(_err(p[0], q[0]), _err(p[1], q[1])) <= 5e-2
