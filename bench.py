@@ -554,7 +554,54 @@ def cli_leg():
                            "from PFM/FLO/PGM files), both filterings written; best of 3, process start, CUDA context "
                            "creation and file I/O included")
         out["cores"] = os.cpu_count()
+        try:
+            out["pipeline"] = cli_pipeline(d, w, h, sigma, pfm, env)
+        except Exception as exc:
+            out["pipeline"] = {"error": repr(exc)}
         return out
+
+
+def cli_pipeline(d, w, h, sigma, pfm, env, nf=5):
+    """The forward half of the pipeline script (scripts/nlkalman-seq.sh:31-102) on a short C1-sized sequence,
+    flows and masks included: the reference's own programs chained through files the way the script chains
+    them (tvl1flow-ref, plambda-ref, nlkalman-flt-ref twice per frame; PFM / FLO files, the formats this
+    build of iio writes) against ONE nlkalman-seq --tvl1 1 process (everything resident on the GPU)."""
+    from bwd_nlkalman_b200 import synth
+    R = os.path.join(ROOT, "oracle", "_ref")
+    tv, pl, fl = (os.path.join(R, n) for n in ("tvl1flow-ref", "plambda-ref", "nlkalman-flt-ref"))
+    seq = os.path.join(ROOT, "bwd_nlkalman_b200", "bin", "nlkalman-seq")
+    if not all(os.path.exists(x) for x in (tv, pl, fl, seq)):
+        return {"error": "programs not built"}
+    p = lambda n: os.path.join(d, n)
+    for t in range(nf):
+        pfm(p(f"s{t}.pfm"), synth.noisy_frame(w, h, 1, t, sigma))
+    run = lambda *a: subprocess.run([str(x) for x in a], check=True, capture_output=True, env=env)
+    expr = "x(0,0)[0] x(-1,0)[0] - x(0,0)[1] x(0,-1)[1] - + fabs 0.75 > 255 *"
+    t0 = time.perf_counter()
+    run(fl, "-i", p("s0.pfm"), "-s", sigma, "--flt11", p("r1_0.pfm"), "--flt21", p("r2_0.pfm"))
+    for t in range(1, nf):
+        run(tv, p(f"s{t}.pfm"), p(f"r2_{t-1}.pfm"), p(f"rb{t}.flo"), 8, 0, 0.25, 0, 0, 1)
+        run(pl, p(f"rb{t}.flo"), expr, "-o", p(f"ro{t}.pfm"))
+        run(fl, "-i", p(f"s{t}.pfm"), "-s", sigma, "--f2_p", 0, "-o", p(f"rb{t}.flo"), "-k", p(f"ro{t}.pfm"),
+            "--flt10", p(f"r1_{t-1}.pfm"), "--flt11", p(f"r1_{t}.pfm"))
+        run(fl, "-i", p(f"s{t}.pfm"), "-s", sigma, "--f1_p", 0, "-o", p(f"rb{t}.flo"), "-k", p(f"ro{t}.pfm"),
+            "--flt11", p(f"r1_{t}.pfm"), "--flt20", p(f"r2_{t-1}.pfm"), "--flt21", p(f"r2_{t}.pfm"))
+    ref_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    run(seq, "-i", p("s%d.pfm"), "-f", 0, "-l", nf - 1, "-s", sigma, "--first_f2", 1, "--tvl1", 1,
+        "--filt1", p("o1_%d.pfm"), "--filt2", p("o2_%d.pfm"))
+    ours_s = time.perf_counter() - t0
+
+    def rd(name):
+        raw = open(p(name), "rb").read().split(b"\n", 3)
+        return np.frombuffer(raw[3], np.float32)
+    diff = float(np.mean(np.abs(rd(f"o2_{nf-1}.pfm") - rd(f"r2_{nf-1}.pfm"))))
+    return {"reference_s": ref_s, "ours_s": ours_s, "frames": nf,
+            "mean_abs_diff_last_frame": diff,
+            "workload": f"{nf} frames 854x480 gray, sigma 20: backward TV-L1 flow (FSCALE 1, DW 0.25), occlusion mask "
+                        "(TH 0.75), first and second filtering per frame; reference = its programs chained through "
+                        "files as scripts/nlkalman-seq.sh does (4 processes per frame), ours = one nlkalman-seq "
+                        "--tvl1 1 process; wall time, process starts and file I/O included"}
 
 
 def main():
