@@ -140,6 +140,10 @@ struct Tvl1GraphEntry {
     unsigned long long stamp;
 };
 
+enum { TVL1_LOOP_KERNEL = 1,   // one cooperative launch per warping step, grid barriers between half iterations
+       TVL1_LOOP_GRAPH = 2,    // one CUDA graph per level, WHILE nodes around { k_tvl1_u, k_tvl1_p }
+       TVL1_LOOP_HOST = 3 };   // the host queues batches of iterations and reads the error back
+
 struct nlk_ctx {
     int w = 0, h = 0, ch = 0, device = 0, num_sms = 148;
     Lane lane[2];
@@ -152,7 +156,8 @@ struct nlk_ctx {
     float *tv_herr = nullptr;       // pinned word the TV-L1 level solver reads its stopping error back into
     std::vector<Tvl1GraphEntry> tv_graphs;         // instantiated level graphs (tvl1_level_graph)
     cudaStream_t tv_st2 = nullptr;  // captures the loop bodies
-    int tv_graph_state = 0;         // 0: not decided, 1: graphs, -1: stream launches
+    int tv_loop = 0;                // how a warping step's iterations run: 0 not decided, TVL1_LOOP_* below
+    int tv_coop_blocks = 0;         // co-resident blocks of k_tvl1_iterate on this device
     unsigned long long tv_stamp = 0;
     // host-call staging
     DevBuf s_in1, s_prev0, s_bsic, s_out, s_of, s_msk;
@@ -1084,8 +1089,9 @@ struct Tvl1Level {
     size_t size;
     float *I1x, *I1y, *I1wx, *I1wy, *grad, *rho_c, *p11, *p12, *p21, *p22, *err;
     int *cnt, *nloop;
+    unsigned *bars;                                           // one grid-barrier counter per warping step
     static constexpr int ES = TVL1_MAX_ITERATIONS + 4;        // error slots per warping step
-    static size_t bytes(size_t size, int warps) { return (10 * size + (size_t)warps * ES + 64) * 4 + (size_t)warps * 8 + 64; }
+    static size_t bytes(size_t size, int warps) { return (10 * size + (size_t)warps * ES + 64) * 4 + (size_t)warps * 12 + 64; }
     Tvl1Level(float *base, int nx_, int ny_, int warps_) : nx(nx_), ny(ny_), warps(warps_), size((size_t)nx_ * ny_)
     {
         I1x = base; I1y = I1x + size; I1wx = I1y + size; I1wy = I1wx + size; grad = I1wy + size; rho_c = grad + size;
@@ -1093,8 +1099,9 @@ struct Tvl1Level {
         err = p22 + size;
         cnt = reinterpret_cast<int *>(err + (size_t)warps * ES);
         nloop = cnt + warps;
+        bars = reinterpret_cast<unsigned *>(nloop + warps);
     }
-    size_t zero_bytes() const { return ((size_t)warps * ES) * 4 + (size_t)warps * 8; }     // err, cnt, nloop
+    size_t zero_bytes() const { return ((size_t)warps * ES) * 4 + (size_t)warps * 12; }    // err, cnt, nloop, bars
     dim3 grid() const { return dim3((nx + 31) / 32, (ny + 7) / 8); }
 };
 }
@@ -1168,16 +1175,33 @@ static cudaError_t tvl1_build_graph(nlk_ctx *c, Tvl1GraphEntry &E)
     return cudaSuccess;
 }
 
-// the cached graph of this level, built on first use; nullptr: graphs are off (NLK_TVL1_GRAPH=0) or not
-// available on this driver (said once on stderr), the caller queues the kernels itself
+// NLK_TVL1_LOOP = kernel (default) | graph | host
+static void tvl1_pick_loop(nlk_ctx *c)
+{
+    if (c->tv_loop) return;
+    const char *env = getenv("NLK_TVL1_LOOP");
+    c->tv_loop = TVL1_LOOP_KERNEL;
+    if (env && !strcmp(env, "graph")) c->tv_loop = TVL1_LOOP_GRAPH;
+    if (env && !strcmp(env, "host")) c->tv_loop = TVL1_LOOP_HOST;
+    if (c->tv_loop == TVL1_LOOP_KERNEL) {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tvl1_iterate, TVL1_IT_THREADS, 0) == cudaSuccess &&
+            per_sm > 0)
+            c->tv_coop_blocks = per_sm * c->num_sms;
+        else {
+            cudaGetLastError();
+            c->tv_loop = TVL1_LOOP_GRAPH;
+        }
+    }
+}
+
+// the cached graph of this level, built on first use; nullptr: another loop form is selected, or graphs
+// are not available on this driver (said once on stderr) and the caller queues the kernels itself
 static cudaGraphExec_t tvl1_level_graph(nlk_ctx *c, const float *I0, const float *I1, float *u1, float *u2, float *base,
                                         int nx, int ny, float tau, float lambda, float theta, int warps, float epsilon)
 {
-    if (c->tv_graph_state == 0) {
-        const char *env = getenv("NLK_TVL1_GRAPH");
-        c->tv_graph_state = (env && atoi(env) == 0) ? -1 : 1;
-    }
-    if (c->tv_graph_state < 0 || warps < 1 || warps > 64) return nullptr;
+    if (c->tv_loop != TVL1_LOOP_GRAPH || warps < 1 || warps > 64) return nullptr;
     for (Tvl1GraphEntry &E : c->tv_graphs)
         if (E.I0 == I0 && E.I1 == I1 && E.u1 == u1 && E.u2 == u2 && E.base == base && E.nx == nx && E.ny == ny &&
             E.warps == warps && E.tau == tau && E.lambda == lambda && E.theta == theta && E.epsilon == epsilon) {
@@ -1189,7 +1213,7 @@ static cudaGraphExec_t tvl1_level_graph(nlk_ctx *c, const float *I0, const float
     if (e != cudaSuccess) {
         fprintf(stderr, "[nlkalman_b200] TV-L1: CUDA graph loop not available (%s); queueing the iterations from the host\n",
                 cudaGetErrorString(e));
-        c->tv_graph_state = -1;
+        c->tv_loop = TVL1_LOOP_HOST;
         return nullptr;
     }
     if (c->tv_graphs.size() >= 48) {      // evict the least recently used
@@ -1216,7 +1240,35 @@ extern "C" int nlk_tvl1_level_dev(nlk_ctx *c, const float *d_I0, const float *d_
     const Tvl1Level L(c->tv_scratch.as<float>(), nx, ny, warps);
     cudaStream_t st = c->L->st;
     int rc = NLK_OK;
-    if (cudaGraphExec_t exec = tvl1_level_graph(c, d_I0, d_I1, d_u1, d_u2, c->tv_scratch.as<float>(), nx, ny, tau, lambda,
+    if (!c->tv_herr) {
+        CU_TRY(cudaMallocHost(&c->tv_herr, 64));
+        memset(c->tv_herr, 0, 64);
+    }
+    int *host_flag = reinterpret_cast<int *>(c->tv_herr) + 8;     // raised by a grid barrier that gave up
+    if (*(volatile int *)host_flag) return set_err(NLK_ERR_CUDA, "TV-L1: a grid barrier of k_tvl1_iterate timed out");
+    tvl1_pick_loop(c);
+    if (c->tv_loop == TVL1_LOOP_KERNEL && warps > 0) {
+        float l_t = lambda * theta, taut = tau / theta, eps2 = epsilon * epsilon, th = theta;
+        int nxv = nx, nyv = ny;
+        const dim3 nt(32, 8), nb = L.grid();
+        CU_TRY(cudaMemsetAsync(L.p11, 0, 4 * size * 4, st));                       // p = 0 (:130-134)
+        CU_TRY(cudaMemsetAsync(L.err, 0, L.zero_bytes(), st));
+        k_tvl1_centered_gradient<<<nb, nt, 0, st>>>(d_I1, L.I1x, L.I1y, nx, ny);
+        int blocks = (int)((size + TVL1_IT_THREADS - 1) / TVL1_IT_THREADS);
+        if (blocks > c->tv_coop_blocks) blocks = c->tv_coop_blocks;
+        for (int wi = 0; wi < warps; ++wi) {
+            k_tvl1_warp<<<nb, nt, 0, st>>>(d_I0, d_I1, L.I1x, L.I1y, d_u1, d_u2, L.I1wx, L.I1wy, L.grad, L.rho_c, nx, ny);
+            float *e = L.err + (size_t)wi * Tvl1Level::ES;
+            int *cnt = L.cnt + wi;
+            unsigned *bar = L.bars + wi;
+            float *rho_c = L.rho_c, *I1wx = L.I1wx, *I1wy = L.I1wy, *grad = L.grad, *p11 = L.p11, *p12 = L.p12, *p21 = L.p21,
+                  *p22 = L.p22;
+            void *args[] = {&rho_c, &I1wx, &I1wy, &grad, &p11, &p12, &p21, &p22, &d_u1, &d_u2, &e, &cnt, &bar, &host_flag,
+                            &nxv, &nyv, &l_t, &th, &taut, &eps2};
+            CU_TRY(cudaLaunchCooperativeKernel((const void *)k_tvl1_iterate, dim3(blocks), dim3(TVL1_IT_THREADS), args, 0, st));
+        }
+        if (int r = check_launch(c, 1 + 2 * warps, "tvl1 level")) return r;
+    } else if (cudaGraphExec_t exec = tvl1_level_graph(c, d_I0, d_I1, d_u1, d_u2, c->tv_scratch.as<float>(), nx, ny, tau, lambda,
                                                 theta, warps, epsilon)) {
         CU_TRY(cudaGraphLaunch(exec, st));
         c->launches += 1;
@@ -1227,7 +1279,6 @@ extern "C" int nlk_tvl1_level_dev(nlk_ctx *c, const float *d_I0, const float *d_
         CU_TRY(cudaMemsetAsync(L.err, 0, L.zero_bytes(), st));
         k_tvl1_centered_gradient<<<nb, nt, 0, st>>>(d_I1, L.I1x, L.I1y, nx, ny);
         if (int r = check_launch(c, 1, "tvl1 gradient")) return r;
-        if (!c->tv_herr) CU_TRY(cudaMallocHost(&c->tv_herr, 64));
         float *h_err = c->tv_herr;
         for (int wi = 0; wi < warps && rc == NLK_OK; ++wi) {
             float *e = L.err + (size_t)wi * Tvl1Level::ES;
@@ -1262,6 +1313,7 @@ extern "C" int nlk_tvl1_level_dev(nlk_ctx *c, const float *d_I0, const float *d_
     if (iterations && warps > 0) {
         CU_TRY(cudaMemcpyAsync(iterations, L.cnt, (size_t)warps * 4, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
+        if (*(volatile int *)host_flag) return set_err(NLK_ERR_CUDA, "TV-L1: a grid barrier of k_tvl1_iterate timed out");
     }
     return NLK_OK;
 }

@@ -195,6 +195,25 @@ __global__ void __launch_bounds__(256) k_tvl1_u(const float *__restrict__ rho_c,
 }
 #endif
 
+// forward gradient of u and the dual update of one pixel (mask.c:101-144, tvl1flow_lib.c:235-248)
+__device__ __forceinline__ void tvl1_p_pixel(const float *u1, const float *u2, float *p11, float *p12, float *p21, float *p22,
+                                             int i, int j, int nx, int ny, float taut)
+{
+    const int p = i * nx + j;
+    // forward differences, zero across the last column / row
+    const float a = u1[p], b = u2[p];
+    const float u1x = j < nx - 1 ? __fsub_rn(u1[p + 1], a) : 0.f, u1y = i < ny - 1 ? __fsub_rn(u1[p + nx], a) : 0.f;
+    const float u2x = j < nx - 1 ? __fsub_rn(u2[p + 1], b) : 0.f, u2y = i < ny - 1 ? __fsub_rn(u2[p + nx], b) : 0.f;
+    // (the reference's hypot and `1.0 +` are double: :239-242)
+    const double g1 = hypot((double)u1x, (double)u1y), g2 = hypot((double)u2x, (double)u2y);
+    const float ng1 = (float)__dadd_rn(1.0, (double)__fmul_rn(taut, (float)g1));
+    const float ng2 = (float)__dadd_rn(1.0, (double)__fmul_rn(taut, (float)g2));
+    p11[p] = __fdiv_rn(__fadd_rn(p11[p], __fmul_rn(taut, u1x)), ng1);
+    p12[p] = __fdiv_rn(__fadd_rn(p12[p], __fmul_rn(taut, u1y)), ng1);
+    p21[p] = __fdiv_rn(__fadd_rn(p21[p], __fmul_rn(taut, u2x)), ng2);
+    p22[p] = __fdiv_rn(__fadd_rn(p22[p], __fmul_rn(taut, u2y)), ng2);
+}
+
 __global__ void __launch_bounds__(256) k_tvl1_p(const float *__restrict__ u1, const float *__restrict__ u2,
                                                 float *__restrict__ p11, float *__restrict__ p12,
                                                 float *__restrict__ p21, float *__restrict__ p22, const float *err, int n,
@@ -221,20 +240,89 @@ __global__ void __launch_bounds__(256) k_tvl1_p(const float *__restrict__ u1, co
 #endif
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
     if (j >= nx || i >= ny) return;
-    const int p = i * nx + j;
-    // forward differences, zero across the last column / row (mask.c:101-144)
-    const float a = u1[p], b = u2[p];
-    const float u1x = j < nx - 1 ? u1[p + 1] - a : 0.f, u1y = i < ny - 1 ? u1[p + nx] - a : 0.f;
-    const float u2x = j < nx - 1 ? u2[p + 1] - b : 0.f, u2y = i < ny - 1 ? u2[p + nx] - b : 0.f;
-    // (the reference's hypot and `1.0 +` are double: :239-242)
-    const double g1 = hypot((double)u1x, (double)u1y), g2 = hypot((double)u2x, (double)u2y);
-    const float ng1 = (float)__dadd_rn(1.0, (double)__fmul_rn(taut, (float)g1));
-    const float ng2 = (float)__dadd_rn(1.0, (double)__fmul_rn(taut, (float)g2));
-    p11[p] = __fdiv_rn(__fadd_rn(p11[p], __fmul_rn(taut, u1x)), ng1);
-    p12[p] = __fdiv_rn(__fadd_rn(p12[p], __fmul_rn(taut, u1y)), ng1);
-    p21[p] = __fdiv_rn(__fadd_rn(p21[p], __fmul_rn(taut, u2x)), ng2);
-    p22[p] = __fdiv_rn(__fadd_rn(p22[p], __fmul_rn(taut, u2y)), ng2);
+    tvl1_p_pixel(u1, u2, p11, p12, p21, p22, i, j, nx, ny, taut);
 }
+
+#ifndef NLK_HOST_MODEL
+// ---- the iterations of a warping step in ONE launch ----------------------------------------------------
+// Most iterations of a pyramid run on scales of a few ten thousand pixels, where a kernel per half
+// iteration is all launch latency.  k_tvl1_iterate keeps a co-resident grid (cooperative launch) for the
+// whole warping step: u-phase, grid barrier, p-phase and stopping test, grid barrier, next iteration.
+// Same per-pixel functions, same in-place updates, so the same flow bit for bit; the error of an iteration
+// is complete after the first barrier and every thread evaluates the reference's loop condition (:164) on it.
+constexpr int TVL1_IT_THREADS = 512;
+constexpr long long TVL1_BARRIER_LIMIT = 400000000ll;      // cycles (~0.2 s): a barrier that long is a bug, not a wait
+
+__device__ __forceinline__ unsigned tvl1_ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all blocks of the (co-resident) grid; `target` = barriers so far * gridDim.x.  False: gave up waiting.
+__device__ __forceinline__ bool tvl1_grid_barrier(unsigned *bar, unsigned target, int *s_fail)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const long long t0 = clock64();
+        int fail = 0;
+        while (tvl1_ld_acquire(bar) < target)
+            if (clock64() - t0 > TVL1_BARRIER_LIMIT) { fail = 1; break; }
+        __threadfence();
+        *s_fail = fail;
+    }
+    __syncthreads();
+    return *s_fail == 0;
+}
+
+__global__ void __launch_bounds__(TVL1_IT_THREADS) k_tvl1_iterate(const float *__restrict__ rho_c, const float *__restrict__ I1wx,
+                                                                  const float *__restrict__ I1wy, const float *__restrict__ grad,
+                                                                  float *p11, float *p12, float *p21, float *p22, float *u1,
+                                                                  float *u2, float *err, int *count, unsigned *bar,
+                                                                  int *host_flag, int nx, int ny, float l_t, float theta,
+                                                                  float taut, float eps2)
+{
+    __shared__ float s_red[TVL1_IT_THREADS / 32];
+    __shared__ int s_fail;
+    const int size = nx * ny;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned arrived = 0;
+    int n = 1;
+    for (;; ++n) {
+        float e = 0.f;
+        for (int p = tid; p < size; p += nthr) {
+            const int i = p / nx, j = p - i * nx;
+            e += tvl1_u_pixel(rho_c, I1wx, I1wy, grad, p11, p12, p21, p22, u1, u2, i, j, nx, ny, l_t, theta);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        if (lane == 0) s_red[warp] = e;
+        __syncthreads();
+        if (warp == 0) {
+            e = lane < TVL1_IT_THREADS / 32 ? s_red[lane] : 0.f;
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            if (lane == 0) atomicAdd(err + n, e);
+        }
+        arrived += gridDim.x;
+        if (!tvl1_grid_barrier(bar, arrived, &s_fail)) break;
+        for (int p = tid; p < size; p += nthr) {
+            const int i = p / nx, j = p - i * nx;
+            tvl1_p_pixel(u1, u2, p11, p12, p21, p22, i, j, nx, ny, taut);
+        }
+        const bool more = n < TVL1_MAX_ITERATIONS && __fdiv_rn(__ldcg(err + n), (float)size) > eps2;
+        if (!more) break;           // (uniform over the grid: everybody reads the same completed sum)
+        arrived += gridDim.x;
+        if (!tvl1_grid_barrier(bar, arrived, &s_fail)) break;
+    }
+    if (tid == 0) *count = n;
+    if (threadIdx.x == 0 && s_fail) *host_flag = 1;      // (pinned host memory: the host sees it without a copy)
+}
+#endif
 
 #ifndef NLK_HOST_MODEL
 __global__ void k_tvl1_loop_init(int *n_loop, int warps)

@@ -155,26 +155,31 @@ def test_flow_mask_between_resident_frames(nlk):
         assert np.array_equal(of.cpu().numpy()[..., 0], want[0])
 
 
-def test_tvl1_graph_loop_and_host_queued_iterations_agree(nlk, monkeypatch):
-    """the level solver runs as one CUDA graph per level (WHILE nodes around the iteration kernels); with
-    NLK_TVL1_GRAPH=0 the host queues the iterations in batches.  Same kernels, same stopping iteration:
-    identical flows and iteration counts -- and far fewer launches on the graph path (which also shows it
-    is the path in use, not a silent fallback)."""
+def test_tvl1_three_loop_forms_agree(nlk, monkeypatch):
+    """how the iterations of a warping step are driven (NLK_TVL1_LOOP): `kernel` (default) = one cooperative
+    launch per warping step, grid barriers between the half iterations; `graph` = one CUDA graph per level,
+    WHILE nodes around the two iteration kernels; `host` = the host queues batches and reads the error back.
+    Same per-pixel functions, same stopping iteration: identical flows and iteration counts -- and the
+    launch counts show which form ran (no silent fallback)."""
     from oracle import oracle as O
     nx, ny = 320, 240
     I0, I1 = O.tvl1_frames(nx, ny, seed=4)
     out = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("NLK_TVL1_GRAPH", mode)
+    for mode in ("kernel", "graph", "host"):
+        monkeypatch.setenv("NLK_TVL1_LOOP", mode)
         with nlk.Context(nx, ny, 1) as ctx:
             l0 = ctx.launches
             flow, its = ctx.tvl1_flow(I0, I1, lam=0.25)
-            flow2, its2 = ctx.tvl1_flow(I0, I1, lam=0.25)      # the cached graphs, launched again
+            flow2, its2 = ctx.tvl1_flow(I0, I1, lam=0.25)      # (graph: the cached graphs, launched again)
             out[mode] = (flow, its, ctx.launches - l0)
             assert np.array_equal(flow, flow2) and np.array_equal(its, its2)
-    assert np.array_equal(out["1"][0], out["0"][0]) and np.array_equal(out["1"][1], out["0"][1])
-    print(f"launches for two flows: graph loop {out['1'][2]}, host-queued {out['0'][2]}; iterations {out['1'][1].sum(1).tolist()}")
-    assert out["1"][2] * 4 < out["0"][2]
+    for mode in ("graph", "host"):
+        assert np.array_equal(out["kernel"][0], out[mode][0]) and np.array_equal(out["kernel"][1], out[mode][1]), mode
+    nscales = out["kernel"][1].shape[0]
+    print(f"launches for two flows: kernel {out['kernel'][2]}, graph {out['graph'][2]}, host {out['host'][2]}; "
+          f"iterations {out['kernel'][1].sum(1).tolist()}")
+    assert out["graph"][2] < out["kernel"][2] < out["host"][2] / 4
+    assert out["kernel"][2] >= 2 * nscales * (1 + 2 * 5)     # gradient + (warp, iterate) x 5 per scale
 
 
 def test_reference_entry_points_of_the_flow_library(nlk):
