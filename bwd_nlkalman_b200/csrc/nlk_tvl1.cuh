@@ -261,17 +261,17 @@ __device__ __forceinline__ unsigned tvl1_ld_acquire(const unsigned *p)
 }
 
 // all blocks of the (co-resident) grid; `target` = barriers so far * gridDim.x.  False: gave up waiting.
+// Release / acquire at GPU scope through thread 0 (the block barriers on either side make it cumulative
+// for the block's other threads; the acquiring load also drops the SM's stale L1 lines), no full fences.
 __device__ __forceinline__ bool tvl1_grid_barrier(unsigned *bar, unsigned target, int *s_fail)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
         const long long t0 = clock64();
         int fail = 0;
         while (tvl1_ld_acquire(bar) < target)
             if (clock64() - t0 > TVL1_BARRIER_LIMIT) { fail = 1; break; }
-        __threadfence();
         *s_fail = fail;
     }
     __syncthreads();
