@@ -42,7 +42,8 @@ def measure(nx=1920, ny=1080, reps=5, lam=0.25, fscale=1, device=0, with_referen
         dt = (time.perf_counter() - t0) / reps
         res.update({"value": nx * ny / dt / 1e6, "ms_per_pair": dt * 1e3,
                     "gpu_launches_per_pair": (ctx.launches - l0) // reps,
-                    "launch_note": "one CUDA graph launch per scale (the iterations run inside WHILE nodes) + the pyramid kernels"})
+                    "launch_note": "per scale: gradient + per warping step the warp kernel and ONE cooperative launch that runs all "
+                                   "its iterations (NLK_TVL1_LOOP=kernel, the default); plus the pyramid kernels"})
         flow, its = ctx.tvl1_flow(I0, I1, **kw)
         res["iterations_per_scale"] = its.sum(1).tolist()
     dx, dy = O.tvl1_truth(nx, ny)
