@@ -16,44 +16,59 @@
 #include "nlk_opts.h"
 #include "nlkalman_b200.h"
 
-#define PAR_DEFAULT_OUTFLOW "flow.flo"
-#define PAR_DEFAULT_TAU     0.25
-#define PAR_DEFAULT_LAMBDA  0.15
-#define PAR_DEFAULT_THETA   0.3
-#define PAR_DEFAULT_NSCALES 100
-#define PAR_DEFAULT_FSCALE  0
-#define PAR_DEFAULT_ZFACTOR 0.5
-#define PAR_DEFAULT_NWARPS  5
-#define PAR_DEFAULT_EPSILON 0.01
+/* The numeric arguments after `out`, in command-line order, with the value that replaces a missing or
+ * out-of-range one (reference lib/tvl1flow/main.c:26-35 for the values, :108-148 for the ranges). */
+enum { A_NPROC, A_TAU, A_LAMBDA, A_THETA, A_NSCALES, A_FSCALE, A_ZFACTOR, A_NWARPS, A_EPSILON, A_VERBOSE, A_COUNT };
+static const struct {
+    const char *name;
+    int integer;        /* parsed with atoi (else atof) */
+    double dflt;
+    double above;       /* valid: value > above ...                    */
+    double upto;        /* ... and value <= upto (0: no upper bound)   */
+    int below_only;     /* upper bound is exclusive (zfactor < 1)      */
+    int checked;        /* 0: any value is taken as it is              */
+} ARGS[A_COUNT] = {
+    {"nproc",   1, 0,    0, 0,    0, 0},    /* OpenMP team of the reference: accepted, unused */
+    {"tau",     0, 0.25, 0, 0.25, 0, 1},
+    {"lambda",  0, 0.15, 0, 0,    0, 1},
+    {"theta",   0, 0.3,  0, 0,    0, 1},
+    {"nscales", 1, 100,  0, 0,    0, 1},
+    {"fscale",  1, 0,    0, 0,    0, 0},
+    {"zfactor", 0, 0.5,  0, 1,    1, 1},
+    {"nwarps",  1, 5,    0, 0,    0, 1},
+    {"epsilon", 0, 0.01, 0, 0,    0, 1},
+    {"verbose", 1, 0,    0, 0,    0, 0},
+};
 
 int main(int argc, char *argv[])
 {
     if (argc < 3) {
-        fprintf(stderr, "Usage: %s I0 I1 [out nproc tau lambda theta nscales fscale zfactor nwarps epsilon verbose]\n",
-                *argv);
+        fprintf(stderr, "Usage: %s I0 I1 [out", *argv);
+        for (int k = 0; k < A_COUNT; ++k) fprintf(stderr, " %s", ARGS[k].name);
+        fprintf(stderr, "]\n");
         return EXIT_FAILURE;
     }
-    int i = 1;
-    const char *image1_name = argv[i++], *image2_name = argv[i++];
-    const char *outfile = (argc > i) ? argv[i] : PAR_DEFAULT_OUTFLOW; i++;
-    i++;                                                          /* nproc */
-    float tau     = (argc > i) ? atof(argv[i]) : PAR_DEFAULT_TAU;     i++;
-    float lambda  = (argc > i) ? atof(argv[i]) : PAR_DEFAULT_LAMBDA;  i++;
-    float theta   = (argc > i) ? atof(argv[i]) : PAR_DEFAULT_THETA;   i++;
-    int   nscales = (argc > i) ? atoi(argv[i]) : PAR_DEFAULT_NSCALES; i++;
-    int   fscale  = (argc > i) ? atoi(argv[i]) : PAR_DEFAULT_FSCALE;  i++;
-    float zfactor = (argc > i) ? atof(argv[i]) : PAR_DEFAULT_ZFACTOR; i++;
-    int   nwarps  = (argc > i) ? atoi(argv[i]) : PAR_DEFAULT_NWARPS;  i++;
-    float epsilon = (argc > i) ? atof(argv[i]) : PAR_DEFAULT_EPSILON; i++;
-    int   verbose = (argc > i) ? atoi(argv[i]) : 0;                   i++;
-
-    if (tau <= 0 || tau > 0.25) { tau = PAR_DEFAULT_TAU; if (verbose) fprintf(stderr, "warning: tau changed to %g\n", tau); }
-    if (lambda <= 0) { lambda = PAR_DEFAULT_LAMBDA; if (verbose) fprintf(stderr, "warning: lambda changed to %g\n", lambda); }
-    if (theta <= 0) { theta = PAR_DEFAULT_THETA; if (verbose) fprintf(stderr, "warning: theta changed to %g\n", theta); }
-    if (nscales <= 0) { nscales = PAR_DEFAULT_NSCALES; if (verbose) fprintf(stderr, "warning: nscales changed to %d\n", nscales); }
-    if (zfactor <= 0 || zfactor >= 1) { zfactor = PAR_DEFAULT_ZFACTOR; if (verbose) fprintf(stderr, "warning: zfactor changed to %g\n", zfactor); }
-    if (nwarps <= 0) { nwarps = PAR_DEFAULT_NWARPS; if (verbose) fprintf(stderr, "warning: nwarps changed to %d\n", nwarps); }
-    if (epsilon <= 0) { epsilon = PAR_DEFAULT_EPSILON; if (verbose) fprintf(stderr, "warning: epsilon changed to %f\n", epsilon); }
+    const char *image1_name = argv[1], *image2_name = argv[2];
+    const char *outfile = argc > 3 ? argv[3] : "flow.flo";
+    double v[A_COUNT];
+    int replaced[A_COUNT];
+    for (int k = 0; k < A_COUNT; ++k) {
+        const char *a = argc > 4 + k ? argv[4 + k] : NULL;
+        /* float arguments go through float like in the reference (atof assigned to a float) */
+        v[k] = !a ? ARGS[k].dflt : (ARGS[k].integer ? (double)atoi(a) : (double)(float)atof(a));
+        const int ok = !ARGS[k].checked ||
+                       (v[k] > ARGS[k].above && (ARGS[k].upto == 0 || (ARGS[k].below_only ? v[k] < ARGS[k].upto : v[k] <= ARGS[k].upto)));
+        replaced[k] = !ok;
+        if (!ok) v[k] = ARGS[k].dflt;
+    }
+    const int verbose = (int)v[A_VERBOSE];
+    if (verbose)
+        for (int k = 0; k < A_COUNT; ++k)
+            if (replaced[k]) fprintf(stderr, "warning: %s changed to %g\n", ARGS[k].name, v[k]);
+    const float tau = (float)v[A_TAU], lambda = (float)v[A_LAMBDA], theta = (float)v[A_THETA], zfactor = (float)v[A_ZFACTOR],
+                epsilon = (float)v[A_EPSILON];
+    int nscales = (int)v[A_NSCALES], fscale = (int)v[A_FSCALE];
+    const int nwarps = (int)v[A_NWARPS];
     if (fscale < 0) fscale = 0;     /* (the reference would index below its pyramid) */
 
     int nx, ny, nx2, ny2;

@@ -5,6 +5,7 @@ GPU (option table, mode rules and messages of reference src/main-flt.c:129-149,
 src/main-smo.c:87-92)."""
 import ctypes as C
 import os
+import re
 import struct
 import subprocess
 
@@ -303,3 +304,40 @@ def test_scalar_read_follows_iio(io, tmp_path):
             assert r.returncode == 0, r.stderr
         assert np.array_equal(io.read(tmp_path / "colour.flo"), io.read(tmp_path / "grey.flo")), ext
         assert np.abs(io.read(tmp_path / "colour.flo")).max() > 0.5
+
+
+def test_tvl1flow_arguments_follow_the_reference_program(io, tmp_path):
+    """bin/tvl1flow takes the positional command line of the reference's program (lib/tvl1flow/main.c:73-148):
+    missing and out-of-range values become the defaults (the pipeline script passes 0 for tau, theta and
+    nscales), nscales is capped by the image size.  With verbose = 1 both programs print what they will
+    run with before computing anything: compared here (the computation itself needs the GPU)."""
+    rng = np.random.default_rng(3)
+    for name in ("a", "b"):
+        io.write(tmp_path / f"{name}.pfm", rng.uniform(0, 255, (60, 80)).astype(np.float32))
+    ours = os.path.join(BIN, "tvl1flow")
+    ref = os.path.join(ROOT, "oracle", "_ref", "tvl1flow-ref")
+    cases = [("8", "0", "0.40", "0", "0", "1", "0", "0", "0", "1"),            # the script's, then zeros, verbose
+             ("1", "0.2", "0.3", "0.25", "2", "0", "0.6", "3", "0.02", "1"),   # everything given
+             ("0", "0.3", "-1", "-2", "-5", "7", "1.0", "-1", "-0.5", "1")]    # everything out of range
+    want_values = [dict(tau=0.25, lam=0.4, theta=0.3, zfactor=0.5, nwarps=5, epsilon=0.01),
+                   dict(tau=0.2, lam=0.3, theta=0.25, zfactor=0.6, nwarps=3, epsilon=0.02),
+                   dict(tau=0.25, lam=0.15, theta=0.3, zfactor=0.5, nwarps=5, epsilon=0.01)]
+    pat = re.compile(r"tau=(\S+) lambda=(\S+) theta=(\S+) nscales=(\d+) zfactor=(\S+) nwarps=(\d+) epsilon=(\S+)")
+    for args, want in zip(cases, want_values):
+        r = subprocess.run([ours, str(tmp_path / "a.pfm"), str(tmp_path / "b.pfm"), str(tmp_path / "o.flo"), *args],
+                           capture_output=True, text=True)
+        assert r.returncode in (0, 2), r.stderr      # 2: no CUDA device here
+        m = pat.search(r.stderr)
+        assert m, r.stderr
+        tau, lam, theta, nscales, zf, nw, eps = m.groups()
+        got = dict(tau=float(tau), lam=float(lam), theta=float(theta), zfactor=float(zf), nwarps=int(nw), epsilon=float(eps))
+        assert all(abs(got[k] - want[k]) < 1e-6 for k in want), (got, want)
+        warned = sorted(re.findall(r"warning: (\w+) changed", r.stderr))
+        if os.path.exists(ref):
+            q = subprocess.run([ref, str(tmp_path / "a.pfm"), str(tmp_path / "b.pfm"), str(tmp_path / "r.flo"), *args],
+                               capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS="1"))
+            assert q.returncode == 0, q.stderr
+            assert pat.search(q.stderr).groups() == m.groups(), (q.stderr, r.stderr)
+            assert sorted(w for w in re.findall(r"warning: (\w+) changed", q.stderr) if w != "nproc") == warned
+    r = subprocess.run([ours], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("Usage:") and "zfactor nwarps epsilon verbose" in r.stderr
