@@ -150,7 +150,8 @@ int main(int argc, const char *argv[])
     const int timing = getenv("NLK_CLI_TIMING") != NULL;
     const double t_start = now_s();
     pthread_t warm;
-    const int warm_on = pthread_create(&warm, NULL, gpu_warmup, &dev) == 0;
+    const char *warm_env = getenv("NLK_CLI_WARMUP");      /* 0: bring the GPU up after the files, in this thread */
+    const int warm_on = !(warm_env && atoi(warm_env) == 0) && pthread_create(&warm, NULL, gpu_warmup, &dev) == 0;
 
     /* load data (reference src/main-flt.c:215-332: same checks, same messages) */
     int w, h, c, w1, h1, c1;
