@@ -1397,6 +1397,9 @@ extern "C" int nlk_tvl1_flow_dev(nlk_ctx *c, const float *d_I0, const float *d_I
         return set_err(NLK_ERR_PARAM, "%s (%dx%d, %d scales from %d, zoom %g, %d warpings)", P.error, nxx, nyy, nscales,
                        fscale, (double)zfactor, warps);
     if (int r = c->tv_pyr.ensure(P.floats * 4)) return r;
+    // the level solver's planes, sized once for the finest scale it will see (it runs coarse to fine)
+    if (fscale < nscales)
+        if (int r = c->tv_scratch.ensure(Tvl1Level::bytes(P.size(fscale), warps))) return r;
     Tvl1Cuda ex{c, c->L->st, tau, lambda, theta, epsilon, warps};
     if (int r = P.run(ex, c->tv_pyr.as<float>(), d_I0, d_I1, d_u1, d_u2, iterations)) return r;
     return check_launch(c, ex.launches, "tvl1 pyramid");
@@ -1871,20 +1874,20 @@ static void legacy_die(const char *what)
     exit(1);
 }
 
-static nlk_ctx *legacy_ctx(int w, int h, int ch)
+static nlk_ctx *legacy_ctx(int w, int h, int ch, nlk_ctx **slot = &g_legacy)
 {
-    if (g_legacy && (g_legacy->w != w || g_legacy->h != h || g_legacy->ch != ch)) {
-        nlk_ctx_destroy(g_legacy);
-        g_legacy = nullptr;
+    if (*slot && ((*slot)->w != w || (*slot)->h != h || (*slot)->ch != ch)) {
+        nlk_ctx_destroy(*slot);
+        *slot = nullptr;
     }
-    if (!g_legacy) {
+    if (!*slot) {
         int dev = 0;
         if (const char *e = getenv("NLK_DEVICE")) dev = atoi(e);
-        g_legacy = nlk_ctx_create(w, h, ch, dev);
-        if (!g_legacy) legacy_die("no usable CUDA device (there is no CPU fallback)");
+        *slot = nlk_ctx_create(w, h, ch, dev);
+        if (!*slot) legacy_die("no usable CUDA device (there is no CPU fallback)");
     }
-    if (enter(g_legacy)) legacy_die("cudaSetDevice");
-    return g_legacy;
+    if (enter(*slot)) legacy_die("cudaSetDevice");
+    return *slot;
 }
 
 static void legacy_colour(float *im, int w, int h, int ch, int inverse)
@@ -2028,13 +2031,16 @@ extern "C" int nlk_fp32_peak(nlk_ctx *c, float ms, double *tflops)
 }
 
 // ---- the two entry points of the reference's TV-L1 library (include/tvl1flow.h) ----------------------
+// (a context of their own: a caller alternating between the flow of single-channel images and the filter
+// of colour frames keeps both)
+static nlk_ctx *g_legacy_flow = nullptr;
 
 extern "C" void Dual_TVL1_optic_flow(float *I0, float *I1, float *u1, float *u2, const int nx, const int ny,
                                      const float tau, const float lambda, const float theta, const int warps,
                                      const float epsilon, const bool verbose)
 {
     std::lock_guard<std::mutex> lk(g_legacy_mu);
-    nlk_ctx *c = legacy_ctx(nx, ny, 1);
+    nlk_ctx *c = legacy_ctx(nx, ny, 1, &g_legacy_flow);
     std::vector<int> its(warps > 0 ? warps : 1, 0);
     if (nlk_tvl1_level_host(c, I0, I1, u1, u2, nx, ny, tau, lambda, theta, warps, epsilon, its.data()))
         legacy_die("Dual_TVL1_optic_flow");
@@ -2048,7 +2054,7 @@ extern "C" void Dual_TVL1_optic_flow_multiscale(float *I0, float *I1, float *u1,
                                                 const float epsilon, const bool verbose)
 {
     std::lock_guard<std::mutex> lk(g_legacy_mu);
-    nlk_ctx *c = legacy_ctx(nxx, nyy, 1);
+    nlk_ctx *c = legacy_ctx(nxx, nyy, 1, &g_legacy_flow);
     const size_t n = (size_t)nxx * nyy;
     std::vector<float> flow(2 * n);
     std::vector<int> its((size_t)(nscales > 0 ? nscales : 1) * (warps > 0 ? warps : 1), 0);
