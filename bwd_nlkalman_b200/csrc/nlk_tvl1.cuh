@@ -2,17 +2,21 @@
 // Dual_TVL1_optic_flow computes (lib/tvl1flow/tvl1flow_lib.c:93-280, Zach-Pock-Bischof with
 // Chambolle's dual update), the heavy per-frame step in front of the filter in
 // scripts/nlkalman-seq.sh:60-65.  All of it is per-pixel / 5-point-stencil work on ~14 float planes:
-// HBM / L2 bound, so the steps of an iteration are fused into two kernels,
+// HBM / L2 bound at the fine scales, launch-latency bound at the coarse ones (where most iterations
+// run).  An iteration is two per-pixel steps,
 //
-//   k_tvl1_u:  thresholding step v = TH(u) (:172-206), divergence of the dual variable
-//              (mask.c:43-94), u = v + theta div p and the squared update for the stopping test (:213-227)
-//   k_tvl1_p:  forward gradient of the new u (mask.c:101-144), dual update p (:235-248)
+//   tvl1_u_pixel:  thresholding step v = TH(u) (:172-206), divergence of the dual variable
+//                  (mask.c:43-94), u = v + theta div p and the squared update for the stopping test (:213-227)
+//   tvl1_p_pixel:  forward gradient of the new u (mask.c:101-144), dual update p (:235-248)
 //
 // and the three bicubic warps of a warping step (I1, dI1/dx, dI1/dy at the same positions) plus rho_c
-// and |grad|^2 (:140-157) into one.  The stopping rule `error > eps^2 && n < 300` (:164) is evaluated
-// ON THE DEVICE: an iteration's kernels look at the error of the previous one and return at once when
-// it is below the threshold, so a batch of iterations can be queued without a host round trip and
-// the result is that of the exact stopping iteration.
+// and |grad|^2 (:140-157) are one kernel.  The stopping rule `error > eps^2 && n < 300` (:164) is evaluated
+// ON THE DEVICE in every form the loop of a warping step takes (nlk_lib.cu: nlk_tvl1_level_dev):
+//   k_tvl1_iterate          all iterations in one cooperative launch, grid barriers between the steps (default)
+//   k_tvl1_u + k_tvl1_p     the body of a CUDA graph WHILE node (k_tvl1_p sets the loop condition), or
+//                           queued in batches by the host, each kernel returning at once when the previous
+//                           iteration met the stopping rule
+// so the result is always that of the exact stopping iteration.
 //
 // Around the level solver, the pyramid of Dual_TVL1_optic_flow_multiscale (:345-477): joint
 // normalisation, separable Gaussian, zoom out / zoom in (kernels at the end of this file; the sequence of
