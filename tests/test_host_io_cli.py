@@ -210,6 +210,11 @@ def test_smo_and_seq_option_tables():
         assert opt in r.stdout, opt
     r = _run("nlkalman-seq", "--f1_p", "0")
     assert r.returncode == 1 and "f1_p == 0" in r.stderr
+    # the whole pipeline in one process: flows computed on the GPU, the script's OPM values
+    assert "--tvl1" in _run("nlkalman-seq", "-h").stdout and "--of_prms" in _run("nlkalman-seq", "-h").stdout
+    r = _run("nlkalman-seq", "-i", "n%d.pfm", "-f", "0", "-l", "1", "-s", "20", "--filt1", "o%d.pfm", "--tvl1", "1",
+             "--of_prms", "1 0.25 0.75")
+    assert r.returncode == 1 and "six values" in r.stderr
 
 
 def test_decoders_reject_malformed_headers(io, tmp_path):
