@@ -120,3 +120,39 @@ def test_flow_against_golden(model):
         got = np.zeros((2, ny, nx), np.float32)
         assert model.model_tvl1_flow(_p(I0), _p(I1), _p(got), nx, ny, 0.25, lam, 0.3, nscales, fscale, 0.5, 5, 0.01, None) == 0
         assert np.array_equal(got, g[key]), key
+
+
+def test_flow_bit_exact_on_random_requests(model, ref):
+    """sizes, zoom factors, weights, warpings, tolerances, scale counts and first scales drawn at random; smooth
+    scenes, noise, and constant images (the normalisation's max = min branch): every flow identical to
+    the reference's"""
+    rng = np.random.default_rng(0)
+    checked = 0
+    for trial in range(36):
+        nx, ny = int(rng.integers(17, 140)), int(rng.integers(17, 110))
+        zf = float(rng.choice([0.3, 0.5, 0.6, 0.75, 0.9]))
+        p = dict(tau=float(rng.choice([0.1, 0.25])), lam=float(rng.choice([0.05, 0.15, 0.4, 1.0])),
+                 theta=float(rng.choice([0.1, 0.3, 0.6])), nscales=int(rng.choice([1, 2, 3, 100])), fscale=0, zfactor=zf,
+                 warps=int(rng.integers(1, 6)), epsilon=float(rng.choice([0.0005, 0.01, 0.05])))
+        if trial % 3 == 0:
+            I0, I1 = O.tvl1_frames(nx, ny, seed=trial)
+        elif trial % 3 == 1:
+            I0 = rng.uniform(0, 255, (ny, nx)).astype(np.float32)
+            I1 = np.roll(I0, 1, 1) + rng.normal(0, 3, (ny, nx)).astype(np.float32)
+        else:
+            I0 = np.full((ny, nx), 7.0, np.float32)
+            I1 = I0.copy()
+            I1[ny // 2, nx // 2] += trial % 2
+        ns = model.model_tvl1_scales(nx, ny, zf, p["nscales"])
+        if ns < 1:
+            continue
+        p["fscale"] = int(rng.integers(0, ns + 1))
+        got = np.zeros((2, ny, nx), np.float32)
+        rc = model.model_tvl1_flow(_p(I0), _p(I1), _p(got), nx, ny, p["tau"], p["lam"], p["theta"], ns, p["fscale"], zf,
+                                   p["warps"], p["epsilon"], None)
+        if rc != 0:
+            continue        # a request the library refuses (the reference aborts or reads out of bounds on it)
+        want, ns_ref = ref.flow(np.ascontiguousarray(I0), np.ascontiguousarray(I1), **p)
+        assert ns_ref == ns and np.array_equal(got, want, equal_nan=True), (trial, nx, ny, p)
+        checked += 1
+    assert checked >= 30
